@@ -1,0 +1,106 @@
+"""ctypes binding of the C ABI in include/iins_b200.h.
+
+The product path loads exactly one library: the nvcc-built, in-tree ``libiins_b200.so`` (sm_100a).
+If it is missing it is built with nvcc; if that is impossible the import raises -- there is no CPU
+or PyTorch fallback anywhere in this package.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libiins_b200.so")
+
+EXPORTS = [
+    "iins_abi_version", "iins_last_error", "iins_validate_config",
+    "iins_encoder_num_params", "iins_encoder_ws_floats", "iins_encoder_scratch_floats",
+    "iins_encoder_forward", "iins_encoder_backward",
+    "iins_decoder_num_params", "iins_decoder_ws_floats", "iins_decoder_scratch_floats",
+    "iins_decoder_forward", "iins_decoder_backward",
+    "iins_restorer_num_params", "iins_restorer_ws_floats", "iins_restorer_scratch_floats",
+    "iins_restorer_forward", "iins_restorer_backward",
+    "iins_classifier_num_params", "iins_classifier_ws_floats", "iins_classifier_scratch_floats",
+    "iins_classifier_forward", "iins_classifier_backward",
+    "iins_loss_forward_backward", "iins_adam_step",
+    "iins_adaptive_pool_forward", "iins_adaptive_pool_backward",
+]
+
+
+class IinsConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("batch", "cir_len", "dim", "n_residual", "n_downsample", "env_dim",
+                                       "range_dim", "num_classes", "cls_filters")]
+
+
+class IinsError(RuntimeError):
+    pass
+
+
+_P = C.c_void_p
+_PP = C.POINTER(C.c_void_p)
+_CFG = C.POINTER(IinsConfig)
+
+
+class IinsLib:
+    """Typed view of one loaded shared object exporting the iins_* symbols."""
+
+    def __init__(self, path: str):
+        self.path = path
+        self.dll = C.CDLL(path)
+        d = self.dll
+        d.iins_abi_version.restype = C.c_int
+        d.iins_last_error.restype = C.c_char_p
+        d.iins_validate_config.argtypes = [_CFG]
+        for mod in ("encoder", "decoder", "restorer", "classifier"):
+            getattr(d, f"iins_{mod}_num_params").argtypes = [_CFG]
+            for q in ("ws", "scratch"):
+                f = getattr(d, f"iins_{mod}_{q}_floats")
+                f.argtypes = [_CFG]
+                f.restype = C.c_size_t
+        d.iins_encoder_forward.argtypes = [_CFG, _PP, _P, _P, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P]
+        d.iins_encoder_backward.argtypes = [_CFG, _PP, _P, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, _PP, _P, _P]
+        d.iins_decoder_forward.argtypes = [_CFG, _PP, _P, _P, _P, _P, _P]
+        d.iins_decoder_backward.argtypes = [_CFG, _PP, _P, _P, _P, _P, _PP, _P, _P, C.c_int, _P, _P]
+        d.iins_restorer_forward.argtypes = [_CFG, _PP, _P, _P, _P, _P]
+        d.iins_restorer_backward.argtypes = [_CFG, _PP, _P, _P, _P, _PP, _P, C.c_int, _P, _P]
+        d.iins_classifier_forward.argtypes = [_CFG, _PP, _P, _P, _P, _P]
+        d.iins_classifier_backward.argtypes = [_CFG, _PP, _P, _P, _P, _PP, _P, C.c_int, _P, _P]
+        d.iins_loss_forward_backward.argtypes = [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P,
+                                                 C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P]
+        d.iins_adam_step.argtypes = [_P, _P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                     C.c_int, _P, _P, C.c_double, C.c_double, C.c_float, _P]
+        d.iins_adaptive_pool_forward.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P]
+        d.iins_adaptive_pool_backward.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P]
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            raise IinsError(f"{what} failed ({rc}): {self.dll.iins_last_error().decode()}")
+
+    def __getattr__(self, name):
+        return getattr(self.dll, name)
+
+
+def ptr(t):
+    """Device (or, in the simulator tests, host) address of a tensor, or NULL."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+_lib = None
+
+
+def get_lib() -> IinsLib:
+    """The sm_100a library.  Built in-tree on first use when nvcc is present; otherwise raises."""
+    global _lib
+    if _lib is None:
+        from . import build as _build
+        if _build.needs_build():
+            _build.build()
+        _lib = IinsLib(LIB_PATH)
+        if _lib.iins_abi_version() != 1:
+            raise IinsError("libiins_b200.so ABI version mismatch")
+    return _lib

@@ -1,0 +1,151 @@
+// Common definitions for the IIns-VAE sm_100a kernels.
+#pragma once
+
+#ifdef IINS_CPUSIM
+#include "cuda_sim.h"          // tests/cpusim: logic simulator, never part of the product build
+#else
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#define IINS_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define IINS_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+#endif
+
+#define IINS_HD __host__ __device__ __forceinline__
+#define IINS_D __device__ __forceinline__
+
+enum { IINS_PAD_ZERO = 0, IINS_PAD_REFLECT = 1, IINS_PAD_UP2 = 2 };
+enum { IINS_ACT_NONE = 0, IINS_ACT_RELU = 1, IINS_ACT_LRELU = 2, IINS_ACT_TANH = 3 };
+enum { IINS_NORM_NONE = 0, IINS_NORM_IN = 1, IINS_NORM_ADAIN = 2, IINS_NORM_LN = 3 };
+enum { IINS_NLC = 0, IINS_NCL = 1 };
+
+#define IINS_EPS 1e-5f          // InstanceNorm1d / AdaIN / custom LayerNorm eps (models.py:152,965,1049)
+
+IINS_HD float iins_act(float v, int act, float slope) {
+    if (act == IINS_ACT_RELU) return v > 0.f ? v : 0.f;
+    if (act == IINS_ACT_LRELU) return v > 0.f ? v : v * slope;
+    if (act == IINS_ACT_TANH) return tanhf(v);
+    return v;
+}
+
+// derivative of the activation expressed through its OUTPUT y (sign-preserving activations)
+IINS_HD float iins_dact_from_y(float y, int act, float slope) {
+    if (act == IINS_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+    if (act == IINS_ACT_LRELU) return y > 0.f ? 1.f : slope;
+    if (act == IINS_ACT_TANH) return 1.f - y * y;
+    return 1.f;
+}
+
+IINS_D float iins_warp_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// sum over aligned groups of G consecutive lanes (G power of two <= 32)
+IINS_D float iins_group_sum(float v, int G) {
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Geometry of one conv1d / linear layer.  Activations are channels-last (NLC) in HBM unless a
+// layout flag says NCL (the reference's layout, used only at the module boundary).
+struct IinsGeom {
+    int B;                 // samples
+    int Lin, Lout;         // positions per sample, input / output (1 for a Linear layer)
+    int Cin, Cout;
+    int ks, stride, pad;   // kernel taps, stride, padding amount
+    int mode;              // IINS_PAD_ZERO | IINS_PAD_REFLECT | IINS_PAD_UP2 (nearest x2 then zero pad)
+    int in_layout;         // layout of the layer input  (IINS_NLC / IINS_NCL)
+    int out_layout;        // layout of the layer output
+};
+
+// How a gradient w.r.t. the conv OUTPUT (pre-norm pre-activation "dz") is read.
+//   dz[b,l,co] = dy[...] * dy_scale * act'(y[b,l,co])
+// dy is indexed like the layer output unless dy_bcast (then dy is (B,Cout), broadcast over l:
+// the backward of AdaptiveAvgPool1d(1), models.py:279).
+struct IinsDz {
+    const float* dy;
+    const float* y;        // layer output (post activation) for act', or nullptr
+    int act;
+    float slope;
+    int dy_bcast;
+    float dy_scale;
+};
+
+// source position inside the (un-padded, un-upsampled) input for output row l, tap t; -1 = zero
+IINS_HD int iins_src_pos(const IinsGeom& g, int l, int t) {
+    int u = l * g.stride + t - g.pad;
+    if (g.mode == IINS_PAD_REFLECT) {
+        if (u < 0) u = -u;
+        else if (u >= g.Lin) u = 2 * (g.Lin - 1) - u;
+        return u;
+    }
+    if (g.mode == IINS_PAD_UP2) {
+        if (u < 0 || u >= 2 * g.Lin) return -1;
+        return u >> 1;
+    }
+    if (u < 0 || u >= g.Lin) return -1;
+    return u;
+}
+
+IINS_HD long iins_in_index(const IinsGeom& g, int b, int pos, int ci) {
+    return g.in_layout == IINS_NCL ? ((long)b * g.Cin + ci) * g.Lin + pos : ((long)b * g.Lin + pos) * g.Cin + ci;
+}
+IINS_HD long iins_out_index(const IinsGeom& g, int b, int l, int co) {
+    return g.out_layout == IINS_NCL ? ((long)b * g.Cout + co) * g.Lout + l : ((long)b * g.Lout + l) * g.Cout + co;
+}
+
+// forward implicit-GEMM A operand: row = (b,l), k = t*Cin + ci
+IINS_D float iins_a_fwd(const IinsGeom& g, const float* __restrict__ x, int b, int l, int t, int ci) {
+    int pos = iins_src_pos(g, l, t);
+    if (pos < 0) return 0.f;
+    return __ldg(x + iins_in_index(g, b, pos, ci));
+}
+
+IINS_D float iins_dz_at(const IinsGeom& g, const IinsDz& d, int b, int l, int co) {
+    long idx = iins_out_index(g, b, l, co);
+    float v = d.dy_bcast ? __ldg(d.dy + (long)b * g.Cout + co) : __ldg(d.dy + idx);
+    v *= d.dy_scale;
+    if (d.y != nullptr && d.act != IINS_ACT_NONE) v *= iins_dact_from_y(__ldg(d.y + idx), d.act, d.slope);
+    return v;
+}
+
+// data-gradient implicit-GEMM A operand: row = (b,pos) of the layer INPUT, k = t*Cout + co.
+// Gathers every output row l whose tap t reads input position pos (<= 3 candidates: the direct
+// one plus the two reflected images, or the two upsampled copies).
+IINS_D float iins_a_dgrad(const IinsGeom& g, const IinsDz& d, int b, int pos, int t, int co) {
+    int q[3];
+    int nq;
+    if (g.mode == IINS_PAD_REFLECT) {
+        q[0] = pos + g.pad;
+        nq = 1;
+        if (pos >= 1 && pos <= g.pad) q[nq++] = g.pad - pos;
+        if (pos <= g.Lin - 2 && pos >= g.Lin - 1 - g.pad) q[nq++] = g.pad + 2 * (g.Lin - 1) - pos;
+    } else if (g.mode == IINS_PAD_UP2) {
+        q[0] = 2 * pos + g.pad;
+        q[1] = 2 * pos + 1 + g.pad;
+        nq = 2;
+    } else {
+        q[0] = pos + g.pad;
+        nq = 1;
+    }
+    float acc = 0.f;
+    for (int j = 0; j < nq; ++j) {
+        int r = q[j] - t;
+        if (r < 0) continue;
+        int l = r / g.stride;
+        if (l * g.stride != r || l >= g.Lout) continue;
+        acc += iins_dz_at(g, d, b, l, co);
+    }
+    return acc;
+}
+
+// conv weight W[co][ci][t]  (torch Conv1d layout; Linear is ks == 1)
+IINS_HD long iins_w_index(const IinsGeom& g, int co, int ci, int t) {
+    return ((long)co * g.Cin + ci) * g.ks + t;
+}

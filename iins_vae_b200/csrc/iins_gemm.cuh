@@ -1,0 +1,316 @@
+// Implicit-GEMM kernels (FP32 SIMT core) shared by every Conv1d / Linear layer of the path.
+//
+//   nt_kernel : C[row][n] = sum_k A[row][k] * Bw[n][k]        forward (A = im2col gather of the layer
+//               input) and data-gradient (A = gather of dz through the transposed tap map)
+//   tn_kernel : dW[n][k] += sum_row dz[row][n] * A[row][k]    weight gradient (+ bias gradient)
+//
+// Tiles are 128 rows = a whole number of samples (every L on the path is a power of two <= 128), so
+// InstanceNorm / AdaIN / the reference's custom LayerNorm, the activation and the residual add run in
+// the epilogue on an SMEM-staged tile and the activation tensor is written exactly once.
+#pragma once
+#include "iins_common.cuh"
+
+struct IinsEpilogue {
+    const float* bias;         // [N] or nullptr
+    int norm;                  // IINS_NORM_*
+    int act;
+    float slope;
+    const float* add;          // same indexing as y; added after norm+act (residual / grad accumulate)
+    float* y;                  // output
+    float* xhat;               // normalised pre-affine values (saved for backward) or nullptr
+    float* rstd;               // IN/AdaIN: [B*N]; LN: [B] (= 1/(std+eps))
+    const float* gamma;        // LN per-channel scale / shift
+    const float* beta;
+    const float* adain;        // AdaIN params (B, adain_ld): bias at +off_b, weight at +off_w
+    int adain_ld, adain_off_b, adain_off_w;
+};
+
+struct IinsNTParams {
+    IinsGeom g;
+    int a_kind;                // 0 = forward gather from x, 1 = dgrad gather from dz
+    const float* x;            // forward input
+    IinsDz dz;                 // dgrad source
+    const float* w;
+    IinsEpilogue ep;
+    int M, N, K;               // GEMM sizes (rows, cols, reduction)
+    int Lrow;                  // rows per sample of the OUTPUT of this GEMM (Lout fwd, Lin dgrad)
+    int out_layout;            // layout of the GEMM output
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256) iins_nt_kernel(const IinsNTParams p) {
+    constexpr int BM = 128, BK = 16, TN = 4;
+    constexpr int CT = BN / TN;            // threads along n
+    constexpr int RT = 256 / CT;           // threads along m
+    constexpr int TM = BM / RT;            // rows per thread
+    constexpr int B_PER_THREAD = (BN * BK + 255) / 256;
+    __shared__ __align__(16) float smem[2048 + BK * BN + BM * BN];
+    float* As = smem;                       // [BK][BM]
+    float* Bs = smem + 2048;                // [BK][BN]
+    float* Cs = smem + 2048 + BK * BN;      // [BM][BN]
+    float* st_mean = smem;                  // epilogue stats alias As (<= 1024 entries each)
+    float* st_rstd = smem + 1024;
+
+    const int tid = threadIdx.x;
+    const int tile_m = blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const IinsGeom& g = p.g;
+    const int Cdim = p.a_kind == 0 ? g.Cin : g.Cout;      // channel extent of the k index
+
+    // ---- A loader: row = tid & 127, 8 consecutive k starting at (tid >> 7) * 8
+    const int a_row = tid & 127;
+    const int a_k0 = (tid >> 7) * 8;
+    const int grow = tile_m + a_row;
+    const bool a_ok = grow < p.M;
+    const int a_b = a_ok ? grow / p.Lrow : 0;
+    const int a_l = a_ok ? grow - a_b * p.Lrow : 0;
+
+    float a_reg[8];
+    float b_reg[B_PER_THREAD];
+
+    auto load_regs = [&](int kb) {
+        int k = kb * BK + a_k0;
+        int t = k / Cdim;
+        int c = k - t * Cdim;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float v = 0.f;
+            if (a_ok && k + i < p.K) {
+                v = p.a_kind == 0 ? iins_a_fwd(g, p.x, a_b, a_l, t, c) : iins_a_dgrad(g, p.dz, a_b, a_l, t, c);
+            }
+            a_reg[i] = v;
+            if (++c == Cdim) { c = 0; ++t; }
+        }
+#pragma unroll
+        for (int j = 0; j < B_PER_THREAD; ++j) {
+            int e = tid + j * 256;
+            float v = 0.f;
+            if (e < BN * BK) {
+                int kk = e / BN, n = e - kk * BN;
+                int kg = kb * BK + kk, ng = n0 + n;
+                if (kg < p.K && ng < p.N) {
+                    int tt = kg / Cdim, cc = kg - tt * Cdim;
+                    long wi = p.a_kind == 0 ? iins_w_index(g, ng, cc, tt) : iins_w_index(g, cc, ng, tt);
+                    v = __ldg(p.w + wi);
+                }
+            }
+            b_reg[j] = v;
+        }
+    };
+    auto store_smem = [&]() {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) As[(a_k0 + i) * BM + a_row] = a_reg[i];
+#pragma unroll
+        for (int j = 0; j < B_PER_THREAD; ++j) {
+            int e = tid + j * 256;
+            if (e < BN * BK) Bs[e] = b_reg[j];          // e == kk*BN + n
+        }
+    };
+
+    const int tx = tid % CT, ty = tid / CT;
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    const int nkb = (p.K + BK - 1) / BK;
+    load_regs(0);
+    store_smem();
+    __syncthreads();
+    for (int kb = 0; kb < nkb; ++kb) {
+        if (kb + 1 < nkb) load_regs(kb + 1);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[kk * BM + ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[kk * BN + tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+        if (kb + 1 < nkb) {
+            store_smem();
+            __syncthreads();
+        }
+    }
+
+    // ---- epilogue: stage (acc + bias) in smem
+    const IinsEpilogue& ep = p.ep;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        int n = n0 + tx * TN + j;
+        float bv = (ep.bias != nullptr && n < p.N) ? __ldg(ep.bias + n) : 0.f;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) Cs[(ty * TM + i) * BN + tx * TN + j] = acc[i][j] + bv;
+    }
+    __syncthreads();
+
+    const int L = p.Lrow;
+    const int S = BM / L;                  // samples per tile (L <= 128 always when norm != NONE)
+    const int ncols = (p.N - n0) < BN ? (p.N - n0) : BN;
+    const int b0 = tile_m / L;             // first sample of the tile
+
+    if (ep.norm == IINS_NORM_IN || ep.norm == IINS_NORM_ADAIN) {
+        // per (sample, channel) statistics over the L rows; biased variance (models.py:152, 1072)
+        const int pairs = S * ncols;
+        int G = 1;
+        while (G < 32 && pairs * G * 2 <= 256) G <<= 1;
+        const int per_iter = 256 / G;
+        for (int p0 = 0; p0 < pairs; p0 += per_iter) {
+            int pr = p0 + tid / G, sub = tid % G;
+            bool ok = pr < pairs;
+            int s = ok ? pr / ncols : 0, c = ok ? pr - s * ncols : 0;
+            float sum = 0.f;
+            if (ok) for (int l = sub; l < L; l += G) sum += Cs[(s * L + l) * BN + c];
+            sum = iins_group_sum(sum, G);
+            float mean = sum / (float)L;
+            float sq = 0.f;
+            if (ok) for (int l = sub; l < L; l += G) { float dv = Cs[(s * L + l) * BN + c] - mean; sq += dv * dv; }
+            sq = iins_group_sum(sq, G);
+            if (ok && sub == 0) {
+                float rs = 1.0f / sqrtf(sq / (float)L + IINS_EPS);
+                st_mean[s * BN + c] = mean;
+                st_rstd[s * BN + c] = rs;
+                int b = b0 + s;
+                if (b < g.B && ep.rstd != nullptr) ep.rstd[(long)b * p.N + n0 + c] = rs;
+            }
+        }
+        __syncthreads();
+    } else if (ep.norm == IINS_NORM_LN) {
+        // per-sample mean and UNBIASED std over (C*L), eps added to std (models.py:976-981)
+        const int warp = tid >> 5, lane = tid & 31;
+        const int nel = L * ncols;
+        for (int s0 = 0; s0 < S; s0 += 8) {
+            int s = s0 + warp;
+            bool ok = s < S;
+            float sum = 0.f;
+            if (ok) for (int e = lane; e < nel; e += 32) sum += Cs[(s * L + e / ncols) * BN + (e % ncols)];
+            sum = iins_warp_sum(sum);
+            float mean = sum / (float)nel;
+            float sq = 0.f;
+            if (ok) for (int e = lane; e < nel; e += 32) { float dv = Cs[(s * L + e / ncols) * BN + (e % ncols)] - mean; sq += dv * dv; }
+            sq = iins_warp_sum(sq);
+            if (ok && lane == 0) {
+                float rs = 1.0f / (sqrtf(sq / (float)(nel - 1)) + IINS_EPS);
+                st_mean[s] = mean;
+                st_rstd[s] = rs;
+                int b = b0 + s;
+                if (b < g.B && ep.rstd != nullptr) ep.rstd[b] = rs;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- apply + store (coalesced over the contiguous NLC tile)
+    for (int e = tid; e < BM * BN; e += 256) {
+        int r = e / BN, n = e - r * BN;
+        int gr = tile_m + r, gn = n0 + n;
+        if (gr >= p.M || gn >= p.N) continue;
+        float v = Cs[e];
+        int s = r / L;
+        int b = gr / L, l = gr - b * L;
+        long oi = p.out_layout == IINS_NCL ? ((long)b * p.N + gn) * L + l : (long)gr * p.N + gn;
+        if (ep.norm == IINS_NORM_IN || ep.norm == IINS_NORM_ADAIN) {
+            v = (v - st_mean[s * BN + n]) * st_rstd[s * BN + n];
+            if (ep.xhat != nullptr) ep.xhat[oi] = v;
+            if (ep.norm == IINS_NORM_ADAIN) {
+                float wv = __ldg(ep.adain + (long)b * ep.adain_ld + ep.adain_off_w + gn);
+                float bv = __ldg(ep.adain + (long)b * ep.adain_ld + ep.adain_off_b + gn);
+                v = fmaf(v, wv, bv);
+            }
+        } else if (ep.norm == IINS_NORM_LN) {
+            v = (v - st_mean[s]) * st_rstd[s];
+            if (ep.xhat != nullptr) ep.xhat[oi] = v;
+            v = fmaf(v, __ldg(ep.gamma + gn), __ldg(ep.beta + gn));
+        }
+        v = iins_act(v, ep.act, ep.slope);
+        if (ep.add != nullptr) v += __ldg(ep.add + oi);
+        ep.y[oi] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------ wgrad
+struct IinsTNParams {
+    IinsGeom g;
+    const float* x;            // forward input of the layer (A operand via the forward gather)
+    IinsDz dz;
+    float* dw;                 // [Cout][Cin][ks], accumulated with atomicAdd
+    float* db;                 // [Cout] or nullptr
+    int M;                     // rows = B * Lout
+    int rows_per_part;         // multiple of 32
+};
+
+// grid = (row parts, ceil(K/64), ceil(N/64)); each CTA owns a 64(n) x 64(k) block of dW, reduces its
+// row range in registers (4x4 per thread) and flushes once with atomicAdd.
+__global__ void __launch_bounds__(256) iins_tn_kernel(const IinsTNParams p) {
+    constexpr int BR = 32, BNK = 64;
+    __shared__ __align__(16) float Ds[BR * BNK];
+    __shared__ __align__(16) float Xs[BR * BNK];
+    const IinsGeom& g = p.g;
+    const int tid = threadIdx.x;
+    const int N = g.Cout, K = g.ks * g.Cin;
+    const int k0 = blockIdx.y * BNK, n0 = blockIdx.z * BNK;
+    const int r_begin = blockIdx.x * p.rows_per_part;
+    int r_end = r_begin + p.rows_per_part;
+    if (r_end > p.M) r_end = p.M;
+    const int tx = tid & 15, ty = tid >> 4;       // tx -> 4 k, ty -> 4 n
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float bsum = 0.f;
+
+    for (int r0 = r_begin; r0 < r_end; r0 += BR) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int e = tid + j * 256;
+            int r = e >> 6, c = e & 63;
+            int row = r0 + r;
+            float dv = 0.f, xv = 0.f;
+            if (row < r_end) {
+                int b = row / g.Lout, l = row - b * g.Lout;
+                if (n0 + c < N) dv = iins_dz_at(g, p.dz, b, l, n0 + c);
+                int k = k0 + c;
+                if (k < K) { int t = k / g.Cin, ci = k - t * g.Cin; xv = iins_a_fwd(g, p.x, b, l, t, ci); }
+            }
+            Ds[e] = dv;
+            Xs[e] = xv;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < BR; ++r) {
+            float d[4], x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = Ds[r * BNK + ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = Xs[r * BNK + tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(d[i], x[j], acc[i][j]);
+        }
+        if (p.db != nullptr && blockIdx.y == 0 && tid < BNK) {
+            for (int r = 0; r < BR; ++r) bsum += Ds[r * BNK + tid];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int n = n0 + ty * 4 + i;
+        if (n >= N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int k = k0 + tx * 4 + j;
+            if (k >= K) continue;
+            int t = k / g.Cin, ci = k - t * g.Cin;
+            atomicAdd(p.dw + iins_w_index(g, n, ci, t), acc[i][j]);
+        }
+    }
+    if (p.db != nullptr && blockIdx.y == 0 && tid < BNK && n0 + tid < N) atomicAdd(p.db + n0 + tid, bsum);
+}

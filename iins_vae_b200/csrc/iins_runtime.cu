@@ -1,0 +1,767 @@
+// Host-side sequencing of the IIns-VAE path and the C ABI declared in include/iins_b200.h.
+// One translation unit: kernels (iins_gemm.cuh, iins_misc.cuh) + the module-level launch plans.
+#include "iins_gemm.cuh"
+#include "iins_misc.cuh"
+#include "../../include/iins_b200.h"
+
+#include <stdio.h>
+#include <string.h>
+
+namespace {
+
+thread_local char g_err[256] = "";
+
+int fail(int code, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+
+struct Ctx {
+    cudaStream_t st;
+};
+
+int check_cuda(const char* where) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+        return IINS_ERR_CUDA;
+    }
+    return IINS_OK;
+}
+
+int grid_for(long n) {
+    long b = (n + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+IinsGeom conv_geom(int B, int Lin, int Lout, int Cin, int Cout, int ks, int stride, int pad, int mode) {
+    IinsGeom g;
+    g.B = B; g.Lin = Lin; g.Lout = Lout; g.Cin = Cin; g.Cout = Cout;
+    g.ks = ks; g.stride = stride; g.pad = pad; g.mode = mode;
+    g.in_layout = IINS_NLC; g.out_layout = IINS_NLC;
+    return g;
+}
+IinsGeom linear_geom(int B, int Cin, int Cout) { return conv_geom(B, 1, 1, Cin, Cout, 1, 1, 0, IINS_PAD_ZERO); }
+
+IinsEpilogue plain_epilogue(const float* bias, int act, float slope, float* y) {
+    IinsEpilogue ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.bias = bias; ep.norm = IINS_NORM_NONE; ep.act = act; ep.slope = slope; ep.y = y;
+    return ep;
+}
+
+IinsDz plain_dz(const float* dy) {
+    IinsDz d;
+    d.dy = dy; d.y = nullptr; d.act = IINS_ACT_NONE; d.slope = 0.f; d.dy_bcast = 0; d.dy_scale = 1.f;
+    return d;
+}
+IinsDz act_dz(const float* dy, const float* y, int act, float slope) {
+    IinsDz d = plain_dz(dy);
+    d.y = y; d.act = act; d.slope = slope;
+    return d;
+}
+
+void launch_nt(const Ctx& c, const IinsNTParams& p) {
+    int bn = p.N <= 8 ? 8 : (p.N <= 16 ? 16 : (p.N <= 32 ? 32 : 64));
+    dim3 grid((p.M + 127) / 128, (p.N + bn - 1) / bn, 1);
+    if (bn == 8) IINS_LAUNCH(iins_nt_kernel<8>, grid, 256, 0, c.st, p);
+    else if (bn == 16) IINS_LAUNCH(iins_nt_kernel<16>, grid, 256, 0, c.st, p);
+    else if (bn == 32) IINS_LAUNCH(iins_nt_kernel<32>, grid, 256, 0, c.st, p);
+    else IINS_LAUNCH(iins_nt_kernel<64>, grid, 256, 0, c.st, p);
+}
+
+// y = epilogue(conv(x, w))
+void conv_forward(const Ctx& c, const IinsGeom& g, const float* x, const float* w, const IinsEpilogue& ep) {
+    IinsNTParams p;
+    memset(&p, 0, sizeof(p));
+    p.g = g; p.a_kind = 0; p.x = x; p.w = w; p.ep = ep;
+    p.M = g.B * g.Lout; p.N = g.Cout; p.K = g.ks * g.Cin;
+    p.Lrow = g.Lout; p.out_layout = g.out_layout;
+    launch_nt(c, p);
+}
+
+// dx = conv_transpose(dz, w) (+ add);  dx has the layer INPUT's layout
+void conv_dgrad(const Ctx& c, const IinsGeom& g, const IinsDz& dz, const float* w, float* dx, const float* add) {
+    IinsNTParams p;
+    memset(&p, 0, sizeof(p));
+    p.g = g; p.a_kind = 1; p.dz = dz; p.w = w;
+    p.ep = plain_epilogue(nullptr, IINS_ACT_NONE, 0.f, dx);
+    p.ep.add = add;
+    p.M = g.B * g.Lin; p.N = g.Cin; p.K = g.ks * g.Cout;
+    p.Lrow = g.Lin; p.out_layout = g.in_layout;
+    launch_nt(c, p);
+}
+
+void conv_wgrad(const Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, float* dw, float* db) {
+    IinsTNParams p;
+    memset(&p, 0, sizeof(p));
+    p.g = g; p.x = x; p.dz = dz; p.dw = dw; p.db = db;
+    p.M = g.B * g.Lout;
+    int K = g.ks * g.Cin;
+    int ky = (K + 63) / 64, nz = (g.Cout + 63) / 64;
+    // enough row parts to fill the machine (148 SMs x a few CTAs), at least 32 rows each
+    long want = (148L * 4 + (long)ky * nz - 1) / ((long)ky * nz);
+    long max_parts = (p.M + 255) / 256;
+    if (want > max_parts) want = max_parts;
+    if (want < 1) want = 1;
+    long rpp = (p.M + want - 1) / want;
+    rpp = (rpp + 31) / 32 * 32;
+    int parts = (int)((p.M + rpp - 1) / rpp);
+    p.rows_per_part = (int)rpp;
+    IINS_LAUNCH(iins_tn_kernel, dim3(parts, ky, nz), 256, 0, c.st, p);
+}
+
+void norm_backward(const Ctx& c, int B, int L, int C, int norm, int act, const float* dy, const float* xhat,
+                   const float* rstd, const float* gamma, const float* beta, float* dgamma, float* dbeta,
+                   const float* adain, float* dadain, int ld, int off_b, int off_w, float* dz) {
+    IinsNormBwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.L = L; p.C = C; p.norm = norm; p.act = act; p.dy = dy; p.xhat = xhat; p.rstd = rstd;
+    p.gamma = gamma; p.beta = beta; p.dgamma = dgamma; p.dbeta = dbeta;
+    p.adain = adain; p.dadain = dadain; p.adain_ld = ld; p.adain_off_b = off_b; p.adain_off_w = off_w; p.dz = dz;
+    int S = 128 / L;
+    IINS_LAUNCH(iins_norm_bwd_kernel, (B + S - 1) / S, 256, 0, c.st, p);
+}
+
+// ------------------------------------------------------------------------------ shape helpers
+struct Shapes {
+    int B, Lc, d, nres, ndown, E, R, NC, F;
+    int P;        // pooled length 128 (models.py:146)
+    int D;        // trunk channels  dim * 2^n_downsample
+    int Lt;       // trunk length    128 / 2^n_downsample
+    int env_extra;
+    int n_adain;
+};
+
+int make_shapes(const iins_config* cfg, Shapes& s) {
+    if (cfg == nullptr) return fail(IINS_ERR_NULL, "config is NULL");
+    s.B = cfg->batch; s.Lc = cfg->cir_len; s.d = cfg->dim; s.nres = cfg->n_residual; s.ndown = cfg->n_downsample;
+    s.E = cfg->env_dim; s.R = cfg->range_dim; s.NC = cfg->num_classes; s.F = cfg->cls_filters;
+    s.P = 128;
+    if (s.B < 1) return fail(IINS_ERR_BAD_CONFIG, "batch must be >= 1");
+    if (s.Lc < 8 || s.Lc > 4096) return fail(IINS_ERR_BAD_CONFIG, "cir_len out of range");
+    if (s.ndown < 4 || s.ndown > 4) return fail(IINS_ERR_BAD_CONFIG, "n_downsample must be 4 (code length 8)");
+    if (s.d < 1 || s.d * (1 << s.ndown) > 64)
+        return fail(IINS_ERR_BAD_CONFIG, "dim * 2^n_downsample must be <= 64 in this build (norm epilogue tile)");
+    if (s.nres < 0 || s.nres > 16) return fail(IINS_ERR_BAD_CONFIG, "n_residual out of range");
+    if (s.E < 2 || (s.E & 1)) return fail(IINS_ERR_BAD_CONFIG, "env_dim must be even");
+    if (s.R < 1 || s.R > 64) return fail(IINS_ERR_BAD_CONFIG, "range_dim out of range");
+    if (s.NC < 1 || s.NC > 64) return fail(IINS_ERR_BAD_CONFIG, "num_classes out of range");
+    if (s.F < 1) return fail(IINS_ERR_BAD_CONFIG, "cls_filters must be >= 1");
+    s.D = s.d << s.ndown;
+    s.Lt = s.P >> s.ndown;
+    s.env_extra = s.ndown - 4 > 0 ? s.ndown - 4 : 0;
+    s.n_adain = 4 * s.nres * s.D;
+    return IINS_OK;
+}
+
+// bump allocator over a float workspace (same walk in forward and backward)
+struct Bump {
+    float* base;
+    size_t off;
+    float* take(size_t n) { float* p = base ? base + off : nullptr; off += (n + 3) & ~(size_t)3; return p; }
+};
+
+// ===================================================================================== Encoder
+struct EncLayer { float* y; float* xhat; float* rstd; };
+struct EncPlan {
+    float* xp;
+    EncLayer stem;
+    EncLayer down[8];
+    EncLayer res1[16], res2[16];
+    float* e_y[8];       // env conv outputs (stem + downs)
+    float* pooled;
+    int n_env;           // number of env conv layers incl. stem
+};
+
+size_t plan_encoder(const Shapes& s, float* ws, EncPlan& pl) {
+    Bump b{ws, 0};
+    size_t B = s.B;
+    pl.xp = b.take(B * s.P);
+    auto layer = [&](int L, int C) { EncLayer l; l.y = b.take(B * L * C); l.xhat = b.take(B * L * C); l.rstd = b.take(B * C); return l; };
+    pl.stem = layer(s.P, s.d);
+    int L = s.P, C = s.d;
+    for (int i = 0; i < s.ndown; ++i) { L >>= 1; C <<= 1; pl.down[i] = layer(L, C); }
+    for (int i = 0; i < s.nres; ++i) { pl.res1[i] = layer(L, C); pl.res2[i] = layer(L, C); }
+    int eC = 4 * s.d, eL = s.P;
+    pl.n_env = 3 + s.env_extra;
+    pl.e_y[0] = b.take(B * eL * eC);
+    for (int i = 1; i < pl.n_env; ++i) { eL >>= 1; if (i <= 2) eC <<= 1; pl.e_y[i] = b.take(B * eL * eC); }
+    pl.pooled = b.take(B * eC);
+    return b.off;
+}
+
+int enc_num_params(const Shapes& s) { return 2 * (1 + s.ndown + 2 * s.nres + 1) + 2 * (1 + 2 + s.env_extra + 1); }
+
+int encoder_forward(const Shapes& s, const float* const* P, const float* x, const float* noise, uint64_t seed, uint64_t offset,
+                    float* rc, float* cat, float* latent, float* kl, float* ws, cudaStream_t st) {
+    Ctx c{st};
+    EncPlan pl;
+    plan_encoder(s, ws, pl);
+    const int B = s.B;
+    IINS_LAUNCH(iins_pool_fwd_kernel, grid_for((long)B * s.P), 256, 0, st, x, pl.xp, B, s.Lc, s.P);
+    int pi = 0;
+    // ---- range encoder (models.py:146-171)
+    {
+        IinsGeom g = conv_geom(B, s.P, s.P, 1, s.d, 7, 1, 3, IINS_PAD_REFLECT);
+        IinsEpilogue ep = plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, pl.stem.y);
+        ep.norm = IINS_NORM_IN; ep.xhat = pl.stem.xhat; ep.rstd = pl.stem.rstd;
+        conv_forward(c, g, pl.xp, P[pi], ep);
+        pi += 2;
+    }
+    const float* h = pl.stem.y;
+    int L = s.P, C = s.d;
+    for (int i = 0; i < s.ndown; ++i) {
+        IinsGeom g = conv_geom(B, L, L / 2, C, 2 * C, 4, 2, 1, IINS_PAD_ZERO);
+        IinsEpilogue ep = plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, pl.down[i].y);
+        ep.norm = IINS_NORM_IN; ep.xhat = pl.down[i].xhat; ep.rstd = pl.down[i].rstd;
+        conv_forward(c, g, h, P[pi], ep);
+        pi += 2;
+        h = pl.down[i].y; L /= 2; C *= 2;
+    }
+    for (int i = 0; i < s.nres; ++i) {
+        IinsGeom g = conv_geom(B, L, L, C, C, 3, 1, 1, IINS_PAD_REFLECT);
+        IinsEpilogue e1 = plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, pl.res1[i].y);
+        e1.norm = IINS_NORM_IN; e1.xhat = pl.res1[i].xhat; e1.rstd = pl.res1[i].rstd;
+        conv_forward(c, g, h, P[pi], e1);
+        IinsEpilogue e2 = plain_epilogue(P[pi + 3], IINS_ACT_NONE, 0.f, pl.res2[i].y);
+        e2.norm = IINS_NORM_IN; e2.xhat = pl.res2[i].xhat; e2.rstd = pl.res2[i].rstd; e2.add = h;
+        conv_forward(c, g, pl.res1[i].y, P[pi + 2], e2);
+        pi += 4;
+        h = pl.res2[i].y;
+    }
+    {
+        IinsGeom g = conv_geom(B, L, L, C, s.R, 1, 1, 0, IINS_PAD_ZERO);
+        g.out_layout = IINS_NCL;
+        conv_forward(c, g, h, P[pi], plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, rc));
+        pi += 2;
+    }
+    // ---- env encoder (models.py:264-279)
+    {
+        IinsGeom g = conv_geom(B, s.P, s.P, 1, 4 * s.d, 7, 1, 3, IINS_PAD_REFLECT);
+        conv_forward(c, g, pl.xp, P[pi], plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, pl.e_y[0]));
+        pi += 2;
+    }
+    int eL = s.P, eC = 4 * s.d;
+    for (int i = 1; i < pl.n_env; ++i) {
+        int oc = i <= 2 ? 2 * eC : eC;
+        IinsGeom g = conv_geom(B, eL, eL / 2, eC, oc, 4, 2, 1, IINS_PAD_ZERO);
+        conv_forward(c, g, pl.e_y[i - 1], P[pi], plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, pl.e_y[i]));
+        pi += 2;
+        eL /= 2; eC = oc;
+    }
+    IINS_LAUNCH(iins_mean_l_kernel, grid_for((long)B * eC), 256, 0, st, pl.e_y[pl.n_env - 1], pl.pooled, B, eL, eC);
+    conv_forward(c, linear_geom(B, eC, s.E), pl.pooled, P[pi], plain_epilogue(P[pi + 1], IINS_ACT_NONE, 0.f, cat));
+    cudaMemsetAsync(kl, 0, sizeof(float), st);
+    IINS_LAUNCH(iins_reparam_kl_kernel, grid_for((long)B * s.E / 2), 256, 0, st, cat, noise, latent, kl, B, s.E,
+                (unsigned long long)seed, (unsigned long long)offset);
+    return check_cuda("encoder_forward");
+}
+
+size_t encoder_scratch(const Shapes& s) {
+    size_t B = s.B;
+    size_t act = (size_t)128 * 4 * s.d;                 // largest activation per sample (env stem: 128 x 4d)
+    if ((size_t)s.Lt * s.D > act) act = (size_t)s.Lt * s.D;
+    return 3 * (B * act + 4) + B * (16 * (size_t)s.d + 4) + B * ((size_t)s.E + 4);
+}
+
+int encoder_backward(const Shapes& s, const float* const* P, const float* noise, uint64_t seed, uint64_t offset,
+                     const float* rc, const float* cat, const float* ws, const float* d_rc, const float* d_cat,
+                     const float* d_lat, const float* d_kl, float* const* G, float* scratch, cudaStream_t st) {
+    Ctx c{st};
+    EncPlan pl;
+    plan_encoder(s, const_cast<float*>(ws), pl);
+    const int B = s.B;
+    size_t act = (size_t)128 * 4 * s.d;
+    if ((size_t)s.Lt * s.D > act) act = (size_t)s.Lt * s.D;
+    Bump b{scratch, 0};
+    float* ga = b.take((size_t)B * act);
+    float* gb = b.take((size_t)B * act);
+    float* dzb = b.take((size_t)B * act);
+    float* dpooled = b.take((size_t)B * 16 * s.d);
+    float* dcat = b.take((size_t)B * s.E);
+    const int n_range = 2 * (1 + s.ndown + 2 * s.nres + 1);
+
+    // ---------------- env branch
+    if (d_cat != nullptr || d_lat != nullptr || d_kl != nullptr) {
+        IINS_LAUNCH(iins_reparam_kl_bwd_kernel, grid_for((long)B * s.E / 2), 256, 0, st, cat, noise, d_cat, d_lat, d_kl,
+                    dcat, B, s.E, (unsigned long long)seed, (unsigned long long)offset);
+        int pi = n_range + 2 * pl.n_env;               // final 1x1 conv (after the pool)
+        int eC = 16 * s.d, eL = s.P >> (pl.n_env - 1);
+        IinsGeom gl = linear_geom(B, eC, s.E);
+        conv_wgrad(c, gl, pl.pooled, plain_dz(dcat), G[pi], G[pi + 1]);
+        conv_dgrad(c, gl, plain_dz(dcat), P[pi], dpooled, nullptr);
+        // walk the stride-2 convs backwards; the last one receives the broadcast pooled gradient
+        const float* dy = dpooled;
+        int bcast = 1;
+        float scale = 1.0f / (float)eL;
+        int C = eC, L = eL;
+        float* bufs[2] = {ga, gb};
+        int flip = 0;
+        for (int i = pl.n_env - 1; i >= 1; --i) {
+            pi -= 2;
+            int ic = i <= 2 ? C / 2 : C;
+            IinsGeom g = conv_geom(B, 2 * L, L, ic, C, 4, 2, 1, IINS_PAD_ZERO);
+            IinsDz dz = act_dz(dy, pl.e_y[i], IINS_ACT_RELU, 0.f);
+            dz.dy_bcast = bcast; dz.dy_scale = scale;
+            conv_wgrad(c, g, pl.e_y[i - 1], dz, G[pi], G[pi + 1]);
+            conv_dgrad(c, g, dz, P[pi], bufs[flip], nullptr);
+            dy = bufs[flip]; flip ^= 1; bcast = 0; scale = 1.f;
+            C = ic; L *= 2;
+        }
+        pi -= 2;
+        IinsGeom g0 = conv_geom(B, s.P, s.P, 1, 4 * s.d, 7, 1, 3, IINS_PAD_REFLECT);
+        IinsDz dz0 = act_dz(dy, pl.e_y[0], IINS_ACT_RELU, 0.f);
+        dz0.dy_bcast = bcast; dz0.dy_scale = scale;
+        conv_wgrad(c, g0, pl.xp, dz0, G[pi], G[pi + 1]);
+    }
+
+    // ---------------- range branch
+    if (d_rc != nullptr) {
+        int pi = n_range - 2;
+        int L = s.Lt, C = s.D;
+        const float* h_last = s.nres > 0 ? pl.res2[s.nres - 1].y : pl.down[s.ndown - 1].y;
+        IinsGeom go = conv_geom(B, L, L, C, s.R, 1, 1, 0, IINS_PAD_ZERO);
+        go.out_layout = IINS_NCL;
+        IinsDz dzo = act_dz(d_rc, rc, IINS_ACT_RELU, 0.f);
+        conv_wgrad(c, go, h_last, dzo, G[pi], G[pi + 1]);
+        float* dh = ga;          // gradient w.r.t. the trunk activation h
+        float* tmp = gb;
+        conv_dgrad(c, go, dzo, P[pi], dh, nullptr);
+        IinsGeom gr = conv_geom(B, L, L, C, C, 3, 1, 1, IINS_PAD_REFLECT);
+        for (int i = s.nres - 1; i >= 0; --i) {
+            pi -= 4;
+            const float* h_in = i > 0 ? pl.res2[i - 1].y : pl.down[s.ndown - 1].y;
+            // second conv of the block: out = h_in + IN(conv2(t))
+            norm_backward(c, B, L, C, IINS_NORM_IN, IINS_ACT_NONE, dh, pl.res2[i].xhat, pl.res2[i].rstd,
+                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, dzb);
+            conv_wgrad(c, gr, pl.res1[i].y, plain_dz(dzb), G[pi + 2], G[pi + 3]);
+            conv_dgrad(c, gr, plain_dz(dzb), P[pi + 2], tmp, nullptr);
+            // first conv: t = relu(IN(conv1(h_in)))
+            norm_backward(c, B, L, C, IINS_NORM_IN, IINS_ACT_RELU, tmp, pl.res1[i].xhat, pl.res1[i].rstd,
+                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, dzb);
+            conv_wgrad(c, gr, h_in, plain_dz(dzb), G[pi], G[pi + 1]);
+            conv_dgrad(c, gr, plain_dz(dzb), P[pi], tmp, dh);       // + skip gradient
+            float* sw = dh; dh = tmp; tmp = sw;
+        }
+        for (int i = s.ndown - 1; i >= 0; --i) {
+            pi -= 2;
+            const float* h_in = i > 0 ? pl.down[i - 1].y : pl.stem.y;
+            IinsGeom g = conv_geom(B, 2 * L, L, C / 2, C, 4, 2, 1, IINS_PAD_ZERO);
+            norm_backward(c, B, L, C, IINS_NORM_IN, IINS_ACT_RELU, dh, pl.down[i].xhat, pl.down[i].rstd,
+                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, dzb);
+            conv_wgrad(c, g, h_in, plain_dz(dzb), G[pi], G[pi + 1]);
+            conv_dgrad(c, g, plain_dz(dzb), P[pi], tmp, nullptr);
+            float* sw = dh; dh = tmp; tmp = sw;
+            L *= 2; C /= 2;
+        }
+        pi -= 2;
+        IinsGeom g0 = conv_geom(B, s.P, s.P, 1, s.d, 7, 1, 3, IINS_PAD_REFLECT);
+        norm_backward(c, B, s.P, s.d, IINS_NORM_IN, IINS_ACT_RELU, dh, pl.stem.xhat, pl.stem.rstd,
+                      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, dzb);
+        conv_wgrad(c, g0, pl.xp, plain_dz(dzb), G[pi], G[pi + 1]);
+    }
+    return check_cuda("encoder_backward");
+}
+
+// ===================================================================================== Decoder
+struct DecPlan {
+    float* m1; float* m2; float* adain;
+    float* d0;
+    EncLayer res1[16], res2[16];
+    EncLayer up[8];
+    float* yt;           // tanh output (B,128)
+};
+
+size_t plan_decoder(const Shapes& s, float* ws, DecPlan& pl) {
+    Bump b{ws, 0};
+    size_t B = s.B;
+    pl.m1 = b.take(B * 256); pl.m2 = b.take(B * 256); pl.adain = b.take(B * s.n_adain);
+    pl.d0 = b.take(B * s.Lt * s.D);
+    auto layer = [&](int L, int C, int nstat) { EncLayer l; l.y = b.take(B * L * C); l.xhat = b.take(B * L * C); l.rstd = b.take(B * nstat); return l; };
+    for (int i = 0; i < s.nres; ++i) { pl.res1[i] = layer(s.Lt, s.D, s.D); pl.res2[i] = layer(s.Lt, s.D, s.D); }
+    int L = s.Lt, C = s.D;
+    for (int i = 0; i < s.ndown; ++i) { L *= 2; C /= 2; pl.up[i] = layer(L, C, 1); }
+    pl.yt = b.take(B * s.P);
+    return b.off;
+}
+
+int dec_num_params(const Shapes& s) { return 2 + 4 * s.nres + 4 * s.ndown + 2 + 6; }
+
+// parameter index map of Decoder.named_parameters(): decoder.model.* first, then decoder.mlp.*
+struct DecIdx { int d0, res0, up0, out, mlp; };
+DecIdx dec_idx(const Shapes& s) {
+    DecIdx i;
+    i.d0 = 0; i.res0 = 2; i.up0 = 2 + 4 * s.nres; i.out = i.up0 + 4 * s.ndown; i.mlp = i.out + 2;
+    return i;
+}
+
+int decoder_forward(const Shapes& s, const float* const* P, const float* rc, const float* cat, float* xrec, float* ws,
+                    cudaStream_t st) {
+    Ctx c{st};
+    DecPlan pl;
+    plan_decoder(s, ws, pl);
+    DecIdx ix = dec_idx(s);
+    const int B = s.B;
+    // MLP -> AdaIN parameters (models.py:951-962, 468)
+    conv_forward(c, linear_geom(B, s.E, 256), cat, P[ix.mlp], plain_epilogue(P[ix.mlp + 1], IINS_ACT_RELU, 0.f, pl.m1));
+    conv_forward(c, linear_geom(B, 256, 256), pl.m1, P[ix.mlp + 2], plain_epilogue(P[ix.mlp + 3], IINS_ACT_RELU, 0.f, pl.m2));
+    conv_forward(c, linear_geom(B, 256, s.n_adain), pl.m2, P[ix.mlp + 4], plain_epilogue(P[ix.mlp + 5], IINS_ACT_NONE, 0.f, pl.adain));
+    // 1x1 conv on the range code (NCL in)
+    {
+        IinsGeom g = conv_geom(B, s.Lt, s.Lt, s.R, s.D, 1, 1, 0, IINS_PAD_ZERO);
+        g.in_layout = IINS_NCL;
+        conv_forward(c, g, rc, P[ix.d0], plain_epilogue(P[ix.d0 + 1], IINS_ACT_RELU, 0.f, pl.d0));
+    }
+    const float* h = pl.d0;
+    IinsGeom gr = conv_geom(B, s.Lt, s.Lt, s.D, s.D, 3, 1, 1, IINS_PAD_REFLECT);
+    for (int i = 0; i < s.nres; ++i) {
+        int pi = ix.res0 + 4 * i;
+        int off = 4 * s.D * i;         // assign_adain_params: [bias1 | weight1 | bias2 | weight2] (models.py:457-464)
+        IinsEpilogue e1 = plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, pl.res1[i].y);
+        e1.norm = IINS_NORM_ADAIN; e1.xhat = pl.res1[i].xhat; e1.rstd = pl.res1[i].rstd;
+        e1.adain = pl.adain; e1.adain_ld = s.n_adain; e1.adain_off_b = off; e1.adain_off_w = off + s.D;
+        conv_forward(c, gr, h, P[pi], e1);
+        IinsEpilogue e2 = plain_epilogue(P[pi + 3], IINS_ACT_NONE, 0.f, pl.res2[i].y);
+        e2.norm = IINS_NORM_ADAIN; e2.xhat = pl.res2[i].xhat; e2.rstd = pl.res2[i].rstd; e2.add = h;
+        e2.adain = pl.adain; e2.adain_ld = s.n_adain; e2.adain_off_b = off + 2 * s.D; e2.adain_off_w = off + 3 * s.D;
+        conv_forward(c, gr, pl.res1[i].y, P[pi + 2], e2);
+        h = pl.res2[i].y;
+    }
+    int L = s.Lt, C = s.D;
+    for (int i = 0; i < s.ndown; ++i) {
+        int pi = ix.up0 + 4 * i;
+        IinsGeom g = conv_geom(B, L, 2 * L, C, C / 2, 5, 1, 2, IINS_PAD_UP2);
+        IinsEpilogue ep = plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, pl.up[i].y);
+        ep.norm = IINS_NORM_LN; ep.xhat = pl.up[i].xhat; ep.rstd = pl.up[i].rstd; ep.gamma = P[pi + 2]; ep.beta = P[pi + 3];
+        conv_forward(c, g, h, P[pi], ep);
+        h = pl.up[i].y; L *= 2; C /= 2;
+    }
+    {
+        IinsGeom g = conv_geom(B, L, L, C, 1, 7, 1, 3, IINS_PAD_REFLECT);
+        conv_forward(c, g, h, P[ix.out], plain_epilogue(P[ix.out + 1], IINS_ACT_TANH, 0.f, pl.yt));
+    }
+    IINS_LAUNCH(iins_pool_fwd_kernel, grid_for((long)B * s.Lc), 256, 0, st, pl.yt, xrec, B, s.P, s.Lc);
+    return check_cuda("decoder_forward");
+}
+
+size_t decoder_scratch(const Shapes& s) {
+    size_t B = s.B;
+    size_t act = (size_t)s.Lt * s.D;
+    return 3 * (B * act + 4) + B * ((size_t)s.n_adain + 4) + 2 * (B * 256 + 4) + B * ((size_t)s.P + 4);
+}
+
+int decoder_backward(const Shapes& s, const float* const* P, const float* rc, const float* cat, const float* ws,
+                     const float* d_xrec, float* const* G, float* d_rc, float* d_cat, int accumulate, float* scratch,
+                     cudaStream_t st) {
+    Ctx c{st};
+    DecPlan pl;
+    plan_decoder(s, const_cast<float*>(ws), pl);
+    DecIdx ix = dec_idx(s);
+    const int B = s.B;
+    size_t act = (size_t)s.Lt * s.D;
+    Bump b{scratch, 0};
+    float* ga = b.take((size_t)B * act);
+    float* gb = b.take((size_t)B * act);
+    float* dzb = b.take((size_t)B * act);
+    float* dadain = b.take((size_t)B * s.n_adain);
+    float* dm2 = b.take((size_t)B * 256);
+    float* dm1 = b.take((size_t)B * 256);
+    float* dyt = b.take((size_t)B * s.P);
+
+    // pool(128 -> cir_len) backward fused with tanh'
+    IINS_LAUNCH(iins_pool_bwd_kernel, grid_for((long)B * s.P), 256, 0, st, d_xrec, pl.yt, dyt, B, s.P, s.Lc);
+    int L = s.P, C = s.d;          // spatial size / channels at the decoder's output end
+    float* dh = ga;
+    float* tmp = gb;
+    {
+        IinsGeom g = conv_geom(B, L, L, C, 1, 7, 1, 3, IINS_PAD_REFLECT);
+        const float* h_in = pl.up[s.ndown - 1].y;
+        conv_wgrad(c, g, h_in, plain_dz(dyt), G[ix.out], G[ix.out + 1]);
+        conv_dgrad(c, g, plain_dz(dyt), P[ix.out], dh, nullptr);
+    }
+    for (int i = s.ndown - 1; i >= 0; --i) {
+        int pi = ix.up0 + 4 * i;
+        const float* h_in = i > 0 ? pl.up[i - 1].y : (s.nres > 0 ? pl.res2[s.nres - 1].y : pl.d0);
+        IinsGeom g = conv_geom(B, L / 2, L, 2 * C, C, 5, 1, 2, IINS_PAD_UP2);
+        norm_backward(c, B, L, C, IINS_NORM_LN, IINS_ACT_RELU, dh, pl.up[i].xhat, pl.up[i].rstd, P[pi + 2], P[pi + 3],
+                      G[pi + 2], G[pi + 3], nullptr, nullptr, 0, 0, 0, dzb);
+        conv_wgrad(c, g, h_in, plain_dz(dzb), G[pi], G[pi + 1]);
+        conv_dgrad(c, g, plain_dz(dzb), P[pi], tmp, nullptr);
+        float* sw = dh; dh = tmp; tmp = sw;
+        L /= 2; C *= 2;
+    }
+    IinsGeom gr = conv_geom(B, s.Lt, s.Lt, s.D, s.D, 3, 1, 1, IINS_PAD_REFLECT);
+    for (int i = s.nres - 1; i >= 0; --i) {
+        int pi = ix.res0 + 4 * i;
+        int off = 4 * s.D * i;
+        const float* h_in = i > 0 ? pl.res2[i - 1].y : pl.d0;
+        norm_backward(c, B, s.Lt, s.D, IINS_NORM_ADAIN, IINS_ACT_NONE, dh, pl.res2[i].xhat, pl.res2[i].rstd, nullptr, nullptr,
+                      nullptr, nullptr, pl.adain, dadain, s.n_adain, off + 2 * s.D, off + 3 * s.D, dzb);
+        conv_wgrad(c, gr, pl.res1[i].y, plain_dz(dzb), G[pi + 2], G[pi + 3]);
+        conv_dgrad(c, gr, plain_dz(dzb), P[pi + 2], tmp, nullptr);
+        norm_backward(c, B, s.Lt, s.D, IINS_NORM_ADAIN, IINS_ACT_RELU, tmp, pl.res1[i].xhat, pl.res1[i].rstd, nullptr, nullptr,
+                      nullptr, nullptr, pl.adain, dadain, s.n_adain, off, off + s.D, dzb);
+        conv_wgrad(c, gr, h_in, plain_dz(dzb), G[pi], G[pi + 1]);
+        conv_dgrad(c, gr, plain_dz(dzb), P[pi], tmp, dh);
+        float* sw = dh; dh = tmp; tmp = sw;
+    }
+    {
+        IinsGeom g = conv_geom(B, s.Lt, s.Lt, s.R, s.D, 1, 1, 0, IINS_PAD_ZERO);
+        g.in_layout = IINS_NCL;
+        IinsDz dz = act_dz(dh, pl.d0, IINS_ACT_RELU, 0.f);
+        conv_wgrad(c, g, rc, dz, G[ix.d0], G[ix.d0 + 1]);
+        if (d_rc != nullptr) conv_dgrad(c, g, dz, P[ix.d0], d_rc, accumulate ? d_rc : nullptr);
+    }
+    // MLP backward
+    {
+        IinsGeom g3 = linear_geom(B, 256, s.n_adain), g2 = linear_geom(B, 256, 256), g1 = linear_geom(B, s.E, 256);
+        if (s.nres == 0) cudaMemsetAsync(dadain, 0, (size_t)B * s.n_adain * sizeof(float), st);
+        conv_wgrad(c, g3, pl.m2, plain_dz(dadain), G[ix.mlp + 4], G[ix.mlp + 5]);
+        conv_dgrad(c, g3, plain_dz(dadain), P[ix.mlp + 4], dm2, nullptr);
+        IinsDz z2 = act_dz(dm2, pl.m2, IINS_ACT_RELU, 0.f);
+        conv_wgrad(c, g2, pl.m1, z2, G[ix.mlp + 2], G[ix.mlp + 3]);
+        conv_dgrad(c, g2, z2, P[ix.mlp + 2], dm1, nullptr);
+        IinsDz z1 = act_dz(dm1, pl.m1, IINS_ACT_RELU, 0.f);
+        conv_wgrad(c, g1, cat, z1, G[ix.mlp], G[ix.mlp + 1]);
+        if (d_cat != nullptr) conv_dgrad(c, g1, z1, P[ix.mlp], d_cat, accumulate ? d_cat : nullptr);
+    }
+    return check_cuda("decoder_backward");
+}
+
+// ============================================================================ Restorer / Classifier
+// A stack of Linear + LeakyReLU layers; `dims` has n+1 entries, `slopes[i] < 0` means no activation.
+struct MlpSpec { int n; int dims[6]; float slopes[5]; };
+
+MlpSpec restorer_spec(const Shapes& s) {
+    MlpSpec m; m.n = 4;
+    m.dims[0] = s.R * s.Lt; m.dims[1] = 512; m.dims[2] = 256; m.dims[3] = 256; m.dims[4] = 1;
+    m.slopes[0] = m.slopes[1] = m.slopes[2] = 0.2f; m.slopes[3] = -1.f;         // models.py:621-631
+    return m;
+}
+MlpSpec classifier_spec(const Shapes& s) {
+    MlpSpec m; m.n = 4;
+    m.dims[0] = s.E; m.dims[1] = s.F; m.dims[2] = 2 * s.F; m.dims[3] = s.F; m.dims[4] = s.NC;
+    m.slopes[0] = m.slopes[1] = m.slopes[2] = 0.01f; m.slopes[3] = 0.2f;        // models.py:847-855
+    return m;
+}
+
+size_t mlp_ws(const Shapes& s, const MlpSpec& m) {
+    size_t n = 0;
+    for (int i = 1; i < m.n; ++i) n += ((size_t)s.B * m.dims[i] + 3) & ~(size_t)3;
+    return n;
+}
+size_t mlp_scratch(const Shapes& s, const MlpSpec& m) {
+    size_t mx = 0;
+    for (int i = 1; i < m.n; ++i) if ((size_t)m.dims[i] > mx) mx = m.dims[i];
+    return 2 * (((size_t)s.B * mx + 3) & ~(size_t)3);
+}
+
+int mlp_forward(const Shapes& s, const MlpSpec& m, const float* const* P, const float* in, float* out, float* ws, cudaStream_t st) {
+    Ctx c{st};
+    Bump b{ws, 0};
+    const float* h = in;
+    for (int i = 0; i < m.n; ++i) {
+        float* y = i == m.n - 1 ? out : b.take((size_t)s.B * m.dims[i + 1]);
+        int act = m.slopes[i] < 0.f ? IINS_ACT_NONE : IINS_ACT_LRELU;
+        conv_forward(c, linear_geom(s.B, m.dims[i], m.dims[i + 1]), h, P[2 * i], plain_epilogue(P[2 * i + 1], act, m.slopes[i], y));
+        h = y;
+    }
+    return check_cuda("mlp_forward");
+}
+
+int mlp_backward(const Shapes& s, const MlpSpec& m, const float* const* P, const float* in, const float* out_saved,
+                 const float* ws, const float* d_out, float* const* G, float* d_in, int accumulate, float* scratch,
+                 cudaStream_t st) {
+    Ctx c{st};
+    Bump b{const_cast<float*>(ws), 0};
+    const float* acts[6];
+    acts[0] = in;
+    for (int i = 1; i < m.n; ++i) acts[i] = b.take((size_t)s.B * m.dims[i]);
+    acts[m.n] = out_saved;
+    size_t half = mlp_scratch(s, m) / 2;
+    float* bufs[2] = {scratch, scratch + half};
+    const float* dy = d_out;
+    for (int i = m.n - 1; i >= 0; --i) {
+        IinsGeom g = linear_geom(s.B, m.dims[i], m.dims[i + 1]);
+        IinsDz dz = m.slopes[i] < 0.f ? plain_dz(dy) : act_dz(dy, acts[i + 1], IINS_ACT_LRELU, m.slopes[i]);
+        conv_wgrad(c, g, acts[i], dz, G[2 * i], G[2 * i + 1]);
+        if (i > 0) {
+            float* dx = bufs[i & 1];
+            conv_dgrad(c, g, dz, P[2 * i], dx, nullptr);
+            dy = dx;
+        } else if (d_in != nullptr) {
+            conv_dgrad(c, g, dz, P[0], d_in, accumulate ? d_in : nullptr);
+        }
+    }
+    return check_cuda("mlp_backward");
+}
+
+#define IINS_SHAPES_OR_RETURN(cfg, s) Shapes s; { int rc_ = make_shapes(cfg, s); if (rc_ != IINS_OK) return rc_; }
+
+}  // namespace
+
+// ============================================================================================ C ABI
+extern "C" {
+
+int iins_abi_version(void) { return 1; }
+const char* iins_last_error(void) { return g_err; }
+int iins_validate_config(const iins_config* cfg) { Shapes s; return make_shapes(cfg, s); }
+
+int iins_encoder_num_params(const iins_config* cfg) { IINS_SHAPES_OR_RETURN(cfg, s); return enc_num_params(s); }
+size_t iins_encoder_ws_floats(const iins_config* cfg) {
+    Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0;
+    EncPlan pl; return plan_encoder(s, nullptr, pl);
+}
+size_t iins_encoder_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return encoder_scratch(s); }
+
+int iins_encoder_forward(const iins_config* cfg, const float* const* params, const float* x, const float* noise,
+                         uint64_t seed, uint64_t offset, float* range_code, float* env_code, float* env_code_rv,
+                         float* kl, float* ws, iins_stream_t stream) {
+    IINS_SHAPES_OR_RETURN(cfg, s);
+    if (!params || !x || !range_code || !env_code || !kl || !ws) return fail(IINS_ERR_NULL, "encoder_forward: NULL argument");
+    return encoder_forward(s, params, x, noise, seed, offset, range_code, env_code, env_code_rv, kl, ws, (cudaStream_t)stream);
+}
+
+int iins_encoder_backward(const iins_config* cfg, const float* const* params, const float* noise, uint64_t seed,
+                          uint64_t offset, const float* range_code, const float* env_code, const float* ws,
+                          const float* d_range_code, const float* d_env_code, const float* d_env_code_rv,
+                          const float* d_kl, float* const* grads, float* scratch, iins_stream_t stream) {
+    IINS_SHAPES_OR_RETURN(cfg, s);
+    if (!params || !range_code || !env_code || !ws || !grads || !scratch) return fail(IINS_ERR_NULL, "encoder_backward: NULL argument");
+    return encoder_backward(s, params, noise, seed, offset, range_code, env_code, ws, d_range_code, d_env_code,
+                            d_env_code_rv, d_kl, grads, scratch, (cudaStream_t)stream);
+}
+
+int iins_decoder_num_params(const iins_config* cfg) { IINS_SHAPES_OR_RETURN(cfg, s); return dec_num_params(s); }
+size_t iins_decoder_ws_floats(const iins_config* cfg) {
+    Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0;
+    DecPlan pl; return plan_decoder(s, nullptr, pl);
+}
+size_t iins_decoder_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return decoder_scratch(s); }
+
+int iins_decoder_forward(const iins_config* cfg, const float* const* params, const float* range_code,
+                         const float* env_code, float* x_recon, float* ws, iins_stream_t stream) {
+    IINS_SHAPES_OR_RETURN(cfg, s);
+    if (!params || !range_code || !env_code || !x_recon || !ws) return fail(IINS_ERR_NULL, "decoder_forward: NULL argument");
+    return decoder_forward(s, params, range_code, env_code, x_recon, ws, (cudaStream_t)stream);
+}
+
+int iins_decoder_backward(const iins_config* cfg, const float* const* params, const float* range_code,
+                          const float* env_code, const float* ws, const float* d_x_recon, float* const* grads,
+                          float* d_range_code, float* d_env_code, int accumulate, float* scratch, iins_stream_t stream) {
+    IINS_SHAPES_OR_RETURN(cfg, s);
+    if (!params || !range_code || !env_code || !ws || !d_x_recon || !grads || !scratch)
+        return fail(IINS_ERR_NULL, "decoder_backward: NULL argument");
+    return decoder_backward(s, params, range_code, env_code, ws, d_x_recon, grads, d_range_code, d_env_code, accumulate,
+                            scratch, (cudaStream_t)stream);
+}
+
+int iins_restorer_num_params(const iins_config* cfg) { IINS_SHAPES_OR_RETURN(cfg, s); return 10; }
+size_t iins_restorer_ws_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return mlp_ws(s, restorer_spec(s)); }
+size_t iins_restorer_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return mlp_scratch(s, restorer_spec(s)); }
+int iins_restorer_forward(const iins_config* cfg, const float* const* params, const float* range_code, float* err_est,
+                          float* ws, iins_stream_t stream) {
+    IINS_SHAPES_OR_RETURN(cfg, s);
+    if (!params || !range_code || !err_est || !ws) return fail(IINS_ERR_NULL, "restorer_forward: NULL argument");
+    return mlp_forward(s, restorer_spec(s), params, range_code, err_est, ws, (cudaStream_t)stream);
+}
+int iins_restorer_backward(const iins_config* cfg, const float* const* params, const float* range_code, const float* ws,
+                           const float* d_err_est, float* const* grads, float* d_range_code, int accumulate,
+                           float* scratch, iins_stream_t stream) {
+    IINS_SHAPES_OR_RETURN(cfg, s);
+    if (!params || !range_code || !ws || !d_err_est || !grads || !scratch) return fail(IINS_ERR_NULL, "restorer_backward: NULL argument");
+    // the last layer has no activation, so its saved output is never read: pass NULL
+    return mlp_backward(s, restorer_spec(s), params, range_code, nullptr, ws, d_err_est, grads, d_range_code, accumulate,
+                        scratch, (cudaStream_t)stream);
+}
+
+int iins_classifier_num_params(const iins_config* cfg) { IINS_SHAPES_OR_RETURN(cfg, s); return 8; }
+size_t iins_classifier_ws_floats(const iins_config* cfg) {
+    Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0;
+    return mlp_ws(s, classifier_spec(s)) + (((size_t)s.B * s.NC + 3) & ~(size_t)3);
+}
+size_t iins_classifier_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return mlp_scratch(s, classifier_spec(s)); }
+int iins_classifier_forward(const iins_config* cfg, const float* const* params, const float* env_code, float* logits,
+                            float* ws, iins_stream_t stream) {
+    IINS_SHAPES_OR_RETURN(cfg, s);
+    if (!params || !env_code || !logits || !ws) return fail(IINS_ERR_NULL, "classifier_forward: NULL argument");
+    // the logits pass through LeakyReLU(0.2) (models.py:854): keep a private copy for backward, because the
+    // caller is free to modify its output tensor
+    MlpSpec m = classifier_spec(s);
+    float* saved = ws + mlp_ws(s, m);
+    int rc = mlp_forward(s, m, params, env_code, saved, ws, (cudaStream_t)stream);
+    if (rc != IINS_OK) return rc;
+    cudaMemcpyAsync(logits, saved, (size_t)s.B * s.NC * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    return check_cuda("classifier_forward");
+}
+int iins_classifier_backward(const iins_config* cfg, const float* const* params, const float* env_code, const float* ws,
+                             const float* d_logits, float* const* grads, float* d_env_code, int accumulate,
+                             float* scratch, iins_stream_t stream) {
+    IINS_SHAPES_OR_RETURN(cfg, s);
+    if (!params || !env_code || !ws || !d_logits || !grads || !scratch) return fail(IINS_ERR_NULL, "classifier_backward: NULL argument");
+    MlpSpec m = classifier_spec(s);
+    return mlp_backward(s, m, params, env_code, ws + mlp_ws(s, m), ws, d_logits, grads, d_env_code, accumulate, scratch,
+                        (cudaStream_t)stream);
+}
+
+int iins_loss_forward_backward(int batch, int cir_len, int num_classes, const float* x, const float* x_recon,
+                               const float* err, const float* err_est, const float* logits, const float* label,
+                               const int64_t* label_i64, float lam_ae, float lam_res, float lam_env, float* out,
+                               float* d_x_recon, float* d_err_est, float* d_logits, int32_t* pred, iins_stream_t stream) {
+    if (!out) return fail(IINS_ERR_NULL, "loss: out is NULL");
+    if (batch < 1 || num_classes > 64) return fail(IINS_ERR_BAD_CONFIG, "loss: bad sizes");
+    if (x && !x_recon) return fail(IINS_ERR_NULL, "loss: x_recon is NULL");
+    if (err && (!err_est || !logits || (!label && !label_i64))) return fail(IINS_ERR_NULL, "loss: supervised inputs missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    IinsLossParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = batch; p.L = cir_len; p.NC = num_classes;
+    p.x = x; p.xrec = x_recon; p.err = err; p.err_est = err_est; p.logits = logits; p.label = label;
+    p.label_i64 = (const long long*)label_i64;
+    p.lam_ae = lam_ae; p.lam_res = lam_res; p.lam_env = lam_env; p.out = out;
+    p.d_xrec = d_x_recon; p.d_err_est = d_err_est; p.d_logits = d_logits; p.pred = (int*)pred;
+    cudaMemsetAsync(out, 0, 8 * sizeof(float), st);
+    long n = x ? (long)batch * cir_len : batch;
+    IINS_LAUNCH(iins_loss_kernel, grid_for(n), 256, 0, st, p);
+    return check_cuda("loss");
+}
+
+int iins_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const int64_t* group_begin,
+                   const int64_t* group_end, const int32_t* group_active, int n_groups, int32_t* steps, const float* lr,
+                   double beta1, double beta2, float eps, iins_stream_t stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !group_begin || !group_end || !group_active || !steps || !lr)
+        return fail(IINS_ERR_NULL, "adam: NULL argument");
+    if (n_groups < 1 || n_groups > 8) return fail(IINS_ERR_BAD_CONFIG, "adam: 1..8 groups");
+    cudaStream_t st = (cudaStream_t)stream;
+    IinsAdamParams a;
+    memset(&a, 0, sizeof(a));
+    a.p = params; a.g = grads; a.m = exp_avg; a.v = exp_avg_sq; a.steps = (int*)steps; a.lr = lr;
+    a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.n_groups = n_groups;
+    unsigned mask = 0;
+    long total = 0;
+    for (int i = 0; i < n_groups; ++i) {
+        a.groups[i].begin = (long)group_begin[i]; a.groups[i].end = (long)group_end[i]; a.groups[i].active = group_active[i];
+        if (group_active[i]) { mask |= 1u << i; total += (long)(group_end[i] - group_begin[i]); }
+    }
+    if (mask == 0) return IINS_OK;
+    IINS_LAUNCH(iins_adam_tick_kernel, 1, 32, 0, st, (int*)steps, n_groups, mask);
+    IINS_LAUNCH(iins_adam_kernel, grid_for(total), 256, 0, st, a);
+    return check_cuda("adam");
+}
+
+int iins_adaptive_pool_forward(const float* x, float* y, int batch, int lin, int lout, iins_stream_t stream) {
+    if (!x || !y) return fail(IINS_ERR_NULL, "pool: NULL argument");
+    IINS_LAUNCH(iins_pool_fwd_kernel, grid_for((long)batch * lout), 256, 0, (cudaStream_t)stream, x, y, batch, lin, lout);
+    return check_cuda("pool_forward");
+}
+int iins_adaptive_pool_backward(const float* dy, float* dx, int batch, int lin, int lout, iins_stream_t stream) {
+    if (!dy || !dx) return fail(IINS_ERR_NULL, "pool: NULL argument");
+    IINS_LAUNCH(iins_pool_bwd_kernel, grid_for((long)batch * lin), 256, 0, (cudaStream_t)stream, dy, (const float*)nullptr, dx,
+                batch, lin, lout);
+    return check_cuda("pool_backward");
+}
+
+}  // extern "C"

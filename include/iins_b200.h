@@ -1,0 +1,139 @@
+/* iins_b200.h -- C ABI of the B200-native IIns-VAE hot path (libiins_b200.so).
+ *
+ * The reference (JadeLilyx/IIns-VAE) is pure Python/PyTorch and has no FFI of its own: its
+ * boundary for this path is the nn.Module API of models.py.  Each entry point below therefore
+ * replaces one reference *method*; the Python classes in iins_vae_b200/models.py keep the
+ * reference's constructor / forward signatures and state_dict keys and bind these symbols with
+ * ctypes (see INTEGRATION.md for the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 unless stated; tensors are contiguous;
+ *   - "params" / "grads" are arrays (on the HOST) of device pointers, one per parameter tensor, in
+ *     the module's named_parameters() order (== state_dict order without the AdaIN dummy buffers);
+ *   - no allocation inside: the caller passes workspaces sized by the *_floats() queries;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), nothing synchronises;
+ *   - gradients are ACCUMULATED into `grads` (zero them first) -- weight gradients are reduced with
+ *     atomics; gradient outputs w.r.t. module inputs are overwritten unless `accumulate` is set;
+ *   - return value: 0 on success, negative iins_status otherwise; iins_last_error() gives text.
+ */
+#ifndef IINS_B200_H
+#define IINS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* iins_stream_t;      /* cudaStream_t */
+
+typedef enum iins_status {
+    IINS_OK = 0,
+    IINS_ERR_BAD_CONFIG = -1,     /* unsupported shape options (fails loudly, never falls back) */
+    IINS_ERR_NULL = -2,
+    IINS_ERR_CUDA = -3
+} iins_status;
+
+/* Shape options of the 1-D path: models.py:33 (Encoder), :68 (Decoder), :97 (Restorer),
+ * :118 (Classifier); call sites train_semi.py:77-82. */
+typedef struct iins_config {
+    int batch;          /* B                                              */
+    int cir_len;        /* 157 (zenodo) / 152 (ewine): train_semi.py:44   */
+    int dim;            /* Encoder/Decoder dim, 4                         */
+    int n_residual;     /* 3                                              */
+    int n_downsample;   /* 4 (== Decoder n_upsample)                      */
+    int env_dim;        /* style_dim, 16                                  */
+    int range_dim;      /* out_dim, 2                                     */
+    int num_classes;    /* Classifier num_classes                         */
+    int cls_filters;    /* Classifier filters, 16                         */
+} iins_config;
+
+int iins_abi_version(void);
+const char* iins_last_error(void);
+int iins_validate_config(const iins_config* cfg);
+
+/* ---- Encoder: models.py:49-61 (RangeEncoder1d :140-176, EnvEncoder1d :258-298) ------------------
+ * x (B,cir_len) -> range_code (B,range_dim,code_len) NCL, env_code (B,env_dim) [= cat],
+ * env_code_rv (B,env_dim/2) [= noise*exp(log_sigma)+mu], kl (scalar, zeroed then accumulated).
+ * noise: explicit (B,env_dim/2) standard normals, or NULL -> Philox4x32-10(seed, offset).
+ * ws: iins_encoder_ws_floats() floats holding the activations saved for backward. */
+int iins_encoder_num_params(const iins_config* cfg);
+size_t iins_encoder_ws_floats(const iins_config* cfg);
+size_t iins_encoder_scratch_floats(const iins_config* cfg);
+int iins_encoder_forward(const iins_config* cfg, const float* const* params, const float* x,
+                         const float* noise, uint64_t seed, uint64_t offset,
+                         float* range_code, float* env_code, float* env_code_rv, float* kl,
+                         float* ws, iins_stream_t stream);
+/* backward of the above; any of d_range_code / d_env_code / d_env_code_rv / d_kl may be NULL (== 0).
+ * d_kl is a device scalar.  range_code / env_code are the forward outputs. */
+int iins_encoder_backward(const iins_config* cfg, const float* const* params, const float* noise,
+                          uint64_t seed, uint64_t offset, const float* range_code, const float* env_code,
+                          const float* ws, const float* d_range_code, const float* d_env_code,
+                          const float* d_env_code_rv, const float* d_kl, float* const* grads,
+                          float* scratch, iins_stream_t stream);
+
+/* ---- Decoder: models.py:81-91 (Decoder1d :405-471, MLP :951-962, AdaIN :1048-1076, LN :965-985) ---
+ * (range_code NCL, env_code) -> x_recon (B,cir_len). */
+int iins_decoder_num_params(const iins_config* cfg);
+size_t iins_decoder_ws_floats(const iins_config* cfg);
+size_t iins_decoder_scratch_floats(const iins_config* cfg);
+int iins_decoder_forward(const iins_config* cfg, const float* const* params, const float* range_code,
+                         const float* env_code, float* x_recon, float* ws, iins_stream_t stream);
+int iins_decoder_backward(const iins_config* cfg, const float* const* params, const float* range_code,
+                          const float* env_code, const float* ws, const float* d_x_recon,
+                          float* const* grads, float* d_range_code, float* d_env_code, int accumulate,
+                          float* scratch, iins_stream_t stream);
+
+/* ---- Restorer (RestorerLinear, soft=False): models.py:642-658.  range_code -> err_est (B,1).
+ * params: 10 tensors (layers.{0,2,4}, linear_layer1, linear_layer2); linear_layer2 is never touched
+ * and its gradient slots are left as they are (grad None in the reference). */
+int iins_restorer_num_params(const iins_config* cfg);
+size_t iins_restorer_ws_floats(const iins_config* cfg);
+size_t iins_restorer_scratch_floats(const iins_config* cfg);
+int iins_restorer_forward(const iins_config* cfg, const float* const* params, const float* range_code,
+                          float* err_est, float* ws, iins_stream_t stream);
+int iins_restorer_backward(const iins_config* cfg, const float* const* params, const float* range_code,
+                           const float* ws, const float* d_err_est, float* const* grads,
+                           float* d_range_code, int accumulate, float* scratch, iins_stream_t stream);
+
+/* ---- Classifier (ClassifierLinear): models.py:858-862.  env_code -> logits (B,num_classes). */
+int iins_classifier_num_params(const iins_config* cfg);
+size_t iins_classifier_ws_floats(const iins_config* cfg);
+size_t iins_classifier_scratch_floats(const iins_config* cfg);
+int iins_classifier_forward(const iins_config* cfg, const float* const* params, const float* env_code,
+                            float* logits, float* ws, iins_stream_t stream);
+int iins_classifier_backward(const iins_config* cfg, const float* const* params, const float* env_code,
+                             const float* ws, const float* d_logits, float* const* grads,
+                             float* d_env_code, int accumulate, float* scratch, iins_stream_t stream);
+
+/* ---- Fused loss + seed gradients + metrics: train_semi.py:199-225, train.py:87-91, :104-115 -------
+ * out[8] (zeroed inside): [0] mean|x-x_recon|  [1] mean|err-err_est|  [2] mean CE  [3] lam-weighted sum
+ * of [0..2] (the KL term lives in the encoder)  [4] mean (err_est-err)^2  [5] #correct argmax.
+ * x/x_recon may be NULL (train.py variant), err/err_est/logits/label may be NULL (unsupervised batch).
+ * label: fp32 holding integers (dataset.py:122) or, if label_i64 != NULL, int64. */
+int iins_loss_forward_backward(int batch, int cir_len, int num_classes,
+                               const float* x, const float* x_recon, const float* err, const float* err_est,
+                               const float* logits, const float* label, const int64_t* label_i64,
+                               float lam_ae, float lam_res, float lam_env, float* out,
+                               float* d_x_recon, float* d_err_est, float* d_logits, int32_t* pred,
+                               iins_stream_t stream);
+
+/* ---- Fused Adam over a flat parameter buffer: torch.optim.Adam as used at train_semi.py:118-122 -----
+ * groups: up to 8 half-open element ranges [begin,end) with an `active` flag; an inactive group is
+ * skipped entirely (grad None in the reference).  steps: device int32[n_groups] step counters, advanced
+ * by this call for active groups.  lr: device scalar. */
+int iins_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                   const int64_t* group_begin, const int64_t* group_end, const int32_t* group_active,
+                   int n_groups, int32_t* steps, const float* lr, double beta1, double beta2, float eps,
+                   iins_stream_t stream);
+
+/* ---- small helpers used at the module boundary ----------------------------------------------------- */
+/* AdaptiveAvgPool1d over (B,Lin)->(B,Lout) (models.py:146, 436) and its backward */
+int iins_adaptive_pool_forward(const float* x, float* y, int batch, int lin, int lout, iins_stream_t stream);
+int iins_adaptive_pool_backward(const float* dy, float* dx, int batch, int lin, int lout, iins_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IINS_B200_H */
