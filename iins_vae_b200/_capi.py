@@ -22,6 +22,7 @@ EXPORTS = [
     "iins_classifier_forward", "iins_classifier_backward",
     "iins_loss_forward_backward", "iins_adam_step",
     "iins_adaptive_pool_forward", "iins_adaptive_pool_backward",
+    "iins_launch_count", "iins_profile_begin", "iins_profile_collect",
 ]
 
 
@@ -69,6 +70,19 @@ class IinsLib:
                                      C.c_int, _P, _P, C.c_double, C.c_double, C.c_float, _P]
         d.iins_adaptive_pool_forward.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P]
         d.iins_adaptive_pool_backward.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P]
+        d.iins_launch_count.restype = C.c_ulonglong
+        d.iins_profile_collect.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int]
+
+    def profile(self, fn):
+        """Run fn() with a CUDA-event pair around every kernel launch; returns [(kernel name, ms, flops), ...]."""
+        self.check(self.dll.iins_profile_begin(), "profile_begin")
+        fn()
+        cap = 4096
+        names = (C.c_char_p * cap)()
+        ms = (C.c_float * cap)()
+        fl = (C.c_double * cap)()
+        n = self.dll.iins_profile_collect(names, ms, fl, cap)
+        return [(names[i].decode(), float(ms[i]), float(fl[i])) for i in range(n)]
 
     def check(self, rc: int, what: str):
         if rc != 0:

@@ -7,9 +7,44 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
-#define IINS_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#include <string.h>
+// Launch bookkeeping: a launch counter (bench.py reports it as gpu_launches) and an optional per-launch
+// CUDA-event profile (iins_profile_begin / iins_profile_collect) used to time individual kernels inside
+// a real step without an external profiler.
+struct IinsProfState {
+    unsigned long long launches;
+    int enabled;
+    int n;                               // recorded launches
+    const char* names[4096];
+    double flops[4096];
+    double cur_flops;                    // set by the GEMM launchers just before IINS_LAUNCH
+    cudaEvent_t ev0[4096], ev1[4096];
+    int ev_ready;
+};
+static IinsProfState g_iins_prof;
+static inline void iins_prof_pre(const char* name, cudaStream_t st) {
+    g_iins_prof.launches++;
+    if (g_iins_prof.enabled && g_iins_prof.n < 4096) {
+        g_iins_prof.names[g_iins_prof.n] = name;
+        g_iins_prof.flops[g_iins_prof.n] = g_iins_prof.cur_flops;
+        cudaEventRecord(g_iins_prof.ev0[g_iins_prof.n], st);
+    }
+}
+static inline void iins_prof_post(cudaStream_t st) {
+    if (g_iins_prof.enabled && g_iins_prof.n < 4096) {
+        cudaEventRecord(g_iins_prof.ev1[g_iins_prof.n], st);
+        g_iins_prof.n++;
+    }
+    g_iins_prof.cur_flops = 0.0;
+}
+#define IINS_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
+    do {                                                                    \
+        iins_prof_pre(#kernel, (stream));                                   \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);         \
+        iins_prof_post((stream));                                           \
+    } while (0)
 #define IINS_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+#define IINS_SET_FLOPS(f) (g_iins_prof.cur_flops = (f))
 #endif
 
 #define IINS_HD __host__ __device__ __forceinline__

@@ -254,8 +254,10 @@ __global__ void __launch_bounds__(256) iins_reparam_kl_kernel(const float* __res
         long b = i / H;
         int j = (int)(i - b * H);
         float mu = __ldg(cat + b * E + j), ls = __ldg(cat + b * E + H + j);
-        float nz = noise != nullptr ? __ldg(noise + i) : iins_noise_at(seed, offset, b, j);
-        if (latent != nullptr) latent[i] = fmaf(nz, expf(ls), mu);
+        if (latent != nullptr) {
+            float nz = noise != nullptr ? __ldg(noise + i) : iins_noise_at(seed, offset, b, j);
+            latent[i] = fmaf(nz, expf(ls), mu);
+        }
         part += 0.5f * (expf(2.f * ls) + mu * mu - 1.f - 2.f * ls);
     }
     part = iins_warp_sum(part);

@@ -66,6 +66,7 @@ IinsDz act_dz(const float* dy, const float* y, int act, float slope) {
 void launch_nt(const Ctx& c, const IinsNTParams& p) {
     int bn = p.N <= 8 ? 8 : (p.N <= 16 ? 16 : (p.N <= 32 ? 32 : 64));
     dim3 grid((p.M + 127) / 128, (p.N + bn - 1) / bn, 1);
+    IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K);
     if (bn == 8) IINS_LAUNCH(iins_nt_kernel<8>, grid, 256, 0, c.st, p);
     else if (bn == 16) IINS_LAUNCH(iins_nt_kernel<16>, grid, 256, 0, c.st, p);
     else if (bn == 32) IINS_LAUNCH(iins_nt_kernel<32>, grid, 256, 0, c.st, p);
@@ -110,6 +111,7 @@ void conv_wgrad(const Ctx& c, const IinsGeom& g, const float* x, const IinsDz& d
     rpp = (rpp + 31) / 32 * 32;
     int parts = (int)((p.M + rpp - 1) / rpp);
     p.rows_per_part = (int)rpp;
+    IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K);
     IINS_LAUNCH(iins_tn_kernel, dim3(parts, ky, nz), 256, 0, c.st, p);
 }
 
@@ -751,6 +753,42 @@ int iins_adam_step(float* params, const float* grads, float* exp_avg, float* exp
     IINS_LAUNCH(iins_adam_kernel, grid_for(total), 256, 0, st, a);
     return check_cuda("adam");
 }
+
+#ifndef IINS_CPUSIM
+unsigned long long iins_launch_count(void) { return g_iins_prof.launches; }
+
+int iins_profile_begin(void) {
+    if (!g_iins_prof.ev_ready) {
+        for (int i = 0; i < 4096; ++i) {
+            if (cudaEventCreate(&g_iins_prof.ev0[i]) != cudaSuccess || cudaEventCreate(&g_iins_prof.ev1[i]) != cudaSuccess)
+                return fail(IINS_ERR_CUDA, "profile: cudaEventCreate failed");
+        }
+        g_iins_prof.ev_ready = 1;
+    }
+    g_iins_prof.n = 0;
+    g_iins_prof.enabled = 1;
+    return IINS_OK;
+}
+
+// Stops recording, synchronises the device and writes, for up to `cap` recorded launches in launch order,
+// the kernel name (pointer to a static string) and its duration in milliseconds.  Returns the count.
+int iins_profile_collect(const char** names, float* ms, double* flops, int cap) {
+    g_iins_prof.enabled = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(IINS_ERR_CUDA, "profile: synchronize failed");
+    int n = g_iins_prof.n < cap ? g_iins_prof.n : cap;
+    for (int i = 0; i < n; ++i) {
+        names[i] = g_iins_prof.names[i];
+        if (flops) flops[i] = g_iins_prof.flops[i];
+        ms[i] = 0.f;
+        cudaEventElapsedTime(&ms[i], g_iins_prof.ev0[i], g_iins_prof.ev1[i]);
+    }
+    return n;
+}
+#else
+unsigned long long iins_launch_count(void) { return 0; }
+int iins_profile_begin(void) { return IINS_OK; }
+int iins_profile_collect(const char**, float*, double*, int) { return 0; }
+#endif
 
 int iins_adaptive_pool_forward(const float* x, float* y, int batch, int lin, int lout, iins_stream_t stream) {
     if (!x || !y) return fail(IINS_ERR_NULL, "pool: NULL argument");

@@ -1,0 +1,307 @@
+"""Fused train / inference engines: the whole step of train_semi.py:183-228 (or train.py:75-94) as a fixed
+sequence of C-ABI calls on one CUDA stream -- no autograd graph, no per-step allocation, one flat
+parameter / gradient / Adam-state buffer, optionally replayed from a CUDA graph.
+
+The nn.Modules stay the owners of the parameters (their ``.data`` become views into the flat buffer), so
+``state_dict()`` / ``torch.save`` keep working exactly like the reference's checkpoints
+(train_semi.py:281-286).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._capi import IinsConfig, get_lib, ptr, ptr_array
+
+LAMBDA_AE, LAMBDA_RES, LAMBDA_RANGE, LAMBDA_ENV = 1.0, 10.0, 1.0, 1.0      # train_semi.py:111-114
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _Flat:
+    """Flatten the parameters of several modules into one buffer (module order, named_parameters order)."""
+
+    def __init__(self, modules, device):
+        self.params, self.spans = [], []
+        off = 0
+        for m in modules:
+            begin = off
+            for p in m.parameters():
+                self.params.append(p)
+                off += p.numel()
+            self.spans.append((begin, off))
+        self.total = off
+        self.flat = torch.empty(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
+        self.exp_avg = torch.zeros(off, dtype=torch.float32, device=device)
+        self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=device)
+        o = 0
+        self.grad_views = []
+        for p in self.params:
+            n = p.numel()
+            self.flat[o:o + n].copy_(p.data.reshape(-1).to(device=device, dtype=torch.float32))
+            p.data = self.flat[o:o + n].view(p.shape)
+            self.grad_views.append(self.grad[o:o + n].view(p.shape))
+            o += n
+
+
+class SemiTrainEngine:
+    """One object = the reference's (Enc, Dec, Res, Cls, Adam) training state, stepped by fused kernels.
+
+    mode="semi"       : loss_ae + kl (+ 10*L1(err) + CE when the batch is supervised)  -- train_semi.py:199-225
+    mode="supervised" : CE + L1(err) on Encoder -> (Classifier, Restorer), no decoder -- train.py:82-91
+    """
+
+    def __init__(self, Enc, Dec, Res, Cls, batch_size, cir_len=157, lr=1e-4, betas=(0.5, 0.999), eps=1e-8,
+                 mode="semi", use_graph=True, process_group=None, device=None):
+        self.lib = get_lib()
+        self.mode = mode
+        self.device = torch.device(device if device is not None else torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise RuntimeError("iins_vae_b200 engines run on CUDA only")
+        self.Enc, self.Dec, self.Res, self.Cls = Enc, Dec, Res, Cls
+        mods = [Enc] + ([Dec] if mode == "semi" else []) + [Res, Cls]
+        self.flat = _Flat(mods, self.device)
+        o = Enc.opts
+        self.B, self.L = int(batch_size), int(cir_len)
+        self.E, self.R, self.NC = o["env_dim"], o["range_dim"], Cls.num_classes
+        self.cfg = IinsConfig(self.B, self.L, o["dim"], o["n_residual"], o["n_downsample"], self.E, self.R, self.NC,
+                              Cls.filters)
+        self.lib.check(self.lib.iins_validate_config(self.cfg), "engine config")
+        self.betas, self.eps = betas, eps
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        dev, B = self.device, self.B
+        f = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+        # static I/O
+        self.cir, self.err, self.label = f(B, self.L), f(B, 1), f(B, 1)
+        self.rc, self.cat, self.kl = f(B, self.R, 128 >> o["n_downsample"]), f(B, self.E), f(1)
+        self.xrec, self.err_est, self.logits = f(B, self.L), f(B, 1), f(B, self.NC)
+        self.out = f(8)
+        self.pred = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.d_xrec, self.d_err, self.d_logits = f(B, self.L), f(B, 1), f(B, self.NC)
+        self.d_rc, self.d_cat = torch.zeros_like(self.rc), torch.zeros_like(self.cat)
+        self.d_kl = torch.full((1,), LAMBDA_RANGE, dtype=torch.float32, device=dev)
+        self.lr = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self.steps = torch.zeros(8, dtype=torch.int32, device=dev)
+        lib = self.lib
+        names = ("encoder", "decoder", "restorer", "classifier")
+        self.ws = {m: f(int(getattr(lib, f"iins_{m}_ws_floats")(self.cfg)) + 16) for m in names}
+        self.scratch = {m: f(int(getattr(lib, f"iins_{m}_scratch_floats")(self.cfg)) + 16) for m in names}
+        # pointer tables per module
+        self._tables(mods)
+        self._graphs = {}
+        self.use_graph = use_graph and self.world == 1
+        self.n_steps = 0
+
+    # ------------------------------------------------------------------------------------------------
+    def _tables(self, mods):
+        fl = self.flat
+        self.ptab, self.gtab, self.mod_span = {}, {}, {}
+        i = 0
+        for m, name in zip(mods, ["enc"] + (["dec"] if self.mode == "semi" else []) + ["res", "cls"]):
+            n = len(list(m.parameters()))
+            self.ptab[name] = ptr_array(fl.params[i:i + n])
+            self.gtab[name] = ptr_array(fl.grad_views[i:i + n])
+            i += n
+        spans = dict(zip(["enc"] + (["dec"] if self.mode == "semi" else []) + ["res", "cls"], fl.spans))
+        self.spans = spans
+        # Adam groups (half-open element ranges): always-on [Enc (+Dec)], Res without linear_layer2, Cls.
+        res_b, res_e = spans["res"]
+        res_used = res_e - (2 * 256 + 2)                 # linear_layer2.{weight,bias} are the last 514 elements
+        always_end = spans["dec"][1] if self.mode == "semi" else spans["enc"][1]
+        self.groups = [(0, always_end), (res_b, res_used), spans["cls"]]
+        self._gb = (C.c_int64 * 3)(*[g[0] for g in self.groups])
+        self._ge = (C.c_int64 * 3)(*[g[1] for g in self.groups])
+
+    def set_lr(self, lr: float):
+        self.lr.fill_(float(lr))
+
+    # ------------------------------------------------------------------------------------------------
+    def _forward(self, supervised: bool):
+        lib, cfg, st = self.lib, self.cfg, _stream()
+        lib.check(lib.iins_encoder_forward(cfg, self.ptab["enc"], ptr(self.cir), None, 0, 0, ptr(self.rc), ptr(self.cat),
+                                           None, ptr(self.kl), ptr(self.ws["encoder"]), st), "encoder forward")
+        if self.mode == "semi":
+            lib.check(lib.iins_decoder_forward(cfg, self.ptab["dec"], ptr(self.rc), ptr(self.cat), ptr(self.xrec),
+                                               ptr(self.ws["decoder"]), st), "decoder forward")
+        if supervised:
+            lib.check(lib.iins_restorer_forward(cfg, self.ptab["res"], ptr(self.rc), ptr(self.err_est),
+                                                ptr(self.ws["restorer"]), st), "restorer forward")
+            lib.check(lib.iins_classifier_forward(cfg, self.ptab["cls"], ptr(self.cat), ptr(self.logits),
+                                                  ptr(self.ws["classifier"]), st), "classifier forward")
+
+    def _loss(self, supervised: bool):
+        lib, semi = self.lib, self.mode == "semi"
+        lam_res = LAMBDA_RES if semi else 1.0
+        lib.check(lib.iins_loss_forward_backward(
+            self.B, self.L, self.NC, ptr(self.cir) if semi else None, ptr(self.xrec) if semi else None,
+            ptr(self.err) if supervised else None, ptr(self.err_est) if supervised else None,
+            ptr(self.logits) if supervised else None, ptr(self.label) if supervised else None, None,
+            LAMBDA_AE, lam_res, LAMBDA_ENV, ptr(self.out), ptr(self.d_xrec) if semi else None,
+            ptr(self.d_err) if supervised else None, ptr(self.d_logits) if supervised else None, ptr(self.pred),
+            _stream()), "loss")
+
+    def _backward(self, supervised: bool):
+        lib, cfg, st, semi = self.lib, self.cfg, _stream(), self.mode == "semi"
+        self.flat.grad.zero_()
+        acc = 0
+        if semi:
+            lib.check(lib.iins_decoder_backward(cfg, self.ptab["dec"], ptr(self.rc), ptr(self.cat), ptr(self.ws["decoder"]),
+                                                ptr(self.d_xrec), self.gtab["dec"], ptr(self.d_rc), ptr(self.d_cat), 0,
+                                                ptr(self.scratch["decoder"]), st), "decoder backward")
+            acc = 1
+        if supervised:
+            lib.check(lib.iins_restorer_backward(cfg, self.ptab["res"], ptr(self.rc), ptr(self.ws["restorer"]), ptr(self.d_err),
+                                                 self.gtab["res"], ptr(self.d_rc), acc, ptr(self.scratch["restorer"]), st),
+                      "restorer backward")
+            lib.check(lib.iins_classifier_backward(cfg, self.ptab["cls"], ptr(self.cat), ptr(self.ws["classifier"]),
+                                                   ptr(self.d_logits), self.gtab["cls"], ptr(self.d_cat), acc,
+                                                   ptr(self.scratch["classifier"]), st), "classifier backward")
+        lib.check(lib.iins_encoder_backward(cfg, self.ptab["enc"], None, 0, 0, ptr(self.rc), ptr(self.cat),
+                                            ptr(self.ws["encoder"]), ptr(self.d_rc), ptr(self.d_cat), None,
+                                            ptr(self.d_kl) if semi else None, self.gtab["enc"],
+                                            ptr(self.scratch["encoder"]), st), "encoder backward")
+
+    def _allreduce(self, supervised: bool):
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        end = self.flat.total if supervised else self.groups[0][1]
+        g = self.flat.grad[:end]
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
+        g.mul_(1.0 / self.world)
+
+    def _adam(self, supervised: bool):
+        act = (C.c_int32 * 3)(1, int(supervised), int(supervised))
+        fl = self.flat
+        self.lib.check(self.lib.iins_adam_step(ptr(fl.flat), ptr(fl.grad), ptr(fl.exp_avg), ptr(fl.exp_avg_sq), self._gb,
+                                               self._ge, act, 3, ptr(self.steps), ptr(self.lr), self.betas[0], self.betas[1],
+                                               self.eps, _stream()), "adam")
+
+    def _step_body(self, supervised: bool, update: bool = True):
+        self._forward(supervised)
+        self._loss(supervised)
+        self._backward(supervised)
+        self._allreduce(supervised)
+        if update:
+            self._adam(supervised)
+
+    # ------------------------------------------------------------------------------------------------
+    def load_batch(self, cir, err, label):
+        """Stage one batch (host or device tensors) into the static input buffers (async on the stream)."""
+        self.cir.copy_(cir.view(self.B, self.L), non_blocking=True)
+        self.err.copy_(err.view(self.B, 1), non_blocking=True)
+        self.label.copy_(label.view(self.B, 1).to(torch.float32) if label.dtype != torch.float32 else label.view(self.B, 1),
+                         non_blocking=True)
+
+    def step(self, cir=None, err=None, label=None, supervised=True, update=True):
+        """One optimisation step.  Returns the device tensor ``out`` (8 floats, see iins_b200.h) -- nothing
+        synchronises; read ``loss_terms()`` when a host value is needed."""
+        if self.mode == "supervised":
+            supervised = True
+        if cir is not None:
+            self.load_batch(cir, err, label)
+        key = (bool(supervised), bool(update))
+        if self.use_graph:
+            g = self._graphs.get(key)
+            if g is None:
+                # warm up once eagerly on a side stream (also validates every call), then capture
+                state = (self.flat.flat.clone(), self.flat.exp_avg.clone(), self.flat.exp_avg_sq.clone(), self.steps.clone())
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._step_body(*key)
+                torch.cuda.current_stream().wait_stream(s)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_body(*key)
+                # the warm-up and the capture pass must not count as optimisation steps
+                self.flat.flat.copy_(state[0]); self.flat.exp_avg.copy_(state[1]); self.flat.exp_avg_sq.copy_(state[2])
+                self.steps.copy_(state[3])
+                self._graphs[key] = g
+            g.replay()
+        else:
+            self._step_body(*key)
+        self.n_steps += 1
+        return self.out
+
+    def loss_terms(self):
+        """Host copy of the loss terms of the last step (this synchronises)."""
+        o = self.out.tolist()
+        kl = float(self.kl) if self.mode == "semi" else 0.0
+        lam_res = LAMBDA_RES if self.mode == "semi" else 1.0
+        d = dict(loss_ae=LAMBDA_AE * o[0], loss_range=LAMBDA_RANGE * kl, loss_res=lam_res * o[1], loss_env=LAMBDA_ENV * o[2],
+                 rmse=float(np.sqrt(max(o[4], 0.0))), mae=o[1], accuracy=o[5] / self.B)
+        d["loss"] = o[3] + (LAMBDA_RANGE * kl if self.mode == "semi" else 0.0)
+        return d
+
+    def named_grads(self):
+        """{module-prefixed parameter name: gradient view} of the last step (for tests / inspection)."""
+        out = {}
+        i = 0
+        mods = [("enc", self.Enc)] + ([("dec", self.Dec)] if self.mode == "semi" else []) + [("res", self.Res), ("cls", self.Cls)]
+        for pre, m in mods:
+            for n, _ in m.named_parameters():
+                out[f"{pre}.{n}"] = self.flat.grad_views[i]
+                i += 1
+        return out
+
+
+class InferenceEngine:
+    """test.py:66-85: Encoder -> (Classifier, Restorer), no grad, fused metrics.  Static buffers + CUDA graph."""
+
+    def __init__(self, Enc, Res, Cls, batch_size, cir_len=157, use_graph=True, device=None):
+        self.lib = get_lib()
+        self.device = torch.device(device if device is not None else torch.cuda.current_device())
+        o = Enc.opts
+        self.B, self.L, self.NC = int(batch_size), int(cir_len), Cls.num_classes
+        self.cfg = IinsConfig(self.B, self.L, o["dim"], o["n_residual"], o["n_downsample"], o["env_dim"], o["range_dim"],
+                              self.NC, Cls.filters)
+        self.lib.check(self.lib.iins_validate_config(self.cfg), "engine config")
+        dev, B = self.device, self.B
+        f = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+        self.cir, self.err, self.label = f(B, self.L), f(B, 1), f(B, 1)
+        self.rc, self.cat, self.kl = f(B, o["range_dim"], 128 >> o["n_downsample"]), f(B, o["env_dim"]), f(1)
+        self.err_est, self.logits, self.out = f(B, 1), f(B, self.NC), f(8)
+        self.pred = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.ws = {m: f(int(getattr(self.lib, f"iins_{m}_ws_floats")(self.cfg)) + 16) for m in ("encoder", "restorer", "classifier")}
+        self.ptab = {n: ptr_array(list(m.parameters())) for n, m in (("enc", Enc), ("res", Res), ("cls", Cls))}
+        self._keep = (Enc, Res, Cls)
+        self.use_graph, self._graph = use_graph, None
+
+    def _body(self, with_metrics: bool):
+        lib, cfg, st = self.lib, self.cfg, _stream()
+        lib.check(lib.iins_encoder_forward(cfg, self.ptab["enc"], ptr(self.cir), None, 0, 0, ptr(self.rc), ptr(self.cat), None,
+                                           ptr(self.kl), ptr(self.ws["encoder"]), st), "encoder forward")
+        lib.check(lib.iins_restorer_forward(cfg, self.ptab["res"], ptr(self.rc), ptr(self.err_est), ptr(self.ws["restorer"]), st),
+                  "restorer forward")
+        lib.check(lib.iins_classifier_forward(cfg, self.ptab["cls"], ptr(self.cat), ptr(self.logits), ptr(self.ws["classifier"]),
+                                              st), "classifier forward")
+        lib.check(lib.iins_loss_forward_backward(self.B, self.L, self.NC, None, None, ptr(self.err), ptr(self.err_est),
+                                                 ptr(self.logits), ptr(self.label), None, 1.0, 1.0, 1.0, ptr(self.out), None, None,
+                                                 None, ptr(self.pred), st), "metrics")
+
+    def run(self, cir=None, err=None, label=None):
+        """Returns (err_est (B,1), pred (B,) int32, out[8]) as device tensors (static buffers, overwritten next call)."""
+        if cir is not None:
+            self.cir.copy_(cir.view(self.B, self.L), non_blocking=True)
+        if err is not None:
+            self.err.copy_(err.view(self.B, 1), non_blocking=True)
+            self.label.copy_(label.view(self.B, 1).float(), non_blocking=True)
+        if self.use_graph:
+            if self._graph is None:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._body(True)
+                torch.cuda.current_stream().wait_stream(s)
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._body(True)
+            self._graph.replay()
+        else:
+            self._body(True)
+        return self.err_est, self.pred, self.out

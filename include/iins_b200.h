@@ -133,6 +133,12 @@ int iins_adam_step(float* params, const float* grads, float* exp_avg, float* exp
 int iins_adaptive_pool_forward(const float* x, float* y, int batch, int lin, int lout, iins_stream_t stream);
 int iins_adaptive_pool_backward(const float* dy, float* dx, int batch, int lin, int lout, iins_stream_t stream);
 
+/* ---- launch accounting / in-process kernel timing (used by bench.py; not a profiler replacement) ------ */
+unsigned long long iins_launch_count(void);           /* kernels launched by this library so far */
+int iins_profile_begin(void);                          /* record a CUDA-event pair around every launch */
+int iins_profile_collect(const char** names, float* ms, double* flops, int cap);
+        /* sync; per launch: kernel name, milliseconds, algorithmic FLOPs (2*M*N*K for the GEMM kernels, else 0) */
+
 #ifdef __cplusplus
 }
 #endif
