@@ -239,10 +239,22 @@ def adaptive_pool_windows(lin: int, lout: int):
     return [((i * lin) // lout, -((-(i + 1) * lin) // lout)) for i in range(lout)]
 
 
+_POOL_CACHE = {}
+
+
+def adaptive_pool_matrix(lin: int, lout: int, dtype=torch.float32) -> torch.Tensor:
+    """(lout, lin) averaging matrix of the window table above (row i = 1/len on window i)."""
+    key = (lin, lout, dtype)
+    if key not in _POOL_CACHE:
+        m = torch.zeros(lout, lin, dtype=dtype)
+        for i, (s, e) in enumerate(adaptive_pool_windows(lin, lout)):
+            m[i, s:e] = 1.0 / (e - s)
+        _POOL_CACHE[key] = m
+    return _POOL_CACHE[key]
+
+
 def adaptive_avg_pool1d(x: torch.Tensor, lout: int) -> torch.Tensor:
-    lin = x.shape[-1]
-    cols = [x[..., s:e].mean(dim=-1) for s, e in adaptive_pool_windows(lin, lout)]
-    return torch.stack(cols, dim=-1)
+    return x @ adaptive_pool_matrix(x.shape[-1], lout, x.dtype).t()
 
 
 def reflect_index(u: int, n: int) -> int:
@@ -255,9 +267,10 @@ def reflect_index(u: int, n: int) -> int:
 
 
 def reflection_pad1d(x: torch.Tensor, p: int) -> torch.Tensor:
-    n = x.shape[-1]
-    idx = torch.tensor([reflect_index(q - p, n) for q in range(n + 2 * p)])
-    return x.index_select(-1, idx)
+    """out[q] = x[reflect_index(q - p)]: the p samples next to each edge mirrored, edge not repeated."""
+    left = x[..., 1:p + 1].flip(-1)
+    right = x[..., -p - 1:-1].flip(-1)
+    return torch.cat([left, x, right], dim=-1)
 
 
 def instance_norm1d(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:

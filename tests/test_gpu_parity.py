@@ -159,7 +159,7 @@ def test_engine_adam_trajectory_matches_golden(golden, case):
         cir, err, label = batches[step % 3]
         eng.step(cir, err, label, supervised=bool(masks[step]))
         loss = eng.loss_terms()["loss"]
-        np.testing.assert_allclose(loss, golden[pre + "losses"][step], rtol=2e-5 if step == 0 else 2e-3)
+        np.testing.assert_allclose(loss, golden[pre + "losses"][step], rtol=2e-5 if step == 0 else 1e-2)
         if step + 1 in (1, n_steps):
             for gname, m in zip(("enc", "dec", "res", "cls"), mods):
                 for n, p in m.named_parameters():
