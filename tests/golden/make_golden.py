@@ -163,6 +163,9 @@ def make_case(cfg, seed, batch, supervised, store, prefix):
             assert float(p.grad.abs().max()) < 1e-5 * gmax, k
             continue
         scale = float(truth.norm())
+        # the reference's OWN fp32 rounding error on this tensor (vs the fp64 evaluation): the parity tests
+        # scale their tolerance with it (tests/parity.py)
+        store[prefix + "grad." + k + "|referr"] = np.float64(float((p.grad.double() - truth).norm()) / (scale + 1e-300))
         for tag, got in (("ref", p.grad), ("orc", o_grads[k])):
             e = float((got.double() - truth).norm()) / scale
             if e > KINK_FREE and VERBOSE:

@@ -86,3 +86,61 @@ def assert_update_close(name, got, ref, start, n_steps, lr=1e-4, rel=0.5):
     upd_ref = ref - start
     err = np.linalg.norm((got - start) - upd_ref)
     assert err <= rel * np.linalg.norm(upd_ref) + 1e-7, f"{name}: update differs {err:.3e} vs {np.linalg.norm(upd_ref):.3e}"
+
+
+# ---------------------------------------------------------------------------------------------------
+# Gradient parity at realistic batch sizes.
+#
+# Measured (tools/diag_parity.py, DESIGN.md "Parity"): two fp32 evaluations of this network do NOT agree to
+# 1e-4 on every gradient tensor once B >= 64.  Two mechanisms, both properties of the reference itself:
+#   (1) conditioning -- InstanceNorm over L=8 multiplies rounding noise by up to 1/sqrt(eps) = 316 for
+#       (sample, channel) pairs whose 8 values are nearly equal; at B=4096 the fp32 CPU reference/oracle is
+#       2.5e-3 away from an fp64 evaluation on the range-encoder gradients;
+#   (2) kink flips -- an activation within rounding of 0 gets ReLU'/LeakyReLU'/sign() decided differently by
+#       two correct implementations; that moves every upstream gradient tensor by O(1/B) of its norm.
+# So the bar is: per tensor, error vs the fp64 oracle <= max(1e-4, 3 x the fp32 oracle's own error vs fp64)
+# ("strict"); a tensor may instead be within the kink-flip bound FLIP_C / B.  Small batches must be strict.
+FLIP_C = 8.0
+REF_FACTOR = 3.0
+
+
+def grad_report(got, truth, ref32, gscale):
+    """Per-tensor rel-L2 errors vs the fp64 truth: [(name, rel_got, rel_ref32, strict_ok)]."""
+    rows = []
+    for name, t in truth.items():
+        if t is None:
+            continue
+        g = to_np(got[name]).ravel()
+        t64 = to_np(t).ravel()
+        if orc.grad_is_structurally_zero(name):
+            rows.append((name, float(np.abs(g).max()) / gscale, 0.0, float(np.abs(g).max()) <= ZERO_G * gscale))
+            continue
+        n = float(np.linalg.norm(t64)) + 1e-300
+        floor = ATOL_G * gscale * np.sqrt(t64.size)
+        e_got = float(np.linalg.norm(g - t64))
+        e_ref = float(np.linalg.norm(to_np(ref32[name]).ravel() - t64)) if ref32 is not None else 0.0
+        strict = e_got <= max(RTOL_FP32 * n, REF_FACTOR * e_ref) + floor
+        rows.append((name, e_got / n, e_ref / n, strict))
+    return rows
+
+
+def assert_grads(rows, batch, require_strict, label=""):
+    bad_strict = [r for r in rows if not r[3]]
+    if require_strict:
+        assert not bad_strict, f"{label}: {len(bad_strict)} tensors beyond the strict bound, e.g. {bad_strict[0]}"
+        return 0
+    flip = FLIP_C / batch
+    beyond = [r for r in bad_strict if r[1] > flip]
+    assert not beyond, f"{label}: {len(beyond)} tensors beyond even the kink-flip bound {flip:.1e}, e.g. {beyond[0]}"
+    return len(bad_strict)
+
+
+def digest_rel_error(golden, key, got):
+    """rel-L2 error of a tensor against a golden digest (full tensor or 64 samples)."""
+    got = to_np(got).ravel()
+    if key + "|full" in golden.files:
+        ref = golden[key + "|full"].astype(np.float64).ravel()
+        return float(np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-300))
+    pos = sample_positions(got.size)
+    ref = golden[key + "|samples"].astype(np.float64)
+    return float(np.linalg.norm(got[pos] - ref) / (np.linalg.norm(ref) + 1e-300))
