@@ -23,6 +23,7 @@ EXPORTS = [
     "iins_loss_forward_backward", "iins_adam_step",
     "iins_adaptive_pool_forward", "iins_adaptive_pool_backward",
     "iins_launch_count", "iins_profile_begin", "iins_profile_collect",
+    "iins_set_compute_mode", "iins_get_compute_mode", "iins_profile_shapes",
 ]
 
 
@@ -82,6 +83,8 @@ class IinsLib:
         ms = (C.c_float * cap)()
         fl = (C.c_double * cap)()
         n = self.dll.iins_profile_collect(names, ms, fl, cap)
+        self.last_shapes = (C.c_int * (3 * cap))()
+        self.dll.iins_profile_shapes(self.last_shapes, cap)
         return [(names[i].decode(), float(ms[i]), float(fl[i])) for i in range(n)]
 
     def check(self, rc: int, what: str):

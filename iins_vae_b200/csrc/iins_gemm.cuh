@@ -37,6 +37,100 @@ struct IinsNTParams {
     int out_layout;            // layout of the GEMM output
 };
 
+// Norm / activation / residual / store on one SMEM-staged tile Cs[128][LD] (bias already added).
+// st_mean / st_rstd: scratch for the statistics (>= 1024 floats each).  Called by every thread of a
+// 256-thread CTA; contains __syncthreads().
+template <int BN, int LD>
+__device__ __forceinline__ void iins_epilogue_tile(const IinsNTParams& p, const float* Cs, float* st_mean, float* st_rstd,
+                                                   int tile_m, int n0) {
+    constexpr int BM = 128;
+    const int tid = threadIdx.x;
+    const IinsGeom& g = p.g;
+    const IinsEpilogue& ep = p.ep;
+    const int L = p.Lrow;
+    const int S = BM / L;                  // samples per tile (L <= 128 always when norm != NONE)
+    const int ncols = (p.N - n0) < BN ? (p.N - n0) : BN;
+    const int b0 = tile_m / L;             // first sample of the tile
+
+    if (ep.norm == IINS_NORM_IN || ep.norm == IINS_NORM_ADAIN) {
+        // per (sample, channel) statistics over the L rows; biased variance (models.py:152, 1072)
+        const int pairs = S * ncols;
+        int G = 1;
+        while (G < 32 && pairs * G * 2 <= 256) G <<= 1;
+        const int per_iter = 256 / G;
+        for (int p0 = 0; p0 < pairs; p0 += per_iter) {
+            int pr = p0 + tid / G, sub = tid % G;
+            bool ok = pr < pairs;
+            int s = ok ? pr / ncols : 0, c = ok ? pr - s * ncols : 0;
+            float sum = 0.f;
+            if (ok) for (int l = sub; l < L; l += G) sum += Cs[(s * L + l) * LD + c];
+            sum = iins_group_sum(sum, G);
+            float mean = sum / (float)L;
+            float sq = 0.f;
+            if (ok) for (int l = sub; l < L; l += G) { float dv = Cs[(s * L + l) * LD + c] - mean; sq += dv * dv; }
+            sq = iins_group_sum(sq, G);
+            if (ok && sub == 0) {
+                float rs = 1.0f / sqrtf(sq / (float)L + IINS_EPS);
+                st_mean[s * BN + c] = mean;
+                st_rstd[s * BN + c] = rs;
+                int b = b0 + s;
+                if (b < g.B && ep.rstd != nullptr) ep.rstd[(long)b * p.N + n0 + c] = rs;
+            }
+        }
+        __syncthreads();
+    } else if (ep.norm == IINS_NORM_LN) {
+        // per-sample mean and UNBIASED std over (C*L), eps added to std (models.py:976-981)
+        const int warp = tid >> 5, lane = tid & 31;
+        const int nel = L * ncols;
+        for (int s0 = 0; s0 < S; s0 += 8) {
+            int s = s0 + warp;
+            bool ok = s < S;
+            float sum = 0.f;
+            if (ok) for (int e = lane; e < nel; e += 32) sum += Cs[(s * L + e / ncols) * LD + (e % ncols)];
+            sum = iins_warp_sum(sum);
+            float mean = sum / (float)nel;
+            float sq = 0.f;
+            if (ok) for (int e = lane; e < nel; e += 32) { float dv = Cs[(s * L + e / ncols) * LD + (e % ncols)] - mean; sq += dv * dv; }
+            sq = iins_warp_sum(sq);
+            if (ok && lane == 0) {
+                float rs = 1.0f / (sqrtf(sq / (float)(nel - 1)) + IINS_EPS);
+                st_mean[s] = mean;
+                st_rstd[s] = rs;
+                int b = b0 + s;
+                if (b < g.B && ep.rstd != nullptr) ep.rstd[b] = rs;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- apply + store (coalesced over the contiguous NLC tile)
+    for (int e = tid; e < BM * BN; e += 256) {
+        int r = e / BN, n = e - r * BN;
+        int gr = tile_m + r, gn = n0 + n;
+        if (gr >= p.M || gn >= p.N) continue;
+        float v = Cs[r * LD + n];
+        int s = r / L;
+        int b = gr / L, l = gr - b * L;
+        long oi = p.out_layout == IINS_NCL ? ((long)b * p.N + gn) * L + l : (long)gr * p.N + gn;
+        if (ep.norm == IINS_NORM_IN || ep.norm == IINS_NORM_ADAIN) {
+            v = (v - st_mean[s * BN + n]) * st_rstd[s * BN + n];
+            if (ep.xhat != nullptr) ep.xhat[oi] = v;
+            if (ep.norm == IINS_NORM_ADAIN) {
+                float wv = __ldg(ep.adain + (long)b * ep.adain_ld + ep.adain_off_w + gn);
+                float bv = __ldg(ep.adain + (long)b * ep.adain_ld + ep.adain_off_b + gn);
+                v = fmaf(v, wv, bv);
+            }
+        } else if (ep.norm == IINS_NORM_LN) {
+            v = (v - st_mean[s]) * st_rstd[s];
+            if (ep.xhat != nullptr) ep.xhat[oi] = v;
+            v = fmaf(v, __ldg(ep.gamma + gn), __ldg(ep.beta + gn));
+        }
+        v = iins_act(v, ep.act, ep.slope);
+        if (ep.add != nullptr) v += __ldg(ep.add + oi);
+        ep.y[oi] = v;
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(256) iins_nt_kernel(const IinsNTParams p) {
     constexpr int BM = 128, BK = 16, TN = 4;
@@ -150,88 +244,7 @@ __global__ void __launch_bounds__(256) iins_nt_kernel(const IinsNTParams p) {
     }
     __syncthreads();
 
-    const int L = p.Lrow;
-    const int S = BM / L;                  // samples per tile (L <= 128 always when norm != NONE)
-    const int ncols = (p.N - n0) < BN ? (p.N - n0) : BN;
-    const int b0 = tile_m / L;             // first sample of the tile
-
-    if (ep.norm == IINS_NORM_IN || ep.norm == IINS_NORM_ADAIN) {
-        // per (sample, channel) statistics over the L rows; biased variance (models.py:152, 1072)
-        const int pairs = S * ncols;
-        int G = 1;
-        while (G < 32 && pairs * G * 2 <= 256) G <<= 1;
-        const int per_iter = 256 / G;
-        for (int p0 = 0; p0 < pairs; p0 += per_iter) {
-            int pr = p0 + tid / G, sub = tid % G;
-            bool ok = pr < pairs;
-            int s = ok ? pr / ncols : 0, c = ok ? pr - s * ncols : 0;
-            float sum = 0.f;
-            if (ok) for (int l = sub; l < L; l += G) sum += Cs[(s * L + l) * BN + c];
-            sum = iins_group_sum(sum, G);
-            float mean = sum / (float)L;
-            float sq = 0.f;
-            if (ok) for (int l = sub; l < L; l += G) { float dv = Cs[(s * L + l) * BN + c] - mean; sq += dv * dv; }
-            sq = iins_group_sum(sq, G);
-            if (ok && sub == 0) {
-                float rs = 1.0f / sqrtf(sq / (float)L + IINS_EPS);
-                st_mean[s * BN + c] = mean;
-                st_rstd[s * BN + c] = rs;
-                int b = b0 + s;
-                if (b < g.B && ep.rstd != nullptr) ep.rstd[(long)b * p.N + n0 + c] = rs;
-            }
-        }
-        __syncthreads();
-    } else if (ep.norm == IINS_NORM_LN) {
-        // per-sample mean and UNBIASED std over (C*L), eps added to std (models.py:976-981)
-        const int warp = tid >> 5, lane = tid & 31;
-        const int nel = L * ncols;
-        for (int s0 = 0; s0 < S; s0 += 8) {
-            int s = s0 + warp;
-            bool ok = s < S;
-            float sum = 0.f;
-            if (ok) for (int e = lane; e < nel; e += 32) sum += Cs[(s * L + e / ncols) * BN + (e % ncols)];
-            sum = iins_warp_sum(sum);
-            float mean = sum / (float)nel;
-            float sq = 0.f;
-            if (ok) for (int e = lane; e < nel; e += 32) { float dv = Cs[(s * L + e / ncols) * BN + (e % ncols)] - mean; sq += dv * dv; }
-            sq = iins_warp_sum(sq);
-            if (ok && lane == 0) {
-                float rs = 1.0f / (sqrtf(sq / (float)(nel - 1)) + IINS_EPS);
-                st_mean[s] = mean;
-                st_rstd[s] = rs;
-                int b = b0 + s;
-                if (b < g.B && ep.rstd != nullptr) ep.rstd[b] = rs;
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- apply + store (coalesced over the contiguous NLC tile)
-    for (int e = tid; e < BM * BN; e += 256) {
-        int r = e / BN, n = e - r * BN;
-        int gr = tile_m + r, gn = n0 + n;
-        if (gr >= p.M || gn >= p.N) continue;
-        float v = Cs[e];
-        int s = r / L;
-        int b = gr / L, l = gr - b * L;
-        long oi = p.out_layout == IINS_NCL ? ((long)b * p.N + gn) * L + l : (long)gr * p.N + gn;
-        if (ep.norm == IINS_NORM_IN || ep.norm == IINS_NORM_ADAIN) {
-            v = (v - st_mean[s * BN + n]) * st_rstd[s * BN + n];
-            if (ep.xhat != nullptr) ep.xhat[oi] = v;
-            if (ep.norm == IINS_NORM_ADAIN) {
-                float wv = __ldg(ep.adain + (long)b * ep.adain_ld + ep.adain_off_w + gn);
-                float bv = __ldg(ep.adain + (long)b * ep.adain_ld + ep.adain_off_b + gn);
-                v = fmaf(v, wv, bv);
-            }
-        } else if (ep.norm == IINS_NORM_LN) {
-            v = (v - st_mean[s]) * st_rstd[s];
-            if (ep.xhat != nullptr) ep.xhat[oi] = v;
-            v = fmaf(v, __ldg(ep.gamma + gn), __ldg(ep.beta + gn));
-        }
-        v = iins_act(v, ep.act, ep.slope);
-        if (ep.add != nullptr) v += __ldg(ep.add + oi);
-        ep.y[oi] = v;
-    }
+    iins_epilogue_tile<BN, BN>(p, Cs, st_mean, st_rstd, tile_m, n0);
 }
 
 // ------------------------------------------------------------------------------------ wgrad

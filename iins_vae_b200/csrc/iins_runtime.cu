@@ -1,6 +1,7 @@
 // Host-side sequencing of the IIns-VAE path and the C ABI declared in include/iins_b200.h.
 // One translation unit: kernels (iins_gemm.cuh, iins_misc.cuh) + the module-level launch plans.
 #include "iins_gemm.cuh"
+#include "iins_tc.cuh"
 #include "iins_misc.cuh"
 #include "../../include/iins_b200.h"
 
@@ -16,8 +17,17 @@ int fail(int code, const char* msg) {
     return code;
 }
 
+// Compute mode of the GEMM-bearing layers (process-wide; set through iins_set_compute_mode):
+//   0  tcgen05 tensor cores, fp32-grade: operands split into 3 bf16 pieces, 6 MMAs / k-step ("bf16x3")
+//   1  tcgen05 tensor cores, plain bf16 operands, fp32 accumulate (looser tolerance, BASELINE configs[2])
+//   2  fp32 SIMT (FFMA) kernels -- the bring-up / cross-check path
+int g_mode = 0;
+#define IINS_WPACK_FLOATS ((size_t)1 << 19)       // 2 MB scratch for one layer's packed weight tiles
+
 struct Ctx {
     cudaStream_t st;
+    float* wpack = nullptr;     // IINS_WPACK_FLOATS floats of scratch for the tensor-core weight tiles
+    int err = 0;
 };
 
 int check_cuda(const char* where) {
@@ -63,18 +73,55 @@ IinsDz act_dz(const float* dy, const float* y, int act, float slope) {
     return d;
 }
 
-void launch_nt(const Ctx& c, const IinsNTParams& p) {
+void launch_nt_simt(const Ctx& c, const IinsNTParams& p) {
     int bn = p.N <= 8 ? 8 : (p.N <= 16 ? 16 : (p.N <= 32 ? 32 : 64));
     dim3 grid((p.M + 127) / 128, (p.N + bn - 1) / bn, 1);
-    IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K);
+    IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K); IINS_SET_SHAPE(p.M, p.N, p.K);
     if (bn == 8) IINS_LAUNCH(iins_nt_kernel<8>, grid, 256, 0, c.st, p);
     else if (bn == 16) IINS_LAUNCH(iins_nt_kernel<16>, grid, 256, 0, c.st, p);
     else if (bn == 32) IINS_LAUNCH(iins_nt_kernel<32>, grid, 256, 0, c.st, p);
     else IINS_LAUNCH(iins_nt_kernel<64>, grid, 256, 0, c.st, p);
 }
 
+#ifndef IINS_CPUSIM
+template <int NT>
+void launch_tc_nt_t(Ctx& c, const IinsTCParams& tp, dim3 grid) {
+    constexpr int smem = 2 * (3 * 8192 + 3 * 4 * NT * 16) + 8192;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(iins_tc_nt_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    IINS_LAUNCH(iins_tc_nt_kernel<NT>, grid, 256, smem, c.st, tp);
+}
+
+void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
+    int nt = p.N <= 16 ? 16 : (p.N <= 32 ? 32 : 64);
+    IinsPackParams pk;
+    memset(&pk, 0, sizeof(pk));
+    pk.g = p.g; pk.kind = p.a_kind; pk.w = p.w; pk.out = reinterpret_cast<uint16_t*>(c.wpack);
+    pk.N = p.N; pk.K = p.K; pk.NT = nt; pk.nkb = (p.K + 31) / 32; pk.nblk = (p.N + nt - 1) / nt;
+    size_t bytes = (size_t)pk.nblk * pk.nkb * 3 * 4 * nt * 16;
+    if (c.wpack == nullptr || bytes > IINS_WPACK_FLOATS * sizeof(float)) { c.err = 1; return; }
+    long chunks = (long)pk.nblk * pk.nkb * 4 * nt;
+    IINS_LAUNCH(iins_pack_kernel, grid_for(chunks), 256, 0, c.st, pk);
+    IinsTCParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.nt = p; tp.wpack = pk.out; tp.pieces = g_mode == 1 ? 1 : 3; tp.nkb = pk.nkb;
+    dim3 grid((p.M + 127) / 128, pk.nblk, 1);
+    IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K); IINS_SET_SHAPE(p.M, p.N, p.K);
+    if (nt == 16) launch_tc_nt_t<16>(c, tp, grid);
+    else if (nt == 32) launch_tc_nt_t<32>(c, tp, grid);
+    else launch_tc_nt_t<64>(c, tp, grid);
+}
+#endif
+
+void launch_nt(Ctx& c, const IinsNTParams& p) {
+#ifndef IINS_CPUSIM
+    if (g_mode != 2) { launch_nt_tc(c, p); return; }
+#endif
+    launch_nt_simt(c, p);
+}
+
 // y = epilogue(conv(x, w))
-void conv_forward(const Ctx& c, const IinsGeom& g, const float* x, const float* w, const IinsEpilogue& ep) {
+void conv_forward(Ctx& c, const IinsGeom& g, const float* x, const float* w, const IinsEpilogue& ep) {
     IinsNTParams p;
     memset(&p, 0, sizeof(p));
     p.g = g; p.a_kind = 0; p.x = x; p.w = w; p.ep = ep;
@@ -84,7 +131,7 @@ void conv_forward(const Ctx& c, const IinsGeom& g, const float* x, const float* 
 }
 
 // dx = conv_transpose(dz, w) (+ add);  dx has the layer INPUT's layout
-void conv_dgrad(const Ctx& c, const IinsGeom& g, const IinsDz& dz, const float* w, float* dx, const float* add) {
+void conv_dgrad(Ctx& c, const IinsGeom& g, const IinsDz& dz, const float* w, float* dx, const float* add) {
     IinsNTParams p;
     memset(&p, 0, sizeof(p));
     p.g = g; p.a_kind = 1; p.dz = dz; p.w = w;
@@ -95,12 +142,45 @@ void conv_dgrad(const Ctx& c, const IinsGeom& g, const IinsDz& dz, const float* 
     launch_nt(c, p);
 }
 
-void conv_wgrad(const Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, float* dw, float* db) {
+#ifndef IINS_CPUSIM
+template <int NT>
+void launch_tc_tn_t(Ctx& c, const IinsTCTNParams& tp, dim3 grid) {
+    constexpr int smem = 2 * (3 * 8192 + 3 * (NT / 8) * 32 * 16);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(iins_tc_tn_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    IINS_LAUNCH(iins_tc_tn_kernel<NT>, grid, 256, smem, c.st, tp);
+}
+#endif
+
+void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, float* dw, float* db) {
     IinsTNParams p;
     memset(&p, 0, sizeof(p));
     p.g = g; p.x = x; p.dz = dz; p.dw = dw; p.db = db;
     p.M = g.B * g.Lout;
     int K = g.ks * g.Cin;
+#ifndef IINS_CPUSIM
+    if (g_mode != 2) {
+        int nt = g.Cout <= 16 ? 16 : (g.Cout <= 32 ? 32 : 64);
+        int ky = (K + 127) / 128, nz = (g.Cout + nt - 1) / nt;
+        long want = (148L * 3 + (long)ky * nz - 1) / ((long)ky * nz);
+        long max_parts = (p.M + 127) / 128;
+        if (want > max_parts) want = max_parts;
+        if (want < 1) want = 1;
+        long rpp = (p.M + want - 1) / want;
+        rpp = (rpp + 31) / 32 * 32;
+        int parts = (int)((p.M + rpp - 1) / rpp);
+        p.rows_per_part = (int)rpp;
+        IinsTCTNParams tp;
+        memset(&tp, 0, sizeof(tp));
+        tp.tn = p; tp.pieces = g_mode == 1 ? 1 : 3; tp.K = K;
+        dim3 grid(parts, ky, nz);
+        IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K); IINS_SET_SHAPE(p.M, g.Cout, K);
+        if (nt == 16) launch_tc_tn_t<16>(c, tp, grid);
+        else if (nt == 32) launch_tc_tn_t<32>(c, tp, grid);
+        else launch_tc_tn_t<64>(c, tp, grid);
+        return;
+    }
+#endif
     int ky = (K + 63) / 64, nz = (g.Cout + 63) / 64;
     // enough row parts to fill the machine (148 SMs x a few CTAs), at least 32 rows each
     long want = (148L * 4 + (long)ky * nz - 1) / ((long)ky * nz);
@@ -111,11 +191,11 @@ void conv_wgrad(const Ctx& c, const IinsGeom& g, const float* x, const IinsDz& d
     rpp = (rpp + 31) / 32 * 32;
     int parts = (int)((p.M + rpp - 1) / rpp);
     p.rows_per_part = (int)rpp;
-    IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K);
+    IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K); IINS_SET_SHAPE(p.M, g.Cout, K);
     IINS_LAUNCH(iins_tn_kernel, dim3(parts, ky, nz), 256, 0, c.st, p);
 }
 
-void norm_backward(const Ctx& c, int B, int L, int C, int norm, int act, const float* dy, const float* xhat,
+void norm_backward(Ctx& c, int B, int L, int C, int norm, int act, const float* dy, const float* xhat,
                    const float* rstd, const float* gamma, const float* beta, float* dgamma, float* dbeta,
                    const float* adain, float* dadain, int ld, int off_b, int off_w, float* dz) {
     IinsNormBwdParams p;
@@ -201,7 +281,7 @@ int encoder_forward(const Shapes& s, const float* const* P, const float* x, cons
                     float* rc, float* cat, float* latent, float* kl, float* ws, cudaStream_t st) {
     Ctx c{st};
     EncPlan pl;
-    plan_encoder(s, ws, pl);
+    c.wpack = ws + plan_encoder(s, ws, pl);
     const int B = s.B;
     IINS_LAUNCH(iins_pool_fwd_kernel, grid_for((long)B * s.P), 256, 0, st, x, pl.xp, B, s.Lc, s.P);
     int pi = 0;
@@ -259,6 +339,7 @@ int encoder_forward(const Shapes& s, const float* const* P, const float* x, cons
     cudaMemsetAsync(kl, 0, sizeof(float), st);
     IINS_LAUNCH(iins_reparam_kl_kernel, grid_for((long)B * s.E / 2), 256, 0, st, cat, noise, latent, kl, B, s.E,
                 (unsigned long long)seed, (unsigned long long)offset);
+    if (c.err) return fail(IINS_ERR_BAD_CONFIG, "encoder_forward: packed weight tile exceeds the scratch");
     return check_cuda("encoder_forward");
 }
 
@@ -266,7 +347,7 @@ size_t encoder_scratch(const Shapes& s) {
     size_t B = s.B;
     size_t act = (size_t)128 * 4 * s.d;                 // largest activation per sample (env stem: 128 x 4d)
     if ((size_t)s.Lt * s.D > act) act = (size_t)s.Lt * s.D;
-    return 3 * (B * act + 4) + B * (16 * (size_t)s.d + 4) + B * ((size_t)s.E + 4);
+    return 3 * (B * act + 4) + B * (16 * (size_t)s.d + 4) + B * ((size_t)s.E + 4) + IINS_WPACK_FLOATS;
 }
 
 int encoder_backward(const Shapes& s, const float* const* P, const float* noise, uint64_t seed, uint64_t offset,
@@ -284,6 +365,7 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
     float* dzb = b.take((size_t)B * act);
     float* dpooled = b.take((size_t)B * 16 * s.d);
     float* dcat = b.take((size_t)B * s.E);
+    c.wpack = b.take(IINS_WPACK_FLOATS);
     const int n_range = 2 * (1 + s.ndown + 2 * s.nres + 1);
 
     // ---------------- env branch
@@ -365,6 +447,7 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, dzb);
         conv_wgrad(c, g0, pl.xp, plain_dz(dzb), G[pi], G[pi + 1]);
     }
+    if (c.err) return fail(IINS_ERR_BAD_CONFIG, "encoder_backward: packed weight tile exceeds the scratch");
     return check_cuda("encoder_backward");
 }
 
@@ -404,7 +487,7 @@ int decoder_forward(const Shapes& s, const float* const* P, const float* rc, con
                     cudaStream_t st) {
     Ctx c{st};
     DecPlan pl;
-    plan_decoder(s, ws, pl);
+    c.wpack = ws + plan_decoder(s, ws, pl);
     DecIdx ix = dec_idx(s);
     const int B = s.B;
     // MLP -> AdaIN parameters (models.py:951-962, 468)
@@ -446,13 +529,14 @@ int decoder_forward(const Shapes& s, const float* const* P, const float* rc, con
         conv_forward(c, g, h, P[ix.out], plain_epilogue(P[ix.out + 1], IINS_ACT_TANH, 0.f, pl.yt));
     }
     IINS_LAUNCH(iins_pool_fwd_kernel, grid_for((long)B * s.Lc), 256, 0, st, pl.yt, xrec, B, s.P, s.Lc);
+    if (c.err) return fail(IINS_ERR_BAD_CONFIG, "decoder_forward: packed weight tile exceeds the scratch");
     return check_cuda("decoder_forward");
 }
 
 size_t decoder_scratch(const Shapes& s) {
     size_t B = s.B;
     size_t act = (size_t)s.Lt * s.D;
-    return 3 * (B * act + 4) + B * ((size_t)s.n_adain + 4) + 2 * (B * 256 + 4) + B * ((size_t)s.P + 4);
+    return 3 * (B * act + 4) + B * ((size_t)s.n_adain + 4) + 2 * (B * 256 + 4) + B * ((size_t)s.P + 4) + IINS_WPACK_FLOATS;
 }
 
 int decoder_backward(const Shapes& s, const float* const* P, const float* rc, const float* cat, const float* ws,
@@ -472,6 +556,7 @@ int decoder_backward(const Shapes& s, const float* const* P, const float* rc, co
     float* dm2 = b.take((size_t)B * 256);
     float* dm1 = b.take((size_t)B * 256);
     float* dyt = b.take((size_t)B * s.P);
+    c.wpack = b.take(IINS_WPACK_FLOATS);
 
     // pool(128 -> cir_len) backward fused with tanh'
     IINS_LAUNCH(iins_pool_bwd_kernel, grid_for((long)B * s.P), 256, 0, st, d_xrec, pl.yt, dyt, B, s.P, s.Lc);
@@ -530,6 +615,7 @@ int decoder_backward(const Shapes& s, const float* const* P, const float* rc, co
         conv_wgrad(c, g1, cat, z1, G[ix.mlp], G[ix.mlp + 1]);
         if (d_cat != nullptr) conv_dgrad(c, g1, z1, P[ix.mlp], d_cat, accumulate ? d_cat : nullptr);
     }
+    if (c.err) return fail(IINS_ERR_BAD_CONFIG, "decoder_backward: packed weight tile exceeds the scratch");
     return check_cuda("decoder_backward");
 }
 
@@ -555,14 +641,17 @@ size_t mlp_ws(const Shapes& s, const MlpSpec& m) {
     for (int i = 1; i < m.n; ++i) n += ((size_t)s.B * m.dims[i] + 3) & ~(size_t)3;
     return n;
 }
+size_t mlp_act_floats(const Shapes& s, const MlpSpec& m) { return mlp_ws(s, m); }
 size_t mlp_scratch(const Shapes& s, const MlpSpec& m) {
     size_t mx = 0;
     for (int i = 1; i < m.n; ++i) if ((size_t)m.dims[i] > mx) mx = m.dims[i];
-    return 2 * (((size_t)s.B * mx + 3) & ~(size_t)3);
+    return 2 * (((size_t)s.B * mx + 3) & ~(size_t)3) + IINS_WPACK_FLOATS;
 }
 
-int mlp_forward(const Shapes& s, const MlpSpec& m, const float* const* P, const float* in, float* out, float* ws, cudaStream_t st) {
+int mlp_forward(const Shapes& s, const MlpSpec& m, const float* const* P, const float* in, float* out, float* ws,
+                float* wpack, cudaStream_t st) {
     Ctx c{st};
+    c.wpack = wpack;
     Bump b{ws, 0};
     const float* h = in;
     for (int i = 0; i < m.n; ++i) {
@@ -571,6 +660,7 @@ int mlp_forward(const Shapes& s, const MlpSpec& m, const float* const* P, const 
         conv_forward(c, linear_geom(s.B, m.dims[i], m.dims[i + 1]), h, P[2 * i], plain_epilogue(P[2 * i + 1], act, m.slopes[i], y));
         h = y;
     }
+    if (c.err) return fail(IINS_ERR_BAD_CONFIG, "mlp_forward: packed weight tile exceeds the scratch");
     return check_cuda("mlp_forward");
 }
 
@@ -583,8 +673,9 @@ int mlp_backward(const Shapes& s, const MlpSpec& m, const float* const* P, const
     acts[0] = in;
     for (int i = 1; i < m.n; ++i) acts[i] = b.take((size_t)s.B * m.dims[i]);
     acts[m.n] = out_saved;
-    size_t half = mlp_scratch(s, m) / 2;
+    size_t half = (mlp_scratch(s, m) - IINS_WPACK_FLOATS) / 2;
     float* bufs[2] = {scratch, scratch + half};
+    c.wpack = scratch + 2 * half;
     const float* dy = d_out;
     for (int i = m.n - 1; i >= 0; --i) {
         IinsGeom g = linear_geom(s.B, m.dims[i], m.dims[i + 1]);
@@ -598,6 +689,7 @@ int mlp_backward(const Shapes& s, const MlpSpec& m, const float* const* P, const
             conv_dgrad(c, g, dz, P[0], d_in, accumulate ? d_in : nullptr);
         }
     }
+    if (c.err) return fail(IINS_ERR_BAD_CONFIG, "mlp_backward: packed weight tile exceeds the scratch");
     return check_cuda("mlp_backward");
 }
 
@@ -609,13 +701,19 @@ int mlp_backward(const Shapes& s, const MlpSpec& m, const float* const* P, const
 extern "C" {
 
 int iins_abi_version(void) { return 1; }
+int iins_set_compute_mode(int mode) {
+    if (mode < 0 || mode > 2) return fail(IINS_ERR_BAD_CONFIG, "compute mode must be 0 (bf16x3 tensor core), 1 (bf16 tensor core) or 2 (fp32 SIMT)");
+    g_mode = mode;
+    return IINS_OK;
+}
+int iins_get_compute_mode(void) { return g_mode; }
 const char* iins_last_error(void) { return g_err; }
 int iins_validate_config(const iins_config* cfg) { Shapes s; return make_shapes(cfg, s); }
 
 int iins_encoder_num_params(const iins_config* cfg) { IINS_SHAPES_OR_RETURN(cfg, s); return enc_num_params(s); }
 size_t iins_encoder_ws_floats(const iins_config* cfg) {
     Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0;
-    EncPlan pl; return plan_encoder(s, nullptr, pl);
+    EncPlan pl; return plan_encoder(s, nullptr, pl) + IINS_WPACK_FLOATS;
 }
 size_t iins_encoder_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return encoder_scratch(s); }
 
@@ -640,7 +738,7 @@ int iins_encoder_backward(const iins_config* cfg, const float* const* params, co
 int iins_decoder_num_params(const iins_config* cfg) { IINS_SHAPES_OR_RETURN(cfg, s); return dec_num_params(s); }
 size_t iins_decoder_ws_floats(const iins_config* cfg) {
     Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0;
-    DecPlan pl; return plan_decoder(s, nullptr, pl);
+    DecPlan pl; return plan_decoder(s, nullptr, pl) + IINS_WPACK_FLOATS;
 }
 size_t iins_decoder_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return decoder_scratch(s); }
 
@@ -662,13 +760,14 @@ int iins_decoder_backward(const iins_config* cfg, const float* const* params, co
 }
 
 int iins_restorer_num_params(const iins_config* cfg) { IINS_SHAPES_OR_RETURN(cfg, s); return 10; }
-size_t iins_restorer_ws_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return mlp_ws(s, restorer_spec(s)); }
+size_t iins_restorer_ws_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return mlp_ws(s, restorer_spec(s)) + IINS_WPACK_FLOATS; }
 size_t iins_restorer_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return mlp_scratch(s, restorer_spec(s)); }
 int iins_restorer_forward(const iins_config* cfg, const float* const* params, const float* range_code, float* err_est,
                           float* ws, iins_stream_t stream) {
     IINS_SHAPES_OR_RETURN(cfg, s);
     if (!params || !range_code || !err_est || !ws) return fail(IINS_ERR_NULL, "restorer_forward: NULL argument");
-    return mlp_forward(s, restorer_spec(s), params, range_code, err_est, ws, (cudaStream_t)stream);
+    MlpSpec m = restorer_spec(s);
+    return mlp_forward(s, m, params, range_code, err_est, ws, ws + mlp_ws(s, m), (cudaStream_t)stream);
 }
 int iins_restorer_backward(const iins_config* cfg, const float* const* params, const float* range_code, const float* ws,
                            const float* d_err_est, float* const* grads, float* d_range_code, int accumulate,
@@ -683,7 +782,7 @@ int iins_restorer_backward(const iins_config* cfg, const float* const* params, c
 int iins_classifier_num_params(const iins_config* cfg) { IINS_SHAPES_OR_RETURN(cfg, s); return 8; }
 size_t iins_classifier_ws_floats(const iins_config* cfg) {
     Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0;
-    return mlp_ws(s, classifier_spec(s)) + (((size_t)s.B * s.NC + 3) & ~(size_t)3);
+    return mlp_ws(s, classifier_spec(s)) + (((size_t)s.B * s.NC + 3) & ~(size_t)3) + IINS_WPACK_FLOATS;
 }
 size_t iins_classifier_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return mlp_scratch(s, classifier_spec(s)); }
 int iins_classifier_forward(const iins_config* cfg, const float* const* params, const float* env_code, float* logits,
@@ -694,7 +793,8 @@ int iins_classifier_forward(const iins_config* cfg, const float* const* params, 
     // caller is free to modify its output tensor
     MlpSpec m = classifier_spec(s);
     float* saved = ws + mlp_ws(s, m);
-    int rc = mlp_forward(s, m, params, env_code, saved, ws, (cudaStream_t)stream);
+    float* wpack = saved + (((size_t)s.B * s.NC + 3) & ~(size_t)3);
+    int rc = mlp_forward(s, m, params, env_code, saved, ws, wpack, (cudaStream_t)stream);
     if (rc != IINS_OK) return rc;
     cudaMemcpyAsync(logits, saved, (size_t)s.B * s.NC * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
     return check_cuda("classifier_forward");
@@ -772,6 +872,12 @@ int iins_profile_begin(void) {
 
 // Stops recording, synchronises the device and writes, for up to `cap` recorded launches in launch order,
 // the kernel name (pointer to a static string) and its duration in milliseconds.  Returns the count.
+int iins_profile_shapes(int* shapes, int cap) {
+    int n = g_iins_prof.n < cap ? g_iins_prof.n : cap;
+    for (int i = 0; i < n; ++i) for (int j = 0; j < 3; ++j) shapes[3 * i + j] = g_iins_prof.shape[i][j];
+    return n;
+}
+
 int iins_profile_collect(const char** names, float* ms, double* flops, int cap) {
     g_iins_prof.enabled = 0;
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(IINS_ERR_CUDA, "profile: synchronize failed");
@@ -788,6 +894,7 @@ int iins_profile_collect(const char** names, float* ms, double* flops, int cap) 
 unsigned long long iins_launch_count(void) { return 0; }
 int iins_profile_begin(void) { return IINS_OK; }
 int iins_profile_collect(const char**, float*, double*, int) { return 0; }
+int iins_profile_shapes(int*, int) { return 0; }
 #endif
 
 int iins_adaptive_pool_forward(const float* x, float* y, int batch, int lin, int lout, iins_stream_t stream) {

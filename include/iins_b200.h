@@ -50,6 +50,13 @@ typedef struct iins_config {
 } iins_config;
 
 int iins_abi_version(void);
+/* Arithmetic of the conv / linear GEMMs (process-wide):
+ *   0 (default) tcgen05 tensor cores, fp32-grade: every fp32 operand is split into three bf16 pieces and the
+ *               six significant piece products are accumulated in fp32 in TMEM ("bf16x3", error ~2^-23);
+ *   1           tcgen05 tensor cores, plain bf16 operands, fp32 accumulation (BASELINE configs[2]);
+ *   2           fp32 SIMT (FFMA) kernels: the bring-up path, kept as an on-device cross-check. */
+int iins_set_compute_mode(int mode);
+int iins_get_compute_mode(void);
 const char* iins_last_error(void);
 int iins_validate_config(const iins_config* cfg);
 
@@ -137,6 +144,7 @@ int iins_adaptive_pool_backward(const float* dy, float* dx, int batch, int lin, 
 unsigned long long iins_launch_count(void);           /* kernels launched by this library so far */
 int iins_profile_begin(void);                          /* record a CUDA-event pair around every launch */
 int iins_profile_collect(const char** names, float* ms, double* flops, int cap);
+int iins_profile_shapes(int* shapes_mnk, int cap);   /* after collect: (M,N,K) of each GEMM launch, zeros otherwise */
         /* sync; per launch: kernel name, milliseconds, algorithmic FLOPs (2*M*N*K for the GEMM kernels, else 0) */
 
 #ifdef __cplusplus

@@ -38,5 +38,10 @@ def run(B, seed, sup=True):
         print(f"  grad {k:46s} gpu {e_gpu:.2e} cpu32 {e_cpu:.2e} |g| {n:.2e}{flag}")
 
 if __name__ == "__main__":
-    for B, seed in ((2, 0), (64, 75), (4096, 4107)):
+    from iins_vae_b200._capi import get_lib
+    mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    cases = [(int(b), 100 + int(b)) for b in sys.argv[2].split(",")] if len(sys.argv) > 2 else [(2, 0), (64, 75), (4096, 4107)]
+    get_lib().check(get_lib().iins_set_compute_mode(mode), "mode")
+    print("compute mode", mode)
+    for B, seed in cases:
         run(B, seed)
