@@ -55,7 +55,9 @@ class SemiTrainEngine:
     """
 
     def __init__(self, Enc, Dec, Res, Cls, batch_size, cir_len=157, lr=1e-4, betas=(0.5, 0.999), eps=1e-8,
-                 mode="semi", use_graph=True, process_group=None, device=None):
+                 mode="semi", use_graph=True, process_group=None, device=None, shared_state=None):
+        """``shared_state``: another engine over the SAME modules (e.g. for a different batch size, the last
+        ragged batch of an epoch): the flat parameter / gradient / Adam buffers and step counters are shared."""
         self.lib = get_lib()
         self.mode = mode
         self.device = torch.device(device if device is not None else torch.cuda.current_device())
@@ -63,7 +65,7 @@ class SemiTrainEngine:
             raise RuntimeError("iins_vae_b200 engines run on CUDA only")
         self.Enc, self.Dec, self.Res, self.Cls = Enc, Dec, Res, Cls
         mods = [Enc] + ([Dec] if mode == "semi" else []) + [Res, Cls]
-        self.flat = _Flat(mods, self.device)
+        self.flat = shared_state.flat if shared_state is not None else _Flat(mods, self.device)
         o = Enc.opts
         self.B, self.L = int(batch_size), int(cir_len)
         self.E, self.R, self.NC = o["env_dim"], o["range_dim"], Cls.num_classes
@@ -84,8 +86,11 @@ class SemiTrainEngine:
         self.d_xrec, self.d_err, self.d_logits = f(B, self.L), f(B, 1), f(B, self.NC)
         self.d_rc, self.d_cat = torch.zeros_like(self.rc), torch.zeros_like(self.cat)
         self.d_kl = torch.full((1,), LAMBDA_RANGE, dtype=torch.float32, device=dev)
-        self.lr = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
-        self.steps = torch.zeros(8, dtype=torch.int32, device=dev)
+        if shared_state is not None:
+            self.lr, self.steps = shared_state.lr, shared_state.steps
+        else:
+            self.lr = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+            self.steps = torch.zeros(8, dtype=torch.int32, device=dev)
         lib = self.lib
         names = ("encoder", "decoder", "restorer", "classifier")
         self.ws = {m: f(int(getattr(lib, f"iins_{m}_ws_floats")(self.cfg)) + 16) for m in names}
@@ -168,11 +173,9 @@ class SemiTrainEngine:
     def _allreduce(self, supervised: bool):
         if self.world == 1:
             return
-        import torch.distributed as dist
-        end = self.flat.total if supervised else self.groups[0][1]
-        g = self.flat.grad[:end]
-        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
-        g.mul_(1.0 / self.world)
+        from .parallel import allreduce_mean_
+        # unsupervised batches: only the always-on bucket [Enc (+Dec)] has gradients (train_semi.py:204-214)
+        allreduce_mean_(self.flat.grad, self.flat.total if supervised else self.groups[0][1], self.pg)
 
     def _adam(self, supervised: bool):
         act = (C.c_int32 * 3)(1, int(supervised), int(supervised))

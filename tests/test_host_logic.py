@@ -1,0 +1,135 @@
+"""CPU tests of the host-side logic: C-ABI library exports, option parsing, LR schedule, data-parallel helpers
+over gloo with world_size 2, state_dict surface of the drop-in modules."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    """include/iins_b200.h <-> libiins_b200.so (no compute calls: there is no GPU here)."""
+    from iins_vae_b200 import build
+    path = build.build()
+    dll = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "iins_b200.h")).read()
+    declared = set(re.findall(r"\b(iins_[a-z0-9_]+)\s*\(", header))
+    declared -= {"iins_config", "iins_status", "iins_stream_t"}
+    assert len(declared) >= 30
+    for sym in sorted(declared):
+        assert hasattr(dll, sym), f"{sym} declared in the header but not exported"
+    from iins_vae_b200._capi import EXPORTS
+    assert set(EXPORTS) <= declared
+    dll.iins_abi_version.restype = ctypes.c_int
+    assert dll.iins_abi_version() == 1
+
+
+def test_config_validation_and_sizes_without_gpu():
+    from iins_vae_b200._capi import IinsConfig, IinsLib
+    from iins_vae_b200 import build
+    lib = IinsLib(build.build())
+    ok = IinsConfig(4096, 157, 4, 3, 4, 16, 2, 5, 16)
+    assert lib.iins_validate_config(ok) == 0
+    assert lib.iins_encoder_num_params(ok) == 32 and lib.iins_decoder_num_params(ok) == 38
+    assert lib.iins_restorer_num_params(ok) == 10 and lib.iins_classifier_num_params(ok) == 8
+    assert lib.iins_encoder_ws_floats(ok) > 4096 * 15000          # saved activations, ~18k floats / sample
+    for bad in (IinsConfig(0, 157, 4, 3, 4, 16, 2, 5, 16), IinsConfig(8, 157, 16, 3, 4, 16, 2, 5, 16),
+                IinsConfig(8, 157, 4, 3, 3, 16, 2, 5, 16), IinsConfig(8, 157, 4, 3, 4, 15, 2, 5, 16)):
+        assert lib.iins_validate_config(bad) != 0
+        assert len(lib.dll.iins_last_error()) > 0
+    assert lib.iins_set_compute_mode(7) != 0 and lib.iins_set_compute_mode(0) == 0
+
+
+def test_modules_fail_loudly_on_cpu_tensors():
+    from iins_vae_b200 import models as M
+    with pytest.raises(RuntimeError, match="CUDA"):
+        M.Encoder(1, 4, 3, 4, 16, 2)(torch.zeros(2, 157))
+    with pytest.raises(NotImplementedError):
+        M.Encoder(conv_type=2)
+    with pytest.raises(NotImplementedError):
+        M.Restorer((2, 8), net_type="Conv1d")
+
+
+def test_state_dict_surface_matches_oracle_inventory():
+    from iins_vae_b200 import models as M, model as M2
+    from oracle import iins_oracle as orc
+    cfg = orc.PathConfig()
+    pairs = [(M.Encoder(1, 4, 3, 4, 16, 2), orc.encoder_param_shapes(cfg)),
+             (M.Decoder(1, 4, 3, 4, 16, 157, 2), orc.decoder_param_shapes(cfg)),
+             (M.Restorer((2, 8)), orc.restorer_param_shapes(cfg)), (M.Classifier(16, 5), orc.classifier_param_shapes(cfg)),
+             (M2.Encoder(1, 4, 3, 4, 16, 2), orc.encoder_param_shapes(cfg)), (M2.Restorer(False, 1, 1, 2, 4), orc.restorer_param_shapes(cfg))]
+    for mod, shapes in pairs:
+        sd = mod.state_dict()
+        assert [(k, tuple(v.shape)) for k, v in sd.items()] == list(shapes.items())
+    net = M.EMNet(cir_len=157, num_classes=2, env_dim=16)
+    assert any(k.startswith("encoder.range_encoder.model.2.") for k in net.state_dict())
+
+
+def test_options_and_lr_schedule():
+    from iins_vae_b200.utils import get_args, num_classes_for
+    from iins_vae_b200.models import LambdaLR
+    opt = get_args(None).parse_args([])
+    assert (opt.batch_size, opt.lr, opt.b1, opt.b2, opt.n_residual, opt.n_downsample, opt.env_dim) == (500, 1e-4, 0.5, 0.999, 3, 4, 16)
+    assert (opt.conv_type, opt.dim, opt.range_dim, opt.restorer_type, opt.classifier_type) == (1, 4, 2, "Linear", "Linear")
+    assert num_classes_for("room_full") == 5 and num_classes_for("nlos") == 2
+    with pytest.raises(ValueError):
+        num_classes_for("nowhere")
+    s = LambdaLR(500, 0, 100)
+    assert s.step(0) == 1.0 and s.step(100) == 1.0 and abs(s.step(300) - 0.5) < 1e-12 and s.step(500) == 0.0
+
+
+def test_supervision_mask_stream_matches_reference_draw():
+    from iins_vae_b200.parallel import SupervisionMask
+    from oracle import iins_oracle as orc
+    a, rng = SupervisionMask(0.1, seed=99), np.random.RandomState(99)
+    seq = [a() for _ in range(200)]
+    assert seq == [orc.supervision_mask(rng, 0.1) for _ in range(200)]
+    assert 0.4 < np.mean(seq) < 0.7            # P(mask=1) = Phi(0.1) ~ 0.54 (a NORMAL draw, train_semi.py:203)
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from iins_vae_b200.parallel import init_distributed, shard_range, allreduce_mean_, SupervisionMask, broadcast_parameters
+rank, local, world, pg = init_distributed("gloo")
+assert world == 2 and pg is not None
+b, e = shard_range(8192, rank, world)
+assert (b, e) == (rank * 4096, (rank + 1) * 4096)
+# gradient buckets: only the first n_active entries are reduced on an unsupervised step
+flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+allreduce_mean_(flat, 6, pg)
+want = torch.arange(10, dtype=torch.float32) * (rank + 1)
+want[:6] = torch.arange(6, dtype=torch.float32) * 1.5
+assert torch.equal(flat, want), (rank, flat)
+# identical supervision decisions on every rank
+m = SupervisionMask(0.1, seed=1234)
+seq = torch.tensor([m() for _ in range(64)])
+other = [torch.zeros_like(seq) for _ in range(world)]
+dist.all_gather(other, seq, group=pg)
+assert all(torch.equal(o, seq) for o in other)
+lin = torch.nn.Linear(3, 2)
+broadcast_parameters([lin], pg)
+w = [torch.zeros_like(lin.weight) for _ in range(world)]
+dist.all_gather(w, lin.weight.data, group=pg)
+assert torch.equal(w[0], w[1])
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_data_parallel_helpers_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = 29500 + os.getpid() % 400
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script), ROOT],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
