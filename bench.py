@@ -308,12 +308,14 @@ def main():
     # ---------------- per-kernel timing inside a real step (CUDA events around every launch, eager pass)
     roofline = None
     kernel_table = None
+    # every rank runs the instrumented steps (they contain the gradient all-reduce); rank 0 reports
+    eng.use_graph = False
+    prof = []
+    for sup in (True, False):
+        prof += lib.profile(lambda: eng.step(*dev[0], supervised=sup))
+    eng.use_graph = eng_eager
+    barrier()
     if rank == 0:
-        eng.use_graph = False
-        prof = []
-        for sup in (True, False):
-            prof += lib.profile(lambda: eng.step(*dev[0], supervised=sup))
-        eng.use_graph = eng_eager
         agg = {}
         for name, kms, fl in prof:
             a = agg.setdefault(name, [0.0, 0.0, 0])
