@@ -33,7 +33,9 @@ struct IinsNTParams {
     const float* w;
     IinsEpilogue ep;
     int M, N, K;               // GEMM sizes (rows, cols, reduction)
-    int Lrow;                  // rows per sample of the OUTPUT of this GEMM (Lout fwd, Lin dgrad)
+    int Lrow;                  // rows per sample of the OUTPUT of this GEMM (Lout fwd, Lin dgrad); a power of two
+    int lshift;                // log2(Lrow)
+    int cshift;                // log2(channel extent of the k index) or -1 if it is not a power of two
     int out_layout;            // layout of the GEMM output
 };
 
@@ -104,30 +106,73 @@ __device__ __forceinline__ void iins_epilogue_tile(const IinsNTParams& p, const 
     }
 
     // ---- apply + store (coalesced over the contiguous NLC tile)
-    for (int e = tid; e < BM * BN; e += 256) {
-        int r = e / BN, n = e - r * BN;
-        int gr = tile_m + r, gn = n0 + n;
-        if (gr >= p.M || gn >= p.N) continue;
-        float v = Cs[r * LD + n];
-        int s = r / L;
-        int b = gr / L, l = gr - b * L;
-        long oi = p.out_layout == IINS_NCL ? ((long)b * p.N + gn) * L + l : (long)gr * p.N + gn;
-        if (ep.norm == IINS_NORM_IN || ep.norm == IINS_NORM_ADAIN) {
-            v = (v - st_mean[s * BN + n]) * st_rstd[s * BN + n];
-            if (ep.xhat != nullptr) ep.xhat[oi] = v;
-            if (ep.norm == IINS_NORM_ADAIN) {
-                float wv = __ldg(ep.adain + (long)b * ep.adain_ld + ep.adain_off_w + gn);
-                float bv = __ldg(ep.adain + (long)b * ep.adain_ld + ep.adain_off_b + gn);
-                v = fmaf(v, wv, bv);
-            }
-        } else if (ep.norm == IINS_NORM_LN) {
-            v = (v - st_mean[s]) * st_rstd[s];
-            if (ep.xhat != nullptr) ep.xhat[oi] = v;
-            v = fmaf(v, __ldg(ep.gamma + gn), __ldg(ep.beta + gn));
+    // Each thread owns 4 consecutive columns and walks the rows with a fixed stride; L is a power of two on
+    // this path (p.lshift), so the row -> (sample, position) split is a shift, and the NLC stores are 16 bytes.
+    constexpr int CG = BN / 4;                 // column groups
+    constexpr int RSTEP = 256 / CG;            // rows covered per pass
+    const int cg = tid % CG, n = cg * 4, gn = n0 + n;
+    const int lsh = p.lshift;
+    const bool vec = p.out_layout == IINS_NLC && (p.N & 3) == 0 && gn + 3 < p.N;
+    float gam[4], bet[4];
+    if (ep.norm == IINS_NORM_LN) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            gam[j] = gn + j < p.N ? __ldg(ep.gamma + gn + j) : 0.f;
+            bet[j] = gn + j < p.N ? __ldg(ep.beta + gn + j) : 0.f;
         }
-        v = iins_act(v, ep.act, ep.slope);
-        if (ep.add != nullptr) v += __ldg(ep.add + oi);
-        ep.y[oi] = v;
+    }
+    if (gn < p.N) {
+#pragma unroll 2
+        for (int r = tid / CG; r < BM; r += RSTEP) {
+            const int gr = tile_m + r;
+            if (gr >= p.M) break;
+            const int s = r >> lsh, b = gr >> lsh, l = gr & (L - 1);
+            float v[4], xh[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = Cs[r * LD + n + j];
+            if (ep.norm == IINS_NORM_IN || ep.norm == IINS_NORM_ADAIN) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[j] = (v[j] - st_mean[s * BN + n + j]) * st_rstd[s * BN + n + j];
+                    xh[j] = v[j];
+                }
+                if (ep.norm == IINS_NORM_ADAIN) {
+                    const float* ab = ep.adain + (long)b * ep.adain_ld;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (gn + j < p.N) v[j] = fmaf(v[j], __ldg(ab + ep.adain_off_w + gn + j), __ldg(ab + ep.adain_off_b + gn + j));
+                }
+            } else if (ep.norm == IINS_NORM_LN) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[j] = (v[j] - st_mean[s]) * st_rstd[s];
+                    xh[j] = v[j];
+                    v[j] = fmaf(v[j], gam[j], bet[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = iins_act(v[j], ep.act, ep.slope);
+            if (vec) {
+                const long oi = (long)gr * p.N + gn;
+                if (ep.norm != IINS_NORM_NONE && ep.xhat != nullptr)
+                    *reinterpret_cast<float4*>(ep.xhat + oi) = make_float4(xh[0], xh[1], xh[2], xh[3]);
+                if (ep.add != nullptr) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(ep.add + oi);
+                    v[0] += a4.x; v[1] += a4.y; v[2] += a4.z; v[3] += a4.w;
+                }
+                *reinterpret_cast<float4*>(ep.y + oi) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (gn + j >= p.N) continue;
+                    const long oi = p.out_layout == IINS_NCL ? (((long)b * p.N + gn + j) << lsh) + l : (long)gr * p.N + gn + j;
+                    if (ep.norm != IINS_NORM_NONE && ep.xhat != nullptr) ep.xhat[oi] = xh[j];
+                    float o = v[j];
+                    if (ep.add != nullptr) o += ep.add[oi];
+                    ep.y[oi] = o;
+                }
+            }
+        }
     }
 }
 
@@ -326,4 +371,122 @@ __global__ void __launch_bounds__(256) iins_tn_kernel(const IinsTNParams p) {
         }
     }
     if (p.db != nullptr && blockIdx.y == 0 && tid < BNK && n0 + tid < N) atomicAdd(p.db + n0 + tid, bsum);
+}
+
+// ===================================================================== small-channel layers (SIMT, direct)
+// Layers with N <= 16 output columns and K <= 64 (the stems 1->4 / 1->16 k7, 4->8 k4, the last upsampling
+// conv 8->4 k5, the output conv 4->1 k7, their data gradients, the 2-channel range-code convs, the tiny
+// classifier): a 128x16 tensor-core tile would be almost all padding and these layers are pure HBM streams at
+// L = 64..128, so they run as a direct convolution, one thread per output row, weights in shared memory,
+// followed by the SAME fused tile epilogue (norm / activation / residual).
+struct IinsRowParams {
+    IinsNTParams nt;           // geometry, operands, epilogue, M/N/K, Lrow, lshift
+};
+
+__global__ void __launch_bounds__(256) iins_row_nt_kernel(const IinsRowParams rp) {
+    constexpr int BM = 128, NT = 16, LD = NT + 1, KMAX = 64;
+    __shared__ float Ws[KMAX * NT];            // [k][n]
+    __shared__ float Cs[BM * LD];
+    __shared__ float st_mean[1024];
+    __shared__ float st_rstd[1024];
+    const IinsNTParams& p = rp.nt;
+    const IinsGeom& g = p.g;
+    const int tid = threadIdx.x;
+    const int tile_m = blockIdx.x * BM;
+    const int Cdim = p.a_kind == 0 ? g.Cin : g.Cout;
+    // weights -> smem, Ws[k][n] with k = t * Cdim + c
+    for (int e = tid; e < KMAX * NT; e += 256) {
+        int k = e / NT, n = e - k * NT;
+        float v = 0.f;
+        if (k < p.K && n < p.N) {
+            int t = k / Cdim, c = k - t * Cdim;
+            v = __ldg(p.w + (p.a_kind == 0 ? iins_w_index(g, n, c, t) : iins_w_index(g, c, n, t)));
+        }
+        Ws[e] = v;
+    }
+    __syncthreads();
+    const int row = tid & 127, half = tid >> 7;            // two threads per row: columns [8*half, 8*half+8)
+    const int grow = tile_m + row;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (grow < p.M && half * 8 < p.N) {
+        const int b = grow >> p.lshift, l = grow & (p.Lrow - 1);
+        int k = 0;
+        for (int t = 0; t < g.ks; ++t) {
+            for (int c = 0; c < Cdim; ++c, ++k) {
+                const float a = p.a_kind == 0 ? iins_a_fwd(g, p.x, b, l, t, c) : iins_a_dgrad(g, p.dz, b, l, t, c);
+                const float* wr = Ws + k * NT + half * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, wr[j], acc[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int n = half * 8 + j;
+        float bv = (p.ep.bias != nullptr && n < p.N) ? __ldg(p.ep.bias + n) : 0.f;
+        Cs[row * LD + n] = acc[j] + bv;
+    }
+    __syncthreads();
+    iins_epilogue_tile<NT, LD>(p, Cs, st_mean, st_rstd, tile_m, 0);
+}
+
+// Weight gradient for the same small layers: dW[n][k] (N <= 16, K <= 64) = sum_rows dz[row][n] * A[row][k].
+// Persistent CTAs: each stages 64 rows of dz and of the im2col'd input in shared memory, thread (n, k-quad)
+// accumulates in registers over the CTA's row range and flushes once with atomics.
+struct IinsRowTNParams {
+    IinsTNParams tn;
+    int K;
+    int lshift;
+};
+
+__global__ void __launch_bounds__(256) iins_row_tn_kernel(const IinsRowTNParams rp) {
+    constexpr int BR = 64, NT = 16, KMAX = 64;
+    __shared__ float Zs[BR * (NT + 1)];        // [r][n]
+    __shared__ float As[BR * (KMAX + 1)];      // [r][k]
+    const IinsTNParams& p = rp.tn;
+    const IinsGeom& g = p.g;
+    const int tid = threadIdx.x;
+    const int N = g.Cout, K = rp.K;
+    const int n = tid & 15, kq = tid >> 4;     // thread owns dW[n][kq*4 .. kq*4+3]
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float bsum = 0.f;
+    const int r_begin = blockIdx.x * p.rows_per_part;
+    int r_end = r_begin + p.rows_per_part;
+    if (r_end > p.M) r_end = p.M;
+    for (int r0 = r_begin; r0 < r_end; r0 += BR) {
+        // stage: 4 threads per row; each fills a quarter of the taps / columns of that row
+        {
+            const int r = tid >> 2, part = tid & 3;
+            const int row = r0 + r;
+            const bool ok = row < r_end;
+            const int b = ok ? row >> rp.lshift : 0, l = ok ? row & (g.Lout - 1) : 0;
+            for (int nn = part; nn < NT; nn += 4) Zs[r * (NT + 1) + nn] = (ok && nn < N) ? iins_dz_at(g, p.dz, b, l, nn) : 0.f;
+            for (int t = part; t < g.ks; t += 4)
+                for (int c = 0; c < g.Cin; ++c) As[r * (KMAX + 1) + t * g.Cin + c] = ok ? iins_a_fwd(g, p.x, b, l, t, c) : 0.f;
+        }
+        __syncthreads();
+        if (n < N && kq * 4 < K) {
+#pragma unroll 4
+            for (int r = 0; r < BR; ++r) {
+                const float z = Zs[r * (NT + 1) + n];
+                const float* ar = As + r * (KMAX + 1) + kq * 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = fmaf(z, ar[j], acc[j]);
+            }
+        }
+        if (p.db != nullptr && tid < N) {
+            for (int r = 0; r < BR; ++r) bsum += Zs[r * (NT + 1) + tid];
+        }
+        __syncthreads();
+    }
+    if (n < N) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int k = kq * 4 + j;
+            if (k < K) { int t = k / g.Cin, c = k - t * g.Cin; atomicAdd(p.dw + iins_w_index(g, n, c, t), acc[j]); }
+        }
+    }
+    if (p.db != nullptr && tid < N) atomicAdd(p.db + tid, bsum);
 }

@@ -22,6 +22,8 @@ int fail(int code, const char* msg) {
 //   1  tcgen05 tensor cores, plain bf16 operands, fp32 accumulate (looser tolerance, BASELINE configs[2])
 //   2  fp32 SIMT (FFMA) kernels -- the bring-up / cross-check path
 int g_mode = 0;
+long long* g_timeline = nullptr;      // debug: device buffer of 1024 int64 for the per-phase clock trace
+int g_timeline_which = -1, g_timeline_count = 0;   // trace only the which-th tensor-core forward launch
 #define IINS_WPACK_FLOATS ((size_t)1 << 19)       // 2 MB scratch for one layer's packed weight tiles
 
 struct Ctx {
@@ -73,6 +75,12 @@ IinsDz act_dz(const float* dy, const float* y, int act, float slope) {
     return d;
 }
 
+int ilog2_exact(int v) {
+    int s = 0;
+    while ((1 << s) < v) ++s;
+    return (1 << s) == v ? s : -1;
+}
+
 void launch_nt_simt(const Ctx& c, const IinsNTParams& p) {
     int bn = p.N <= 8 ? 8 : (p.N <= 16 ? 16 : (p.N <= 32 ? 32 : 64));
     dim3 grid((p.M + 127) / 128, (p.N + bn - 1) / bn, 1);
@@ -84,12 +92,18 @@ void launch_nt_simt(const Ctx& c, const IinsNTParams& p) {
 }
 
 #ifndef IINS_CPUSIM
-template <int NT>
-void launch_tc_nt_t(Ctx& c, const IinsTCParams& tp, dim3 grid) {
+template <int NT, int PIECES>
+void launch_tc_nt_tp(Ctx& c, const IinsTCParams& tp, dim3 grid) {
     constexpr int smem = 2 * (3 * 8192 + 3 * 4 * NT * 16) + 8192;
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(iins_tc_nt_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    IINS_LAUNCH(iins_tc_nt_kernel<NT>, grid, 256, smem, c.st, tp);
+    auto iins_tc_nt_kernel_ = iins_tc_nt_kernel<NT, PIECES>;
+    if (!attr) { cudaFuncSetAttribute(iins_tc_nt_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    IINS_LAUNCH(iins_tc_nt_kernel_, grid, 256, smem, c.st, tp);
+}
+template <int NT>
+void launch_tc_nt_t(Ctx& c, const IinsTCParams& tp, dim3 grid) {
+    if (tp.pieces == 3) launch_tc_nt_tp<NT, 3>(c, tp, grid);
+    else launch_tc_nt_tp<NT, 1>(c, tp, grid);
 }
 
 void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
@@ -98,13 +112,15 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     memset(&pk, 0, sizeof(pk));
     pk.g = p.g; pk.kind = p.a_kind; pk.w = p.w; pk.out = reinterpret_cast<uint16_t*>(c.wpack);
     pk.N = p.N; pk.K = p.K; pk.NT = nt; pk.nkb = (p.K + 31) / 32; pk.nblk = (p.N + nt - 1) / nt;
-    size_t bytes = (size_t)pk.nblk * pk.nkb * 3 * 4 * nt * 16;
+    pk.pieces = g_mode == 1 ? 1 : 3;
+    size_t bytes = (size_t)pk.nblk * pk.nkb * pk.pieces * 4 * nt * 16;
     if (c.wpack == nullptr || bytes > IINS_WPACK_FLOATS * sizeof(float)) { c.err = 1; return; }
     long chunks = (long)pk.nblk * pk.nkb * 4 * nt;
     IINS_LAUNCH(iins_pack_kernel, grid_for(chunks), 256, 0, c.st, pk);
     IinsTCParams tp;
     memset(&tp, 0, sizeof(tp));
     tp.nt = p; tp.wpack = pk.out; tp.pieces = g_mode == 1 ? 1 : 3; tp.nkb = pk.nkb;
+    tp.timeline = (g_timeline != nullptr && g_timeline_count++ == g_timeline_which) ? g_timeline : nullptr;
     dim3 grid((p.M + 127) / 128, pk.nblk, 1);
     IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K); IINS_SET_SHAPE(p.M, p.N, p.K);
     if (nt == 16) launch_tc_nt_t<16>(c, tp, grid);
@@ -113,7 +129,17 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
 }
 #endif
 
-void launch_nt(Ctx& c, const IinsNTParams& p) {
+void launch_nt(Ctx& c, IinsNTParams p) {
+    p.lshift = ilog2_exact(p.Lrow);
+    p.cshift = ilog2_exact(p.a_kind == 0 ? p.g.Cin : p.g.Cout);
+    if (p.lshift < 0) { c.err = 2; return; }
+    if (p.N <= 16 && p.K <= 64) {                     // small-channel layer: direct SIMT conv + fused epilogue
+        IinsRowParams rp;
+        rp.nt = p;
+        IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K); IINS_SET_SHAPE(p.M, p.N, p.K);
+        IINS_LAUNCH(iins_row_nt_kernel, (p.M + 127) / 128, 256, 0, c.st, rp);
+        return;
+    }
 #ifndef IINS_CPUSIM
     if (g_mode != 2) { launch_nt_tc(c, p); return; }
 #endif
@@ -143,12 +169,18 @@ void conv_dgrad(Ctx& c, const IinsGeom& g, const IinsDz& dz, const float* w, flo
 }
 
 #ifndef IINS_CPUSIM
-template <int NT>
-void launch_tc_tn_t(Ctx& c, const IinsTCTNParams& tp, dim3 grid) {
+template <int NT, int PIECES>
+void launch_tc_tn_tp(Ctx& c, const IinsTCTNParams& tp, dim3 grid) {
     constexpr int smem = 2 * (3 * 8192 + 3 * (NT / 8) * 32 * 16);
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(iins_tc_tn_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    IINS_LAUNCH(iins_tc_tn_kernel<NT>, grid, 256, smem, c.st, tp);
+    auto iins_tc_tn_kernel_ = iins_tc_tn_kernel<NT, PIECES>;
+    if (!attr) { cudaFuncSetAttribute(iins_tc_tn_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    IINS_LAUNCH(iins_tc_tn_kernel_, grid, 256, smem, c.st, tp);
+}
+template <int NT>
+void launch_tc_tn_t(Ctx& c, const IinsTCTNParams& tp, dim3 grid) {
+    if (tp.pieces == 3) launch_tc_tn_tp<NT, 3>(c, tp, grid);
+    else launch_tc_tn_tp<NT, 1>(c, tp, grid);
 }
 #endif
 
@@ -158,6 +190,20 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
     p.g = g; p.x = x; p.dz = dz; p.dw = dw; p.db = db;
     p.M = g.B * g.Lout;
     int K = g.ks * g.Cin;
+    if (g.Cout <= 16 && K <= 64) {                    // small-channel layer
+        IinsRowTNParams rp;
+        memset(&rp, 0, sizeof(rp));
+        rp.K = K; rp.lshift = ilog2_exact(g.Lout);
+        if (rp.lshift < 0) { c.err = 2; return; }
+        long want = 148L * 4, max_parts = (p.M + 63) / 64;
+        if (want > max_parts) want = max_parts;
+        long rpp = ((p.M + want - 1) / want + 63) / 64 * 64;
+        p.rows_per_part = (int)rpp;
+        rp.tn = p;
+        IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K); IINS_SET_SHAPE(p.M, g.Cout, K);
+        IINS_LAUNCH(iins_row_tn_kernel, (int)((p.M + rpp - 1) / rpp), 256, 0, c.st, rp);
+        return;
+    }
 #ifndef IINS_CPUSIM
     if (g_mode != 2) {
         int nt = g.Cout <= 16 ? 16 : (g.Cout <= 32 ? 32 : 64);
@@ -173,6 +219,8 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
         IinsTCTNParams tp;
         memset(&tp, 0, sizeof(tp));
         tp.tn = p; tp.pieces = g_mode == 1 ? 1 : 3; tp.K = K;
+        tp.lshift = ilog2_exact(g.Lout); tp.cshift_in = ilog2_exact(g.Cin); tp.cshift_out = ilog2_exact(g.Cout);
+        if (tp.lshift < 0) { c.err = 2; return; }
         dim3 grid(parts, ky, nz);
         IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K); IINS_SET_SHAPE(p.M, g.Cout, K);
         if (nt == 16) launch_tc_tn_t<16>(c, tp, grid);
@@ -707,6 +755,9 @@ int iins_set_compute_mode(int mode) {
     return IINS_OK;
 }
 int iins_get_compute_mode(void) { return g_mode; }
+void iins_debug_set_timeline(void* dev_buf_1024_i64, int which) {
+    g_timeline = (long long*)dev_buf_1024_i64; g_timeline_which = which; g_timeline_count = 0;
+}
 const char* iins_last_error(void) { return g_err; }
 int iins_validate_config(const iins_config* cfg) { Shapes s; return make_shapes(cfg, s); }
 

@@ -4,9 +4,9 @@
 //       channels-last activations (im2col on the fly: reflection / zero padding, stride, nearest x2
 //       upsampling, or the transposed tap map for dgrad), split into bf16 pieces and written to shared
 //       memory in the UMMA K-major no-swizzle layout; the weight tile arrives pre-split through a TMA bulk
-//       copy (cp.async.bulk + mbarrier); one thread issues tcgen05.mma (M=128, N=16..64, K=16), the fp32
-//       accumulator lives in TMEM, the epilogue (bias, InstanceNorm / AdaIN / LayerNorm, activation,
-//       residual) runs on the TMEM -> SMEM staged tile.
+//       copy (cp.async.bulk + mbarrier); one elected lane of warp 0 issues tcgen05.mma (M=128, N=16..64,
+//       K=16), the fp32 accumulator lives in TMEM, the epilogue (bias, InstanceNorm / AdaIN / LayerNorm,
+//       activation, residual) runs on the TMEM -> SMEM staged tile.
 //   iins_tc_tn_kernel : weight gradient  dW^T[k][n] = sum_rows A[row][k] * dz[row][n]  with both operands
 //       MN-major (the reduction runs over rows), accumulated in TMEM over the CTA's row range and flushed
 //       with atomics.
@@ -14,14 +14,17 @@
 // Precision: fp32 parity needs more than TF32/BF16 single-pass products, so each fp32 operand is split into
 // three bf16 pieces (8+8+8 mantissa bits) and the six significant piece products are accumulated in fp32
 // ("bf16x3": error ~2^-23, same class as an fp32 FMA chain).  pieces == 1 is the plain bf16 mode.
+//
+// Latency notes (measured with the IINS_TL clock trace, tools/timeline.py): the MMA issue path must be
+// warp-uniform (descriptors in uniform registers; a divergent `if (tid == 0)` costs ~170 cycles per MMA in
+// R2UR traffic), the raw operand data of K block kb+1 is prefetched into registers before the barrier of
+// block kb, and the row / k index splits are shifts (every L and channel count on the path is a power of 2).
 #pragma once
 #include "iins_gemm.cuh"
 #ifndef IINS_CPUSIM
 #include "iins_umma.cuh"
 
-// ----------------------------------------------------------------------------------------- 8-wide gathers
 // generic (scalar) gathers for layouts / channel counts the 16-byte fast paths do not cover; kept out of line
-// and rolled so the kernels stay small (instruction-cache footprint)
 __device__ __noinline__ void iins_gather8_fwd_generic(const IinsGeom& g, const float* __restrict__ x, int K, int b, int l, int k0, float* v) {
     int t = k0 / g.Cin, c = k0 - t * g.Cin;
 #pragma unroll 1
@@ -30,12 +33,9 @@ __device__ __noinline__ void iins_gather8_fwd_generic(const IinsGeom& g, const f
         if (++c == g.Cin) { c = 0; ++t; }
     }
 }
-__device__ __noinline__ void iins_dz8_generic(const IinsGeom& g, const IinsDz& d, int b, int l, int n0, float* v, bool accumulate) {
+__device__ __noinline__ void iins_dz8_generic(const IinsGeom& g, const IinsDz& d, int b, int l, int n0, float* v) {
 #pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
-        float u = (n0 + i < g.Cout) ? iins_dz_at(g, d, b, l, n0 + i) : 0.f;
-        v[i] = accumulate ? v[i] + u : u;
-    }
+    for (int i = 0; i < 8; ++i) v[i] = (n0 + i < g.Cout) ? iins_dz_at(g, d, b, l, n0 + i) : 0.f;
 }
 __device__ __noinline__ void iins_gather8_dgrad_generic(const IinsGeom& g, const IinsDz& d, int K, int b, int pos, int k0, float* v) {
     int t = k0 / g.Cout, c = k0 - t * g.Cout;
@@ -46,78 +46,70 @@ __device__ __noinline__ void iins_gather8_dgrad_generic(const IinsGeom& g, const
     }
 }
 
-// forward A operand: 8 consecutive k of row (b,l), k0 % 8 == 0
-__device__ __forceinline__ void iins_gather8_fwd(const IinsGeom& g, const float* __restrict__ x, int K, int b, int l, int k0, float* v) {
-    if (k0 >= K) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        return;
-    }
-    if ((g.Cin & 7) == 0 && g.in_layout == IINS_NLC) {
-        int t = k0 / g.Cin, c0 = k0 - t * g.Cin;
-        int pos = iins_src_pos(g, l, t);
-        if (pos < 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = 0.f;
-            return;
-        }
-        const float4* src = reinterpret_cast<const float4*>(x + ((long)b * g.Lin + pos) * g.Cin + c0);
-        float4 a = __ldg(src), c = __ldg(src + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-        return;
-    }
-    iins_gather8_fwd_generic(g, x, K, b, l, k0, v);
-}
-
-// 8 consecutive output channels of dz at (b,l): n0 % 8 == 0
-__device__ __forceinline__ void iins_dz8(const IinsGeom& g, const IinsDz& d, int b, int l, int n0, float* v, bool accumulate) {
-    if ((g.Cout & 7) == 0 && g.out_layout == IINS_NLC) {
-        long idx = ((long)b * g.Lout + l) * g.Cout + n0;
-        const float4* src = reinterpret_cast<const float4*>(d.dy_bcast ? d.dy + (long)b * g.Cout + n0 : d.dy + idx);
-        float4 a = __ldg(src), c = __ldg(src + 1);
-        float u[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-        if (d.y != nullptr && d.act != IINS_ACT_NONE) {
-            const float4* ys = reinterpret_cast<const float4*>(d.y + idx);
-            float4 ya = __ldg(ys), yc = __ldg(ys + 1);
-            float yy[8] = {ya.x, ya.y, ya.z, ya.w, yc.x, yc.y, yc.z, yc.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) u[i] *= iins_dact_from_y(yy[i], d.act, d.slope);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = accumulate ? v[i] + u[i] * d.dy_scale : u[i] * d.dy_scale;
-        return;
-    }
-    iins_dz8_generic(g, d, b, l, n0, v, accumulate);
-}
-
-// dgrad A operand: 8 consecutive k = (t, co0..co0+7) of input row (b,pos)
-__device__ __forceinline__ void iins_gather8_dgrad(const IinsGeom& g, const IinsDz& d, int K, int b, int pos, int k0, float* v) {
+__device__ __forceinline__ void iins_zero8(float* v) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = 0.f;
-    if (k0 >= K) return;
-    if ((g.Cout & 7) == 0 && g.out_layout == IINS_NLC) {
-        int t = k0 / g.Cout, c0 = k0 - t * g.Cout;
-        int q[3], nq;
-        if (g.mode == IINS_PAD_REFLECT) {
-            q[0] = pos + g.pad; nq = 1;
-            if (pos >= 1 && pos <= g.pad) q[nq++] = g.pad - pos;
-            if (pos <= g.Lin - 2 && pos >= g.Lin - 1 - g.pad) q[nq++] = g.pad + 2 * (g.Lin - 1) - pos;
-        } else if (g.mode == IINS_PAD_UP2) {
-            q[0] = 2 * pos + g.pad; q[1] = 2 * pos + 1 + g.pad; nq = 2;
-        } else {
-            q[0] = pos + g.pad; nq = 1;
-        }
-#pragma unroll 1
-        for (int j = 0; j < nq; ++j) {
-            int r = q[j] - t;
-            if (r < 0) continue;
-            int l = r / g.stride;
-            if (l * g.stride != r || l >= g.Lout) continue;
-            iins_dz8(g, d, b, l, c0, v, true);
-        }
-        return;
+}
+__device__ __forceinline__ void iins_ld8(const float* __restrict__ src, bool ok, float* v) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+    if (ok) {
+        a = __ldg(reinterpret_cast<const float4*>(src));
+        c = __ldg(reinterpret_cast<const float4*>(src) + 1);
     }
-    iins_gather8_dgrad_generic(g, d, K, b, pos, k0, v);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+}
+
+// forward A operand, fast path: Cin = 1 << cs (>= 8), NLC input; 8 consecutive k = one tap, 8 channels
+__device__ __forceinline__ void iins_gather8_fwd_fast(const IinsGeom& g, const float* __restrict__ x, int K, int cs, int b, int l,
+                                                      int k0, float* v) {
+    const int t = k0 >> cs, c0 = k0 & (g.Cin - 1);
+    const int pos = iins_src_pos(g, l, t);
+    const bool ok = k0 < K && pos >= 0;
+    iins_ld8(x + (((long)b * g.Lin + (ok ? pos : 0)) << cs) + c0, ok, v);
+}
+
+// 8 consecutive output channels of dz at (b,l), fast path: Cout = 1 << cs (>= 8), NLC
+__device__ __forceinline__ void iins_dz8_fast(const IinsGeom& g, const IinsDz& d, int cs, int b, int l, int n0, bool ok, float* v) {
+    const long idx = (((long)b * g.Lout + (ok ? l : 0)) << cs) + n0;
+    iins_ld8(d.dy_bcast ? d.dy + ((long)b << cs) + n0 : d.dy + idx, ok, v);
+    if (d.y != nullptr && d.act != IINS_ACT_NONE) {
+        float yy[8];
+        iins_ld8(d.y + idx, ok, yy);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= iins_dact_from_y(yy[i], d.act, d.slope);
+    }
+    if (d.dy_scale != 1.f) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= d.dy_scale;
+    }
+}
+
+// dgrad A operand, fast path: sums the (<= 3) output rows whose tap t reads input position pos
+__device__ __forceinline__ void iins_gather8_dgrad_fast(const IinsGeom& g, const IinsDz& d, int K, int cs, int b, int pos, int k0,
+                                                        float* v) {
+    const int t = k0 >> cs, c0 = k0 & (g.Cout - 1);
+    int q0 = pos + g.pad, q1 = -1, q2 = -1;
+    if (g.mode == IINS_PAD_REFLECT) {
+        if (pos >= 1 && pos <= g.pad) q1 = g.pad - pos;
+        if (pos <= g.Lin - 2 && pos >= g.Lin - 1 - g.pad) q2 = g.pad + 2 * (g.Lin - 1) - pos;
+    } else if (g.mode == IINS_PAD_UP2) {
+        q0 = 2 * pos + g.pad;
+        q1 = q0 + 1;
+    }
+    const int sh = g.stride - 1;                       // stride is 1 or 2
+    iins_zero8(v);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int q = j == 0 ? q0 : (j == 1 ? q1 : q2);
+        const int r = q - t;
+        const int l = r >> sh;
+        const bool ok = k0 < K && q >= 0 && r >= 0 && (r & sh) == 0 && l < g.Lout;
+        if (j > 0 && q < 0) continue;                  // warp-divergent only at the padded borders
+        float u[8];
+        iins_dz8_fast(g, d, cs, b, l, c0, ok, u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += u[i];
+    }
 }
 
 // split 8 floats into bf16 pieces and store one 16-byte vector per piece
@@ -146,6 +138,7 @@ struct IinsPackParams {
     const float* w;
     uint16_t* out;
     int N, K, NT, nkb, nblk;
+    int pieces;          // 3 or 1: the pieces are STACKED along the tile's row (n) dimension
 };
 
 __global__ void __launch_bounds__(256) iins_pack_kernel(const IinsPackParams p) {
@@ -169,12 +162,53 @@ __global__ void __launch_bounds__(256) iins_pack_kernel(const IinsPackParams p) 
             v[i] = x;
             if (++c == Cdim) { c = 0; ++t; }
         }
-        const uint32_t piece_stride = 4u * p.NT * 16u;
-        unsigned char* base = reinterpret_cast<unsigned char*>(p.out) +
-                              ((long)(nb * p.nkb + kb) * 3) * piece_stride + ((long)chunk * p.NT + nn) * 16;
-        iins_store8_split(v, base, piece_stride, 3);
+        // tile = [chunk (4)][piece][NT rows][16 B]: row index of the stacked operand = piece * NT + n
+        const uint32_t piece_stride = (uint32_t)p.NT * 16u;
+        const long tile_bytes = 4L * p.pieces * p.NT * 16;
+        unsigned char* base = reinterpret_cast<unsigned char*>(p.out) + (long)(nb * p.nkb + kb) * tile_bytes +
+                              ((long)chunk * p.pieces * p.NT + nn) * 16;
+        iins_store8_split(v, base, piece_stride, p.pieces);
     }
 }
+
+// Issue the MMAs of one k-step (K = 16) for the bf16x3 scheme with the B pieces stacked along N:
+//   D[:, 0:3N) += A0 * [B0|B1|B2],  D[:, 0:2N) += A1 * [B0|B1],  D[:, 0:N) += A2 * B0
+// so the six significant piece products take 3 instructions; the epilogue adds the three N-wide column blocks.
+// adesc / bdesc address piece 0 of this k-step; a_piece16 = byte distance between A pieces >> 4.
+template <int NT, int PIECES, int AMAJ, int BMAJ>
+__device__ __forceinline__ void iins_issue_kstep(uint32_t tmem, uint64_t adesc, uint64_t bdesc, uint32_t a_piece16, bool leader,
+                                                 uint32_t first_acc) {
+    if (PIECES == 3) {
+        if (leader) {
+            umma::mma_bf16_ss(tmem, adesc, bdesc, umma::make_idesc_bf16(128, 3 * NT, AMAJ, BMAJ), first_acc);
+            umma::mma_bf16_ss(tmem, adesc + a_piece16, bdesc, umma::make_idesc_bf16(128, 2 * NT, AMAJ, BMAJ), 1u);
+            umma::mma_bf16_ss(tmem, adesc + 2 * a_piece16, bdesc, umma::make_idesc_bf16(128, NT, AMAJ, BMAJ), 1u);
+        }
+    } else {
+        if (leader) umma::mma_bf16_ss(tmem, adesc, bdesc, umma::make_idesc_bf16(128, NT, AMAJ, BMAJ), first_acc);
+    }
+}
+
+// TMEM -> registers for 16 accumulator columns starting at c (summing the stacked piece blocks)
+template <int NT, int PIECES>
+__device__ __forceinline__ void iins_tmem_acc16(uint32_t taddr_lane, int c, float* v) {
+    umma::tmem_ld16(taddr_lane + (uint32_t)c, v);
+    if (PIECES == 3) {
+        float u[16], w[16];
+        umma::tmem_ld16(taddr_lane + (uint32_t)(c + NT), u);
+        umma::tmem_ld16(taddr_lane + (uint32_t)(c + 2 * NT), w);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += u[i] + w[i];
+    }
+}
+
+template <int NT, int PIECES>
+struct IinsTmemCols {            // power of two >= 32 covering PIECES * NT accumulator columns
+    static constexpr int need = PIECES * NT;
+    static constexpr int value = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : 256));
+};
+
+#define IINS_TL(tag) do { if (tl_ != nullptr && tl_n_ < 500) { tl_[2 * tl_n_] = (tag); tl_[2 * tl_n_ + 1] = clock64(); ++tl_n_; tl_[1022] = tl_n_; } } while (0)
 
 // --------------------------------------------------------------------------------- forward / dgrad GEMM
 struct IinsTCParams {
@@ -182,14 +216,16 @@ struct IinsTCParams {
     const uint16_t* wpack;
     int pieces;          // 3 (fp32-grade) or 1 (bf16)
     int nkb;             // K blocks of 32
+    long long* timeline; // debug: (tag, clock64) pairs of CTA (0,0) thread 0, or nullptr
 };
 
-template <int NT>
+template <int NT, int PIECES>
 __global__ void __launch_bounds__(256) iins_tc_nt_kernel(const IinsTCParams tp) {
     constexpr int BM = 128;
     constexpr uint32_t A_PIECE = 4 * BM * 16;            // 8192 B : [chunk][row][16 B]
-    constexpr uint32_t B_PIECE = 4 * NT * 16;
-    constexpr uint32_t STAGE = 3 * A_PIECE + 3 * B_PIECE;
+    constexpr uint32_t B_TILE = 4 * PIECES * NT * 16;    // [chunk][piece * NT + n][16 B]
+    constexpr uint32_t STAGE = 3 * A_PIECE + 3 * 4 * NT * 16;
+    constexpr int TCOLS = IinsTmemCols<NT, PIECES>::value;
     constexpr int LD = NT + 1;
     extern __shared__ __align__(1024) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar_mma[2];
@@ -210,66 +246,86 @@ __global__ void __launch_bounds__(256) iins_tc_nt_kernel(const IinsTCParams tp) 
         umma::mbar_init(umma::smem_u32(&mbar_b[1]), 1);
         umma::fence_mbar_init();
     }
-    if (warp == 0) umma::tmem_alloc(umma::smem_u32(&tmem_slot), 64);
+    if (warp == 0) umma::tmem_alloc(umma::smem_u32(&tmem_slot), TCOLS);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    long long* tl_ = (tp.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) ? tp.timeline : nullptr;
+    int tl_n_ = 0;
+    IINS_TL(0);
 
     const int a_row = tid & 127, a_half = tid >> 7;
     const int grow = tile_m + a_row;
     const bool a_ok = grow < p.M;
-    const int a_b = a_ok ? grow / p.Lrow : 0;
-    const int a_l = a_ok ? grow - a_b * p.Lrow : 0;
+    const int a_b = a_ok ? grow >> p.lshift : 0;
+    const int a_l = a_ok ? grow & (p.Lrow - 1) : 0;
     const int nkb = tp.nkb;
-    const uint32_t idesc = umma::make_idesc_bf16(BM, NT, 0, 0);
-    const uint32_t b_bytes = (tp.pieces == 3 ? 3u : 1u) * B_PIECE;
+    const int cs = p.cshift;
+    // 16-byte gathers need >= 8 channels (power of two) in channels-last order
+    const bool fast = cs >= 3 && (p.a_kind == 0 ? g.in_layout == IINS_NLC : g.out_layout == IINS_NLC);
+
+    float raw[2][8];
+    auto load_raw = [&](int kb) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int k0 = kb * 32 + (a_half * 2 + jj) * 8;
+            if (!a_ok) iins_zero8(raw[jj]);
+            else if (fast) {
+                if (p.a_kind == 0) iins_gather8_fwd_fast(g, p.x, p.K, cs, a_b, a_l, k0, raw[jj]);
+                else iins_gather8_dgrad_fast(g, p.dz, p.K, cs, a_b, a_l, k0, raw[jj]);
+            } else {
+                float tmp[8];                          // address-taken copy: keeps raw[][] in registers
+                if (p.a_kind == 0) iins_gather8_fwd_generic(g, p.x, p.K, a_b, a_l, k0, tmp);
+                else iins_gather8_dgrad_generic(g, p.dz, p.K, a_b, a_l, k0, tmp);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) raw[jj][i] = tmp[i];
+            }
+        }
+    };
+    load_raw(0);
 
     for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb & 1;
         unsigned char* sA = dsm + s * STAGE;
         unsigned char* sB = sA + 3 * A_PIECE;
         if (kb >= 2) umma::mbar_wait(umma::smem_u32(&mbar_mma[s]), (uint32_t)(((kb >> 1) - 1) & 1));
-        if (tid == 0) {
+        IINS_TL(1);
+        if (warp == 0 && umma::elect_one()) {
             const unsigned char* src = reinterpret_cast<const unsigned char*>(tp.wpack) +
-                                       ((long)blockIdx.y * nkb + kb) * (3 * B_PIECE);
-            umma::mbar_arrive_expect_tx(umma::smem_u32(&mbar_b[s]), b_bytes);
-            umma::tma_bulk_g2s(umma::smem_u32(sB), src, b_bytes, umma::smem_u32(&mbar_b[s]));
+                                       ((long)blockIdx.y * nkb + kb) * B_TILE;
+            umma::mbar_arrive_expect_tx(umma::smem_u32(&mbar_b[s]), B_TILE);
+            umma::tma_bulk_g2s(umma::smem_u32(sB), src, B_TILE, umma::smem_u32(&mbar_b[s]));
         }
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-            const int j = a_half * 2 + jj;
-            float v[8];
-            if (a_ok) {
-                if (p.a_kind == 0) iins_gather8_fwd(g, p.x, p.K, a_b, a_l, kb * 32 + j * 8, v);
-                else iins_gather8_dgrad(g, p.dz, p.K, a_b, a_l, kb * 32 + j * 8, v);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.f;
-            }
-            iins_store8_split(v, sA + (j * BM + a_row) * 16, A_PIECE, tp.pieces);
-        }
+        for (int jj = 0; jj < 2; ++jj)
+            iins_store8_split(raw[jj], sA + ((a_half * 2 + jj) * BM + a_row) * 16, A_PIECE, PIECES);
+        IINS_TL(2);
+        if (kb + 1 < nkb) load_raw(kb + 1);           // in flight across the barrier and the MMA issue
         umma::fence_async_smem();
+        IINS_TL(3);
         __syncthreads();
-        if (tid == 0) {
+        IINS_TL(4);
+        if (warp == 0) {                               // warp-uniform issue path
             umma::mbar_wait(umma::smem_u32(&mbar_b[s]), (uint32_t)((kb >> 1) & 1));
             umma::tc_fence_after();
-            const uint32_t a0 = umma::smem_u32(sA), b0 = umma::smem_u32(sB);
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                for (int pa = 0; pa < tp.pieces; ++pa)
-                    for (int pb = 0; pb + pa < tp.pieces; ++pb) {
-                        uint64_t ad = umma::make_desc(a0 + pa * A_PIECE + ks * 2 * BM * 16, BM * 16, 128);
-                        uint64_t bd = umma::make_desc(b0 + pb * B_PIECE + ks * 2 * NT * 16, NT * 16, 128);
-                        umma::mma_bf16_ss(tmem, ad, bd, idesc, (kb | ks | pa | pb) ? 1u : 0u);
-                    }
-            }
-            umma::commit(umma::smem_u32(&mbar_mma[s]));
+            IINS_TL(5);
+            // K-major, no swizzle: LBO = distance between 8-wide k chunks, SBO = 128 B between 8-row groups
+            const uint64_t ad = umma::make_desc(umma::smem_u32(sA), BM * 16, 128);
+            const uint64_t bd = umma::make_desc(umma::smem_u32(sB), PIECES * NT * 16, 128);
+            const bool leader = umma::elect_one();
+            iins_issue_kstep<NT, PIECES, 0, 0>(tmem, ad, bd, A_PIECE >> 4, leader, kb > 0 ? 1u : 0u);
+            iins_issue_kstep<NT, PIECES, 0, 0>(tmem, ad + ((2 * BM * 16) >> 4), bd + ((2 * PIECES * NT * 16) >> 4), A_PIECE >> 4,
+                                               leader, 1u);
+            if (leader) umma::commit(umma::smem_u32(&mbar_mma[s]));
+            __syncwarp();
+            IINS_TL(6);
         }
     }
     if (nkb >= 2) umma::mbar_wait(umma::smem_u32(&mbar_mma[(nkb - 2) & 1]), (uint32_t)(((nkb - 2) >> 1) & 1));
     umma::mbar_wait(umma::smem_u32(&mbar_mma[(nkb - 1) & 1]), (uint32_t)(((nkb - 1) >> 1) & 1));
     umma::tc_fence_after();
+    IINS_TL(13);
 
     // ---- TMEM -> SMEM (+ bias).  Warp w owns TMEM lanes 32*(w&3) .. +31; with NT >= 32 the two warps sharing
     // a lane quarter split the columns.
@@ -282,7 +338,7 @@ __global__ void __launch_bounds__(256) iins_tc_nt_kernel(const IinsTCParams tp) 
 #pragma unroll
             for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 16) {
                 float v[16];
-                umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cbeg + c0), v);
+                iins_tmem_acc16<NT, PIECES>(tmem + ((uint32_t)(q * 32) << 16), cbeg + c0, v);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     int n = n0 + cbeg + c0 + i;
@@ -294,9 +350,11 @@ __global__ void __launch_bounds__(256) iins_tc_nt_kernel(const IinsTCParams tp) 
     }
     umma::tc_fence_before();
     __syncthreads();
+    IINS_TL(14);
     iins_epilogue_tile<NT, LD>(p, Cs, st_mean, st_rstd, tile_m, n0);
+    IINS_TL(15);
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 64);
+    if (warp == 0) umma::tmem_dealloc(tmem, TCOLS);
 }
 
 // ------------------------------------------------------------------------------------------- weight grad
@@ -304,15 +362,19 @@ struct IinsTCTNParams {
     IinsTNParams tn;
     int pieces;
     int K;               // ks * Cin
+    int lshift;          // log2(Lout) (rows per sample)
+    int cshift_in;       // log2(Cin) or -1
+    int cshift_out;      // log2(Cout) or -1
 };
 
 // grid = (row parts, ceil(K/128), ceil(Cout/NT)).  D^T[k][n] accumulated in TMEM (128 lanes = 128 k entries).
-template <int NT>
+template <int NT, int PIECES>
 __global__ void __launch_bounds__(256) iins_tc_tn_kernel(const IinsTCTNParams tp) {
     constexpr int BR = 32;                               // rows per stage (2 MMA k-steps of 16)
     constexpr uint32_t A_PIECE = 16 * BR * 16;           // [k group of 8][row][16 B] = 8192 B
-    constexpr uint32_t B_PIECE = (NT / 8) * BR * 16;
+    constexpr uint32_t B_PIECE = (NT / 8) * BR * 16;     // [n group of 8][row][16 B]; pieces stacked = more n groups
     constexpr uint32_t STAGE = 3 * A_PIECE + 3 * B_PIECE;
+    constexpr int TCOLS = IinsTmemCols<NT, PIECES>::value;
     extern __shared__ __align__(1024) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar_mma[2];
     __shared__ uint32_t tmem_slot;
@@ -331,67 +393,78 @@ __global__ void __launch_bounds__(256) iins_tc_tn_kernel(const IinsTCTNParams tp
         umma::fence_mbar_init();
     }
     if (tid < 64) s_bias[tid] = 0.f;
-    if (warp == 0) umma::tmem_alloc(umma::smem_u32(&tmem_slot), 64);
+    if (warp == 0) umma::tmem_alloc(umma::smem_u32(&tmem_slot), TCOLS);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t idesc = umma::make_idesc_bf16(128, NT, 1, 1);
     const bool do_bias = p.db != nullptr && blockIdx.y == 0;
+    const bool fast_a = tp.cshift_in >= 3 && g.in_layout == IINS_NLC;
+    const bool fast_z = tp.cshift_out >= 3 && g.out_layout == IINS_NLC;
+    const bool has_z = warp < NT / 8;
     float bsum[8];
+    iins_zero8(bsum);
+
+    float rawa[2][8], rawz[8];
+    auto load_raw = [&](int it) {
+        const int row = r_begin + it * BR + lane;
+        const bool ok = row < r_end;
+        const int b = ok ? row >> tp.lshift : 0;
+        const int l = ok ? row & (g.Lout - 1) : 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
+        for (int jj = 0; jj < 2; ++jj) {
+            const int k0 = ktile0 + (warp + 8 * jj) * 8;
+            if (!ok) iins_zero8(rawa[jj]);
+            else if (fast_a) iins_gather8_fwd_fast(g, p.x, tp.K, tp.cshift_in, b, l, k0, rawa[jj]);
+            else {
+                float tmp[8];
+                iins_gather8_fwd_generic(g, p.x, tp.K, b, l, k0, tmp);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rawa[jj][i] = tmp[i];
+            }
+        }
+        if (has_z) {
+            if (!ok) iins_zero8(rawz);
+            else if (fast_z) iins_dz8_fast(g, p.dz, tp.cshift_out, b, l, n0 + warp * 8, true, rawz);
+            else {
+                float tmp[8];
+                iins_dz8_generic(g, p.dz, b, l, n0 + warp * 8, tmp);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rawz[i] = tmp[i];
+            }
+        }
+    };
 
     const int nit = (r_end - r_begin + BR - 1) / BR;
+    if (nit > 0) load_raw(0);
     for (int it = 0; it < nit; ++it) {
         const int s = it & 1;
         unsigned char* sA = dsm + s * STAGE;
         unsigned char* sB = sA + 3 * A_PIECE;
         if (it >= 2) umma::mbar_wait(umma::smem_u32(&mbar_mma[s]), (uint32_t)(((it >> 1) - 1) & 1));
-        const int row = r_begin + it * BR + lane;
-        const bool ok = row < r_end;
-        const int b = ok ? row / g.Lout : 0;
-        const int l = ok ? row - b * g.Lout : 0;
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-            const int kg = warp + 8 * jj;                // k group (8 consecutive k) of this tile
-            float v[8];
-            if (ok) iins_gather8_fwd(g, p.x, tp.K, b, l, ktile0 + kg * 8, v);
-            else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.f;
-            }
-            iins_store8_split(v, sA + (kg * BR + lane) * 16, A_PIECE, tp.pieces);
-        }
-        if (warp < NT / 8) {
-            float v[8];
-            if (ok) iins_dz8(g, p.dz, b, l, n0 + warp * 8, v, false);
-            else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.f;
-            }
+        for (int jj = 0; jj < 2; ++jj)
+            iins_store8_split(rawa[jj], sA + ((warp + 8 * jj) * BR + lane) * 16, A_PIECE, PIECES);
+        if (has_z) {
             if (do_bias) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) bsum[i] += v[i];
+                for (int i = 0; i < 8; ++i) bsum[i] += rawz[i];
             }
-            iins_store8_split(v, sB + (warp * BR + lane) * 16, B_PIECE, tp.pieces);
+            iins_store8_split(rawz, sB + (warp * BR + lane) * 16, B_PIECE, PIECES);
         }
+        if (it + 1 < nit) load_raw(it + 1);
         umma::fence_async_smem();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             umma::tc_fence_after();
-            const uint32_t a0 = umma::smem_u32(sA), b0 = umma::smem_u32(sB);
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                for (int pa = 0; pa < tp.pieces; ++pa)
-                    for (int pb = 0; pb + pa < tp.pieces; ++pb) {
-                        // MN-major: LBO = distance between 8-row groups (128 B), SBO = distance between MN groups
-                        uint64_t ad = umma::make_desc(a0 + pa * A_PIECE + ks * 256, 128, BR * 16);
-                        uint64_t bd = umma::make_desc(b0 + pb * B_PIECE + ks * 256, 128, BR * 16);
-                        umma::mma_bf16_ss(tmem, ad, bd, idesc, (it | ks | pa | pb) ? 1u : 0u);
-                    }
-            }
-            umma::commit(umma::smem_u32(&mbar_mma[s]));
+            // MN-major: LBO = distance between 8-row groups (128 B), SBO = distance between MN groups of 8
+            const uint64_t ad = umma::make_desc(umma::smem_u32(sA), 128, BR * 16);
+            const uint64_t bd = umma::make_desc(umma::smem_u32(sB), 128, BR * 16);
+            const bool leader = umma::elect_one();
+            iins_issue_kstep<NT, PIECES, 1, 1>(tmem, ad, bd, A_PIECE >> 4, leader, it > 0 ? 1u : 0u);
+            iins_issue_kstep<NT, PIECES, 1, 1>(tmem, ad + (256 >> 4), bd + (256 >> 4), A_PIECE >> 4, leader, 1u);
+            if (leader) umma::commit(umma::smem_u32(&mbar_mma[s]));
+            __syncwarp();
         }
     }
     if (nit >= 2) umma::mbar_wait(umma::smem_u32(&mbar_mma[(nit - 2) & 1]), (uint32_t)(((nit - 2) >> 1) & 1));
@@ -410,7 +483,7 @@ __global__ void __launch_bounds__(256) iins_tc_tn_kernel(const IinsTCTNParams tp
 #pragma unroll
             for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 16) {
                 float v[16];
-                umma::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cbeg + c0), v);
+                iins_tmem_acc16<NT, PIECES>(tmem + ((uint32_t)(q * 32) << 16), cbeg + c0, v);
                 if (kok) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -420,7 +493,7 @@ __global__ void __launch_bounds__(256) iins_tc_tn_kernel(const IinsTCTNParams tp
                 }
             }
         }
-        if (do_bias && warp < NT / 8) {
+        if (do_bias && has_z) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) atomicAdd(&s_bias[warp * 8 + i], bsum[i]);
         }
@@ -428,7 +501,7 @@ __global__ void __launch_bounds__(256) iins_tc_tn_kernel(const IinsTCTNParams tp
     umma::tc_fence_before();
     __syncthreads();
     if (do_bias && tid < NT && n0 + tid < g.Cout && nit >= 1) atomicAdd(p.db + n0 + tid, s_bias[tid]);
-    if (warp == 0) umma::tmem_dealloc(tmem, 64);
+    if (warp == 0) umma::tmem_dealloc(tmem, TCOLS);
 }
 
 #endif  // !IINS_CPUSIM
