@@ -25,137 +25,107 @@ struct IinsNormBwdParams {
     float* dz;                 // out (NLC)
 };
 
+// One WARP per sample (the per-sample tensors are 2 KB: L*C = 512 on this path): two passes over the sample's
+// (L, C) block, 16 bytes per lane per access, reductions by warp shuffles -- no shared memory, no block barrier.
+//   pass 1: accumulate sum_l g and sum_l g*xhat per channel (IN / AdaIN) or over the whole sample (LN)
+//   pass 2: reload (L1-resident) and write dz
+// Requires C a power of two, 4 <= C <= 128, and L*C a multiple of 128.
 __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNormBwdParams p) {
-    __shared__ float s_g[1024];        // sum_l g        per (s,c)   | LN: per sample [0..7]
-    __shared__ float s_gx[1024];       // sum_l g*xhat
-    const int tid = threadIdx.x;
-    const int L = p.L, C = p.C;
-    const int S = 128 / L;             // samples per tile
-    const int b0 = blockIdx.x * S;
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int C = p.C, L = p.L;
+    const int CG = C >> 2;                          // float4 column groups per row (<= 32)
+    const int nstep = (L * C) >> 7;                 // float4 steps of 32 lanes
     const bool relu = p.act == IINS_ACT_RELU;
-
-    // g(b,l,c) = dy * mask * scale   and the value u whose sign is the ReLU mask
-    auto load_g = [&](int b, int l, int c, float& xh) -> float {
-        long i = ((long)b * L + l) * C + c;
-        xh = __ldg(p.xhat + i);
-        float g = __ldg(p.dy + i);
-        float u = xh, scale = 1.f;
-        if (p.norm == IINS_NORM_ADAIN) {
-            scale = __ldg(p.adain + (long)b * p.adain_ld + p.adain_off_w + c);
-            u = fmaf(xh, scale, __ldg(p.adain + (long)b * p.adain_ld + p.adain_off_b + c));
-        } else if (p.norm == IINS_NORM_LN) {
-            scale = __ldg(p.gamma + c);
-            u = fmaf(xh, scale, __ldg(p.beta + c));
+    const bool live = b < p.B;                      // warp-uniform
+    const int cg = lane & (CG - 1), c0 = cg * 4;    // CG <= 32 and nstep*32 is a multiple of CG: the lane's channels are fixed
+    float scale[4] = {1.f, 1.f, 1.f, 1.f}, shift[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live && p.norm == IINS_NORM_ADAIN) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            scale[j] = __ldg(p.adain + (long)b * p.adain_ld + p.adain_off_w + c0 + j);
+            shift[j] = __ldg(p.adain + (long)b * p.adain_ld + p.adain_off_b + c0 + j);
         }
-        if (relu && !(u > 0.f)) g = 0.f;
-        return g * scale;              // gradient w.r.t. xhat; (g w.r.t. affine output) = value / scale
-    };
-
-    if (p.norm == IINS_NORM_IN || p.norm == IINS_NORM_ADAIN) {
-        const int pairs = S * C;
-        int G = 1;
-        while (G < 32 && pairs * G * 2 <= 256) G <<= 1;
-        const int per_iter = 256 / G;
-        for (int p0 = 0; p0 < pairs; p0 += per_iter) {
-            int pr = p0 + tid / G, sub = tid % G;
-            int s = pr / C, c = pr - s * C;
-            int b = b0 + s;
-            bool ok = pr < pairs && b < p.B;
-            float sg = 0.f, sgx = 0.f, sraw = 0.f, srawx = 0.f;
-            if (ok) {
-                float scale = p.norm == IINS_NORM_ADAIN ? __ldg(p.adain + (long)b * p.adain_ld + p.adain_off_w + c) : 1.f;
-                for (int l = sub; l < L; l += G) {
-                    float xh;
-                    float g = load_g(b, l, c, xh);
-                    sg += g;
-                    sgx += g * xh;
-                    if (p.norm == IINS_NORM_ADAIN) {
-                        // raw = dy*mask (gradient w.r.t. the affine output): recompute without the scale
-                        long i = ((long)b * L + l) * C + c;
-                        float u = fmaf(xh, scale, __ldg(p.adain + (long)b * p.adain_ld + p.adain_off_b + c));
-                        float raw = (relu && !(u > 0.f)) ? 0.f : __ldg(p.dy + i);
-                        sraw += raw;
-                        srawx += raw * xh;
-                    }
-                }
-            }
-            sg = iins_group_sum(sg, G);
-            sgx = iins_group_sum(sgx, G);
-            if (p.norm == IINS_NORM_ADAIN) {
-                sraw = iins_group_sum(sraw, G);
-                srawx = iins_group_sum(srawx, G);
-            }
-            if (ok && sub == 0) {
-                s_g[s * C + c] = sg;
-                s_gx[s * C + c] = sgx;
-                if (p.norm == IINS_NORM_ADAIN && p.dadain != nullptr) {
-                    p.dadain[(long)b * p.adain_ld + p.adain_off_b + c] = sraw;
-                    p.dadain[(long)b * p.adain_ld + p.adain_off_w + c] = srawx;
-                }
+    } else if (p.norm == IINS_NORM_LN) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { scale[j] = __ldg(p.gamma + c0 + j); shift[j] = __ldg(p.beta + c0 + j); }
+    }
+    const float4* dy4 = reinterpret_cast<const float4*>(p.dy + (long)(live ? b : 0) * L * C);
+    const float4* xh4 = reinterpret_cast<const float4*>(p.xhat + (long)(live ? b : 0) * L * C);
+    float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};        // grad wrt xhat
+    float sr[4] = {0.f, 0.f, 0.f, 0.f}, srx[4] = {0.f, 0.f, 0.f, 0.f};        // grad wrt the affine output
+    if (live) {
+        for (int i = 0; i < nstep; ++i) {
+            const float4 d = __ldg(dy4 + lane + 32 * i), x = __ldg(xh4 + lane + 32 * i);
+            const float dv[4] = {d.x, d.y, d.z, d.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float u = fmaf(xv[j], scale[j], shift[j]);
+                const float raw = (relu && !(u > 0.f)) ? 0.f : dv[j];
+                const float gx = raw * scale[j];
+                sr[j] += raw; srx[j] += raw * xv[j];
+                sg[j] += gx; sgx[j] += gx * xv[j];
             }
         }
-        __syncthreads();
-        const float invL = 1.0f / (float)L;
-        for (int e = tid; e < 128 * C; e += 256) {
-            int r = e / C, c = e - r * C;
-            int s = r / L, l = r - s * L;
-            int b = b0 + s;
-            if (b >= p.B) continue;
-            float xh;
-            float g = load_g(b, l, c, xh);
-            float rs = __ldg(p.rstd + (long)b * C + c);
-            p.dz[((long)b * L + l) * C + c] = rs * (g - s_g[s * C + c] * invL - xh * s_gx[s * C + c] * invL);
+    }
+    float tot_g = 0.f, tot_gx = 0.f;
+    if (p.norm == IINS_NORM_LN) {
+        tot_g = iins_warp_sum(sg[0] + sg[1] + sg[2] + sg[3]);
+        tot_gx = iins_warp_sum(sgx[0] + sgx[1] + sgx[2] + sgx[3]);
+    }
+    // per-channel totals: combine the lanes that share this lane's column group (lane bits >= log2(CG))
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        for (int o = 16; o >= CG; o >>= 1) {
+            sg[j] += __shfl_xor_sync(0xffffffffu, sg[j], o);
+            sgx[j] += __shfl_xor_sync(0xffffffffu, sgx[j], o);
+            sr[j] += __shfl_xor_sync(0xffffffffu, sr[j], o);
+            srx[j] += __shfl_xor_sync(0xffffffffu, srx[j], o);
         }
-    } else {   // LN
-        const int warp = tid >> 5, lane = tid & 31;
+    }
+    if (p.norm == IINS_NORM_LN) {
+        // dgamma / dbeta: this sample's contribution; lanes 0..CG-1 hold distinct column groups
+        if (live && lane < CG) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { atomicAdd(p.dgamma + c0 + j, srx[j]); atomicAdd(p.dbeta + c0 + j, sr[j]); }
+        }
+    } else if (p.norm == IINS_NORM_ADAIN && p.dadain != nullptr) {
+        if (live && lane < CG) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                p.dadain[(long)b * p.adain_ld + p.adain_off_b + c0 + j] = sr[j];
+                p.dadain[(long)b * p.adain_ld + p.adain_off_w + c0 + j] = srx[j];
+            }
+        }
+    }
+    if (!live) return;
+    float4* dz4 = reinterpret_cast<float4*>(p.dz + (long)b * L * C);
+    float rs[4];
+    float coef = 0.f, mean_g = 0.f;
+    if (p.norm == IINS_NORM_LN) {
+        const float r = __ldg(p.rstd + b);
+        const float sd = 1.0f / r - IINS_EPS;
         const int nel = L * C;
-        for (int s0 = 0; s0 < S; s0 += 8) {
-            int s = s0 + warp;
-            int b = b0 + s;
-            bool ok = s < S && b < p.B;
-            float sg = 0.f, sgx = 0.f;
-            if (ok) for (int e = lane; e < nel; e += 32) {
-                float xh;
-                float g = load_g(b, e / C, e % C, xh);
-                sg += g;
-                sgx += g * xh;
-            }
-            sg = iins_warp_sum(sg);
-            sgx = iins_warp_sum(sgx);
-            if (ok && lane == 0) { s_g[s] = sg; s_gx[s] = sgx; }
+        rs[0] = rs[1] = rs[2] = rs[3] = r;
+        coef = tot_gx / ((float)(nel - 1) * sd);
+        mean_g = tot_g / (float)nel;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rs[j] = __ldg(p.rstd + (long)b * C + c0 + j);
+    }
+    const float invL = 1.0f / (float)L;
+    for (int i = 0; i < nstep; ++i) {
+        const float4 d = __ldg(dy4 + lane + 32 * i), x = __ldg(xh4 + lane + 32 * i);
+        const float dv[4] = {d.x, d.y, d.z, d.w}, xv[4] = {x.x, x.y, x.z, x.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float u = fmaf(xv[j], scale[j], shift[j]);
+            const float gx = ((relu && !(u > 0.f)) ? 0.f : dv[j]) * scale[j];
+            if (p.norm == IINS_NORM_LN) o[j] = rs[j] * (gx - mean_g) - xv[j] * coef;
+            else o[j] = rs[j] * (gx - sg[j] * invL - xv[j] * sgx[j] * invL);
         }
-        __syncthreads();
-        // per-channel dgamma / dbeta over every row of the tile: thread c (< C) loops the rows
-        // (C <= 64; rows 128) -- small next to the conv work of the layer.
-        for (int c = tid; c < C; c += 256) {
-            float dg = 0.f, dbt = 0.f;
-            float gm = __ldg(p.gamma + c), bt = __ldg(p.beta + c);
-            for (int r = 0; r < 128; ++r) {
-                int s = r / L, l = r - s * L;
-                int b = b0 + s;
-                if (b >= p.B) break;
-                long i = ((long)b * L + l) * C + c;
-                float xh = __ldg(p.xhat + i);
-                float u = fmaf(xh, gm, bt);
-                float raw = (relu && !(u > 0.f)) ? 0.f : __ldg(p.dy + i);
-                dg += raw * xh;
-                dbt += raw;
-            }
-            atomicAdd(p.dgamma + c, dg);
-            atomicAdd(p.dbeta + c, dbt);
-        }
-        const float inv_n = 1.0f / (float)nel;
-        for (int e = tid; e < 128 * C; e += 256) {
-            int r = e / C, c = e - r * C;
-            int s = r / L, l = r - s * L;
-            int b = b0 + s;
-            if (b >= p.B) continue;
-            float xh;
-            float g = load_g(b, l, c, xh);
-            float rs = __ldg(p.rstd + b);
-            float sd = 1.0f / rs - IINS_EPS;
-            p.dz[((long)b * L + l) * C + c] = rs * (g - s_g[s] * inv_n) - xh * s_gx[s] / ((float)(nel - 1) * sd);
-        }
+        dz4[lane + 32 * i] = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 

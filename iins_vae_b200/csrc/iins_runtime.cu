@@ -251,8 +251,9 @@ void norm_backward(Ctx& c, int B, int L, int C, int norm, int act, const float* 
     p.B = B; p.L = L; p.C = C; p.norm = norm; p.act = act; p.dy = dy; p.xhat = xhat; p.rstd = rstd;
     p.gamma = gamma; p.beta = beta; p.dgamma = dgamma; p.dbeta = dbeta;
     p.adain = adain; p.dadain = dadain; p.adain_ld = ld; p.adain_off_b = off_b; p.adain_off_w = off_w; p.dz = dz;
-    int S = 128 / L;
-    IINS_LAUNCH(iins_norm_bwd_kernel, (B + S - 1) / S, 256, 0, c.st, p);
+    // one warp per sample: C power of two in [4,128], L*C a multiple of 128
+    if (ilog2_exact(C) < 2 || C > 128 || ((L * C) & 127) != 0) { c.err = 3; return; }
+    IINS_LAUNCH(iins_norm_bwd_kernel, (B + 7) / 8, 256, 0, c.st, p);
 }
 
 // ------------------------------------------------------------------------------ shape helpers
