@@ -231,7 +231,7 @@ def main():
         m.load_state_dict(p)
         m.cuda()
     eng = SemiTrainEngine(Enc, Dec, Res, Cls, batch_size=B, cir_len=cfg.cir_len, lr=1e-4, betas=(0.5, 0.999),
-                          use_graph=(world == 1), process_group=pg)
+                          use_graph=True, process_group=pg)
 
     host = [tuple(t.pin_memory() for t in orc.synthetic_batch(cfg, B, 1234 + 100 * rank + j)) for j in range(N_BATCHES)]
     dev = [tuple(t.cuda() for t in b) for b in host]
@@ -358,7 +358,13 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that captured NCCL kernels keep the communicator busy at teardown (destroy_process_group
+        # was observed to hang): synchronise, rendezvous once more, flush and leave without the teardown.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -122,7 +122,7 @@ __device__ __forceinline__ void iins_epilogue_tile(const IinsNTParams& p, const 
         }
     }
     if (gn < p.N) {
-#pragma unroll 2
+#pragma unroll 4
         for (int r = tid / CG; r < BM; r += RSTEP) {
             const int gr = tile_m + r;
             if (gr >= p.M) break;
@@ -410,23 +410,71 @@ __global__ void __launch_bounds__(256) iins_row_nt_kernel(const IinsRowParams rp
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    if (grow < p.M && half * 8 < p.N) {
+    // With N <= 8 the second thread of a row would idle: instead the two threads split the TAPS and the
+    // partial sums are combined through shared memory (Cs) below.
+    const bool split_taps = p.N <= 8;
+    const int ncol0 = split_taps ? 0 : half * 8;
+    if (grow < p.M && (split_taps || half * 8 < p.N)) {
         const int b = grow >> p.lshift, l = grow & (p.Lrow - 1);
-        int k = 0;
-        for (int t = 0; t < g.ks; ++t) {
-            for (int c = 0; c < Cdim; ++c, ++k) {
-                const float a = p.a_kind == 0 ? iins_a_fwd(g, p.x, b, l, t, c) : iins_a_dgrad(g, p.dz, b, l, t, c);
-                const float* wr = Ws + k * NT + half * 8;
+        const int tstep = split_taps ? 2 : 1;
+        for (int t = split_taps ? half : 0; t < g.ks; t += tstep) {
+            const float* wr0 = Ws + (t * Cdim) * NT + ncol0;
+            if (p.a_kind == 0) {
+                const int pos = iins_src_pos(g, l, t);
+                if (pos < 0) continue;
+                const float* xr = p.x + iins_in_index(g, b, pos, 0);
+                const long cstride = g.in_layout == IINS_NCL ? g.Lin : 1;
+                for (int c = 0; c < Cdim; ++c) {
+                    const float a = __ldg(xr + c * cstride);
+                    const float* wr = wr0 + c * NT;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, wr[j], acc[j]);
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, wr[j], acc[j]);
+                }
+            } else {
+                // data gradient: output rows whose tap t reads this input position (<= 3 candidates)
+                int q[3] = {l + g.pad, -1, -1};
+                if (g.mode == IINS_PAD_REFLECT) {
+                    if (l >= 1 && l <= g.pad) q[1] = g.pad - l;
+                    if (l <= g.Lin - 2 && l >= g.Lin - 1 - g.pad) q[2] = g.pad + 2 * (g.Lin - 1) - l;
+                } else if (g.mode == IINS_PAD_UP2) {
+                    q[0] = 2 * l + g.pad;
+                    q[1] = q[0] + 1;
+                }
+                for (int jq = 0; jq < 3; ++jq) {
+                    if (q[jq] < 0) continue;
+                    const int r = q[jq] - t;
+                    if (r < 0) continue;
+                    const int lo = r / g.stride;
+                    if (lo * g.stride != r || lo >= g.Lout) continue;
+                    for (int c = 0; c < Cdim; ++c) {
+                        const float a = iins_dz_at(g, p.dz, b, lo, c);
+                        const float* wr = wr0 + c * NT;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, wr[j], acc[j]);
+                    }
+                }
             }
         }
     }
+    if (split_taps) {
+        if (half == 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        int n = half * 8 + j;
-        float bv = (p.ep.bias != nullptr && n < p.N) ? __ldg(p.ep.bias + n) : 0.f;
-        Cs[row * LD + n] = acc[j] + bv;
+            for (int j = 0; j < 8; ++j) Cs[row * LD + 8 + j] = acc[j];      // columns 8..15 are unused when N <= 8
+        }
+        __syncthreads();
+        if (half == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += Cs[row * LD + 8 + j];
+        }
+        __syncthreads();
+    }
+    if (!split_taps || half == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int n = ncol0 + j;
+            float bv = (p.ep.bias != nullptr && n < p.N) ? __ldg(p.ep.bias + n) : 0.f;
+            Cs[row * LD + n] = acc[j] + bv;
+        }
     }
     __syncthreads();
     iins_epilogue_tile<NT, LD>(p, Cs, st_mean, st_rstd, tile_m, 0);
@@ -463,8 +511,12 @@ __global__ void __launch_bounds__(256) iins_row_tn_kernel(const IinsRowTNParams 
             const bool ok = row < r_end;
             const int b = ok ? row >> rp.lshift : 0, l = ok ? row & (g.Lout - 1) : 0;
             for (int nn = part; nn < NT; nn += 4) Zs[r * (NT + 1) + nn] = (ok && nn < N) ? iins_dz_at(g, p.dz, b, l, nn) : 0.f;
-            for (int t = part; t < g.ks; t += 4)
-                for (int c = 0; c < g.Cin; ++c) As[r * (KMAX + 1) + t * g.Cin + c] = ok ? iins_a_fwd(g, p.x, b, l, t, c) : 0.f;
+            for (int t = part; t < g.ks; t += 4) {
+                const int pos = ok ? iins_src_pos(g, l, t) : -1;
+                const float* xr = p.x + (pos >= 0 ? iins_in_index(g, b, pos, 0) : 0);
+                const long cstride = g.in_layout == IINS_NCL ? g.Lin : 1;
+                for (int c = 0; c < g.Cin; ++c) As[r * (KMAX + 1) + t * g.Cin + c] = pos >= 0 ? __ldg(xr + c * cstride) : 0.f;
+            }
         }
         __syncthreads();
         if (n < N && kq * 4 < K) {

@@ -208,7 +208,9 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
     if (g_mode != 2) {
         int nt = g.Cout <= 16 ? 16 : (g.Cout <= 32 ? 32 : 64);
         int ky = (K + 127) / 128, nz = (g.Cout + nt - 1) / nt;
-        long want = (148L * 3 + (long)ky * nz - 1) / ((long)ky * nz);
+        static long tn_ctas = 0;               // total CTAs aimed for (tuning knob: env IINS_TN_CTAS)
+        if (tn_ctas == 0) { const char* e = getenv("IINS_TN_CTAS"); tn_ctas = e ? atol(e) : 148L * 2; if (tn_ctas < 1) tn_ctas = 148; }
+        long want = (tn_ctas + (long)ky * nz - 1) / ((long)ky * nz);
         long max_parts = (p.M + 127) / 128;
         if (want > max_parts) want = max_parts;
         if (want < 1) want = 1;

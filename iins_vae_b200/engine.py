@@ -98,7 +98,8 @@ class SemiTrainEngine:
         # pointer tables per module
         self._tables(mods)
         self._graphs = {}
-        self.use_graph = use_graph and self.world == 1
+        # NCCL all-reduce is capturable: the data-parallel step is replayed from a CUDA graph as well
+        self.use_graph = use_graph
         self.n_steps = 0
 
     # ------------------------------------------------------------------------------------------------
