@@ -24,12 +24,20 @@ int fail(int code, const char* msg) {
 int g_mode = 0;
 long long* g_timeline = nullptr;      // debug: device buffer of 1024 int64 for the per-phase clock trace
 int g_timeline_which = -1, g_timeline_count = 0;   // trace only the which-th tensor-core forward launch
-#define IINS_WPACK_FLOATS ((size_t)1 << 19)       // 2 MB scratch for one layer's packed weight tiles
+#define IINS_WPACK_FLOATS ((size_t)1 << 21)       // 8 MB arena: the packed weight tiles of every layer of one module pass
 
+// A module pass runs its launch plan twice when the tensor-core path is on: phase 1 only COLLECTS the weight
+// packing jobs (no launch), one kernel then packs every layer's weights, phase 2 launches the layers.
 struct Ctx {
     cudaStream_t st;
     float* wpack = nullptr;     // IINS_WPACK_FLOATS floats of scratch for the tensor-core weight tiles
     int err = 0;
+    int phase = 0;              // 0 = pack inline per layer, 1 = collect, 2 = execute with pre-packed tiles
+    int njobs = 0, job_i = 0;
+    size_t arena = 0;           // bytes of the arena handed out so far
+#ifndef IINS_CPUSIM
+    IinsPackAllParams jobs;
+#endif
 };
 
 int check_cuda(const char* where) {
@@ -114,9 +122,22 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     pk.N = p.N; pk.K = p.K; pk.NT = nt; pk.nkb = (p.K + 31) / 32; pk.nblk = (p.N + nt - 1) / nt;
     pk.pieces = g_mode == 1 ? 1 : 3;
     size_t bytes = (size_t)pk.nblk * pk.nkb * pk.pieces * 4 * nt * 16;
-    if (c.wpack == nullptr || bytes > IINS_WPACK_FLOATS * sizeof(float)) { c.err = 1; return; }
     long chunks = (long)pk.nblk * pk.nkb * 4 * nt;
-    IINS_LAUNCH(iins_pack_kernel, grid_for(chunks), 256, 0, c.st, pk);
+    if (c.phase == 1) {                                // collect
+        if (c.wpack == nullptr || c.arena + bytes > IINS_WPACK_FLOATS * sizeof(float) || c.njobs >= IINS_PACK_MAX_JOBS) { c.err = 1; return; }
+        IinsPackJob& j = c.jobs.jobs[c.njobs++];
+        j.w = p.w; j.out = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(c.wpack) + c.arena);
+        j.Cin = p.g.Cin; j.Cout = p.g.Cout; j.ks = p.g.ks; j.kind = p.a_kind; j.N = p.N; j.K = p.K; j.NT = nt;
+        j.nkb = pk.nkb; j.nblk = pk.nblk; j.chunk_begin = c.jobs.total;
+        c.jobs.total += chunks;
+        c.arena += (bytes + 255) & ~(size_t)255;
+        return;
+    }
+    if (c.phase == 2) pk.out = c.jobs.jobs[c.job_i++].out;
+    else {
+        if (c.wpack == nullptr || bytes > IINS_WPACK_FLOATS * sizeof(float)) { c.err = 1; return; }
+        IINS_LAUNCH(iins_pack_kernel, grid_for(chunks), 256, 0, c.st, pk);
+    }
     IinsTCParams tp;
     memset(&tp, 0, sizeof(tp));
     tp.nt = p; tp.wpack = pk.out; tp.pieces = g_mode == 1 ? 1 : 3; tp.nkb = pk.nkb;
@@ -134,6 +155,7 @@ void launch_nt(Ctx& c, IinsNTParams p) {
     p.cshift = ilog2_exact(p.a_kind == 0 ? p.g.Cin : p.g.Cout);
     if (p.lshift < 0) { c.err = 2; return; }
     if (p.N <= 16 && p.K <= 64) {                     // small-channel layer: direct SIMT conv + fused epilogue
+        if (c.phase == 1) return;
         IinsRowParams rp;
         rp.nt = p;
         IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K); IINS_SET_SHAPE(p.M, p.N, p.K);
@@ -188,6 +210,7 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
     IinsTNParams p;
     memset(&p, 0, sizeof(p));
     p.g = g; p.x = x; p.dz = dz; p.dw = dw; p.db = db;
+    if (c.phase == 1) return;
     p.M = g.B * g.Lout;
     int K = g.ks * g.Cin;
     if (g.Cout <= 16 && K <= 64) {                    // small-channel layer
@@ -248,6 +271,7 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
 void norm_backward(Ctx& c, int B, int L, int C, int norm, int act, const float* dy, const float* xhat,
                    const float* rstd, const float* gamma, const float* beta, float* dgamma, float* dbeta,
                    const float* adain, float* dadain, int ld, int off_b, int off_w, float* dz) {
+    if (c.phase == 1) return;
     IinsNormBwdParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.L = L; p.C = C; p.norm = norm; p.act = act; p.dy = dy; p.xhat = xhat; p.rstd = rstd;
@@ -257,6 +281,29 @@ void norm_backward(Ctx& c, int B, int L, int C, int norm, int act, const float* 
     if (ilog2_exact(C) < 2 || C > 128 || ((L * C) & 127) != 0) { c.err = 3; return; }
     IINS_LAUNCH(iins_norm_bwd_kernel, (B + 7) / 8, 256, 0, c.st, p);
 }
+
+template <class F>
+void run_phases(Ctx& c, F&& body) {
+#ifndef IINS_CPUSIM
+    if (g_mode != 2) {
+        c.phase = 1; c.njobs = 0; c.arena = 0; c.jobs.total = 0;
+        body();
+        if (c.err) return;
+        if (c.njobs > 0) {
+            c.jobs.njobs = c.njobs;
+            c.jobs.pieces = g_mode == 1 ? 1 : 3;
+            IINS_LAUNCH(iins_pack_all_kernel, grid_for(c.jobs.total), 256, 0, c.st, c.jobs);
+        }
+        c.phase = 2; c.job_i = 0;
+        body();
+        c.phase = 0;
+        return;
+    }
+#endif
+    c.phase = 0;
+    body();
+}
+#define IINS_SKIP_IN_COLLECT(c) if ((c).phase == 1) {} else
 
 // ------------------------------------------------------------------------------ shape helpers
 struct Shapes {
@@ -334,7 +381,8 @@ int encoder_forward(const Shapes& s, const float* const* P, const float* x, cons
     EncPlan pl;
     c.wpack = ws + plan_encoder(s, ws, pl);
     const int B = s.B;
-    IINS_LAUNCH(iins_pool_fwd_kernel, grid_for((long)B * s.P), 256, 0, st, x, pl.xp, B, s.Lc, s.P);
+    run_phases(c, [&]() {
+    IINS_SKIP_IN_COLLECT(c) IINS_LAUNCH(iins_pool_fwd_kernel, grid_for((long)B * s.P), 256, 0, st, x, pl.xp, B, s.Lc, s.P);
     int pi = 0;
     // ---- range encoder (models.py:146-171)
     {
@@ -385,11 +433,14 @@ int encoder_forward(const Shapes& s, const float* const* P, const float* x, cons
         pi += 2;
         eL /= 2; eC = oc;
     }
-    IINS_LAUNCH(iins_mean_l_kernel, grid_for((long)B * eC), 256, 0, st, pl.e_y[pl.n_env - 1], pl.pooled, B, eL, eC);
+    IINS_SKIP_IN_COLLECT(c) IINS_LAUNCH(iins_mean_l_kernel, grid_for((long)B * eC), 256, 0, st, pl.e_y[pl.n_env - 1], pl.pooled, B, eL, eC);
     conv_forward(c, linear_geom(B, eC, s.E), pl.pooled, P[pi], plain_epilogue(P[pi + 1], IINS_ACT_NONE, 0.f, cat));
-    cudaMemsetAsync(kl, 0, sizeof(float), st);
-    IINS_LAUNCH(iins_reparam_kl_kernel, grid_for((long)B * s.E / 2), 256, 0, st, cat, noise, latent, kl, B, s.E,
-                (unsigned long long)seed, (unsigned long long)offset);
+    IINS_SKIP_IN_COLLECT(c) {
+        cudaMemsetAsync(kl, 0, sizeof(float), st);
+        IINS_LAUNCH(iins_reparam_kl_kernel, grid_for((long)B * s.E / 2), 256, 0, st, cat, noise, latent, kl, B, s.E,
+                    (unsigned long long)seed, (unsigned long long)offset);
+    }
+    });
     if (c.err) return fail(IINS_ERR_BAD_CONFIG, "encoder_forward: packed weight tile exceeds the scratch");
     return check_cuda("encoder_forward");
 }
@@ -419,9 +470,10 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
     c.wpack = b.take(IINS_WPACK_FLOATS);
     const int n_range = 2 * (1 + s.ndown + 2 * s.nres + 1);
 
+    run_phases(c, [&]() {
     // ---------------- env branch
     if (d_cat != nullptr || d_lat != nullptr || d_kl != nullptr) {
-        IINS_LAUNCH(iins_reparam_kl_bwd_kernel, grid_for((long)B * s.E / 2), 256, 0, st, cat, noise, d_cat, d_lat, d_kl,
+        IINS_SKIP_IN_COLLECT(c) IINS_LAUNCH(iins_reparam_kl_bwd_kernel, grid_for((long)B * s.E / 2), 256, 0, st, cat, noise, d_cat, d_lat, d_kl,
                     dcat, B, s.E, (unsigned long long)seed, (unsigned long long)offset);
         int pi = n_range + 2 * pl.n_env;               // final 1x1 conv (after the pool)
         int eC = 16 * s.d, eL = s.P >> (pl.n_env - 1);
@@ -498,6 +550,7 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, dzb);
         conv_wgrad(c, g0, pl.xp, plain_dz(dzb), G[pi], G[pi + 1]);
     }
+    });
     if (c.err) return fail(IINS_ERR_BAD_CONFIG, "encoder_backward: packed weight tile exceeds the scratch");
     return check_cuda("encoder_backward");
 }
@@ -541,6 +594,7 @@ int decoder_forward(const Shapes& s, const float* const* P, const float* rc, con
     c.wpack = ws + plan_decoder(s, ws, pl);
     DecIdx ix = dec_idx(s);
     const int B = s.B;
+    run_phases(c, [&]() {
     // MLP -> AdaIN parameters (models.py:951-962, 468)
     conv_forward(c, linear_geom(B, s.E, 256), cat, P[ix.mlp], plain_epilogue(P[ix.mlp + 1], IINS_ACT_RELU, 0.f, pl.m1));
     conv_forward(c, linear_geom(B, 256, 256), pl.m1, P[ix.mlp + 2], plain_epilogue(P[ix.mlp + 3], IINS_ACT_RELU, 0.f, pl.m2));
@@ -579,7 +633,8 @@ int decoder_forward(const Shapes& s, const float* const* P, const float* rc, con
         IinsGeom g = conv_geom(B, L, L, C, 1, 7, 1, 3, IINS_PAD_REFLECT);
         conv_forward(c, g, h, P[ix.out], plain_epilogue(P[ix.out + 1], IINS_ACT_TANH, 0.f, pl.yt));
     }
-    IINS_LAUNCH(iins_pool_fwd_kernel, grid_for((long)B * s.Lc), 256, 0, st, pl.yt, xrec, B, s.P, s.Lc);
+    IINS_SKIP_IN_COLLECT(c) IINS_LAUNCH(iins_pool_fwd_kernel, grid_for((long)B * s.Lc), 256, 0, st, pl.yt, xrec, B, s.P, s.Lc);
+    });
     if (c.err) return fail(IINS_ERR_BAD_CONFIG, "decoder_forward: packed weight tile exceeds the scratch");
     return check_cuda("decoder_forward");
 }
@@ -609,8 +664,9 @@ int decoder_backward(const Shapes& s, const float* const* P, const float* rc, co
     float* dyt = b.take((size_t)B * s.P);
     c.wpack = b.take(IINS_WPACK_FLOATS);
 
+    run_phases(c, [&]() {
     // pool(128 -> cir_len) backward fused with tanh'
-    IINS_LAUNCH(iins_pool_bwd_kernel, grid_for((long)B * s.P), 256, 0, st, d_xrec, pl.yt, dyt, B, s.P, s.Lc);
+    IINS_SKIP_IN_COLLECT(c) IINS_LAUNCH(iins_pool_bwd_kernel, grid_for((long)B * s.P), 256, 0, st, d_xrec, pl.yt, dyt, B, s.P, s.Lc);
     int L = s.P, C = s.d;          // spatial size / channels at the decoder's output end
     float* dh = ga;
     float* tmp = gb;
@@ -656,7 +712,7 @@ int decoder_backward(const Shapes& s, const float* const* P, const float* rc, co
     // MLP backward
     {
         IinsGeom g3 = linear_geom(B, 256, s.n_adain), g2 = linear_geom(B, 256, 256), g1 = linear_geom(B, s.E, 256);
-        if (s.nres == 0) cudaMemsetAsync(dadain, 0, (size_t)B * s.n_adain * sizeof(float), st);
+        if (s.nres == 0 && c.phase != 1) cudaMemsetAsync(dadain, 0, (size_t)B * s.n_adain * sizeof(float), st);
         conv_wgrad(c, g3, pl.m2, plain_dz(dadain), G[ix.mlp + 4], G[ix.mlp + 5]);
         conv_dgrad(c, g3, plain_dz(dadain), P[ix.mlp + 4], dm2, nullptr);
         IinsDz z2 = act_dz(dm2, pl.m2, IINS_ACT_RELU, 0.f);
@@ -666,6 +722,7 @@ int decoder_backward(const Shapes& s, const float* const* P, const float* rc, co
         conv_wgrad(c, g1, cat, z1, G[ix.mlp], G[ix.mlp + 1]);
         if (d_cat != nullptr) conv_dgrad(c, g1, z1, P[ix.mlp], d_cat, accumulate ? d_cat : nullptr);
     }
+    });
     if (c.err) return fail(IINS_ERR_BAD_CONFIG, "decoder_backward: packed weight tile exceeds the scratch");
     return check_cuda("decoder_backward");
 }
@@ -703,6 +760,7 @@ int mlp_forward(const Shapes& s, const MlpSpec& m, const float* const* P, const 
                 float* wpack, cudaStream_t st) {
     Ctx c{st};
     c.wpack = wpack;
+    run_phases(c, [&]() {
     Bump b{ws, 0};
     const float* h = in;
     for (int i = 0; i < m.n; ++i) {
@@ -711,6 +769,7 @@ int mlp_forward(const Shapes& s, const MlpSpec& m, const float* const* P, const 
         conv_forward(c, linear_geom(s.B, m.dims[i], m.dims[i + 1]), h, P[2 * i], plain_epilogue(P[2 * i + 1], act, m.slopes[i], y));
         h = y;
     }
+    });
     if (c.err) return fail(IINS_ERR_BAD_CONFIG, "mlp_forward: packed weight tile exceeds the scratch");
     return check_cuda("mlp_forward");
 }
@@ -727,6 +786,7 @@ int mlp_backward(const Shapes& s, const MlpSpec& m, const float* const* P, const
     size_t half = (mlp_scratch(s, m) - IINS_WPACK_FLOATS) / 2;
     float* bufs[2] = {scratch, scratch + half};
     c.wpack = scratch + 2 * half;
+    run_phases(c, [&]() {
     const float* dy = d_out;
     for (int i = m.n - 1; i >= 0; --i) {
         IinsGeom g = linear_geom(s.B, m.dims[i], m.dims[i + 1]);
@@ -740,6 +800,7 @@ int mlp_backward(const Shapes& s, const MlpSpec& m, const float* const* P, const
             conv_dgrad(c, g, dz, P[0], d_in, accumulate ? d_in : nullptr);
         }
     }
+    });
     if (c.err) return fail(IINS_ERR_BAD_CONFIG, "mlp_backward: packed weight tile exceeds the scratch");
     return check_cuda("mlp_backward");
 }

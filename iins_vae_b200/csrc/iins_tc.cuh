@@ -171,6 +171,54 @@ __global__ void __launch_bounds__(256) iins_pack_kernel(const IinsPackParams p) 
     }
 }
 
+// All layers of one module pass packed by ONE launch: a table of jobs in the kernel parameters.
+#define IINS_PACK_MAX_JOBS 48
+struct IinsPackJob {
+    const float* w;
+    uint16_t* out;
+    int Cin, Cout, ks, kind, N, K, NT, nkb, nblk;
+    long chunk_begin;            // prefix sum of 16-byte destination chunks
+};
+struct IinsPackAllParams {
+    int njobs, pieces;
+    long total;
+    IinsPackJob jobs[IINS_PACK_MAX_JOBS];
+};
+
+__global__ void __launch_bounds__(256) iins_pack_all_kernel(const IinsPackAllParams pp) {
+    int j = 0;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < pp.total; e += (long)gridDim.x * blockDim.x) {
+        while (j + 1 < pp.njobs && e >= pp.jobs[j + 1].chunk_begin) ++j;
+        const IinsPackJob& q = pp.jobs[j];
+        const long le = e - q.chunk_begin;
+        const int Cdim = q.kind == 0 ? q.Cin : q.Cout;
+        int nn = (int)(le % q.NT);
+        long r = le / q.NT;
+        int chunk = (int)(r & 3);
+        r >>= 2;
+        int kb = (int)(r % q.nkb), nb = (int)(r / q.nkb);
+        int n = nb * q.NT + nn;
+        int k0 = kb * 32 + chunk * 8;
+        float v[8];
+        int t = k0 / Cdim, c = k0 - t * Cdim;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float x = 0.f;
+            if (n < q.N && k0 + i < q.K) {
+                long wi = q.kind == 0 ? ((long)n * q.Cin + c) * q.ks + t : ((long)c * q.Cin + n) * q.ks + t;
+                x = __ldg(q.w + wi);
+            }
+            v[i] = x;
+            if (++c == Cdim) { c = 0; ++t; }
+        }
+        const uint32_t piece_stride = (uint32_t)q.NT * 16u;
+        const long tile_bytes = 4L * pp.pieces * q.NT * 16;
+        unsigned char* base = reinterpret_cast<unsigned char*>(q.out) + (long)(nb * q.nkb + kb) * tile_bytes +
+                              ((long)chunk * pp.pieces * q.NT + nn) * 16;
+        iins_store8_split(v, base, piece_stride, pp.pieces);
+    }
+}
+
 // Issue the MMAs of one k-step (K = 16) for the bf16x3 scheme with the B pieces stacked along N:
 //   D[:, 0:3N) += A0 * [B0|B1|B2],  D[:, 0:2N) += A1 * [B0|B1],  D[:, 0:N) += A2 * B0
 // so the six significant piece products take 3 instructions; the epilogue adds the three N-wide column blocks.
