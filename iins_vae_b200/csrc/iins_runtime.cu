@@ -35,6 +35,7 @@ struct Ctx {
     int phase = 0;              // 0 = pack inline per layer, 1 = collect, 2 = execute with pre-packed tiles
     int njobs = 0, job_i = 0;
     size_t arena = 0;           // bytes of the arena handed out so far
+    cudaStream_t st2 = nullptr; // side stream: weight gradients run here, concurrently with the dgrad chain
 #ifndef IINS_CPUSIM
     IinsPackAllParams jobs;
 #endif
@@ -190,19 +191,51 @@ void conv_dgrad(Ctx& c, const IinsGeom& g, const IinsDz& dz, const float* w, flo
     launch_nt(c, p);
 }
 
+// ---- side stream for the weight gradients --------------------------------------------------------------
+// dgrad(l) -> norm_bwd(l-1) -> dgrad(l-1) ... is a dependent chain of small kernels that each fill the machine
+// for one wave at best; wgrad(l) only needs dz(l) and the saved activations, so it runs on a second stream
+// (forked / joined with events, which CUDA-graph capture turns into parallel branches).  Every gradient
+// buffer of a backward pass is written exactly once (fresh scratch per layer), so there is no WAR hazard.
+#ifndef IINS_CPUSIM
+int g_async_wgrad = -1;
+cudaStream_t g_side_stream = nullptr;
+cudaEvent_t g_fork_events[64];
+int g_fork_i = 0;
+
+cudaStream_t side_stream() {
+    if (g_async_wgrad < 0) { const char* e = getenv("IINS_ASYNC_WGRAD"); g_async_wgrad = e ? atoi(e) : 0; }   // opt-in: pays off only once the GEMM kernels leave SM room
+    if (!g_async_wgrad) return nullptr;
+    if (g_side_stream == nullptr) {
+        if (cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking) != cudaSuccess) { g_async_wgrad = 0; return nullptr; }
+        for (int i = 0; i < 64; ++i) cudaEventCreateWithFlags(&g_fork_events[i], cudaEventDisableTiming);
+    }
+    return g_side_stream;
+}
+void fork_to(cudaStream_t from, cudaStream_t to) {
+    cudaEvent_t e = g_fork_events[g_fork_i++ & 63];
+    cudaEventRecord(e, from);
+    cudaStreamWaitEvent(to, e, 0);
+}
+#else
+cudaStream_t side_stream() { return nullptr; }
+void fork_to(cudaStream_t, cudaStream_t) {}
+#endif
+void begin_async_wgrad(Ctx& c) { if (c.phase != 1) c.st2 = side_stream(); }
+void end_async_wgrad(Ctx& c) { if (c.phase != 1 && c.st2 != nullptr) { fork_to(c.st2, c.st); c.st2 = nullptr; } }
+
 #ifndef IINS_CPUSIM
 template <int NT, int PIECES>
-void launch_tc_tn_tp(Ctx& c, const IinsTCTNParams& tp, dim3 grid) {
+void launch_tc_tn_tp(cudaStream_t st, const IinsTCTNParams& tp, dim3 grid) {
     constexpr int smem = 2 * (3 * 8192 + 3 * (NT / 8) * 32 * 16);
     static bool attr = false;
     auto iins_tc_tn_kernel_ = iins_tc_tn_kernel<NT, PIECES>;
     if (!attr) { cudaFuncSetAttribute(iins_tc_tn_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    IINS_LAUNCH(iins_tc_tn_kernel_, grid, 256, smem, c.st, tp);
+    IINS_LAUNCH(iins_tc_tn_kernel_, grid, 256, smem, st, tp);
 }
 template <int NT>
-void launch_tc_tn_t(Ctx& c, const IinsTCTNParams& tp, dim3 grid) {
-    if (tp.pieces == 3) launch_tc_tn_tp<NT, 3>(c, tp, grid);
-    else launch_tc_tn_tp<NT, 1>(c, tp, grid);
+void launch_tc_tn_t(cudaStream_t st, const IinsTCTNParams& tp, dim3 grid) {
+    if (tp.pieces == 3) launch_tc_tn_tp<NT, 3>(st, tp, grid);
+    else launch_tc_tn_tp<NT, 1>(st, tp, grid);
 }
 #endif
 
@@ -211,6 +244,8 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
     memset(&p, 0, sizeof(p));
     p.g = g; p.x = x; p.dz = dz; p.dw = dw; p.db = db;
     if (c.phase == 1) return;
+    cudaStream_t wst = c.st;
+    if (c.st2 != nullptr) { fork_to(c.st, c.st2); wst = c.st2; }
     p.M = g.B * g.Lout;
     int K = g.ks * g.Cin;
     if (g.Cout <= 16 && K <= 64) {                    // small-channel layer
@@ -224,7 +259,7 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
         p.rows_per_part = (int)rpp;
         rp.tn = p;
         IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K); IINS_SET_SHAPE(p.M, g.Cout, K);
-        IINS_LAUNCH(iins_row_tn_kernel, (int)((p.M + rpp - 1) / rpp), 256, 0, c.st, rp);
+        IINS_LAUNCH(iins_row_tn_kernel, (int)((p.M + rpp - 1) / rpp), 256, 0, wst, rp);
         return;
     }
 #ifndef IINS_CPUSIM
@@ -248,9 +283,9 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
         if (tp.lshift < 0) { c.err = 2; return; }
         dim3 grid(parts, ky, nz);
         IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K); IINS_SET_SHAPE(p.M, g.Cout, K);
-        if (nt == 16) launch_tc_tn_t<16>(c, tp, grid);
-        else if (nt == 32) launch_tc_tn_t<32>(c, tp, grid);
-        else launch_tc_tn_t<64>(c, tp, grid);
+        if (nt == 16) launch_tc_tn_t<16>(wst, tp, grid);
+        else if (nt == 32) launch_tc_tn_t<32>(wst, tp, grid);
+        else launch_tc_tn_t<64>(wst, tp, grid);
         return;
     }
 #endif
@@ -265,7 +300,7 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
     int parts = (int)((p.M + rpp - 1) / rpp);
     p.rows_per_part = (int)rpp;
     IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K); IINS_SET_SHAPE(p.M, g.Cout, K);
-    IINS_LAUNCH(iins_tn_kernel, dim3(parts, ky, nz), 256, 0, c.st, p);
+    IINS_LAUNCH(iins_tn_kernel, dim3(parts, ky, nz), 256, 0, wst, p);
 }
 
 void norm_backward(Ctx& c, int B, int L, int C, int norm, int act, const float* dy, const float* xhat,
@@ -449,7 +484,8 @@ size_t encoder_scratch(const Shapes& s) {
     size_t B = s.B;
     size_t act = (size_t)128 * 4 * s.d;                 // largest activation per sample (env stem: 128 x 4d)
     if ((size_t)s.Lt * s.D > act) act = (size_t)s.Lt * s.D;
-    return 3 * (B * act + 4) + B * (16 * (size_t)s.d + 4) + B * ((size_t)s.E + 4) + IINS_WPACK_FLOATS;
+    size_t n_fresh = 4 + 2 + 4 * (size_t)s.nres + 2 * (size_t)s.ndown + 2;      // one buffer per gradient tensor
+    return n_fresh * (B * act + 4) + B * (16 * (size_t)s.d + 4) + B * ((size_t)s.E + 4) + IINS_WPACK_FLOATS;
 }
 
 int encoder_backward(const Shapes& s, const float* const* P, const float* noise, uint64_t seed, uint64_t offset,
@@ -462,15 +498,17 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
     size_t act = (size_t)128 * 4 * s.d;
     if ((size_t)s.Lt * s.D > act) act = (size_t)s.Lt * s.D;
     Bump b{scratch, 0};
-    float* ga = b.take((size_t)B * act);
-    float* gb = b.take((size_t)B * act);
-    float* dzb = b.take((size_t)B * act);
     float* dpooled = b.take((size_t)B * 16 * s.d);
     float* dcat = b.take((size_t)B * s.E);
     c.wpack = b.take(IINS_WPACK_FLOATS);
+    const size_t fresh_base = b.off;
     const int n_range = 2 * (1 + s.ndown + 2 * s.nres + 1);
 
     run_phases(c, [&]() {
+    Bump fb{scratch, fresh_base};
+    auto fresh = [&]() { return fb.take((size_t)B * act); };      // every gradient tensor gets its own buffer
+    float* dzb = nullptr;
+    begin_async_wgrad(c);
     // ---------------- env branch
     if (d_cat != nullptr || d_lat != nullptr || d_kl != nullptr) {
         IINS_SKIP_IN_COLLECT(c) IINS_LAUNCH(iins_reparam_kl_bwd_kernel, grid_for((long)B * s.E / 2), 256, 0, st, cat, noise, d_cat, d_lat, d_kl,
@@ -485,8 +523,6 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
         int bcast = 1;
         float scale = 1.0f / (float)eL;
         int C = eC, L = eL;
-        float* bufs[2] = {ga, gb};
-        int flip = 0;
         for (int i = pl.n_env - 1; i >= 1; --i) {
             pi -= 2;
             int ic = i <= 2 ? C / 2 : C;
@@ -494,8 +530,9 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
             IinsDz dz = act_dz(dy, pl.e_y[i], IINS_ACT_RELU, 0.f);
             dz.dy_bcast = bcast; dz.dy_scale = scale;
             conv_wgrad(c, g, pl.e_y[i - 1], dz, G[pi], G[pi + 1]);
-            conv_dgrad(c, g, dz, P[pi], bufs[flip], nullptr);
-            dy = bufs[flip]; flip ^= 1; bcast = 0; scale = 1.f;
+            float* dprev = fresh();
+            conv_dgrad(c, g, dz, P[pi], dprev, nullptr);
+            dy = dprev; bcast = 0; scale = 1.f;
             C = ic; L *= 2;
         }
         pi -= 2;
@@ -514,42 +551,50 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
         go.out_layout = IINS_NCL;
         IinsDz dzo = act_dz(d_rc, rc, IINS_ACT_RELU, 0.f);
         conv_wgrad(c, go, h_last, dzo, G[pi], G[pi + 1]);
-        float* dh = ga;          // gradient w.r.t. the trunk activation h
-        float* tmp = gb;
+        float* dh = fresh();     // gradient w.r.t. the trunk activation h
+        float* tmp = nullptr;
         conv_dgrad(c, go, dzo, P[pi], dh, nullptr);
         IinsGeom gr = conv_geom(B, L, L, C, C, 3, 1, 1, IINS_PAD_REFLECT);
         for (int i = s.nres - 1; i >= 0; --i) {
             pi -= 4;
             const float* h_in = i > 0 ? pl.res2[i - 1].y : pl.down[s.ndown - 1].y;
             // second conv of the block: out = h_in + IN(conv2(t))
+            dzb = fresh();
             norm_backward(c, B, L, C, IINS_NORM_IN, IINS_ACT_NONE, dh, pl.res2[i].xhat, pl.res2[i].rstd,
                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, dzb);
             conv_wgrad(c, gr, pl.res1[i].y, plain_dz(dzb), G[pi + 2], G[pi + 3]);
+            tmp = fresh();
             conv_dgrad(c, gr, plain_dz(dzb), P[pi + 2], tmp, nullptr);
             // first conv: t = relu(IN(conv1(h_in)))
+            dzb = fresh();
             norm_backward(c, B, L, C, IINS_NORM_IN, IINS_ACT_RELU, tmp, pl.res1[i].xhat, pl.res1[i].rstd,
                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, dzb);
             conv_wgrad(c, gr, h_in, plain_dz(dzb), G[pi], G[pi + 1]);
+            tmp = fresh();
             conv_dgrad(c, gr, plain_dz(dzb), P[pi], tmp, dh);       // + skip gradient
-            float* sw = dh; dh = tmp; tmp = sw;
+            dh = tmp;
         }
         for (int i = s.ndown - 1; i >= 0; --i) {
             pi -= 2;
             const float* h_in = i > 0 ? pl.down[i - 1].y : pl.stem.y;
             IinsGeom g = conv_geom(B, 2 * L, L, C / 2, C, 4, 2, 1, IINS_PAD_ZERO);
+            dzb = fresh();
             norm_backward(c, B, L, C, IINS_NORM_IN, IINS_ACT_RELU, dh, pl.down[i].xhat, pl.down[i].rstd,
                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, dzb);
             conv_wgrad(c, g, h_in, plain_dz(dzb), G[pi], G[pi + 1]);
+            tmp = fresh();
             conv_dgrad(c, g, plain_dz(dzb), P[pi], tmp, nullptr);
-            float* sw = dh; dh = tmp; tmp = sw;
+            dh = tmp;
             L *= 2; C /= 2;
         }
         pi -= 2;
         IinsGeom g0 = conv_geom(B, s.P, s.P, 1, s.d, 7, 1, 3, IINS_PAD_REFLECT);
+        dzb = fresh();
         norm_backward(c, B, s.P, s.d, IINS_NORM_IN, IINS_ACT_RELU, dh, pl.stem.xhat, pl.stem.rstd,
                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, dzb);
         conv_wgrad(c, g0, pl.xp, plain_dz(dzb), G[pi], G[pi + 1]);
     }
+    end_async_wgrad(c);
     });
     if (c.err) return fail(IINS_ERR_BAD_CONFIG, "encoder_backward: packed weight tile exceeds the scratch");
     return check_cuda("encoder_backward");
@@ -642,7 +687,8 @@ int decoder_forward(const Shapes& s, const float* const* P, const float* rc, con
 size_t decoder_scratch(const Shapes& s) {
     size_t B = s.B;
     size_t act = (size_t)s.Lt * s.D;
-    return 3 * (B * act + 4) + B * ((size_t)s.n_adain + 4) + 2 * (B * 256 + 4) + B * ((size_t)s.P + 4) + IINS_WPACK_FLOATS;
+    size_t n_fresh = 2 + 2 * (size_t)s.ndown + 4 * (size_t)s.nres + 2;
+    return n_fresh * (B * act + 4) + B * ((size_t)s.n_adain + 4) + 2 * (B * 256 + 4) + B * ((size_t)s.P + 4) + IINS_WPACK_FLOATS;
 }
 
 int decoder_backward(const Shapes& s, const float* const* P, const float* rc, const float* cat, const float* ws,
@@ -655,21 +701,23 @@ int decoder_backward(const Shapes& s, const float* const* P, const float* rc, co
     const int B = s.B;
     size_t act = (size_t)s.Lt * s.D;
     Bump b{scratch, 0};
-    float* ga = b.take((size_t)B * act);
-    float* gb = b.take((size_t)B * act);
-    float* dzb = b.take((size_t)B * act);
     float* dadain = b.take((size_t)B * s.n_adain);
     float* dm2 = b.take((size_t)B * 256);
     float* dm1 = b.take((size_t)B * 256);
     float* dyt = b.take((size_t)B * s.P);
     c.wpack = b.take(IINS_WPACK_FLOATS);
+    const size_t fresh_base = b.off;
 
     run_phases(c, [&]() {
+    Bump fb{scratch, fresh_base};
+    auto fresh = [&]() { return fb.take((size_t)B * act); };
+    float* dzb = nullptr;
+    begin_async_wgrad(c);
     // pool(128 -> cir_len) backward fused with tanh'
     IINS_SKIP_IN_COLLECT(c) IINS_LAUNCH(iins_pool_bwd_kernel, grid_for((long)B * s.P), 256, 0, st, d_xrec, pl.yt, dyt, B, s.P, s.Lc);
     int L = s.P, C = s.d;          // spatial size / channels at the decoder's output end
-    float* dh = ga;
-    float* tmp = gb;
+    float* dh = fresh();
+    float* tmp = nullptr;
     {
         IinsGeom g = conv_geom(B, L, L, C, 1, 7, 1, 3, IINS_PAD_REFLECT);
         const float* h_in = pl.up[s.ndown - 1].y;
@@ -680,11 +728,13 @@ int decoder_backward(const Shapes& s, const float* const* P, const float* rc, co
         int pi = ix.up0 + 4 * i;
         const float* h_in = i > 0 ? pl.up[i - 1].y : (s.nres > 0 ? pl.res2[s.nres - 1].y : pl.d0);
         IinsGeom g = conv_geom(B, L / 2, L, 2 * C, C, 5, 1, 2, IINS_PAD_UP2);
+        dzb = fresh();
         norm_backward(c, B, L, C, IINS_NORM_LN, IINS_ACT_RELU, dh, pl.up[i].xhat, pl.up[i].rstd, P[pi + 2], P[pi + 3],
                       G[pi + 2], G[pi + 3], nullptr, nullptr, 0, 0, 0, dzb);
         conv_wgrad(c, g, h_in, plain_dz(dzb), G[pi], G[pi + 1]);
+        tmp = fresh();
         conv_dgrad(c, g, plain_dz(dzb), P[pi], tmp, nullptr);
-        float* sw = dh; dh = tmp; tmp = sw;
+        dh = tmp;
         L /= 2; C *= 2;
     }
     IinsGeom gr = conv_geom(B, s.Lt, s.Lt, s.D, s.D, 3, 1, 1, IINS_PAD_REFLECT);
@@ -692,15 +742,19 @@ int decoder_backward(const Shapes& s, const float* const* P, const float* rc, co
         int pi = ix.res0 + 4 * i;
         int off = 4 * s.D * i;
         const float* h_in = i > 0 ? pl.res2[i - 1].y : pl.d0;
+        dzb = fresh();
         norm_backward(c, B, s.Lt, s.D, IINS_NORM_ADAIN, IINS_ACT_NONE, dh, pl.res2[i].xhat, pl.res2[i].rstd, nullptr, nullptr,
                       nullptr, nullptr, pl.adain, dadain, s.n_adain, off + 2 * s.D, off + 3 * s.D, dzb);
         conv_wgrad(c, gr, pl.res1[i].y, plain_dz(dzb), G[pi + 2], G[pi + 3]);
+        tmp = fresh();
         conv_dgrad(c, gr, plain_dz(dzb), P[pi + 2], tmp, nullptr);
+        dzb = fresh();
         norm_backward(c, B, s.Lt, s.D, IINS_NORM_ADAIN, IINS_ACT_RELU, tmp, pl.res1[i].xhat, pl.res1[i].rstd, nullptr, nullptr,
                       nullptr, nullptr, pl.adain, dadain, s.n_adain, off, off + s.D, dzb);
         conv_wgrad(c, gr, h_in, plain_dz(dzb), G[pi], G[pi + 1]);
+        tmp = fresh();
         conv_dgrad(c, gr, plain_dz(dzb), P[pi], tmp, dh);
-        float* sw = dh; dh = tmp; tmp = sw;
+        dh = tmp;
     }
     {
         IinsGeom g = conv_geom(B, s.Lt, s.Lt, s.R, s.D, 1, 1, 0, IINS_PAD_ZERO);
@@ -722,6 +776,7 @@ int decoder_backward(const Shapes& s, const float* const* P, const float* rc, co
         conv_wgrad(c, g1, cat, z1, G[ix.mlp], G[ix.mlp + 1]);
         if (d_cat != nullptr) conv_dgrad(c, g1, z1, P[ix.mlp], d_cat, accumulate ? d_cat : nullptr);
     }
+    end_async_wgrad(c);
     });
     if (c.err) return fail(IINS_ERR_BAD_CONFIG, "decoder_backward: packed weight tile exceeds the scratch");
     return check_cuda("decoder_backward");
@@ -753,7 +808,7 @@ size_t mlp_act_floats(const Shapes& s, const MlpSpec& m) { return mlp_ws(s, m); 
 size_t mlp_scratch(const Shapes& s, const MlpSpec& m) {
     size_t mx = 0;
     for (int i = 1; i < m.n; ++i) if ((size_t)m.dims[i] > mx) mx = m.dims[i];
-    return 2 * (((size_t)s.B * mx + 3) & ~(size_t)3) + IINS_WPACK_FLOATS;
+    return 4 * (((size_t)s.B * mx + 3) & ~(size_t)3) + IINS_WPACK_FLOATS;
 }
 
 int mlp_forward(const Shapes& s, const MlpSpec& m, const float* const* P, const float* in, float* out, float* ws,
@@ -783,23 +838,25 @@ int mlp_backward(const Shapes& s, const MlpSpec& m, const float* const* P, const
     acts[0] = in;
     for (int i = 1; i < m.n; ++i) acts[i] = b.take((size_t)s.B * m.dims[i]);
     acts[m.n] = out_saved;
-    size_t half = (mlp_scratch(s, m) - IINS_WPACK_FLOATS) / 2;
-    float* bufs[2] = {scratch, scratch + half};
-    c.wpack = scratch + 2 * half;
+    size_t quarter = (mlp_scratch(s, m) - IINS_WPACK_FLOATS) / 4;
+    float* bufs[4] = {scratch, scratch + quarter, scratch + 2 * quarter, scratch + 3 * quarter};   // one per layer (n <= 4)
+    c.wpack = scratch + 4 * quarter;
     run_phases(c, [&]() {
+    begin_async_wgrad(c);
     const float* dy = d_out;
     for (int i = m.n - 1; i >= 0; --i) {
         IinsGeom g = linear_geom(s.B, m.dims[i], m.dims[i + 1]);
         IinsDz dz = m.slopes[i] < 0.f ? plain_dz(dy) : act_dz(dy, acts[i + 1], IINS_ACT_LRELU, m.slopes[i]);
         conv_wgrad(c, g, acts[i], dz, G[2 * i], G[2 * i + 1]);
         if (i > 0) {
-            float* dx = bufs[i & 1];
+            float* dx = bufs[i & 3];
             conv_dgrad(c, g, dz, P[2 * i], dx, nullptr);
             dy = dx;
         } else if (d_in != nullptr) {
             conv_dgrad(c, g, dz, P[0], d_in, accumulate ? d_in : nullptr);
         }
     }
+    end_async_wgrad(c);
     });
     if (c.err) return fail(IINS_ERR_BAD_CONFIG, "mlp_backward: packed weight tile exceeds the scratch");
     return check_cuda("mlp_backward");
