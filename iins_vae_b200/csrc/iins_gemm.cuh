@@ -42,7 +42,17 @@ struct IinsNTParams {
 // Norm / activation / residual / store on one SMEM-staged tile Cs[128][LD] (bias already added).
 // st_mean / st_rstd: scratch for the statistics (>= 1024 floats each).  Called by every thread of a
 // 256-thread CTA; contains __syncthreads().
-template <int BN, int LD>
+// 256-thread barrier used inside the epilogue: the whole CTA for the SIMT kernels; named barrier 1 for the
+// warp-specialised tensor-core kernels (their 9th warp, the MMA issuer, does not take part in the epilogue)
+template <bool NAMED>
+__device__ __forceinline__ void iins_epi_sync() {
+#ifndef IINS_CPUSIM
+    if (NAMED) { asm volatile("bar.sync 1, 256;" ::: "memory"); return; }
+#endif
+    __syncthreads();
+}
+
+template <int BN, int LD, bool NAMED = false>
 __device__ __forceinline__ void iins_epilogue_tile(const IinsNTParams& p, const float* Cs, float* st_mean, float* st_rstd,
                                                    int tile_m, int n0) {
     constexpr int BM = 128;
@@ -79,7 +89,7 @@ __device__ __forceinline__ void iins_epilogue_tile(const IinsNTParams& p, const 
                 if (b < g.B && ep.rstd != nullptr) ep.rstd[(long)b * p.N + n0 + c] = rs;
             }
         }
-        __syncthreads();
+        iins_epi_sync<NAMED>();
     } else if (ep.norm == IINS_NORM_LN) {
         // per-sample mean and UNBIASED std over (C*L), eps added to std (models.py:976-981)
         const int warp = tid >> 5, lane = tid & 31;
@@ -102,7 +112,7 @@ __device__ __forceinline__ void iins_epilogue_tile(const IinsNTParams& p, const 
                 if (b < g.B && ep.rstd != nullptr) ep.rstd[b] = rs;
             }
         }
-        __syncthreads();
+        iins_epi_sync<NAMED>();
     }
 
     // ---- apply + store (coalesced over the contiguous NLC tile)
@@ -128,6 +138,10 @@ __device__ __forceinline__ void iins_epilogue_tile(const IinsNTParams& p, const 
             if (gr >= p.M) break;
             const int s = r >> lsh, b = gr >> lsh, l = gr & (L - 1);
             float v[4], xh[4];
+            // residual / accumulate operand first (read-only path: the load may be hoisted over the stores of the
+            // previous rows; every element is read before the same thread overwrites it when add == y)
+            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vec && ep.add != nullptr) a4 = __ldg(reinterpret_cast<const float4*>(ep.add + (long)gr * p.N + gn));
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = Cs[r * LD + n + j];
             if (ep.norm == IINS_NORM_IN || ep.norm == IINS_NORM_ADAIN) {
@@ -156,10 +170,7 @@ __device__ __forceinline__ void iins_epilogue_tile(const IinsNTParams& p, const 
                 const long oi = (long)gr * p.N + gn;
                 if (ep.norm != IINS_NORM_NONE && ep.xhat != nullptr)
                     *reinterpret_cast<float4*>(ep.xhat + oi) = make_float4(xh[0], xh[1], xh[2], xh[3]);
-                if (ep.add != nullptr) {
-                    const float4 a4 = *reinterpret_cast<const float4*>(ep.add + oi);
-                    v[0] += a4.x; v[1] += a4.y; v[2] += a4.z; v[3] += a4.w;
-                }
+                v[0] += a4.x; v[1] += a4.y; v[2] += a4.z; v[3] += a4.w;
                 *reinterpret_cast<float4*>(ep.y + oi) = make_float4(v[0], v[1], v[2], v[3]);
             } else {
 #pragma unroll

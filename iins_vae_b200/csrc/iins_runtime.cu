@@ -107,7 +107,7 @@ void launch_tc_nt_tp(Ctx& c, const IinsTCParams& tp, dim3 grid) {
     static bool attr = false;
     auto iins_tc_nt_kernel_ = iins_tc_nt_kernel<NT, PIECES>;
     if (!attr) { cudaFuncSetAttribute(iins_tc_nt_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    IINS_LAUNCH(iins_tc_nt_kernel_, grid, 256, smem, c.st, tp);
+    IINS_LAUNCH(iins_tc_nt_kernel_, grid, 288, smem, c.st, tp);
 }
 template <int NT>
 void launch_tc_nt_t(Ctx& c, const IinsTCParams& tp, dim3 grid) {
@@ -230,7 +230,7 @@ void launch_tc_tn_tp(cudaStream_t st, const IinsTCTNParams& tp, dim3 grid) {
     static bool attr = false;
     auto iins_tc_tn_kernel_ = iins_tc_tn_kernel<NT, PIECES>;
     if (!attr) { cudaFuncSetAttribute(iins_tc_tn_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    IINS_LAUNCH(iins_tc_tn_kernel_, grid, 256, smem, st, tp);
+    IINS_LAUNCH(iins_tc_tn_kernel_, grid, 288, smem, st, tp);
 }
 template <int NT>
 void launch_tc_tn_t(cudaStream_t st, const IinsTCTNParams& tp, dim3 grid) {

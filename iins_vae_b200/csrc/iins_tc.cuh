@@ -267,8 +267,14 @@ struct IinsTCParams {
     long long* timeline; // debug: (tag, clock64) pairs of CTA (0,0) thread 0, or nullptr
 };
 
+// 288 threads: warps 0-7 are PRODUCERS (gather / split / store the A tile, later the epilogue), warp 8 is the
+// MMA warp (TMA for the weight tile, tcgen05.mma issue, commit).  Hand-off through mbarriers only -- there is no
+// CTA-wide barrier inside the K loop:
+//   full[s]   (count 256)  producers -> MMA warp : stage s holds the A tile of this K block
+//   bready[s] (tx bytes)   TMA       -> MMA warp : stage s holds the weight tile
+//   done[s]   (tcgen05.commit) MMA   -> everyone : the MMAs reading stage s have completed (stage reusable)
 template <int NT, int PIECES>
-__global__ void __launch_bounds__(256) iins_tc_nt_kernel(const IinsTCParams tp) {
+__global__ void __launch_bounds__(288) iins_tc_nt_kernel(const IinsTCParams tp) {
     constexpr int BM = 128;
     constexpr uint32_t A_PIECE = 4 * BM * 16;            // 8192 B : [chunk][row][16 B]
     constexpr uint32_t B_TILE = 4 * PIECES * NT * 16;    // [chunk][piece * NT + n][16 B]
@@ -276,8 +282,9 @@ __global__ void __launch_bounds__(256) iins_tc_nt_kernel(const IinsTCParams tp) 
     constexpr int TCOLS = IinsTmemCols<NT, PIECES>::value;
     constexpr int LD = NT + 1;
     extern __shared__ __align__(1024) unsigned char dsm[];
-    __shared__ __align__(8) unsigned long long mbar_mma[2];
+    __shared__ __align__(8) unsigned long long mbar_done[2];
     __shared__ __align__(8) unsigned long long mbar_b[2];
+    __shared__ __align__(8) unsigned long long mbar_full[2];
     __shared__ uint32_t tmem_slot;
     const IinsNTParams& p = tp.nt;
     const IinsGeom& g = p.g;
@@ -286,15 +293,17 @@ __global__ void __launch_bounds__(256) iins_tc_nt_kernel(const IinsTCParams tp) 
     float* Cs = reinterpret_cast<float*>(dsm);                         // aliases the stages after the MMAs
     float* st_mean = reinterpret_cast<float*>(dsm + 2 * STAGE);
     float* st_rstd = st_mean + 1024;
+    const int nkb = tp.nkb;
 
     if (tid == 0) {
-        umma::mbar_init(umma::smem_u32(&mbar_mma[0]), 1);
-        umma::mbar_init(umma::smem_u32(&mbar_mma[1]), 1);
-        umma::mbar_init(umma::smem_u32(&mbar_b[0]), 1);
-        umma::mbar_init(umma::smem_u32(&mbar_b[1]), 1);
+        for (int i = 0; i < 2; ++i) {
+            umma::mbar_init(umma::smem_u32(&mbar_done[i]), 1);
+            umma::mbar_init(umma::smem_u32(&mbar_b[i]), 1);
+            umma::mbar_init(umma::smem_u32(&mbar_full[i]), 256);
+        }
         umma::fence_mbar_init();
     }
-    if (warp == 0) umma::tmem_alloc(umma::smem_u32(&tmem_slot), TCOLS);
+    if (warp == 8) umma::tmem_alloc(umma::smem_u32(&tmem_slot), TCOLS);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
@@ -303,81 +312,84 @@ __global__ void __launch_bounds__(256) iins_tc_nt_kernel(const IinsTCParams tp) 
     int tl_n_ = 0;
     IINS_TL(0);
 
-    const int a_row = tid & 127, a_half = tid >> 7;
-    const int grow = tile_m + a_row;
-    const bool a_ok = grow < p.M;
-    const int a_b = a_ok ? grow >> p.lshift : 0;
-    const int a_l = a_ok ? grow & (p.Lrow - 1) : 0;
-    const int nkb = tp.nkb;
-    const int cs = p.cshift;
-    // 16-byte gathers need >= 8 channels (power of two) in channels-last order
-    const bool fast = cs >= 3 && (p.a_kind == 0 ? g.in_layout == IINS_NLC : g.out_layout == IINS_NLC);
-
-    float raw[2][8];
-    auto load_raw = [&](int kb) {
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-            const int k0 = kb * 32 + (a_half * 2 + jj) * 8;
-            if (!a_ok) iins_zero8(raw[jj]);
-            else if (fast) {
-                if (p.a_kind == 0) iins_gather8_fwd_fast(g, p.x, p.K, cs, a_b, a_l, k0, raw[jj]);
-                else iins_gather8_dgrad_fast(g, p.dz, p.K, cs, a_b, a_l, k0, raw[jj]);
-            } else {
-                float tmp[8];                          // address-taken copy: keeps raw[][] in registers
-                if (p.a_kind == 0) iins_gather8_fwd_generic(g, p.x, p.K, a_b, a_l, k0, tmp);
-                else iins_gather8_dgrad_generic(g, p.dz, p.K, a_b, a_l, k0, tmp);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) raw[jj][i] = tmp[i];
+    if (warp == 8) {
+        // ------------------------------------------------------------------ MMA warp (warp-uniform code)
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb & 1;
+            unsigned char* sA = dsm + s * STAGE;
+            unsigned char* sB = sA + 3 * A_PIECE;
+            if (kb >= 2) umma::mbar_wait(umma::smem_u32(&mbar_done[s]), (uint32_t)(((kb >> 1) - 1) & 1));
+            const bool leader = umma::elect_one();
+            if (leader) {
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(tp.wpack) + ((long)blockIdx.y * nkb + kb) * B_TILE;
+                umma::mbar_arrive_expect_tx(umma::smem_u32(&mbar_b[s]), B_TILE);
+                umma::tma_bulk_g2s(umma::smem_u32(sB), src, B_TILE, umma::smem_u32(&mbar_b[s]));
             }
-        }
-    };
-    load_raw(0);
-
-    for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb & 1;
-        unsigned char* sA = dsm + s * STAGE;
-        unsigned char* sB = sA + 3 * A_PIECE;
-        if (kb >= 2) umma::mbar_wait(umma::smem_u32(&mbar_mma[s]), (uint32_t)(((kb >> 1) - 1) & 1));
-        IINS_TL(1);
-        if (warp == 0 && umma::elect_one()) {
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(tp.wpack) +
-                                       ((long)blockIdx.y * nkb + kb) * B_TILE;
-            umma::mbar_arrive_expect_tx(umma::smem_u32(&mbar_b[s]), B_TILE);
-            umma::tma_bulk_g2s(umma::smem_u32(sB), src, B_TILE, umma::smem_u32(&mbar_b[s]));
-        }
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj)
-            iins_store8_split(raw[jj], sA + ((a_half * 2 + jj) * BM + a_row) * 16, A_PIECE, PIECES);
-        IINS_TL(2);
-        if (kb + 1 < nkb) load_raw(kb + 1);           // in flight across the barrier and the MMA issue
-        umma::fence_async_smem();
-        IINS_TL(3);
-        __syncthreads();
-        IINS_TL(4);
-        if (warp == 0) {                               // warp-uniform issue path
+            umma::mbar_wait(umma::smem_u32(&mbar_full[s]), (uint32_t)((kb >> 1) & 1));
             umma::mbar_wait(umma::smem_u32(&mbar_b[s]), (uint32_t)((kb >> 1) & 1));
             umma::tc_fence_after();
-            IINS_TL(5);
             // K-major, no swizzle: LBO = distance between 8-wide k chunks, SBO = 128 B between 8-row groups
             const uint64_t ad = umma::make_desc(umma::smem_u32(sA), BM * 16, 128);
             const uint64_t bd = umma::make_desc(umma::smem_u32(sB), PIECES * NT * 16, 128);
-            const bool leader = umma::elect_one();
             iins_issue_kstep<NT, PIECES, 0, 0>(tmem, ad, bd, A_PIECE >> 4, leader, kb > 0 ? 1u : 0u);
             iins_issue_kstep<NT, PIECES, 0, 0>(tmem, ad + ((2 * BM * 16) >> 4), bd + ((2 * PIECES * NT * 16) >> 4), A_PIECE >> 4,
                                                leader, 1u);
-            if (leader) umma::commit(umma::smem_u32(&mbar_mma[s]));
+            if (leader) umma::commit(umma::smem_u32(&mbar_done[s]));
             __syncwarp();
-            IINS_TL(6);
+        }
+    } else {
+        // ------------------------------------------------------------------ producers
+        const int a_row = tid & 127, a_half = tid >> 7;
+        const int grow = tile_m + a_row;
+        const bool a_ok = grow < p.M;
+        const int a_b = a_ok ? grow >> p.lshift : 0;
+        const int a_l = a_ok ? grow & (p.Lrow - 1) : 0;
+        const int cs = p.cshift;
+        // 16-byte gathers need >= 8 channels (power of two) in channels-last order
+        const bool fast = cs >= 3 && (p.a_kind == 0 ? g.in_layout == IINS_NLC : g.out_layout == IINS_NLC);
+        float raw[2][8];
+        auto load_raw = [&](int kb) {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int k0 = kb * 32 + (a_half * 2 + jj) * 8;
+                if (!a_ok) iins_zero8(raw[jj]);
+                else if (fast) {
+                    if (p.a_kind == 0) iins_gather8_fwd_fast(g, p.x, p.K, cs, a_b, a_l, k0, raw[jj]);
+                    else iins_gather8_dgrad_fast(g, p.dz, p.K, cs, a_b, a_l, k0, raw[jj]);
+                } else {
+                    float tmp[8];                          // address-taken copy: keeps raw[][] in registers
+                    if (p.a_kind == 0) iins_gather8_fwd_generic(g, p.x, p.K, a_b, a_l, k0, tmp);
+                    else iins_gather8_dgrad_generic(g, p.dz, p.K, a_b, a_l, k0, tmp);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) raw[jj][i] = tmp[i];
+                }
+            }
+        };
+        load_raw(0);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb & 1;
+            unsigned char* sA = dsm + s * STAGE;
+            if (kb >= 2) umma::mbar_wait(umma::smem_u32(&mbar_done[s]), (uint32_t)(((kb >> 1) - 1) & 1));
+            IINS_TL(1);
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+                iins_store8_split(raw[jj], sA + ((a_half * 2 + jj) * BM + a_row) * 16, A_PIECE, PIECES);
+            umma::fence_async_smem();
+            umma::mbar_arrive(umma::smem_u32(&mbar_full[s]));
+            IINS_TL(2);
+            if (kb + 1 < nkb) load_raw(kb + 1);           // in flight while the MMA warp works on this block
+            IINS_TL(3);
         }
     }
-    if (nkb >= 2) umma::mbar_wait(umma::smem_u32(&mbar_mma[(nkb - 2) & 1]), (uint32_t)(((nkb - 2) >> 1) & 1));
-    umma::mbar_wait(umma::smem_u32(&mbar_mma[(nkb - 1) & 1]), (uint32_t)(((nkb - 1) >> 1) & 1));
+    // every thread observes the completion of the last MMAs (also orders the smem reuse by the epilogue)
+    if (nkb >= 2) umma::mbar_wait(umma::smem_u32(&mbar_done[(nkb - 2) & 1]), (uint32_t)(((nkb - 2) >> 1) & 1));
+    umma::mbar_wait(umma::smem_u32(&mbar_done[(nkb - 1) & 1]), (uint32_t)(((nkb - 1) >> 1) & 1));
     umma::tc_fence_after();
     IINS_TL(13);
 
-    // ---- TMEM -> SMEM (+ bias).  Warp w owns TMEM lanes 32*(w&3) .. +31; with NT >= 32 the two warps sharing
-    // a lane quarter split the columns.
-    {
+    if (warp < 8) {
+        // ---- TMEM -> SMEM (+ bias).  Warp w owns TMEM lanes 32*(w&3) .. +31; with NT >= 32 the two warps
+        // sharing a lane quarter split the columns.
         constexpr int COLS_PER_WARP = NT >= 32 ? NT / 2 : NT;
         const int q = warp & 3, hf = warp >> 2;
         if (NT >= 32 || hf == 0) {
@@ -395,14 +407,15 @@ __global__ void __launch_bounds__(256) iins_tc_nt_kernel(const IinsTCParams tp) 
                 }
             }
         }
+        umma::tc_fence_before();
+        iins_epi_sync<true>();
+        IINS_TL(14);
+        iins_epilogue_tile<NT, LD, true>(p, Cs, st_mean, st_rstd, tile_m, n0);
+        IINS_TL(15);
     }
     umma::tc_fence_before();
     __syncthreads();
-    IINS_TL(14);
-    iins_epilogue_tile<NT, LD>(p, Cs, st_mean, st_rstd, tile_m, n0);
-    IINS_TL(15);
-    __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, TCOLS);
+    if (warp == 8) umma::tmem_dealloc(tmem, TCOLS);
 }
 
 // ------------------------------------------------------------------------------------------- weight grad
@@ -417,14 +430,15 @@ struct IinsTCTNParams {
 
 // grid = (row parts, ceil(K/128), ceil(Cout/NT)).  D^T[k][n] accumulated in TMEM (128 lanes = 128 k entries).
 template <int NT, int PIECES>
-__global__ void __launch_bounds__(256) iins_tc_tn_kernel(const IinsTCTNParams tp) {
+__global__ void __launch_bounds__(288) iins_tc_tn_kernel(const IinsTCTNParams tp) {
     constexpr int BR = 32;                               // rows per stage (2 MMA k-steps of 16)
     constexpr uint32_t A_PIECE = 16 * BR * 16;           // [k group of 8][row][16 B] = 8192 B
     constexpr uint32_t B_PIECE = (NT / 8) * BR * 16;     // [n group of 8][row][16 B]; pieces stacked = more n groups
     constexpr uint32_t STAGE = 3 * A_PIECE + 3 * B_PIECE;
     constexpr int TCOLS = IinsTmemCols<NT, PIECES>::value;
     extern __shared__ __align__(1024) unsigned char dsm[];
-    __shared__ __align__(8) unsigned long long mbar_mma[2];
+    __shared__ __align__(8) unsigned long long mbar_done[2];
+    __shared__ __align__(8) unsigned long long mbar_full[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_bias[64];
     const IinsTNParams& p = tp.tn;
@@ -434,76 +448,32 @@ __global__ void __launch_bounds__(256) iins_tc_tn_kernel(const IinsTCTNParams tp
     const int r_begin = blockIdx.x * p.rows_per_part;
     int r_end = r_begin + p.rows_per_part;
     if (r_end > p.M) r_end = p.M;
+    const int nit = (r_end - r_begin + BR - 1) / BR;
 
     if (tid == 0) {
-        umma::mbar_init(umma::smem_u32(&mbar_mma[0]), 1);
-        umma::mbar_init(umma::smem_u32(&mbar_mma[1]), 1);
+        for (int i = 0; i < 2; ++i) {
+            umma::mbar_init(umma::smem_u32(&mbar_done[i]), 1);
+            umma::mbar_init(umma::smem_u32(&mbar_full[i]), 256);
+        }
         umma::fence_mbar_init();
     }
     if (tid < 64) s_bias[tid] = 0.f;
-    if (warp == 0) umma::tmem_alloc(umma::smem_u32(&tmem_slot), TCOLS);
+    if (warp == 8) umma::tmem_alloc(umma::smem_u32(&tmem_slot), TCOLS);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const bool do_bias = p.db != nullptr && blockIdx.y == 0;
-    const bool fast_a = tp.cshift_in >= 3 && g.in_layout == IINS_NLC;
-    const bool fast_z = tp.cshift_out >= 3 && g.out_layout == IINS_NLC;
     const bool has_z = warp < NT / 8;
     float bsum[8];
     iins_zero8(bsum);
 
-    float rawa[2][8], rawz[8];
-    auto load_raw = [&](int it) {
-        const int row = r_begin + it * BR + lane;
-        const bool ok = row < r_end;
-        const int b = ok ? row >> tp.lshift : 0;
-        const int l = ok ? row & (g.Lout - 1) : 0;
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-            const int k0 = ktile0 + (warp + 8 * jj) * 8;
-            if (!ok) iins_zero8(rawa[jj]);
-            else if (fast_a) iins_gather8_fwd_fast(g, p.x, tp.K, tp.cshift_in, b, l, k0, rawa[jj]);
-            else {
-                float tmp[8];
-                iins_gather8_fwd_generic(g, p.x, tp.K, b, l, k0, tmp);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) rawa[jj][i] = tmp[i];
-            }
-        }
-        if (has_z) {
-            if (!ok) iins_zero8(rawz);
-            else if (fast_z) iins_dz8_fast(g, p.dz, tp.cshift_out, b, l, n0 + warp * 8, true, rawz);
-            else {
-                float tmp[8];
-                iins_dz8_generic(g, p.dz, b, l, n0 + warp * 8, tmp);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) rawz[i] = tmp[i];
-            }
-        }
-    };
-
-    const int nit = (r_end - r_begin + BR - 1) / BR;
-    if (nit > 0) load_raw(0);
-    for (int it = 0; it < nit; ++it) {
-        const int s = it & 1;
-        unsigned char* sA = dsm + s * STAGE;
-        unsigned char* sB = sA + 3 * A_PIECE;
-        if (it >= 2) umma::mbar_wait(umma::smem_u32(&mbar_mma[s]), (uint32_t)(((it >> 1) - 1) & 1));
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj)
-            iins_store8_split(rawa[jj], sA + ((warp + 8 * jj) * BR + lane) * 16, A_PIECE, PIECES);
-        if (has_z) {
-            if (do_bias) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) bsum[i] += rawz[i];
-            }
-            iins_store8_split(rawz, sB + (warp * BR + lane) * 16, B_PIECE, PIECES);
-        }
-        if (it + 1 < nit) load_raw(it + 1);
-        umma::fence_async_smem();
-        __syncthreads();
-        if (warp == 0) {
+    if (warp == 8) {
+        for (int it = 0; it < nit; ++it) {
+            const int s = it & 1;
+            unsigned char* sA = dsm + s * STAGE;
+            unsigned char* sB = sA + 3 * A_PIECE;
+            umma::mbar_wait(umma::smem_u32(&mbar_full[s]), (uint32_t)((it >> 1) & 1));
             umma::tc_fence_after();
             // MN-major: LBO = distance between 8-row groups (128 B), SBO = distance between MN groups of 8
             const uint64_t ad = umma::make_desc(umma::smem_u32(sA), 128, BR * 16);
@@ -511,15 +481,67 @@ __global__ void __launch_bounds__(256) iins_tc_tn_kernel(const IinsTCTNParams tp
             const bool leader = umma::elect_one();
             iins_issue_kstep<NT, PIECES, 1, 1>(tmem, ad, bd, A_PIECE >> 4, leader, it > 0 ? 1u : 0u);
             iins_issue_kstep<NT, PIECES, 1, 1>(tmem, ad + (256 >> 4), bd + (256 >> 4), A_PIECE >> 4, leader, 1u);
-            if (leader) umma::commit(umma::smem_u32(&mbar_mma[s]));
+            if (leader) umma::commit(umma::smem_u32(&mbar_done[s]));
             __syncwarp();
         }
+    } else {
+        const bool fast_a = tp.cshift_in >= 3 && g.in_layout == IINS_NLC;
+        const bool fast_z = tp.cshift_out >= 3 && g.out_layout == IINS_NLC;
+        float rawa[2][8], rawz[8];
+        auto load_raw = [&](int it) {
+            const int row = r_begin + it * BR + lane;
+            const bool ok = row < r_end;
+            const int b = ok ? row >> tp.lshift : 0;
+            const int l = ok ? row & (g.Lout - 1) : 0;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int k0 = ktile0 + (warp + 8 * jj) * 8;
+                if (!ok) iins_zero8(rawa[jj]);
+                else if (fast_a) iins_gather8_fwd_fast(g, p.x, tp.K, tp.cshift_in, b, l, k0, rawa[jj]);
+                else {
+                    float tmp[8];
+                    iins_gather8_fwd_generic(g, p.x, tp.K, b, l, k0, tmp);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rawa[jj][i] = tmp[i];
+                }
+            }
+            if (has_z) {
+                if (!ok) iins_zero8(rawz);
+                else if (fast_z) iins_dz8_fast(g, p.dz, tp.cshift_out, b, l, n0 + warp * 8, true, rawz);
+                else {
+                    float tmp[8];
+                    iins_dz8_generic(g, p.dz, b, l, n0 + warp * 8, tmp);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rawz[i] = tmp[i];
+                }
+            }
+        };
+        if (nit > 0) load_raw(0);
+        for (int it = 0; it < nit; ++it) {
+            const int s = it & 1;
+            unsigned char* sA = dsm + s * STAGE;
+            unsigned char* sB = sA + 3 * A_PIECE;
+            if (it >= 2) umma::mbar_wait(umma::smem_u32(&mbar_done[s]), (uint32_t)(((it >> 1) - 1) & 1));
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+                iins_store8_split(rawa[jj], sA + ((warp + 8 * jj) * BR + lane) * 16, A_PIECE, PIECES);
+            if (has_z) {
+                if (do_bias) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) bsum[i] += rawz[i];
+                }
+                iins_store8_split(rawz, sB + (warp * BR + lane) * 16, B_PIECE, PIECES);
+            }
+            umma::fence_async_smem();
+            umma::mbar_arrive(umma::smem_u32(&mbar_full[s]));
+            if (it + 1 < nit) load_raw(it + 1);
+        }
     }
-    if (nit >= 2) umma::mbar_wait(umma::smem_u32(&mbar_mma[(nit - 2) & 1]), (uint32_t)(((nit - 2) >> 1) & 1));
-    if (nit >= 1) umma::mbar_wait(umma::smem_u32(&mbar_mma[(nit - 1) & 1]), (uint32_t)(((nit - 1) >> 1) & 1));
+    if (nit >= 2) umma::mbar_wait(umma::smem_u32(&mbar_done[(nit - 2) & 1]), (uint32_t)(((nit - 2) >> 1) & 1));
+    if (nit >= 1) umma::mbar_wait(umma::smem_u32(&mbar_done[(nit - 1) & 1]), (uint32_t)(((nit - 1) >> 1) & 1));
     umma::tc_fence_after();
 
-    if (nit >= 1) {
+    if (nit >= 1 && warp < 8) {
         // TMEM lane = k entry of this tile, column = n.  Warp w owns lanes 32*(w&3)..; column halves as above.
         constexpr int COLS_PER_WARP = NT >= 32 ? NT / 2 : NT;
         const int q = warp & 3, hf = warp >> 2;
@@ -549,7 +571,7 @@ __global__ void __launch_bounds__(256) iins_tc_tn_kernel(const IinsTCTNParams tp
     umma::tc_fence_before();
     __syncthreads();
     if (do_bias && tid < NT && n0 + tid < g.Cout && nit >= 1) atomicAdd(p.db + n0 + tid, s_bias[tid]);
-    if (warp == 0) umma::tmem_dealloc(tmem, TCOLS);
+    if (warp == 8) umma::tmem_dealloc(tmem, TCOLS);
 }
 
 #endif  // !IINS_CPUSIM

@@ -79,6 +79,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar_saddr, uint32_t parity) 
         : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar_saddr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar_saddr) : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar_saddr, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_saddr), "r"(bytes) : "memory");
 }
