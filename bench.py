@@ -325,12 +325,22 @@ def main():
         peaks, peak_src = measured_peaks()
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
         achieved = top[1][1] / (top[1][0] * 1e-3) / 1e12 if top[1][0] > 0 else 0.0
+        # DRAM traffic per launch of that kernel from the committed ncu --set full capture (profiles/), if present
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_tc_ncu_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                rows = [r for r in json.load(f) if top[0].rstrip("_") in r["kernel"]]
+            if rows:
+                traffic = sum(r["dram_bytes"] for r in rows) / len(rows)
         roofline = {"bound": "tensor", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": traffic,
                     "share_of_step": top[1][0] / total_ms, "avg_launch_ms": top[1][0] / top[1][2],
                     "peak_source": peak_src + ", bf16 dense sustained (kernel timed inside a long step)",
-                    "note": "fp32 SIMT (FFMA) implicit-GEMM core this round: measured against the tensor-pipe peak "
-                            "the north_star targets; whole-step algorithmic TFLOP/s = "
+                    "note": "achieved = algorithmic 2*M*N*K of the kernel's launches / their CUDA-event time inside an "
+                            "instrumented step; the fp32-grade mode issues 3 bf16 tcgen05.mma per k-step (bf16x3 split), so "
+                            "the tensor pipe does ~3x this work; traffic = mean DRAM bytes per launch from the committed "
+                            "ncu capture (bytes, outputs mostly stay in L2); whole-step algorithmic TFLOP/s = "
                             f"{flops / (ms * 1e-3) / 1e12:.2f}"}
         kernel_table = {k: {"ms": round(v[0], 4), "launches": v[2], "tflops": round(v[1] / max(v[0], 1e-9) / 1e9, 3)}
                         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}

@@ -116,7 +116,10 @@ void launch_tc_nt_t(Ctx& c, const IinsTCParams& tp, dim3 grid) {
 }
 
 void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
+    static int nt_max = 0;                 // tuning knob: cap the tile width (more, smaller CTAs); env IINS_NT_MAX
+    if (nt_max == 0) { const char* e = getenv("IINS_NT_MAX"); nt_max = e ? atoi(e) : 64; if (nt_max != 16 && nt_max != 32) nt_max = 64; }
     int nt = p.N <= 16 ? 16 : (p.N <= 32 ? 32 : 64);
+    if (nt > nt_max && (p.ep.norm == IINS_NORM_NONE || p.ep.norm == IINS_NORM_IN || p.ep.norm == IINS_NORM_ADAIN)) nt = nt_max;
     IinsPackParams pk;
     memset(&pk, 0, sizeof(pk));
     pk.g = p.g; pk.kind = p.a_kind; pk.w = p.w; pk.out = reinterpret_cast<uint16_t*>(c.wpack);
