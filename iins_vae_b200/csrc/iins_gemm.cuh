@@ -390,13 +390,20 @@ __global__ void __launch_bounds__(256) iins_tn_kernel(const IinsTNParams p) {
 // classifier): a 128x16 tensor-core tile would be almost all padding and these layers are pure HBM streams at
 // L = 64..128, so they run as a direct convolution, one thread per output row, weights in shared memory,
 // followed by the SAME fused tile epilogue (norm / activation / residual).
+// acc[0..7] += a * w[0..7]  (w 32-byte aligned in shared memory: two 16-byte loads)
+IINS_D void iins_row_fma8(float* acc, float a, const float* w) {
+    const float4 w0 = *reinterpret_cast<const float4*>(w), w1 = *reinterpret_cast<const float4*>(w + 4);
+    acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]); acc[2] = fmaf(a, w0.z, acc[2]); acc[3] = fmaf(a, w0.w, acc[3]);
+    acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]); acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]);
+}
+
 struct IinsRowParams {
     IinsNTParams nt;           // geometry, operands, epilogue, M/N/K, Lrow, lshift
 };
 
 __global__ void __launch_bounds__(256) iins_row_nt_kernel(const IinsRowParams rp) {
     constexpr int BM = 128, NT = 16, LD = NT + 1, KMAX = 64;
-    __shared__ float Ws[KMAX * NT];            // [k][n]
+    __shared__ __align__(16) float Ws[KMAX * NT];            // [k][n]
     __shared__ float Cs[BM * LD];
     __shared__ float st_mean[1024];
     __shared__ float st_rstd[1024];
@@ -434,12 +441,17 @@ __global__ void __launch_bounds__(256) iins_row_nt_kernel(const IinsRowParams rp
                 const int pos = iins_src_pos(g, l, t);
                 if (pos < 0) continue;
                 const float* xr = p.x + iins_in_index(g, b, pos, 0);
-                const long cstride = g.in_layout == IINS_NCL ? g.Lin : 1;
-                for (int c = 0; c < Cdim; ++c) {
-                    const float a = __ldg(xr + c * cstride);
-                    const float* wr = wr0 + c * NT;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, wr[j], acc[j]);
+                if (g.in_layout == IINS_NLC && (Cdim & 3) == 0) {
+                    for (int c = 0; c < Cdim; c += 4) {
+                        const float4 a4 = __ldg(reinterpret_cast<const float4*>(xr + c));
+                        iins_row_fma8(acc, a4.x, wr0 + c * NT);
+                        iins_row_fma8(acc, a4.y, wr0 + (c + 1) * NT);
+                        iins_row_fma8(acc, a4.z, wr0 + (c + 2) * NT);
+                        iins_row_fma8(acc, a4.w, wr0 + (c + 3) * NT);
+                    }
+                } else {
+                    const long cstride = g.in_layout == IINS_NCL ? g.Lin : 1;
+                    for (int c = 0; c < Cdim; ++c) iins_row_fma8(acc, __ldg(xr + c * cstride), wr0 + c * NT);
                 }
             } else {
                 // data gradient: output rows whose tap t reads this input position (<= 3 candidates)
@@ -457,11 +469,23 @@ __global__ void __launch_bounds__(256) iins_row_nt_kernel(const IinsRowParams rp
                     if (r < 0) continue;
                     const int lo = r / g.stride;
                     if (lo * g.stride != r || lo >= g.Lout) continue;
-                    for (int c = 0; c < Cdim; ++c) {
-                        const float a = iins_dz_at(g, p.dz, b, lo, c);
-                        const float* wr = wr0 + c * NT;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, wr[j], acc[j]);
+                    if (g.out_layout == IINS_NLC && (Cdim & 3) == 0 && !p.dz.dy_bcast) {
+                        const long base = ((long)b * g.Lout + lo) * g.Cout;
+                        for (int c = 0; c < Cdim; c += 4) {
+                            float4 a4 = __ldg(reinterpret_cast<const float4*>(p.dz.dy + base + c));
+                            if (p.dz.y != nullptr && p.dz.act != IINS_ACT_NONE) {
+                                const float4 y4 = __ldg(reinterpret_cast<const float4*>(p.dz.y + base + c));
+                                a4.x *= iins_dact_from_y(y4.x, p.dz.act, p.dz.slope); a4.y *= iins_dact_from_y(y4.y, p.dz.act, p.dz.slope);
+                                a4.z *= iins_dact_from_y(y4.z, p.dz.act, p.dz.slope); a4.w *= iins_dact_from_y(y4.w, p.dz.act, p.dz.slope);
+                            }
+                            const float sc = p.dz.dy_scale;
+                            iins_row_fma8(acc, a4.x * sc, wr0 + c * NT);
+                            iins_row_fma8(acc, a4.y * sc, wr0 + (c + 1) * NT);
+                            iins_row_fma8(acc, a4.z * sc, wr0 + (c + 2) * NT);
+                            iins_row_fma8(acc, a4.w * sc, wr0 + (c + 3) * NT);
+                        }
+                    } else {
+                        for (int c = 0; c < Cdim; ++c) iins_row_fma8(acc, iins_dz_at(g, p.dz, b, lo, c), wr0 + c * NT);
                     }
                 }
             }
@@ -526,7 +550,16 @@ __global__ void __launch_bounds__(256) iins_row_tn_kernel(const IinsRowTNParams 
                 const int pos = ok ? iins_src_pos(g, l, t) : -1;
                 const float* xr = p.x + (pos >= 0 ? iins_in_index(g, b, pos, 0) : 0);
                 const long cstride = g.in_layout == IINS_NCL ? g.Lin : 1;
-                for (int c = 0; c < g.Cin; ++c) As[r * (KMAX + 1) + t * g.Cin + c] = pos >= 0 ? __ldg(xr + c * cstride) : 0.f;
+                if (g.in_layout == IINS_NLC && (g.Cin & 3) == 0) {
+                    for (int c = 0; c < g.Cin; c += 4) {
+                        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (pos >= 0) a4 = __ldg(reinterpret_cast<const float4*>(xr + c));
+                        float* dst = As + r * (KMAX + 1) + t * g.Cin + c;
+                        dst[0] = a4.x; dst[1] = a4.y; dst[2] = a4.z; dst[3] = a4.w;
+                    }
+                } else {
+                    for (int c = 0; c < g.Cin; ++c) As[r * (KMAX + 1) + t * g.Cin + c] = pos >= 0 ? __ldg(xr + c * cstride) : 0.f;
+                }
             }
         }
         __syncthreads();
