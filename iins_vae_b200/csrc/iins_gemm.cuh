@@ -37,6 +37,7 @@ struct IinsNTParams {
     int lshift;                // log2(Lrow)
     int cshift;                // log2(channel extent of the k index) or -1 if it is not a power of two
     int out_layout;            // layout of the GEMM output
+    long long* dbg;            // debug clock trace (CTA 0 / thread 0) or nullptr
 };
 
 // Norm / activation / residual / store on one SMEM-staged tile Cs[128][LD] (bias already added).
@@ -64,25 +65,33 @@ __device__ __forceinline__ void iins_epilogue_tile(const IinsNTParams& p, const 
     const int ncols = (p.N - n0) < BN ? (p.N - n0) : BN;
     const int b0 = tile_m / L;             // first sample of the tile
 
+    long long* edbg = (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) ? p.dbg : nullptr;
+    if (edbg) edbg[900] = clock64();
     if (ep.norm == IINS_NORM_IN || ep.norm == IINS_NORM_ADAIN) {
         // per (sample, channel) statistics over the L rows; biased variance (models.py:152, 1072)
         const int pairs = S * ncols;
         int G = 1;
         while (G < 32 && pairs * G * 2 <= 256) G <<= 1;
         const int per_iter = 256 / G;
+        const float invL = 1.0f / (float)L;
+        const bool pow2 = (ncols & (ncols - 1)) == 0;
+        const int nsh = 31 - __clz(ncols);
         for (int p0 = 0; p0 < pairs; p0 += per_iter) {
             int pr = p0 + tid / G, sub = tid % G;
             bool ok = pr < pairs;
-            int s = ok ? pr / ncols : 0, c = ok ? pr - s * ncols : 0;
+            int s = !ok ? 0 : (pow2 ? pr >> nsh : pr / ncols), c = ok ? pr - s * ncols : 0;
             float sum = 0.f;
             if (ok) for (int l = sub; l < L; l += G) sum += Cs[(s * L + l) * LD + c];
             sum = iins_group_sum(sum, G);
-            float mean = sum / (float)L;
+            float mean = sum * invL;
             float sq = 0.f;
             if (ok) for (int l = sub; l < L; l += G) { float dv = Cs[(s * L + l) * LD + c] - mean; sq += dv * dv; }
             sq = iins_group_sum(sq, G);
             if (ok && sub == 0) {
-                float rs = 1.0f / sqrtf(sq / (float)L + IINS_EPS);
+                // rsqrt + one Newton step: full fp32 accuracy without the IEEE sqrt / divide sequences
+                const float vpe = fmaf(sq, invL, IINS_EPS);
+                float rs = rsqrtf(vpe);
+                rs = rs * fmaf(-0.5f * vpe, rs * rs, 1.5f);
                 st_mean[s * BN + c] = mean;
                 st_rstd[s * BN + c] = rs;
                 int b = b0 + s;
@@ -115,6 +124,7 @@ __device__ __forceinline__ void iins_epilogue_tile(const IinsNTParams& p, const 
         iins_epi_sync<NAMED>();
     }
 
+    if (edbg) edbg[901] = clock64();
     // ---- apply + store (coalesced over the contiguous NLC tile)
     // Each thread owns 4 consecutive columns and walks the rows with a fixed stride; L is a power of two on
     // this path (p.lshift), so the row -> (sample, position) split is a shift, and the NLC stores are 16 bytes.
@@ -185,6 +195,7 @@ __device__ __forceinline__ void iins_epilogue_tile(const IinsNTParams& p, const 
             }
         }
     }
+    if (edbg) edbg[902] = clock64();
 }
 
 template <int BN>

@@ -146,6 +146,7 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     memset(&tp, 0, sizeof(tp));
     tp.nt = p; tp.wpack = pk.out; tp.pieces = g_mode == 1 ? 1 : 3; tp.nkb = pk.nkb;
     tp.timeline = (g_timeline != nullptr && g_timeline_count++ == g_timeline_which) ? g_timeline : nullptr;
+    tp.nt.dbg = tp.timeline;
     dim3 grid((p.M + 127) / 128, pk.nblk, 1);
     IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K); IINS_SET_SHAPE(p.M, p.N, p.K);
     if (nt == 16) launch_tc_nt_t<16>(c, tp, grid);

@@ -34,3 +34,4 @@ for which in [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3, 4]:
         agg[tag] = agg.get(tag, 0) + clk - prev; prev = clk
     for tag, v in agg.items(): print(f"   {names.get(tag, tag):22s} {v:8d} cycles")
     print("   total", t[2 * (n - 1) + 1] - t[1])
+    print(f"   inside epilogue: stats {t[901] - t[900]} cycles, apply+store {t[902] - t[901]} cycles")
