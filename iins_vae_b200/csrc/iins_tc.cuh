@@ -220,17 +220,19 @@ __global__ void __launch_bounds__(256) iins_pack_all_kernel(const IinsPackAllPar
 }
 
 // Issue the MMAs of one k-step (K = 16) for the bf16x3 scheme with the B pieces stacked along N:
-//   D[:, 0:3N) += A0 * [B0|B1|B2],  D[:, 0:2N) += A1 * [B0|B1],  D[:, 0:N) += A2 * B0
-// so the six significant piece products take 3 instructions; the epilogue adds the three N-wide column blocks.
+//   D[:, 0:3N) += A0 * [B0|B1|B2],  D[:, 0:3N) += A1 * [B0|B1|B2],  D[:, 0:2N) += A2 * [B0|B1]
+// so eight of the nine piece products take 3 instructions; the epilogue adds the three N-wide column blocks.
 // adesc / bdesc address piece 0 of this k-step; a_piece16 = byte distance between A pieces >> 4.
 template <int NT, int PIECES, int AMAJ, int BMAJ>
 __device__ __forceinline__ void iins_issue_kstep(uint32_t tmem, uint64_t adesc, uint64_t bdesc, uint32_t a_piece16, bool leader,
                                                  uint32_t first_acc) {
     if (PIECES == 3) {
         if (leader) {
+            // A1 and A2 also take the wider stacked operand: the extra products (A1*B2, A2*B1) cost two more N blocks of
+            // tensor-pipe time (not the bottleneck) and push the split error from 2^-23 to 2^-31 (only A2*B2 is dropped)
             umma::mma_bf16_ss(tmem, adesc, bdesc, umma::make_idesc_bf16(128, 3 * NT, AMAJ, BMAJ), first_acc);
-            umma::mma_bf16_ss(tmem, adesc + a_piece16, bdesc, umma::make_idesc_bf16(128, 2 * NT, AMAJ, BMAJ), 1u);
-            umma::mma_bf16_ss(tmem, adesc + 2 * a_piece16, bdesc, umma::make_idesc_bf16(128, NT, AMAJ, BMAJ), 1u);
+            umma::mma_bf16_ss(tmem, adesc + a_piece16, bdesc, umma::make_idesc_bf16(128, 3 * NT, AMAJ, BMAJ), 1u);
+            umma::mma_bf16_ss(tmem, adesc + 2 * a_piece16, bdesc, umma::make_idesc_bf16(128, 2 * NT, AMAJ, BMAJ), 1u);
         }
     } else {
         if (leader) umma::mma_bf16_ss(tmem, adesc, bdesc, umma::make_idesc_bf16(128, NT, AMAJ, BMAJ), first_acc);
