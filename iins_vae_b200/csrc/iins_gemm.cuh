@@ -597,3 +597,56 @@ __global__ void __launch_bounds__(256) iins_row_tn_kernel(const IinsRowTNParams 
     }
     if (p.db != nullptr && tid < N) atomicAdd(p.db + tid, bsum);
 }
+
+// Weight gradient of "thin" layers: one of the two GEMM dims is <= 4 (the 1x1 conv on the 2-channel range code:
+// K = 2; the Restorer's last Linear: N = 1).  dW is then T <= 4 rank-1 accumulations of a W-wide row vector:
+// thread = one wide column, 256 / W row groups per CTA, coalesced reads of the wide operand, T accumulators per
+// thread, one atomic flush.  These layers would waste a 128-lane tensor-core tile and their operands are not
+// 8-channel gatherable (NCL range code, single output channel).
+struct IinsThinTNParams {
+    IinsTNParams tn;
+    int K;                     // ks * Cin
+    int lshift;                // log2(Lout)
+    int thin_is_k;             // 1: K <= 4 (wide = output channels), 0: Cout <= 4 (wide = k)
+};
+
+__global__ void __launch_bounds__(256) iins_thin_tn_kernel(const IinsThinTNParams tp) {
+    const IinsTNParams& p = tp.tn;
+    const IinsGeom& g = p.g;
+    const int N = g.Cout, K = tp.K;
+    const int W = tp.thin_is_k ? N : K, T = tp.thin_is_k ? K : N;
+    const int col = threadIdx.x % W, grp = threadIdx.x / W, ngrp = 256 / W;       // host guarantees 256 % W == 0
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, bthin[4] = {0.f, 0.f, 0.f, 0.f};
+    float bwide = 0.f;
+    const int r_begin = blockIdx.x * p.rows_per_part;
+    int r_end = r_begin + p.rows_per_part;
+    if (r_end > p.M) r_end = p.M;
+    const int wt = tp.thin_is_k ? 0 : col / g.Cin, wc = tp.thin_is_k ? 0 : col - wt * g.Cin;   // wide k -> (tap, channel)
+#pragma unroll 2
+    for (int row = r_begin + grp; row < r_end; row += ngrp) {
+        const int b = row >> tp.lshift, l = row & (g.Lout - 1);
+        float thin[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float v = 0.f;
+            if (t < T) {
+                if (tp.thin_is_k) { const int tt = t / g.Cin, ci = t - tt * g.Cin; v = iins_a_fwd(g, p.x, b, l, tt, ci); }
+                else v = iins_dz_at(g, p.dz, b, l, t);
+            }
+            thin[t] = v;
+        }
+        const float wv = tp.thin_is_k ? iins_dz_at(g, p.dz, b, l, col) : iins_a_fwd(g, p.x, b, l, wt, wc);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { acc[t] = fmaf(thin[t], wv, acc[t]); bthin[t] += thin[t]; }
+        bwide += wv;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (t >= T) continue;
+        const int n = tp.thin_is_k ? col : t, k = tp.thin_is_k ? t : col;
+        const int tt = k / g.Cin, ci = k - tt * g.Cin;
+        atomicAdd(p.dw + iins_w_index(g, n, ci, tt), acc[t]);
+        if (p.db != nullptr && !tp.thin_is_k && col == 0) atomicAdd(p.db + t, bthin[t]);
+    }
+    if (p.db != nullptr && tp.thin_is_k) atomicAdd(p.db + col, bwide);
+}

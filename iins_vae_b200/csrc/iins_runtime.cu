@@ -147,6 +147,21 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     tp.nt = p; tp.wpack = pk.out; tp.pieces = g_mode == 1 ? 1 : 3; tp.nkb = pk.nkb;
     tp.timeline = (g_timeline != nullptr && g_timeline_count++ == g_timeline_which) ? g_timeline : nullptr;
     tp.nt.dbg = tp.timeline;
+    {   // register-resident epilogue whenever its preconditions hold (iins_tc.cuh); IINS_EP_REGS=0 forces the SMEM path
+        static int ep_regs_on = -1;
+        if (ep_regs_on < 0) { const char* e = getenv("IINS_EP_REGS"); ep_regs_on = e ? atoi(e) : 1; }
+        const IinsEpilogue& ep = p.ep;
+        auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+        bool ok = ep_regs_on && p.out_layout == IINS_NLC && p.N % nt == 0 && al16(ep.y) && al16(ep.add);
+        if (ep.norm != IINS_NORM_NONE) {
+            ok = ok && p.Lrow <= 32 && al16(ep.xhat);
+            if (ep.norm == IINS_NORM_LN) ok = ok && p.N == nt && ep.gamma != nullptr && ep.beta != nullptr;
+            else ok = ok && al16(ep.rstd);
+            if (ep.norm == IINS_NORM_ADAIN)
+                ok = ok && al16(ep.adain) && (ep.adain_ld & 3) == 0 && (ep.adain_off_b & 3) == 0 && (ep.adain_off_w & 3) == 0;
+        }
+        tp.ep_regs = ok ? 1 : 0;
+    }
     dim3 grid((p.M + 127) / 128, pk.nblk, 1);
     IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K); IINS_SET_SHAPE(p.M, p.N, p.K);
     if (nt == 16) launch_tc_nt_t<16>(c, tp, grid);
@@ -157,7 +172,12 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
 
 void launch_nt(Ctx& c, IinsNTParams p) {
     p.lshift = ilog2_exact(p.Lrow);
-    p.cshift = ilog2_exact(p.a_kind == 0 ? p.g.Cin : p.g.Cout);
+    {   // k -> (tap, channel) split of the tensor-core gathers: a shift for power-of-two channel counts; a Linear layer has
+        // one tap, so any channel count that is a multiple of 8 works with the "infinite" shift 31 (t = 0, c = k)
+        const int cdim = p.a_kind == 0 ? p.g.Cin : p.g.Cout;
+        p.cshift = ilog2_exact(cdim);
+        if (p.cshift < 0 && p.g.ks == 1 && cdim % 8 == 0) p.cshift = 31;
+    }
     if (p.lshift < 0) { c.err = 2; return; }
     if (p.N <= 16 && p.K <= 64) {                     // small-channel layer: direct SIMT conv + fused epilogue
         if (c.phase == 1) return;
@@ -168,8 +188,12 @@ void launch_nt(Ctx& c, IinsNTParams p) {
         return;
     }
 #ifndef IINS_CPUSIM
-    if (g_mode != 2) { launch_nt_tc(c, p); return; }
+    // the tensor-core producers gather 16 bytes (8 channels-last channels) at a time; the few layers that cannot
+    // (2-channel range code in NCL, single-output-channel data gradients: K <= 8) run on the fp32 SIMT kernel
+    const bool tc_ok = p.cshift >= 3 && (p.a_kind == 0 ? p.g.in_layout == IINS_NLC : p.g.out_layout == IINS_NLC);
+    if (g_mode != 2 && tc_ok) { launch_nt_tc(c, p); return; }
 #endif
+    if (c.phase == 1) return;
     launch_nt_simt(c, p);
 }
 
@@ -267,7 +291,9 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
         return;
     }
 #ifndef IINS_CPUSIM
-    if (g_mode != 2) {
+    auto chan_ok = [&](int cdim) { return ilog2_exact(cdim) >= 3 || (g.ks == 1 && cdim % 8 == 0); };
+    const bool tc_ok = chan_ok(g.Cin) && g.Cout % 8 == 0 && g.in_layout == IINS_NLC && g.out_layout == IINS_NLC;
+    if (g_mode != 2 && tc_ok) {
         int nt = g.Cout <= 16 ? 16 : (g.Cout <= 32 ? 32 : 64);
         int ky = (K + 127) / 128, nz = (g.Cout + nt - 1) / nt;
         static long tn_ctas = 0;               // total CTAs aimed for (tuning knob: env IINS_TN_CTAS)
@@ -284,6 +310,7 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
         memset(&tp, 0, sizeof(tp));
         tp.tn = p; tp.pieces = g_mode == 1 ? 1 : 3; tp.K = K;
         tp.lshift = ilog2_exact(g.Lout); tp.cshift_in = ilog2_exact(g.Cin); tp.cshift_out = ilog2_exact(g.Cout);
+        if (tp.cshift_in < 0) tp.cshift_in = 31;          // Linear layer, Cin % 8 == 0 (chan_ok): t = 0, c = k
         if (tp.lshift < 0) { c.err = 2; return; }
         dim3 grid(parts, ky, nz);
         IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K); IINS_SET_SHAPE(p.M, g.Cout, K);
@@ -293,6 +320,25 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
         return;
     }
 #endif
+    {   // thin layers (K <= 4 or Cout <= 4 with a wide dim that divides 256): rank-1 accumulation kernel
+        const int thin_k = K <= 4 && g.Cout <= 256 && 256 % g.Cout == 0;
+        const int thin_n = !thin_k && g.Cout <= 4 && K <= 256 && 256 % K == 0;
+        const int ls = ilog2_exact(g.Lout);
+        if ((thin_k || thin_n) && ls >= 0) {
+            IinsThinTNParams tp;
+            memset(&tp, 0, sizeof(tp));
+            const int W = thin_k ? g.Cout : K, ngrp = 256 / W;
+            long want = 148L * 4, max_parts = (p.M + 8L * ngrp - 1) / (8L * ngrp);
+            if (want > max_parts) want = max_parts;
+            if (want < 1) want = 1;
+            long rpp = (p.M + want - 1) / want;
+            p.rows_per_part = (int)rpp;
+            tp.tn = p; tp.K = K; tp.lshift = ls; tp.thin_is_k = thin_k;
+            IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K); IINS_SET_SHAPE(p.M, g.Cout, K);
+            IINS_LAUNCH(iins_thin_tn_kernel, (int)((p.M + rpp - 1) / rpp), 256, 0, wst, tp);
+            return;
+        }
+    }
     int ky = (K + 63) / 64, nz = (g.Cout + 63) / 64;
     // enough row parts to fill the machine (148 SMs x a few CTAs), at least 32 rows each
     long want = (148L * 4 + (long)ky * nz - 1) / ((long)ky * nz);

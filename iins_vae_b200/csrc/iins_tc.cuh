@@ -24,28 +24,6 @@
 #ifndef IINS_CPUSIM
 #include "iins_umma.cuh"
 
-// generic (scalar) gathers for layouts / channel counts the 16-byte fast paths do not cover; kept out of line
-__device__ __noinline__ void iins_gather8_fwd_generic(const IinsGeom& g, const float* __restrict__ x, int K, int b, int l, int k0, float* v) {
-    int t = k0 / g.Cin, c = k0 - t * g.Cin;
-#pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
-        v[i] = (k0 + i < K) ? iins_a_fwd(g, x, b, l, t, c) : 0.f;
-        if (++c == g.Cin) { c = 0; ++t; }
-    }
-}
-__device__ __noinline__ void iins_dz8_generic(const IinsGeom& g, const IinsDz& d, int b, int l, int n0, float* v) {
-#pragma unroll 1
-    for (int i = 0; i < 8; ++i) v[i] = (n0 + i < g.Cout) ? iins_dz_at(g, d, b, l, n0 + i) : 0.f;
-}
-__device__ __noinline__ void iins_gather8_dgrad_generic(const IinsGeom& g, const IinsDz& d, int K, int b, int pos, int k0, float* v) {
-    int t = k0 / g.Cout, c = k0 - t * g.Cout;
-#pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
-        v[i] = (k0 + i < K) ? iins_a_dgrad(g, d, b, pos, t, c) : 0.f;
-        if (++c == g.Cout) { c = 0; ++t; }
-    }
-}
-
 __device__ __forceinline__ void iins_zero8(float* v) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = 0.f;
@@ -59,19 +37,20 @@ __device__ __forceinline__ void iins_ld8(const float* __restrict__ src, bool ok,
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
 }
 
-// forward A operand, fast path: Cin = 1 << cs (>= 8), NLC input; 8 consecutive k = one tap, 8 channels
+// forward A operand, fast path: NLC input, k = t * Cin + c with Cin = 1 << cs (>= 8), or a Linear layer (one tap, any
+// Cin % 8 == 0: the host passes cs = 31 so that t = 0 and c0 = k0); 8 consecutive k = one tap, 8 channels
 __device__ __forceinline__ void iins_gather8_fwd_fast(const IinsGeom& g, const float* __restrict__ x, int K, int cs, int b, int l,
                                                       int k0, float* v) {
-    const int t = k0 >> cs, c0 = k0 & (g.Cin - 1);
+    const int t = k0 >> cs, c0 = k0 & (int)((1u << cs) - 1u);
     const int pos = iins_src_pos(g, l, t);
     const bool ok = k0 < K && pos >= 0;
-    iins_ld8(x + (((long)b * g.Lin + (ok ? pos : 0)) << cs) + c0, ok, v);
+    iins_ld8(x + ((long)b * g.Lin + (ok ? pos : 0)) * g.Cin + c0, ok, v);
 }
 
-// 8 consecutive output channels of dz at (b,l), fast path: Cout = 1 << cs (>= 8), NLC
-__device__ __forceinline__ void iins_dz8_fast(const IinsGeom& g, const IinsDz& d, int cs, int b, int l, int n0, bool ok, float* v) {
-    const long idx = (((long)b * g.Lout + (ok ? l : 0)) << cs) + n0;
-    iins_ld8(d.dy_bcast ? d.dy + ((long)b << cs) + n0 : d.dy + idx, ok, v);
+// 8 consecutive output channels of dz at (b,l), fast path: NLC, Cout % 8 == 0
+__device__ __forceinline__ void iins_dz8_fast(const IinsGeom& g, const IinsDz& d, int b, int l, int n0, bool ok, float* v) {
+    const long idx = ((long)b * g.Lout + (ok ? l : 0)) * g.Cout + n0;
+    iins_ld8(d.dy_bcast ? d.dy + (long)b * g.Cout + n0 : d.dy + idx, ok, v);
     if (d.y != nullptr && d.act != IINS_ACT_NONE) {
         float yy[8];
         iins_ld8(d.y + idx, ok, yy);
@@ -87,7 +66,7 @@ __device__ __forceinline__ void iins_dz8_fast(const IinsGeom& g, const IinsDz& d
 // dgrad A operand, fast path: sums the (<= 3) output rows whose tap t reads input position pos
 __device__ __forceinline__ void iins_gather8_dgrad_fast(const IinsGeom& g, const IinsDz& d, int K, int cs, int b, int pos, int k0,
                                                         float* v) {
-    const int t = k0 >> cs, c0 = k0 & (g.Cout - 1);
+    const int t = k0 >> cs, c0 = k0 & (int)((1u << cs) - 1u);
     int q0 = pos + g.pad, q1 = -1, q2 = -1;
     if (g.mode == IINS_PAD_REFLECT) {
         if (pos >= 1 && pos <= g.pad) q1 = g.pad - pos;
@@ -106,7 +85,7 @@ __device__ __forceinline__ void iins_gather8_dgrad_fast(const IinsGeom& g, const
         const bool ok = k0 < K && q >= 0 && r >= 0 && (r & sh) == 0 && l < g.Lout;
         if (j > 0 && q < 0) continue;                  // warp-divergent only at the padded borders
         float u[8];
-        iins_dz8_fast(g, d, cs, b, l, c0, ok, u);
+        iins_dz8_fast(g, d, b, l, c0, ok, u);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] += u[i];
     }
@@ -258,6 +237,183 @@ struct IinsTmemCols {            // power of two >= 32 covering PIECES * NT accu
     static constexpr int value = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : 256));
 };
 
+
+// ------------------------------------------------------------------------- register-resident tile epilogue
+// The accumulator row of TMEM lane r belongs to thread (r & 31) of warp (r >> 5): a thread owns one GEMM row =
+// one (sample, position) and CW consecutive channels.  The L rows of a sample are L consecutive lanes (L <= 32,
+// a power of two), so the InstanceNorm / AdaIN statistics are xor-shuffle trees over lane bits < log2(L) and the
+// custom LayerNorm's per-sample statistics add one exchange between the two warps that share a lane quarter.
+// Nothing is staged in shared memory; x-hat / y / rstd leave the registers as 16-byte stores (each thread writes
+// whole 64-byte runs of its own row).  Processed in chunks of 16 columns to keep the register footprint small
+// (the LayerNorm passes re-read TMEM, which is cheap).
+// Preconditions (checked on the host, IinsTCParams::ep_regs): NLC output, N % NT == 0, 16-byte aligned y / xhat /
+// add / rstd / adain, Lrow <= 32 when a norm is fused, N == NT for LayerNorm.
+template <int NT, int PIECES>
+__device__ __forceinline__ void iins_tmem_chunk16(uint32_t taddr_lane, int c, float* v) {
+    uint32_t r0[16], r1[16], r2[16];
+    umma::tmem_ld16_nowait(taddr_lane + (uint32_t)c, r0);
+    if (PIECES == 3) {
+        umma::tmem_ld16_nowait(taddr_lane + (uint32_t)(c + NT), r1);
+        umma::tmem_ld16_nowait(taddr_lane + (uint32_t)(c + 2 * NT), r2);
+    }
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        v[i] = __uint_as_float(r0[i]);
+        if (PIECES == 3) v[i] += __uint_as_float(r1[i]) + __uint_as_float(r2[i]);
+    }
+}
+
+// sum over aligned groups of LL lanes (LL a compile-time power of two <= 32): a fully unrolled xor-shuffle tree
+template <int LL>
+__device__ __forceinline__ float iins_lanes_sum(float v) {
+#pragma unroll
+    for (int o = 1; o < LL; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// activation with the kind hoisted out of the element loop (the compiler does not unswitch it)
+template <int N>
+__device__ __forceinline__ void iins_act_vec(float* v, int act, float slope) {
+    if (act == IINS_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = fmaxf(v[i], 0.f);
+    } else if (act == IINS_ACT_LRELU) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * slope;
+    } else if (act == IINS_ACT_TANH) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = tanhf(v[i]);
+    }
+}
+
+template <int NT, int PIECES, int LL>
+__device__ __forceinline__ void iins_tc_epilogue_regs(const IinsNTParams& p, uint32_t tmem, int tile_m, int n0, int warp, int lane,
+                                                      float* xch) {
+    constexpr int CW = NT >= 32 ? NT / 2 : NT;          // columns per thread
+    const IinsEpilogue& ep = p.ep;
+    const int q = warp & 3, hf = warp >> 2;
+    const bool active = NT >= 32 || hf == 0;            // warp-uniform
+    const int row = q * 32 + lane;
+    const int gr = tile_m + row;
+    const bool row_ok = gr < p.M;
+    const int cbeg = NT >= 32 ? hf * CW : 0;
+    constexpr int L = LL;                               // rows per sample (== p.Lrow when a norm is fused)
+    const int b = gr >> p.lshift, l = gr & (p.Lrow - 1);
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    const long orow = (long)gr * p.N + n0 + cbeg;
+
+    float ln_mean = 0.f, ln_rs = 0.f;
+    if (ep.norm == IINS_NORM_LN) {
+        // per-sample mean and UNBIASED std over (C*L), eps added to std (models.py:976-981); two passes
+        const float nel = (float)(L * NT);
+        float part = 0.f;
+        if (active) {
+#pragma unroll
+            for (int c0 = 0; c0 < CW; c0 += 16) {
+                float v[16];
+                iins_tmem_chunk16<NT, PIECES>(tl, cbeg + c0, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) part += v[i] + (ep.bias != nullptr ? __ldg(ep.bias + n0 + cbeg + c0 + i) : 0.f);
+            }
+        }
+        part = iins_lanes_sum<LL>(part);
+        if (NT >= 32) {
+            xch[hf * 128 + row] = part;
+            iins_epi_sync<true>();
+            part += xch[(hf ^ 1) * 128 + row];
+        }
+        ln_mean = part / nel;
+        float sq = 0.f;
+        if (active) {
+#pragma unroll
+            for (int c0 = 0; c0 < CW; c0 += 16) {
+                float v[16];
+                iins_tmem_chunk16<NT, PIECES>(tl, cbeg + c0, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { const float d = v[i] + (ep.bias != nullptr ? __ldg(ep.bias + n0 + cbeg + c0 + i) : 0.f) - ln_mean; sq = fmaf(d, d, sq); }
+            }
+        }
+        sq = iins_lanes_sum<LL>(sq);
+        if (NT >= 32) {
+            xch[256 + hf * 128 + row] = sq;
+            iins_epi_sync<true>();
+            sq += xch[256 + (hf ^ 1) * 128 + row];
+        }
+        ln_rs = 1.0f / (sqrtf(sq / (nel - 1.f)) + IINS_EPS);
+        if (active && row_ok && l == 0 && hf == 0 && ep.rstd != nullptr) ep.rstd[b] = ln_rs;
+    }
+    if (!active) return;
+
+#pragma unroll 1
+    for (int c0 = 0; c0 < CW; c0 += 16) {
+        const int gn = n0 + cbeg + c0;
+        // operands that do not depend on the accumulator first: their latency hides behind the TMEM loads
+        float4 a4[4];
+        if (ep.add != nullptr && row_ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a4[j] = __ldg(reinterpret_cast<const float4*>(ep.add + orow + c0) + j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float v[16];
+        iins_tmem_chunk16<NT, PIECES>(tl, cbeg + c0, v);
+        if (ep.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __ldg(ep.bias + gn + i);
+        }
+        // x-hat and rstd are stored as soon as they exist (short live ranges: the kernel runs 2 CTAs / SM at <= 96 registers)
+        float4* xh_dst = (ep.norm != IINS_NORM_NONE && ep.xhat != nullptr && row_ok) ? reinterpret_cast<float4*>(ep.xhat + orow + c0) : nullptr;
+        if (ep.norm == IINS_NORM_IN || ep.norm == IINS_NORM_ADAIN) {
+            // per (sample, channel) statistics over the L rows; biased variance (models.py:152, 1072)
+            constexpr float invL = 1.0f / (float)L;
+            float4* rs_dst = (ep.rstd != nullptr && row_ok && l == 0) ? reinterpret_cast<float4*>(ep.rstd + (long)b * p.N + gn) : nullptr;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float rs[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float mean = iins_lanes_sum<LL>(v[4 * j + i]) * invL;
+                    const float d = v[4 * j + i] - mean;
+                    const float vpe = fmaf(iins_lanes_sum<LL>(d * d), invL, IINS_EPS);
+                    float r = rsqrtf(vpe);
+                    r = r * fmaf(-0.5f * vpe, r * r, 1.5f);      // one Newton step: full fp32 accuracy
+                    rs[i] = r;
+                    v[4 * j + i] = d * r;
+                }
+                if (rs_dst != nullptr) rs_dst[j] = make_float4(rs[0], rs[1], rs[2], rs[3]);
+                if (xh_dst != nullptr) xh_dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (ep.norm == IINS_NORM_ADAIN) {
+                const float* ab = ep.adain + (long)(row_ok ? b : 0) * ep.adain_ld + gn;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(ab + ep.adain_off_w) + j);
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ab + ep.adain_off_b) + j);
+                    v[4 * j] = fmaf(v[4 * j], w4.x, b4.x); v[4 * j + 1] = fmaf(v[4 * j + 1], w4.y, b4.y);
+                    v[4 * j + 2] = fmaf(v[4 * j + 2], w4.z, b4.z); v[4 * j + 3] = fmaf(v[4 * j + 3], w4.w, b4.w);
+                }
+            }
+        } else if (ep.norm == IINS_NORM_LN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[4 * j + i] = (v[4 * j + i] - ln_mean) * ln_rs;
+                if (xh_dst != nullptr) xh_dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[4 * j + i] = fmaf(v[4 * j + i], __ldg(ep.gamma + gn + 4 * j + i), __ldg(ep.beta + gn + 4 * j + i));
+            }
+        }
+        iins_act_vec<16>(v, ep.act, ep.slope);
+        if (row_ok) {
+            float4* dst = reinterpret_cast<float4*>(ep.y + orow + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                dst[j] = make_float4(v[4 * j] + a4[j].x, v[4 * j + 1] + a4[j].y, v[4 * j + 2] + a4[j].z, v[4 * j + 3] + a4[j].w);
+        }
+    }
+}
+
 #define IINS_TL(tag) do { if (tl_ != nullptr && tl_n_ < 500) { tl_[2 * tl_n_] = (tag); tl_[2 * tl_n_ + 1] = clock64(); ++tl_n_; tl_[1022] = tl_n_; } } while (0)
 
 // --------------------------------------------------------------------------------- forward / dgrad GEMM
@@ -267,6 +423,7 @@ struct IinsTCParams {
     int pieces;          // 3 (fp32-grade) or 1 (bf16)
     int nkb;             // K blocks of 32
     long long* timeline; // debug: (tag, clock64) pairs of CTA (0,0) thread 0, or nullptr
+    int ep_regs;         // 1: register-resident epilogue (iins_tc_epilogue_regs), 0: SMEM-staged generic epilogue
 };
 
 // 288 threads: warps 0-7 are PRODUCERS (gather / split / store the A tile, later the epilogue), warp 8 is the
@@ -276,7 +433,7 @@ struct IinsTCParams {
 //   bready[s] (tx bytes)   TMA       -> MMA warp : stage s holds the weight tile
 //   done[s]   (tcgen05.commit) MMA   -> everyone : the MMAs reading stage s have completed (stage reusable)
 template <int NT, int PIECES>
-__global__ void __launch_bounds__(288) iins_tc_nt_kernel(const IinsTCParams tp) {
+__global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCParams tp) {
     constexpr int BM = 128;
     constexpr uint32_t A_PIECE = 4 * BM * 16;            // 8192 B : [chunk][row][16 B]
     constexpr uint32_t B_TILE = 4 * PIECES * NT * 16;    // [chunk][piece * NT + n][16 B]
@@ -296,6 +453,33 @@ __global__ void __launch_bounds__(288) iins_tc_nt_kernel(const IinsTCParams tp) 
     float* st_mean = reinterpret_cast<float*>(dsm + 2 * STAGE);
     float* st_rstd = st_mean + 1024;
     const int nkb = tp.nkb;
+
+    // ---- producer set-up and the first two K blocks' loads are issued BEFORE the barrier / TMEM set-up, so the first
+    // global-load latency overlaps the CTA prologue
+    const bool is_prod = warp < 8;
+    const int a_row = tid & 127, a_half = (tid >> 7) & 1;
+    const int grow = tile_m + a_row;
+    const bool a_ok = is_prod && grow < p.M;
+    const int a_b = a_ok ? grow >> p.lshift : 0;
+    const int a_l = a_ok ? grow & (p.Lrow - 1) : 0;
+    const int cs = p.cshift;
+    // raw operand data of TWO K blocks ahead lives in registers (the loads of block kb+2 are issued right after
+    // block kb is handed to the MMA warp), so a K block costs its convert/store work, not a global-load latency
+    float raw[2][2][8];
+    auto load_raw = [&](int kb, float (*dst)[8]) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int k0 = kb * 32 + (a_half * 2 + jj) * 8;
+            // the host routes layers without 16-byte gathers (< 8 channels, NCL operand) to the SIMT kernels
+            if (!a_ok) iins_zero8(dst[jj]);
+            else if (p.a_kind == 0) iins_gather8_fwd_fast(g, p.x, p.K, cs, a_b, a_l, k0, dst[jj]);
+            else iins_gather8_dgrad_fast(g, p.dz, p.K, cs, a_b, a_l, k0, dst[jj]);
+        }
+    };
+    if (is_prod) {
+        load_raw(0, raw[0]);
+        if (nkb > 1) load_raw(1, raw[1]);
+    }
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -341,46 +525,23 @@ __global__ void __launch_bounds__(288) iins_tc_nt_kernel(const IinsTCParams tp) 
         }
     } else {
         // ------------------------------------------------------------------ producers
-        const int a_row = tid & 127, a_half = tid >> 7;
-        const int grow = tile_m + a_row;
-        const bool a_ok = grow < p.M;
-        const int a_b = a_ok ? grow >> p.lshift : 0;
-        const int a_l = a_ok ? grow & (p.Lrow - 1) : 0;
-        const int cs = p.cshift;
-        // 16-byte gathers need >= 8 channels (power of two) in channels-last order
-        const bool fast = cs >= 3 && (p.a_kind == 0 ? g.in_layout == IINS_NLC : g.out_layout == IINS_NLC);
-        float raw[2][8];
-        auto load_raw = [&](int kb) {
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const int k0 = kb * 32 + (a_half * 2 + jj) * 8;
-                if (!a_ok) iins_zero8(raw[jj]);
-                else if (fast) {
-                    if (p.a_kind == 0) iins_gather8_fwd_fast(g, p.x, p.K, cs, a_b, a_l, k0, raw[jj]);
-                    else iins_gather8_dgrad_fast(g, p.dz, p.K, cs, a_b, a_l, k0, raw[jj]);
-                } else {
-                    float tmp[8];                          // address-taken copy: keeps raw[][] in registers
-                    if (p.a_kind == 0) iins_gather8_fwd_generic(g, p.x, p.K, a_b, a_l, k0, tmp);
-                    else iins_gather8_dgrad_generic(g, p.dz, p.K, a_b, a_l, k0, tmp);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) raw[jj][i] = tmp[i];
-                }
-            }
-        };
-        load_raw(0);
-        for (int kb = 0; kb < nkb; ++kb) {
+        auto produce = [&](int kb, float (*src)[8]) {
             const int s = kb & 1;
             unsigned char* sA = dsm + s * STAGE;
             if (kb >= 2) umma::mbar_wait(umma::smem_u32(&mbar_done[s]), (uint32_t)(((kb >> 1) - 1) & 1));
             IINS_TL(1);
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj)
-                iins_store8_split(raw[jj], sA + ((a_half * 2 + jj) * BM + a_row) * 16, A_PIECE, PIECES);
+                iins_store8_split(src[jj], sA + ((a_half * 2 + jj) * BM + a_row) * 16, A_PIECE, PIECES);
             umma::fence_async_smem();
             umma::mbar_arrive(umma::smem_u32(&mbar_full[s]));
             IINS_TL(2);
-            if (kb + 1 < nkb) load_raw(kb + 1);           // in flight while the MMA warp works on this block
+            if (kb + 2 < nkb) load_raw(kb + 2, src);      // in flight while the next block is converted
             IINS_TL(3);
+        };
+        for (int kb = 0; kb < nkb; kb += 2) {
+            produce(kb, raw[0]);
+            if (kb + 1 < nkb) produce(kb + 1, raw[1]);
         }
     }
     // every thread observes the completion of the last MMAs (also orders the smem reuse by the epilogue)
@@ -389,9 +550,19 @@ __global__ void __launch_bounds__(288) iins_tc_nt_kernel(const IinsTCParams tp) 
     umma::tc_fence_after();
     IINS_TL(13);
 
-    if (warp < 8) {
-        // ---- TMEM -> SMEM (+ bias).  Warp w owns TMEM lanes 32*(w&3) .. +31; with NT >= 32 the two warps
-        // sharing a lane quarter split the columns.
+    if (warp < 8 && tp.ep_regs) {
+        // rows per sample as a compile-time constant (unrolled shuffle trees); without a fused norm L is irrelevant
+        const int Ln = p.ep.norm == IINS_NORM_NONE ? 1 : p.Lrow;
+        if (Ln == 8) iins_tc_epilogue_regs<NT, PIECES, 8>(p, tmem, tile_m, n0, warp, lane, st_mean);
+        else if (Ln == 16) iins_tc_epilogue_regs<NT, PIECES, 16>(p, tmem, tile_m, n0, warp, lane, st_mean);
+        else if (Ln == 32) iins_tc_epilogue_regs<NT, PIECES, 32>(p, tmem, tile_m, n0, warp, lane, st_mean);
+        else if (Ln == 1) iins_tc_epilogue_regs<NT, PIECES, 1>(p, tmem, tile_m, n0, warp, lane, st_mean);
+        else if (Ln == 2) iins_tc_epilogue_regs<NT, PIECES, 2>(p, tmem, tile_m, n0, warp, lane, st_mean);
+        else iins_tc_epilogue_regs<NT, PIECES, 4>(p, tmem, tile_m, n0, warp, lane, st_mean);
+        IINS_TL(15);
+    } else if (warp < 8) {
+        // ---- generic path: TMEM -> SMEM (+ bias).  Warp w owns TMEM lanes 32*(w&3) .. +31; with NT >= 32 the two
+        // warps sharing a lane quarter split the columns.
         constexpr int COLS_PER_WARP = NT >= 32 ? NT / 2 : NT;
         const int q = warp & 3, hf = warp >> 2;
         if (NT >= 32 || hf == 0) {
@@ -432,7 +603,7 @@ struct IinsTCTNParams {
 
 // grid = (row parts, ceil(K/128), ceil(Cout/NT)).  D^T[k][n] accumulated in TMEM (128 lanes = 128 k entries).
 template <int NT, int PIECES>
-__global__ void __launch_bounds__(288) iins_tc_tn_kernel(const IinsTCTNParams tp) {
+__global__ void __launch_bounds__(288, 2) iins_tc_tn_kernel(const IinsTCTNParams tp) {
     constexpr int BR = 32;                               // rows per stage (2 MMA k-steps of 16)
     constexpr uint32_t A_PIECE = 16 * BR * 16;           // [k group of 8][row][16 B] = 8192 B
     constexpr uint32_t B_PIECE = (NT / 8) * BR * 16;     // [n group of 8][row][16 B]; pieces stacked = more n groups
@@ -487,10 +658,9 @@ __global__ void __launch_bounds__(288) iins_tc_tn_kernel(const IinsTCTNParams tp
             __syncwarp();
         }
     } else {
-        const bool fast_a = tp.cshift_in >= 3 && g.in_layout == IINS_NLC;
-        const bool fast_z = tp.cshift_out >= 3 && g.out_layout == IINS_NLC;
-        float rawa[2][8], rawz[8];
-        auto load_raw = [&](int it) {
+        // two row blocks of raw operand data in flight in registers (see the forward kernel)
+        float rawa[2][2][8], rawz[2][8];
+        auto load_raw = [&](int it, float (*ra)[8], float* rz) {
             const int row = r_begin + it * BR + lane;
             const bool ok = row < r_end;
             const int b = ok ? row >> tp.lshift : 0;
@@ -498,45 +668,38 @@ __global__ void __launch_bounds__(288) iins_tc_tn_kernel(const IinsTCTNParams tp
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int k0 = ktile0 + (warp + 8 * jj) * 8;
-                if (!ok) iins_zero8(rawa[jj]);
-                else if (fast_a) iins_gather8_fwd_fast(g, p.x, tp.K, tp.cshift_in, b, l, k0, rawa[jj]);
-                else {
-                    float tmp[8];
-                    iins_gather8_fwd_generic(g, p.x, tp.K, b, l, k0, tmp);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) rawa[jj][i] = tmp[i];
-                }
+                if (!ok) iins_zero8(ra[jj]);
+                else iins_gather8_fwd_fast(g, p.x, tp.K, tp.cshift_in, b, l, k0, ra[jj]);
             }
             if (has_z) {
-                if (!ok) iins_zero8(rawz);
-                else if (fast_z) iins_dz8_fast(g, p.dz, tp.cshift_out, b, l, n0 + warp * 8, true, rawz);
-                else {
-                    float tmp[8];
-                    iins_dz8_generic(g, p.dz, b, l, n0 + warp * 8, tmp);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) rawz[i] = tmp[i];
-                }
+                if (!ok) iins_zero8(rz);
+                else iins_dz8_fast(g, p.dz, b, l, n0 + warp * 8, true, rz);
             }
         };
-        if (nit > 0) load_raw(0);
-        for (int it = 0; it < nit; ++it) {
+        auto produce = [&](int it, float (*ra)[8], float* rz) {
             const int s = it & 1;
             unsigned char* sA = dsm + s * STAGE;
             unsigned char* sB = sA + 3 * A_PIECE;
             if (it >= 2) umma::mbar_wait(umma::smem_u32(&mbar_done[s]), (uint32_t)(((it >> 1) - 1) & 1));
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj)
-                iins_store8_split(rawa[jj], sA + ((warp + 8 * jj) * BR + lane) * 16, A_PIECE, PIECES);
+                iins_store8_split(ra[jj], sA + ((warp + 8 * jj) * BR + lane) * 16, A_PIECE, PIECES);
             if (has_z) {
                 if (do_bias) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) bsum[i] += rawz[i];
+                    for (int i = 0; i < 8; ++i) bsum[i] += rz[i];
                 }
-                iins_store8_split(rawz, sB + (warp * BR + lane) * 16, B_PIECE, PIECES);
+                iins_store8_split(rz, sB + (warp * BR + lane) * 16, B_PIECE, PIECES);
             }
             umma::fence_async_smem();
             umma::mbar_arrive(umma::smem_u32(&mbar_full[s]));
-            if (it + 1 < nit) load_raw(it + 1);
+            if (it + 2 < nit) load_raw(it + 2, ra, rz);
+        };
+        if (nit > 0) load_raw(0, rawa[0], rawz[0]);
+        if (nit > 1) load_raw(1, rawa[1], rawz[1]);
+        for (int it = 0; it < nit; it += 2) {
+            produce(it, rawa[0], rawz[0]);
+            if (it + 1 < nit) produce(it + 1, rawa[1], rawz[1]);
         }
     }
     if (nit >= 2) umma::mbar_wait(umma::smem_u32(&mbar_done[(nit - 2) & 1]), (uint32_t)(((nit - 2) >> 1) & 1));

@@ -168,7 +168,8 @@ def test_engine_step_matches_oracle(batch, supervised, graph, mode):
     dbl = lambda d: {k: v.double() for k, v in d.items()}
     _, truth = orc.semi_step_with_grads(*(dbl(p) for p in pdicts), cir.double(), err.double(), label.double(), cfg,
                                         supervised, torch.zeros(batch, cfg.env_dim // 2, 1).double())
-    rows = parity.grad_report(got, truth, ref_grads, gscale)
+    rows = parity.grad_report(got, truth, ref_grads, gscale,
+                              parity.REF_FACTOR_TC if mode == "fp32" else parity.REF_FACTOR)
     n_flip = parity.assert_grads(rows, batch, require_strict=(batch <= 2), label=f"B={batch}")
     rel = sorted(r[1] for r in rows if not orc.grad_is_structurally_zero(r[0]))
     ref = sorted(r[2] for r in rows if not orc.grad_is_structurally_zero(r[0]))

@@ -43,5 +43,8 @@ if __name__ == "__main__":
     cases = [(int(b), 100 + int(b)) for b in sys.argv[2].split(",")] if len(sys.argv) > 2 else [(2, 0), (64, 75), (4096, 4107)]
     get_lib().check(get_lib().iins_set_compute_mode(mode), "mode")
     print("compute mode", mode)
+    sup = not (len(sys.argv) > 3 and sys.argv[3] == "unsup")
+    if len(sys.argv) > 4:                       # explicit seed (e.g. the pytest case: seed = 11 + batch)
+        cases = [(b, int(sys.argv[4])) for b, _ in cases]
     for B, seed in cases:
-        run(B, seed)
+        run(B, seed, sup)
