@@ -21,7 +21,7 @@ EXPORTS = [
     "iins_classifier_num_params", "iins_classifier_ws_floats", "iins_classifier_scratch_floats",
     "iins_classifier_forward", "iins_classifier_backward",
     "iins_loss_forward_backward", "iins_adam_step",
-    "iins_adaptive_pool_forward", "iins_adaptive_pool_backward",
+    "iins_adaptive_pool_forward", "iins_adaptive_pool_backward", "iins_accumulate2",
     "iins_launch_count", "iins_profile_begin", "iins_profile_collect",
     "iins_set_compute_mode", "iins_get_compute_mode", "iins_profile_shapes",
 ]
@@ -71,6 +71,7 @@ class IinsLib:
                                      C.c_int, _P, _P, C.c_double, C.c_double, C.c_float, _P]
         d.iins_adaptive_pool_forward.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P]
         d.iins_adaptive_pool_backward.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P]
+        d.iins_accumulate2.argtypes = [_P, _P, C.c_size_t, _P, _P, C.c_size_t, _P]
         d.iins_launch_count.restype = C.c_ulonglong
         d.iins_profile_collect.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int]
 

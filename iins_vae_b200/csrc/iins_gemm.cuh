@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(256) iins_thin_tn_kernel(const IinsThinTNParam
     int r_end = r_begin + p.rows_per_part;
     if (r_end > p.M) r_end = p.M;
     const int wt = tp.thin_is_k ? 0 : col / g.Cin, wc = tp.thin_is_k ? 0 : col - wt * g.Cin;   // wide k -> (tap, channel)
-#pragma unroll 2
+#pragma unroll 4
     for (int row = r_begin + grp; row < r_end; row += ngrp) {
         const int b = row >> tp.lshift, l = row & (g.Lout - 1);
         float thin[4];
@@ -639,6 +639,18 @@ __global__ void __launch_bounds__(256) iins_thin_tn_kernel(const IinsThinTNParam
 #pragma unroll
         for (int t = 0; t < 4; ++t) { acc[t] = fmaf(thin[t], wv, acc[t]); bthin[t] += thin[t]; }
         bwide += wv;
+    }
+    // combine the row groups of the CTA in shared memory, then one atomic per output element and CTA
+    __shared__ float red[9][256];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { red[t][threadIdx.x] = acc[t]; red[4 + t][threadIdx.x] = bthin[t]; }
+    red[8][threadIdx.x] = bwide;
+    __syncthreads();
+    if (grp != 0) return;
+    for (int gi = 1; gi < ngrp; ++gi) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { acc[t] += red[t][gi * W + col]; bthin[t] += red[4 + t][gi * W + col]; }
+        bwide += red[8][gi * W + col];
     }
 #pragma unroll
     for (int t = 0; t < 4; ++t) {

@@ -347,6 +347,16 @@ __global__ void __launch_bounds__(256) iins_loss_kernel(const IinsLossParams p) 
     }
 }
 
+// dst1 += src1, dst2 += src2 in one launch: sums the head gradients (Restorer -> d range_code, Classifier -> d env_code)
+// into the decoder's when the engine runs the heads concurrently with the decoder (engine.py)
+__global__ void __launch_bounds__(256) iins_accumulate2_kernel(float* __restrict__ dst1, const float* __restrict__ src1, long n1,
+                                                               float* __restrict__ dst2, const float* __restrict__ src2, long n2) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += (long)gridDim.x * blockDim.x) {
+        if (i < n1) dst1[i] += __ldg(src1 + i);
+        else dst2[i - n1] += __ldg(src2 + i - n1);
+    }
+}
+
 // ---------------------------------------------------------------------------------- fused Adam
 // torch.optim.Adam semantics (train_semi.py:118-122): per-group step counters live on the device so a
 // captured CUDA graph can replay the update; a group whose gradients are "None" this step (Res/Cls on

@@ -225,31 +225,64 @@ void conv_dgrad(Ctx& c, const IinsGeom& g, const IinsDz& dz, const float* w, flo
 // (forked / joined with events, which CUDA-graph capture turns into parallel branches).  Every gradient
 // buffer of a backward pass is written exactly once (fresh scratch per layer), so there is no WAR hazard.
 #ifndef IINS_CPUSIM
-int g_async_wgrad = -1;
-cudaStream_t g_side_stream = nullptr;
-cudaEvent_t g_fork_events[64];
+// Every caller stream gets its own pair of helper streams (module passes may themselves run concurrently on different
+// streams: the engine overlaps the decoder with the two heads): [0] weight gradients, [1] an independent branch of
+// the module (the env encoder next to the range encoder).  IINS_ASYNC_WGRAD=0 / IINS_BRANCH_STREAMS=0 serialise.
+int g_async_wgrad = -1, g_branch_streams = -1;
+struct HelperStreams { cudaStream_t main; cudaStream_t helper[2]; };
+HelperStreams g_helpers[8];
+int g_n_helpers = 0;
+cudaEvent_t g_fork_events[256];
 int g_fork_i = 0;
+bool g_fork_events_ready = false;
 
-cudaStream_t side_stream() {
-    if (g_async_wgrad < 0) { const char* e = getenv("IINS_ASYNC_WGRAD"); g_async_wgrad = e ? atoi(e) : 0; }   // opt-in: pays off only once the GEMM kernels leave SM room
-    if (!g_async_wgrad) return nullptr;
-    if (g_side_stream == nullptr) {
-        if (cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking) != cudaSuccess) { g_async_wgrad = 0; return nullptr; }
-        for (int i = 0; i < 64; ++i) cudaEventCreateWithFlags(&g_fork_events[i], cudaEventDisableTiming);
+cudaStream_t helper_stream(cudaStream_t main_st, int which) {
+    if (!g_fork_events_ready) {
+        for (int i = 0; i < 256; ++i) cudaEventCreateWithFlags(&g_fork_events[i], cudaEventDisableTiming);
+        g_fork_events_ready = true;
     }
-    return g_side_stream;
+    for (int i = 0; i < g_n_helpers; ++i) if (g_helpers[i].main == main_st) return g_helpers[i].helper[which];
+    if (g_n_helpers >= 8) return nullptr;
+    HelperStreams& h = g_helpers[g_n_helpers];
+    h.main = main_st;
+    for (int k = 0; k < 2; ++k)
+        if (cudaStreamCreateWithFlags(&h.helper[k], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    ++g_n_helpers;
+    return h.helper[which];
+}
+cudaStream_t side_stream(cudaStream_t main_st) {
+    if (g_async_wgrad < 0) { const char* e = getenv("IINS_ASYNC_WGRAD"); g_async_wgrad = e ? atoi(e) : 1; }
+    return g_async_wgrad ? helper_stream(main_st, 0) : nullptr;
+}
+cudaStream_t branch_stream(cudaStream_t main_st) {
+    if (g_branch_streams < 0) { const char* e = getenv("IINS_BRANCH_STREAMS"); g_branch_streams = e ? atoi(e) : 1; }
+    return g_branch_streams ? helper_stream(main_st, 1) : nullptr;
 }
 void fork_to(cudaStream_t from, cudaStream_t to) {
-    cudaEvent_t e = g_fork_events[g_fork_i++ & 63];
+    cudaEvent_t e = g_fork_events[g_fork_i++ & 255];
     cudaEventRecord(e, from);
     cudaStreamWaitEvent(to, e, 0);
 }
 #else
-cudaStream_t side_stream() { return nullptr; }
+cudaStream_t side_stream(cudaStream_t) { return nullptr; }
+cudaStream_t branch_stream(cudaStream_t) { return nullptr; }
 void fork_to(cudaStream_t, cudaStream_t) {}
 #endif
-void begin_async_wgrad(Ctx& c) { if (c.phase != 1) c.st2 = side_stream(); }
+void begin_async_wgrad(Ctx& c) { if (c.phase != 1) c.st2 = side_stream(c.st); }
 void end_async_wgrad(Ctx& c) { if (c.phase != 1 && c.st2 != nullptr) { fork_to(c.st2, c.st); c.st2 = nullptr; } }
+// Run an independent part of a module pass on the branch stream: begin_branch() redirects the launches of `c`,
+// end_branch() restores the main stream; join_branch() makes the main stream wait for the branch.
+struct Branch { cudaStream_t main = nullptr, br = nullptr; };
+void begin_branch(Ctx& c, Branch& b) {
+    if (c.phase == 1) return;
+    b.main = c.st;
+    if (b.br == nullptr) b.br = branch_stream(c.st);
+    if (b.br == nullptr) return;
+    fork_to(c.st, b.br);
+    c.st = b.br;
+}
+void end_branch(Ctx& c, Branch& b) { if (c.phase != 1 && b.br != nullptr) c.st = b.main; }
+void join_branch(Ctx& c, Branch& b) { if (c.phase != 1 && b.br != nullptr) fork_to(b.br, c.st); }
 
 #ifndef IINS_CPUSIM
 template <int NT, int PIECES>
@@ -328,7 +361,7 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
             IinsThinTNParams tp;
             memset(&tp, 0, sizeof(tp));
             const int W = thin_k ? g.Cout : K, ngrp = 256 / W;
-            long want = 148L * 4, max_parts = (p.M + 8L * ngrp - 1) / (8L * ngrp);
+            long want = 148L * 2, max_parts = (p.M + 8L * ngrp - 1) / (8L * ngrp);
             if (want > max_parts) want = max_parts;
             if (want < 1) want = 1;
             long rpp = (p.M + want - 1) / want;
@@ -469,6 +502,32 @@ int encoder_forward(const Shapes& s, const float* const* P, const float* x, cons
     run_phases(c, [&]() {
     IINS_SKIP_IN_COLLECT(c) IINS_LAUNCH(iins_pool_fwd_kernel, grid_for((long)B * s.P), 256, 0, st, x, pl.xp, B, s.Lc, s.P);
     int pi = 0;
+    // ---- env encoder (models.py:264-279): independent of the range encoder, runs on the branch stream
+    Branch br;
+    begin_branch(c, br);
+    pi = 2 * (1 + s.ndown + 2 * s.nres + 1);
+    {
+        IinsGeom g = conv_geom(B, s.P, s.P, 1, 4 * s.d, 7, 1, 3, IINS_PAD_REFLECT);
+        conv_forward(c, g, pl.xp, P[pi], plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, pl.e_y[0]));
+        pi += 2;
+    }
+    int eL = s.P, eC = 4 * s.d;
+    for (int i = 1; i < pl.n_env; ++i) {
+        int oc = i <= 2 ? 2 * eC : eC;
+        IinsGeom g = conv_geom(B, eL, eL / 2, eC, oc, 4, 2, 1, IINS_PAD_ZERO);
+        conv_forward(c, g, pl.e_y[i - 1], P[pi], plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, pl.e_y[i]));
+        pi += 2;
+        eL /= 2; eC = oc;
+    }
+    IINS_SKIP_IN_COLLECT(c) IINS_LAUNCH(iins_mean_l_kernel, grid_for((long)B * eC), 256, 0, c.st, pl.e_y[pl.n_env - 1], pl.pooled, B, eL, eC);
+    conv_forward(c, linear_geom(B, eC, s.E), pl.pooled, P[pi], plain_epilogue(P[pi + 1], IINS_ACT_NONE, 0.f, cat));
+    IINS_SKIP_IN_COLLECT(c) {
+        cudaMemsetAsync(kl, 0, sizeof(float), c.st);
+        IINS_LAUNCH(iins_reparam_kl_kernel, grid_for((long)B * s.E / 2), 256, 0, c.st, cat, noise, latent, kl, B, s.E,
+                    (unsigned long long)seed, (unsigned long long)offset);
+    }
+    end_branch(c, br);
+    pi = 0;
     // ---- range encoder (models.py:146-171)
     {
         IinsGeom g = conv_geom(B, s.P, s.P, 1, s.d, 7, 1, 3, IINS_PAD_REFLECT);
@@ -504,27 +563,7 @@ int encoder_forward(const Shapes& s, const float* const* P, const float* x, cons
         conv_forward(c, g, h, P[pi], plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, rc));
         pi += 2;
     }
-    // ---- env encoder (models.py:264-279)
-    {
-        IinsGeom g = conv_geom(B, s.P, s.P, 1, 4 * s.d, 7, 1, 3, IINS_PAD_REFLECT);
-        conv_forward(c, g, pl.xp, P[pi], plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, pl.e_y[0]));
-        pi += 2;
-    }
-    int eL = s.P, eC = 4 * s.d;
-    for (int i = 1; i < pl.n_env; ++i) {
-        int oc = i <= 2 ? 2 * eC : eC;
-        IinsGeom g = conv_geom(B, eL, eL / 2, eC, oc, 4, 2, 1, IINS_PAD_ZERO);
-        conv_forward(c, g, pl.e_y[i - 1], P[pi], plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, pl.e_y[i]));
-        pi += 2;
-        eL /= 2; eC = oc;
-    }
-    IINS_SKIP_IN_COLLECT(c) IINS_LAUNCH(iins_mean_l_kernel, grid_for((long)B * eC), 256, 0, st, pl.e_y[pl.n_env - 1], pl.pooled, B, eL, eC);
-    conv_forward(c, linear_geom(B, eC, s.E), pl.pooled, P[pi], plain_epilogue(P[pi + 1], IINS_ACT_NONE, 0.f, cat));
-    IINS_SKIP_IN_COLLECT(c) {
-        cudaMemsetAsync(kl, 0, sizeof(float), st);
-        IINS_LAUNCH(iins_reparam_kl_kernel, grid_for((long)B * s.E / 2), 256, 0, st, cat, noise, latent, kl, B, s.E,
-                    (unsigned long long)seed, (unsigned long long)offset);
-    }
+    join_branch(c, br);
     });
     if (c.err) return fail(IINS_ERR_BAD_CONFIG, "encoder_forward: packed weight tile exceeds the scratch");
     return check_cuda("encoder_forward");
@@ -559,9 +598,11 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
     auto fresh = [&]() { return fb.take((size_t)B * act); };      // every gradient tensor gets its own buffer
     float* dzb = nullptr;
     begin_async_wgrad(c);
-    // ---------------- env branch
+    // ---------------- env branch (independent of the range branch: runs on the branch stream)
+    Branch br;
+    begin_branch(c, br);
     if (d_cat != nullptr || d_lat != nullptr || d_kl != nullptr) {
-        IINS_SKIP_IN_COLLECT(c) IINS_LAUNCH(iins_reparam_kl_bwd_kernel, grid_for((long)B * s.E / 2), 256, 0, st, cat, noise, d_cat, d_lat, d_kl,
+        IINS_SKIP_IN_COLLECT(c) IINS_LAUNCH(iins_reparam_kl_bwd_kernel, grid_for((long)B * s.E / 2), 256, 0, c.st, cat, noise, d_cat, d_lat, d_kl,
                     dcat, B, s.E, (unsigned long long)seed, (unsigned long long)offset);
         int pi = n_range + 2 * pl.n_env;               // final 1x1 conv (after the pool)
         int eC = 16 * s.d, eL = s.P >> (pl.n_env - 1);
@@ -592,6 +633,7 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
         conv_wgrad(c, g0, pl.xp, dz0, G[pi], G[pi + 1]);
     }
 
+    end_branch(c, br);
     // ---------------- range branch
     if (d_rc != nullptr) {
         int pi = n_range - 2;
@@ -644,6 +686,7 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, dzb);
         conv_wgrad(c, g0, pl.xp, plain_dz(dzb), G[pi], G[pi + 1]);
     }
+    join_branch(c, br);
     end_async_wgrad(c);
     });
     if (c.err) return fail(IINS_ERR_BAD_CONFIG, "encoder_backward: packed weight tile exceeds the scratch");
@@ -1118,6 +1161,13 @@ int iins_profile_begin(void) { return IINS_OK; }
 int iins_profile_collect(const char**, float*, double*, int) { return 0; }
 int iins_profile_shapes(int*, int) { return 0; }
 #endif
+
+int iins_accumulate2(float* dst1, const float* src1, size_t n1, float* dst2, const float* src2, size_t n2, iins_stream_t stream) {
+    if ((n1 && (!dst1 || !src1)) || (n2 && (!dst2 || !src2))) return fail(IINS_ERR_NULL, "accumulate2: NULL argument");
+    if (n1 + n2 == 0) return IINS_OK;
+    IINS_LAUNCH(iins_accumulate2_kernel, grid_for((long)(n1 + n2)), 256, 0, (cudaStream_t)stream, dst1, src1, (long)n1, dst2, src2, (long)n2);
+    return check_cuda("accumulate2");
+}
 
 int iins_adaptive_pool_forward(const float* x, float* y, int batch, int lin, int lout, iins_stream_t stream) {
     if (!x || !y) return fail(IINS_ERR_NULL, "pool: NULL argument");

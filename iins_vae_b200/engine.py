@@ -85,6 +85,10 @@ class SemiTrainEngine:
         self.pred = torch.zeros(B, dtype=torch.int32, device=dev)
         self.d_xrec, self.d_err, self.d_logits = f(B, self.L), f(B, 1), f(B, self.NC)
         self.d_rc, self.d_cat = torch.zeros_like(self.rc), torch.zeros_like(self.cat)
+        # the two heads run on their own stream next to the decoder (independent consumers of the encoder outputs):
+        # their range_code / env_code gradients land in separate buffers and are summed once both sides are done
+        self.d_rc_heads, self.d_cat_heads = torch.zeros_like(self.rc), torch.zeros_like(self.cat)
+        self.head_stream = torch.cuda.Stream(device=self.device)
         self.d_kl = torch.full((1,), LAMBDA_RANGE, dtype=torch.float32, device=dev)
         if shared_state is not None:
             self.lr, self.steps = shared_state.lr, shared_state.steps
@@ -126,18 +130,32 @@ class SemiTrainEngine:
         self.lr.fill_(float(lr))
 
     # ------------------------------------------------------------------------------------------------
+    def _heads_concurrent(self, supervised: bool) -> bool:
+        return self.mode == "semi" and supervised
+
     def _forward(self, supervised: bool):
         lib, cfg, st = self.lib, self.cfg, _stream()
         lib.check(lib.iins_encoder_forward(cfg, self.ptab["enc"], ptr(self.cir), None, 0, 0, ptr(self.rc), ptr(self.cat),
                                            None, ptr(self.kl), ptr(self.ws["encoder"]), st), "encoder forward")
+
+        def heads(hst):
+            lib.check(lib.iins_restorer_forward(cfg, self.ptab["res"], ptr(self.rc), ptr(self.err_est),
+                                                ptr(self.ws["restorer"]), hst), "restorer forward")
+            lib.check(lib.iins_classifier_forward(cfg, self.ptab["cls"], ptr(self.cat), ptr(self.logits),
+                                                  ptr(self.ws["classifier"]), hst), "classifier forward")
+
+        main = torch.cuda.current_stream()
+        if self._heads_concurrent(supervised):
+            self.head_stream.wait_stream(main)
+            with torch.cuda.stream(self.head_stream):
+                heads(_stream())
         if self.mode == "semi":
             lib.check(lib.iins_decoder_forward(cfg, self.ptab["dec"], ptr(self.rc), ptr(self.cat), ptr(self.xrec),
                                                ptr(self.ws["decoder"]), st), "decoder forward")
-        if supervised:
-            lib.check(lib.iins_restorer_forward(cfg, self.ptab["res"], ptr(self.rc), ptr(self.err_est),
-                                                ptr(self.ws["restorer"]), st), "restorer forward")
-            lib.check(lib.iins_classifier_forward(cfg, self.ptab["cls"], ptr(self.cat), ptr(self.logits),
-                                                  ptr(self.ws["classifier"]), st), "classifier forward")
+        if self._heads_concurrent(supervised):
+            main.wait_stream(self.head_stream)
+        elif supervised:
+            heads(st)
 
     def _loss(self, supervised: bool):
         lib, semi = self.lib, self.mode == "semi"
@@ -153,19 +171,33 @@ class SemiTrainEngine:
     def _backward(self, supervised: bool):
         lib, cfg, st, semi = self.lib, self.cfg, _stream(), self.mode == "semi"
         self.flat.grad.zero_()
+        conc = self._heads_concurrent(supervised)
+        main = torch.cuda.current_stream()
+
+        def heads(hst, d_rc, d_cat, acc):
+            lib.check(lib.iins_restorer_backward(cfg, self.ptab["res"], ptr(self.rc), ptr(self.ws["restorer"]), ptr(self.d_err),
+                                                 self.gtab["res"], ptr(d_rc), acc, ptr(self.scratch["restorer"]), hst),
+                      "restorer backward")
+            lib.check(lib.iins_classifier_backward(cfg, self.ptab["cls"], ptr(self.cat), ptr(self.ws["classifier"]),
+                                                   ptr(self.d_logits), self.gtab["cls"], ptr(d_cat), acc,
+                                                   ptr(self.scratch["classifier"]), hst), "classifier backward")
+
+        if conc:
+            self.head_stream.wait_stream(main)
+            with torch.cuda.stream(self.head_stream):
+                heads(_stream(), self.d_rc_heads, self.d_cat_heads, 0)
         acc = 0
         if semi:
             lib.check(lib.iins_decoder_backward(cfg, self.ptab["dec"], ptr(self.rc), ptr(self.cat), ptr(self.ws["decoder"]),
                                                 ptr(self.d_xrec), self.gtab["dec"], ptr(self.d_rc), ptr(self.d_cat), 0,
                                                 ptr(self.scratch["decoder"]), st), "decoder backward")
             acc = 1
-        if supervised:
-            lib.check(lib.iins_restorer_backward(cfg, self.ptab["res"], ptr(self.rc), ptr(self.ws["restorer"]), ptr(self.d_err),
-                                                 self.gtab["res"], ptr(self.d_rc), acc, ptr(self.scratch["restorer"]), st),
-                      "restorer backward")
-            lib.check(lib.iins_classifier_backward(cfg, self.ptab["cls"], ptr(self.cat), ptr(self.ws["classifier"]),
-                                                   ptr(self.d_logits), self.gtab["cls"], ptr(self.d_cat), acc,
-                                                   ptr(self.scratch["classifier"]), st), "classifier backward")
+        if conc:
+            main.wait_stream(self.head_stream)
+            lib.check(lib.iins_accumulate2(ptr(self.d_rc), ptr(self.d_rc_heads), self.d_rc.numel(), ptr(self.d_cat),
+                                           ptr(self.d_cat_heads), self.d_cat.numel(), st), "accumulate head gradients")
+        elif supervised:
+            heads(st, self.d_rc, self.d_cat, acc)
         lib.check(lib.iins_encoder_backward(cfg, self.ptab["enc"], None, 0, 0, ptr(self.rc), ptr(self.cat),
                                             ptr(self.ws["encoder"]), ptr(self.d_rc), ptr(self.d_cat), None,
                                             ptr(self.d_kl) if semi else None, self.gtab["enc"],

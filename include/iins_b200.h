@@ -140,6 +140,12 @@ int iins_adam_step(float* params, const float* grads, float* exp_avg, float* exp
 int iins_adaptive_pool_forward(const float* x, float* y, int batch, int lin, int lout, iins_stream_t stream);
 int iins_adaptive_pool_backward(const float* dy, float* dx, int batch, int lin, int lout, iins_stream_t stream);
 
+/* dst1[0..n1) += src1, dst2[0..n2) += src2 in ONE launch.  The reference sums the gradients of range_code / env_code
+ * arriving from the decoder and from the two heads inside autograd (train_semi.py:225-227: one backward() through
+ * Dec, Res and Cls); the engine runs the heads concurrently with the decoder and adds their contributions here. */
+int iins_accumulate2(float* dst1, const float* src1, size_t n1, float* dst2, const float* src2, size_t n2,
+                     iins_stream_t stream);
+
 /* ---- launch accounting / in-process kernel timing (used by bench.py; not a profiler replacement) ------ */
 unsigned long long iins_launch_count(void);           /* kernels launched by this library so far */
 int iins_profile_begin(void);                          /* record a CUDA-event pair around every launch */
