@@ -424,10 +424,10 @@ __global__ void __launch_bounds__(256) iins_row_nt_kernel(const IinsRowParams rp
     const int tile_m = blockIdx.x * BM;
     const int Cdim = p.a_kind == 0 ? g.Cin : g.Cout;
     // weights -> smem, Ws[k][n] with k = t * Cdim + c
-    for (int e = tid; e < KMAX * NT; e += 256) {
+    for (int e = tid; e < p.K * NT; e += 256) {     // rows k >= K are never read
         int k = e / NT, n = e - k * NT;
         float v = 0.f;
-        if (k < p.K && n < p.N) {
+        if (n < p.N) {
             int t = k / Cdim, c = k - t * Cdim;
             v = __ldg(p.w + (p.a_kind == 0 ? iins_w_index(g, n, c, t) : iins_w_index(g, c, n, t)));
         }

@@ -31,30 +31,35 @@ struct IinsNormBwdParams {
 //   pass 2: reload (L1-resident) and write dz
 // Requires C a power of two, 4 <= C <= 128, and L*C a multiple of 128.
 __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNormBwdParams p) {
-    const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    // LayerNorm's dgamma / dbeta are sums over the whole batch: every warp keeps a running per-channel total over the
+    // samples it visits (persistent grid), the CTA combines its 8 warps in shared memory and issues ONE atomic per
+    // channel -- one atomic per (sample, channel) serialised 4096 deep on the same few L2 sectors.
+    __shared__ float s_dg[8][128], s_db[8][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = p.C, L = p.L;
     const int CG = C >> 2;                          // float4 column groups per row (<= 32)
     const int nstep = (L * C) >> 7;                 // float4 steps of 32 lanes
     const bool relu = p.act == IINS_ACT_RELU;
-    const bool live = b < p.B;                      // warp-uniform
     const int cg = lane & (CG - 1), c0 = cg * 4;    // CG <= 32 and nstep*32 is a multiple of CG: the lane's channels are fixed
     float scale[4] = {1.f, 1.f, 1.f, 1.f}, shift[4] = {0.f, 0.f, 0.f, 0.f};
-    if (live && p.norm == IINS_NORM_ADAIN) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            scale[j] = __ldg(p.adain + (long)b * p.adain_ld + p.adain_off_w + c0 + j);
-            shift[j] = __ldg(p.adain + (long)b * p.adain_ld + p.adain_off_b + c0 + j);
-        }
-    } else if (p.norm == IINS_NORM_LN) {
+    if (p.norm == IINS_NORM_LN) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { scale[j] = __ldg(p.gamma + c0 + j); shift[j] = __ldg(p.beta + c0 + j); }
     }
-    const float4* dy4 = reinterpret_cast<const float4*>(p.dy + (long)(live ? b : 0) * L * C);
-    const float4* xh4 = reinterpret_cast<const float4*>(p.xhat + (long)(live ? b : 0) * L * C);
-    float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};        // grad wrt xhat
-    float sr[4] = {0.f, 0.f, 0.f, 0.f}, srx[4] = {0.f, 0.f, 0.f, 0.f};        // grad wrt the affine output
-    if (live) {
+    float tot_dg[4] = {0.f, 0.f, 0.f, 0.f}, tot_db[4] = {0.f, 0.f, 0.f, 0.f};
+    const float invL = 1.0f / (float)L;
+    for (int b = blockIdx.x * 8 + warp; b < p.B; b += gridDim.x * 8) {          // warp-uniform
+        if (p.norm == IINS_NORM_ADAIN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                scale[j] = __ldg(p.adain + (long)b * p.adain_ld + p.adain_off_w + c0 + j);
+                shift[j] = __ldg(p.adain + (long)b * p.adain_ld + p.adain_off_b + c0 + j);
+            }
+        }
+        const float4* dy4 = reinterpret_cast<const float4*>(p.dy + (long)b * L * C);
+        const float4* xh4 = reinterpret_cast<const float4*>(p.xhat + (long)b * L * C);
+        float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};        // grad wrt xhat
+        float sr[4] = {0.f, 0.f, 0.f, 0.f}, srx[4] = {0.f, 0.f, 0.f, 0.f};        // grad wrt the affine output
         for (int i = 0; i < nstep; ++i) {
             const float4 d = __ldg(dy4 + lane + 32 * i), x = __ldg(xh4 + lane + 32 * i);
             const float dv[4] = {d.x, d.y, d.z, d.w}, xv[4] = {x.x, x.y, x.z, x.w};
@@ -67,65 +72,74 @@ __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNormBwdPar
                 sg[j] += gx; sgx[j] += gx * xv[j];
             }
         }
-    }
-    float tot_g = 0.f, tot_gx = 0.f;
-    if (p.norm == IINS_NORM_LN) {
-        tot_g = iins_warp_sum(sg[0] + sg[1] + sg[2] + sg[3]);
-        tot_gx = iins_warp_sum(sgx[0] + sgx[1] + sgx[2] + sgx[3]);
-    }
-    // per-channel totals: combine the lanes that share this lane's column group (lane bits >= log2(CG))
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        for (int o = 16; o >= CG; o >>= 1) {
-            sg[j] += __shfl_xor_sync(0xffffffffu, sg[j], o);
-            sgx[j] += __shfl_xor_sync(0xffffffffu, sgx[j], o);
-            sr[j] += __shfl_xor_sync(0xffffffffu, sr[j], o);
-            srx[j] += __shfl_xor_sync(0xffffffffu, srx[j], o);
+        float tot_g = 0.f, tot_gx = 0.f;
+        if (p.norm == IINS_NORM_LN) {
+            tot_g = iins_warp_sum(sg[0] + sg[1] + sg[2] + sg[3]);
+            tot_gx = iins_warp_sum(sgx[0] + sgx[1] + sgx[2] + sgx[3]);
         }
-    }
-    if (p.norm == IINS_NORM_LN) {
-        // dgamma / dbeta: this sample's contribution; lanes 0..CG-1 hold distinct column groups
-        if (live && lane < CG) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { atomicAdd(p.dgamma + c0 + j, srx[j]); atomicAdd(p.dbeta + c0 + j, sr[j]); }
-        }
-    } else if (p.norm == IINS_NORM_ADAIN && p.dadain != nullptr) {
-        if (live && lane < CG) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                p.dadain[(long)b * p.adain_ld + p.adain_off_b + c0 + j] = sr[j];
-                p.dadain[(long)b * p.adain_ld + p.adain_off_w + c0 + j] = srx[j];
-            }
-        }
-    }
-    if (!live) return;
-    float4* dz4 = reinterpret_cast<float4*>(p.dz + (long)b * L * C);
-    float rs[4];
-    float coef = 0.f, mean_g = 0.f;
-    if (p.norm == IINS_NORM_LN) {
-        const float r = __ldg(p.rstd + b);
-        const float sd = 1.0f / r - IINS_EPS;
-        const int nel = L * C;
-        rs[0] = rs[1] = rs[2] = rs[3] = r;
-        coef = tot_gx / ((float)(nel - 1) * sd);
-        mean_g = tot_g / (float)nel;
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rs[j] = __ldg(p.rstd + (long)b * C + c0 + j);
-    }
-    const float invL = 1.0f / (float)L;
-    for (int i = 0; i < nstep; ++i) {
-        const float4 d = __ldg(dy4 + lane + 32 * i), x = __ldg(xh4 + lane + 32 * i);
-        const float dv[4] = {d.x, d.y, d.z, d.w}, xv[4] = {x.x, x.y, x.z, x.w};
-        float o[4];
+        // per-channel totals: combine the lanes that share this lane's column group (lane bits >= log2(CG))
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float u = fmaf(xv[j], scale[j], shift[j]);
-            const float gx = ((relu && !(u > 0.f)) ? 0.f : dv[j]) * scale[j];
-            if (p.norm == IINS_NORM_LN) o[j] = rs[j] * (gx - mean_g) - xv[j] * coef;
-            else o[j] = rs[j] * (gx - sg[j] * invL - xv[j] * sgx[j] * invL);
+            for (int o = 16; o >= CG; o >>= 1) {
+                sg[j] += __shfl_xor_sync(0xffffffffu, sg[j], o);
+                sgx[j] += __shfl_xor_sync(0xffffffffu, sgx[j], o);
+                sr[j] += __shfl_xor_sync(0xffffffffu, sr[j], o);
+                srx[j] += __shfl_xor_sync(0xffffffffu, srx[j], o);
+            }
         }
-        dz4[lane + 32 * i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (p.norm == IINS_NORM_LN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { tot_dg[j] += srx[j]; tot_db[j] += sr[j]; }
+        } else if (p.norm == IINS_NORM_ADAIN && p.dadain != nullptr) {
+            if (lane < CG) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    p.dadain[(long)b * p.adain_ld + p.adain_off_b + c0 + j] = sr[j];
+                    p.dadain[(long)b * p.adain_ld + p.adain_off_w + c0 + j] = srx[j];
+                }
+            }
+        }
+        float4* dz4 = reinterpret_cast<float4*>(p.dz + (long)b * L * C);
+        float rs[4];
+        float coef = 0.f, mean_g = 0.f;
+        if (p.norm == IINS_NORM_LN) {
+            const float r = __ldg(p.rstd + b);
+            const float sd = 1.0f / r - IINS_EPS;
+            const int nel = L * C;
+            rs[0] = rs[1] = rs[2] = rs[3] = r;
+            coef = tot_gx / ((float)(nel - 1) * sd);
+            mean_g = tot_g / (float)nel;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rs[j] = __ldg(p.rstd + (long)b * C + c0 + j);
+        }
+        for (int i = 0; i < nstep; ++i) {
+            const float4 d = __ldg(dy4 + lane + 32 * i), x = __ldg(xh4 + lane + 32 * i);
+            const float dv[4] = {d.x, d.y, d.z, d.w}, xv[4] = {x.x, x.y, x.z, x.w};
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float u = fmaf(xv[j], scale[j], shift[j]);
+                const float gx = ((relu && !(u > 0.f)) ? 0.f : dv[j]) * scale[j];
+                if (p.norm == IINS_NORM_LN) o[j] = rs[j] * (gx - mean_g) - xv[j] * coef;
+                else o[j] = rs[j] * (gx - sg[j] * invL - xv[j] * sgx[j] * invL);
+            }
+            dz4[lane + 32 * i] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    if (p.norm == IINS_NORM_LN) {               // uniform for the whole CTA
+        if (lane < CG) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s_dg[warp][c0 + j] = tot_dg[j]; s_db[warp][c0 + j] = tot_db[j]; }
+        }
+        __syncthreads();
+        if (threadIdx.x < C) {
+            float a = 0.f, bsum = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { a += s_dg[w][threadIdx.x]; bsum += s_db[w][threadIdx.x]; }
+            atomicAdd(p.dgamma + threadIdx.x, a);
+            atomicAdd(p.dbeta + threadIdx.x, bsum);
+        }
     }
 }
 

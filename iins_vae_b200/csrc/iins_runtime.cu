@@ -22,8 +22,6 @@ int fail(int code, const char* msg) {
 //   1  tcgen05 tensor cores, plain bf16 operands, fp32 accumulate (looser tolerance, BASELINE configs[2])
 //   2  fp32 SIMT (FFMA) kernels -- the bring-up / cross-check path
 int g_mode = 0;
-long long* g_timeline = nullptr;      // debug: device buffer of 1024 int64 for the per-phase clock trace
-int g_timeline_which = -1, g_timeline_count = 0;   // trace only the which-th tensor-core forward launch
 #define IINS_WPACK_FLOATS ((size_t)1 << 21)       // 8 MB arena: the packed weight tiles of every layer of one module pass
 
 // A module pass runs its launch plan twice when the tensor-core path is on: phase 1 only COLLECTS the weight
@@ -101,18 +99,27 @@ void launch_nt_simt(const Ctx& c, const IinsNTParams& p) {
 }
 
 #ifndef IINS_CPUSIM
-template <int NT, int PIECES>
-void launch_tc_nt_tp(Ctx& c, const IinsTCParams& tp, dim3 grid) {
+template <int NT, int PIECES, int AKIND, int EPI, int LL>
+void launch_tc_nt_v(Ctx& c, const IinsTCParams& tp, dim3 grid) {
     constexpr int smem = 2 * (3 * 8192 + 3 * 4 * NT * 16) + 8192;
     static bool attr = false;
-    auto iins_tc_nt_kernel_ = iins_tc_nt_kernel<NT, PIECES>;
+    auto iins_tc_nt_kernel_ = iins_tc_nt_kernel<NT, PIECES, AKIND, EPI, LL>;
     if (!attr) { cudaFuncSetAttribute(iins_tc_nt_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
     IINS_LAUNCH(iins_tc_nt_kernel_, grid, 288, smem, c.st, tp);
 }
-template <int NT>
-void launch_tc_nt_t(Ctx& c, const IinsTCParams& tp, dim3 grid) {
-    if (tp.pieces == 3) launch_tc_nt_tp<NT, 3>(c, tp, grid);
-    else launch_tc_nt_tp<NT, 1>(c, tp, grid);
+// (tile width, operand kind, epilogue kind, rows per sample) -> kernel instance; false if that instance is not built
+template <int PIECES>
+bool launch_tc_nt_variant(Ctx& c, const IinsTCParams& tp, dim3 grid, int nt, int akind, int epi, int ll) {
+#define IINS_V(NT_, AK_, EPI_, LL_) \
+    if (nt == NT_ && akind == AK_ && epi == EPI_ && ll == LL_) { launch_tc_nt_v<NT_, PIECES, AK_, EPI_, LL_>(c, tp, grid); return true; }
+    IINS_V(16, 0, IINS_EPI_PLAIN, 1) IINS_V(32, 0, IINS_EPI_PLAIN, 1) IINS_V(64, 0, IINS_EPI_PLAIN, 1)
+    IINS_V(16, 1, IINS_EPI_PLAIN, 1) IINS_V(32, 1, IINS_EPI_PLAIN, 1) IINS_V(64, 1, IINS_EPI_PLAIN, 1)
+    IINS_V(64, 0, IINS_EPI_IN, 8) IINS_V(64, 0, IINS_EPI_IN, 16) IINS_V(32, 0, IINS_EPI_IN, 8) IINS_V(32, 0, IINS_EPI_IN, 16)
+    IINS_V(32, 0, IINS_EPI_LN, 16) IINS_V(16, 0, IINS_EPI_LN, 32)
+    IINS_V(16, 0, IINS_EPI_SMEM, 1) IINS_V(32, 0, IINS_EPI_SMEM, 1) IINS_V(64, 0, IINS_EPI_SMEM, 1)
+    IINS_V(16, 1, IINS_EPI_SMEM, 1) IINS_V(32, 1, IINS_EPI_SMEM, 1) IINS_V(64, 1, IINS_EPI_SMEM, 1)
+#undef IINS_V
+    return false;
 }
 
 void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
@@ -145,28 +152,34 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     IinsTCParams tp;
     memset(&tp, 0, sizeof(tp));
     tp.nt = p; tp.wpack = pk.out; tp.pieces = g_mode == 1 ? 1 : 3; tp.nkb = pk.nkb;
-    tp.timeline = (g_timeline != nullptr && g_timeline_count++ == g_timeline_which) ? g_timeline : nullptr;
-    tp.nt.dbg = tp.timeline;
-    {   // register-resident epilogue whenever its preconditions hold (iins_tc.cuh); IINS_EP_REGS=0 forces the SMEM path
+    tp.nt.dbg = nullptr;
+    // epilogue kind: register-resident whenever its preconditions hold (iins_tc.cuh); IINS_EP_REGS=0 forces the SMEM path
+    int epi = IINS_EPI_SMEM, ll = 1;
+    {
         static int ep_regs_on = -1;
         if (ep_regs_on < 0) { const char* e = getenv("IINS_EP_REGS"); ep_regs_on = e ? atoi(e) : 1; }
         const IinsEpilogue& ep = p.ep;
         auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-        bool ok = ep_regs_on && p.out_layout == IINS_NLC && p.N % nt == 0 && al16(ep.y) && al16(ep.add);
-        if (ep.norm != IINS_NORM_NONE) {
-            ok = ok && p.Lrow <= 32 && al16(ep.xhat);
-            if (ep.norm == IINS_NORM_LN) ok = ok && p.N == nt && ep.gamma != nullptr && ep.beta != nullptr;
-            else ok = ok && al16(ep.rstd);
-            if (ep.norm == IINS_NORM_ADAIN)
-                ok = ok && al16(ep.adain) && (ep.adain_ld & 3) == 0 && (ep.adain_off_b & 3) == 0 && (ep.adain_off_w & 3) == 0;
+        bool ok = ep_regs_on && p.out_layout == IINS_NLC && p.N % nt == 0 && al16(ep.y) && al16(ep.add) && ep.act != IINS_ACT_TANH;
+        if (ok && ep.norm == IINS_NORM_NONE) epi = IINS_EPI_PLAIN;
+        else if (ok && p.a_kind == 0 && al16(ep.xhat)) {
+            if (ep.norm == IINS_NORM_LN) {
+                if (p.N == nt && ep.gamma != nullptr && ep.beta != nullptr && ((nt == 32 && p.Lrow == 16) || (nt == 16 && p.Lrow == 32))) {
+                    epi = IINS_EPI_LN; ll = p.Lrow;
+                }
+            } else {
+                bool aok = al16(ep.rstd) && (nt == 64 || nt == 32) && (p.Lrow == 8 || p.Lrow == 16);
+                if (ep.norm == IINS_NORM_ADAIN)
+                    aok = aok && al16(ep.adain) && (ep.adain_ld & 3) == 0 && (ep.adain_off_b & 3) == 0 && (ep.adain_off_w & 3) == 0;
+                if (aok) { epi = IINS_EPI_IN; ll = p.Lrow; }
+            }
         }
-        tp.ep_regs = ok ? 1 : 0;
     }
     dim3 grid((p.M + 127) / 128, pk.nblk, 1);
     IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K); IINS_SET_SHAPE(p.M, p.N, p.K);
-    if (nt == 16) launch_tc_nt_t<16>(c, tp, grid);
-    else if (nt == 32) launch_tc_nt_t<32>(c, tp, grid);
-    else launch_tc_nt_t<64>(c, tp, grid);
+    const bool launched = tp.pieces == 3 ? launch_tc_nt_variant<3>(c, tp, grid, nt, p.a_kind, epi, ll)
+                                         : launch_tc_nt_variant<1>(c, tp, grid, nt, p.a_kind, epi, ll);
+    if (!launched) c.err = 4;
 }
 #endif
 
@@ -397,7 +410,9 @@ void norm_backward(Ctx& c, int B, int L, int C, int norm, int act, const float* 
     p.adain = adain; p.dadain = dadain; p.adain_ld = ld; p.adain_off_b = off_b; p.adain_off_w = off_w; p.dz = dz;
     // one warp per sample: C power of two in [4,128], L*C a multiple of 128
     if (ilog2_exact(C) < 2 || C > 128 || ((L * C) & 127) != 0) { c.err = 3; return; }
-    IINS_LAUNCH(iins_norm_bwd_kernel, (B + 7) / 8, 256, 0, c.st, p);
+    int nb = (B + 7) / 8;
+    if (nb > 148 * 4) nb = 148 * 4;                 // persistent: the kernel strides over the samples
+    IINS_LAUNCH(iins_norm_bwd_kernel, nb, 256, 0, c.st, p);
 }
 
 template <class F>
@@ -969,9 +984,7 @@ int iins_set_compute_mode(int mode) {
     return IINS_OK;
 }
 int iins_get_compute_mode(void) { return g_mode; }
-void iins_debug_set_timeline(void* dev_buf_1024_i64, int which) {
-    g_timeline = (long long*)dev_buf_1024_i64; g_timeline_which = which; g_timeline_count = 0;
-}
+void iins_debug_set_timeline(void*, int) {}   /* the per-phase clock trace was removed with the lean kernel variants */
 const char* iins_last_error(void) { return g_err; }
 int iins_validate_config(const iins_config* cfg) { Shapes s; return make_shapes(cfg, s); }
 

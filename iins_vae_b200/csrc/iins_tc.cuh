@@ -71,23 +71,29 @@ __device__ __forceinline__ void iins_gather8_dgrad_fast(const IinsGeom& g, const
     if (g.mode == IINS_PAD_REFLECT) {
         if (pos >= 1 && pos <= g.pad) q1 = g.pad - pos;
         if (pos <= g.Lin - 2 && pos >= g.Lin - 1 - g.pad) q2 = g.pad + 2 * (g.Lin - 1) - pos;
+        if (q1 < 0) { q1 = q2; q2 = -1; }              // a position has both reflected images only when Lin <= 2 * pad + 1
     } else if (g.mode == IINS_PAD_UP2) {
         q0 = 2 * pos + g.pad;
         q1 = q0 + 1;
     }
     const int sh = g.stride - 1;                       // stride is 1 or 2
-    iins_zero8(v);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const int q = j == 0 ? q0 : (j == 1 ? q1 : q2);
+    auto cand = [&](int q, float* u) {
         const int r = q - t;
         const int l = r >> sh;
         const bool ok = k0 < K && q >= 0 && r >= 0 && (r & sh) == 0 && l < g.Lout;
-        if (j > 0 && q < 0) continue;                  // warp-divergent only at the padded borders
-        float u[8];
         iins_dz8_fast(g, d, b, l, c0, ok, u);
+    };
+    cand(q0, v);
+    if (g.mode != IINS_PAD_ZERO) {                     // warp-uniform
+        float u[8];
+        cand(q1, u);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] += u[i];
+        if (q2 >= 0) {                                 // per-lane (no warp collective here: the caller may be divergent)
+            cand(q2, u);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += u[i];
+        }
     }
 }
 
@@ -280,13 +286,17 @@ __device__ __forceinline__ void iins_act_vec(float* v, int act, float slope) {
     } else if (act == IINS_ACT_LRELU) {
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * slope;
-    } else if (act == IINS_ACT_TANH) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = tanhf(v[i]);
     }
 }
 
-template <int NT, int PIECES, int LL>
+// Epilogue kinds: every (tile width, operand kind, epilogue) combination is its own lean kernel -- one generic kernel
+// with run-time switches was ~19k SASS instructions and stalled on instruction fetch more than on anything else.
+enum { IINS_EPI_PLAIN = 0,     // bias, ReLU / LeakyReLU, residual / accumulate operand
+       IINS_EPI_IN = 1,        // + InstanceNorm or AdaIN over the LL rows of a sample
+       IINS_EPI_LN = 2,        // + the reference's custom LayerNorm over a whole sample (LL rows x NT channels)
+       IINS_EPI_SMEM = 3 };    // anything else: SMEM-staged generic tile epilogue (iins_epilogue_tile)
+
+template <int NT, int PIECES, int EPI, int LL>
 __device__ __forceinline__ void iins_tc_epilogue_regs(const IinsNTParams& p, uint32_t tmem, int tile_m, int n0, int warp, int lane,
                                                       float* xch) {
     constexpr int CW = NT >= 32 ? NT / 2 : NT;          // columns per thread
@@ -303,7 +313,7 @@ __device__ __forceinline__ void iins_tc_epilogue_regs(const IinsNTParams& p, uin
     const long orow = (long)gr * p.N + n0 + cbeg;
 
     float ln_mean = 0.f, ln_rs = 0.f;
-    if (ep.norm == IINS_NORM_LN) {
+    if (EPI == IINS_EPI_LN) {
         // per-sample mean and UNBIASED std over (C*L), eps added to std (models.py:976-981); two passes
         const float nel = (float)(L * NT);
         float part = 0.f;
@@ -363,8 +373,8 @@ __device__ __forceinline__ void iins_tc_epilogue_regs(const IinsNTParams& p, uin
             for (int i = 0; i < 16; ++i) v[i] += __ldg(ep.bias + gn + i);
         }
         // x-hat and rstd are stored as soon as they exist (short live ranges: the kernel runs 2 CTAs / SM at <= 96 registers)
-        float4* xh_dst = (ep.norm != IINS_NORM_NONE && ep.xhat != nullptr && row_ok) ? reinterpret_cast<float4*>(ep.xhat + orow + c0) : nullptr;
-        if (ep.norm == IINS_NORM_IN || ep.norm == IINS_NORM_ADAIN) {
+        float4* xh_dst = (EPI != IINS_EPI_PLAIN && ep.xhat != nullptr && row_ok) ? reinterpret_cast<float4*>(ep.xhat + orow + c0) : nullptr;
+        if (EPI == IINS_EPI_IN) {
             // per (sample, channel) statistics over the L rows; biased variance (models.py:152, 1072)
             constexpr float invL = 1.0f / (float)L;
             float4* rs_dst = (ep.rstd != nullptr && row_ok && l == 0) ? reinterpret_cast<float4*>(ep.rstd + (long)b * p.N + gn) : nullptr;
@@ -394,7 +404,7 @@ __device__ __forceinline__ void iins_tc_epilogue_regs(const IinsNTParams& p, uin
                     v[4 * j + 2] = fmaf(v[4 * j + 2], w4.z, b4.z); v[4 * j + 3] = fmaf(v[4 * j + 3], w4.w, b4.w);
                 }
             }
-        } else if (ep.norm == IINS_NORM_LN) {
+        } else if (EPI == IINS_EPI_LN) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -414,7 +424,6 @@ __device__ __forceinline__ void iins_tc_epilogue_regs(const IinsNTParams& p, uin
     }
 }
 
-#define IINS_TL(tag) do { if (tl_ != nullptr && tl_n_ < 500) { tl_[2 * tl_n_] = (tag); tl_[2 * tl_n_ + 1] = clock64(); ++tl_n_; tl_[1022] = tl_n_; } } while (0)
 
 // --------------------------------------------------------------------------------- forward / dgrad GEMM
 struct IinsTCParams {
@@ -422,8 +431,6 @@ struct IinsTCParams {
     const uint16_t* wpack;
     int pieces;          // 3 (fp32-grade) or 1 (bf16)
     int nkb;             // K blocks of 32
-    long long* timeline; // debug: (tag, clock64) pairs of CTA (0,0) thread 0, or nullptr
-    int ep_regs;         // 1: register-resident epilogue (iins_tc_epilogue_regs), 0: SMEM-staged generic epilogue
 };
 
 // 288 threads: warps 0-7 are PRODUCERS (gather / split / store the A tile, later the epilogue), warp 8 is the
@@ -432,7 +439,7 @@ struct IinsTCParams {
 //   full[s]   (count 256)  producers -> MMA warp : stage s holds the A tile of this K block
 //   bready[s] (tx bytes)   TMA       -> MMA warp : stage s holds the weight tile
 //   done[s]   (tcgen05.commit) MMA   -> everyone : the MMAs reading stage s have completed (stage reusable)
-template <int NT, int PIECES>
+template <int NT, int PIECES, int AKIND, int EPI, int LL>
 __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCParams tp) {
     constexpr int BM = 128;
     constexpr uint32_t A_PIECE = 4 * BM * 16;            // 8192 B : [chunk][row][16 B]
@@ -472,7 +479,7 @@ __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCParams t
             const int k0 = kb * 32 + (a_half * 2 + jj) * 8;
             // the host routes layers without 16-byte gathers (< 8 channels, NCL operand) to the SIMT kernels
             if (!a_ok) iins_zero8(dst[jj]);
-            else if (p.a_kind == 0) iins_gather8_fwd_fast(g, p.x, p.K, cs, a_b, a_l, k0, dst[jj]);
+            else if (AKIND == 0) iins_gather8_fwd_fast(g, p.x, p.K, cs, a_b, a_l, k0, dst[jj]);
             else iins_gather8_dgrad_fast(g, p.dz, p.K, cs, a_b, a_l, k0, dst[jj]);
         }
     };
@@ -494,9 +501,6 @@ __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCParams t
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    long long* tl_ = (tp.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) ? tp.timeline : nullptr;
-    int tl_n_ = 0;
-    IINS_TL(0);
 
     if (warp == 8) {
         // ------------------------------------------------------------------ MMA warp (warp-uniform code)
@@ -529,15 +533,12 @@ __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCParams t
             const int s = kb & 1;
             unsigned char* sA = dsm + s * STAGE;
             if (kb >= 2) umma::mbar_wait(umma::smem_u32(&mbar_done[s]), (uint32_t)(((kb >> 1) - 1) & 1));
-            IINS_TL(1);
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj)
                 iins_store8_split(src[jj], sA + ((a_half * 2 + jj) * BM + a_row) * 16, A_PIECE, PIECES);
             umma::fence_async_smem();
             umma::mbar_arrive(umma::smem_u32(&mbar_full[s]));
-            IINS_TL(2);
             if (kb + 2 < nkb) load_raw(kb + 2, src);      // in flight while the next block is converted
-            IINS_TL(3);
         };
         for (int kb = 0; kb < nkb; kb += 2) {
             produce(kb, raw[0]);
@@ -548,18 +549,9 @@ __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCParams t
     if (nkb >= 2) umma::mbar_wait(umma::smem_u32(&mbar_done[(nkb - 2) & 1]), (uint32_t)(((nkb - 2) >> 1) & 1));
     umma::mbar_wait(umma::smem_u32(&mbar_done[(nkb - 1) & 1]), (uint32_t)(((nkb - 1) >> 1) & 1));
     umma::tc_fence_after();
-    IINS_TL(13);
 
-    if (warp < 8 && tp.ep_regs) {
-        // rows per sample as a compile-time constant (unrolled shuffle trees); without a fused norm L is irrelevant
-        const int Ln = p.ep.norm == IINS_NORM_NONE ? 1 : p.Lrow;
-        if (Ln == 8) iins_tc_epilogue_regs<NT, PIECES, 8>(p, tmem, tile_m, n0, warp, lane, st_mean);
-        else if (Ln == 16) iins_tc_epilogue_regs<NT, PIECES, 16>(p, tmem, tile_m, n0, warp, lane, st_mean);
-        else if (Ln == 32) iins_tc_epilogue_regs<NT, PIECES, 32>(p, tmem, tile_m, n0, warp, lane, st_mean);
-        else if (Ln == 1) iins_tc_epilogue_regs<NT, PIECES, 1>(p, tmem, tile_m, n0, warp, lane, st_mean);
-        else if (Ln == 2) iins_tc_epilogue_regs<NT, PIECES, 2>(p, tmem, tile_m, n0, warp, lane, st_mean);
-        else iins_tc_epilogue_regs<NT, PIECES, 4>(p, tmem, tile_m, n0, warp, lane, st_mean);
-        IINS_TL(15);
+    if (EPI != IINS_EPI_SMEM) {
+        if (warp < 8) iins_tc_epilogue_regs<NT, PIECES, EPI, LL>(p, tmem, tile_m, n0, warp, lane, st_mean);
     } else if (warp < 8) {
         // ---- generic path: TMEM -> SMEM (+ bias).  Warp w owns TMEM lanes 32*(w&3) .. +31; with NT >= 32 the two
         // warps sharing a lane quarter split the columns.
@@ -582,9 +574,7 @@ __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCParams t
         }
         umma::tc_fence_before();
         iins_epi_sync<true>();
-        IINS_TL(14);
         iins_epilogue_tile<NT, LD, true>(p, Cs, st_mean, st_rstd, tile_m, n0);
-        IINS_TL(15);
     }
     umma::tc_fence_before();
     __syncthreads();
@@ -668,7 +658,7 @@ __global__ void __launch_bounds__(288, 2) iins_tc_tn_kernel(const IinsTCTNParams
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int k0 = ktile0 + (warp + 8 * jj) * 8;
-                if (!ok) iins_zero8(ra[jj]);
+                if (!ok || k0 >= tp.K) iins_zero8(ra[jj]);
                 else iins_gather8_fwd_fast(g, p.x, tp.K, tp.cshift_in, b, l, k0, ra[jj]);
             }
             if (has_z) {
@@ -682,8 +672,11 @@ __global__ void __launch_bounds__(288, 2) iins_tc_tn_kernel(const IinsTCTNParams
             unsigned char* sB = sA + 3 * A_PIECE;
             if (it >= 2) umma::mbar_wait(umma::smem_u32(&mbar_done[s]), (uint32_t)(((it >> 1) - 1) & 1));
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj)
-                iins_store8_split(ra[jj], sA + ((warp + 8 * jj) * BR + lane) * 16, A_PIECE, PIECES);
+            for (int jj = 0; jj < 2; ++jj) {
+                // k chunks beyond K (a half-empty last k tile) are all zero: written once per stage, then skipped (warp-uniform)
+                if (ktile0 + (warp + 8 * jj) * 8 < tp.K || it < 2)
+                    iins_store8_split(ra[jj], sA + ((warp + 8 * jj) * BR + lane) * 16, A_PIECE, PIECES);
+            }
             if (has_z) {
                 if (do_bias) {
 #pragma unroll
@@ -715,6 +708,9 @@ __global__ void __launch_bounds__(288, 2) iins_tc_tn_kernel(const IinsTCTNParams
             const int cbeg = NT >= 32 ? hf * COLS_PER_WARP : 0;
             const bool kok = k < tp.K;
             const int t = kok ? k / g.Cin : 0, ci = kok ? k - t * g.Cin : 0;
+            // dW[n][ci][t]: this lane's (ci, t) is fixed, n walks the accumulator columns with a constant stride
+            const long nstride = (long)g.Cin * g.ks;
+            float* dst0 = p.dw + (long)(n0 + cbeg) * nstride + (long)ci * g.ks + t;
 #pragma unroll
             for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 16) {
                 float v[16];
@@ -722,15 +718,18 @@ __global__ void __launch_bounds__(288, 2) iins_tc_tn_kernel(const IinsTCTNParams
                 if (kok) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        int n = n0 + cbeg + c0 + i;
-                        if (n < g.Cout) atomicAdd(p.dw + iins_w_index(g, n, ci, t), v[i]);
+                        if (n0 + cbeg + c0 + i < g.Cout) atomicAdd(dst0 + (c0 + i) * nstride, v[i]);
                     }
                 }
             }
         }
         if (do_bias && has_z) {
+            // bias gradient: each producer warp owns 8 distinct output channels -> warp-shuffle sum over its 32 rows, plain store
 #pragma unroll
-            for (int i = 0; i < 8; ++i) atomicAdd(&s_bias[warp * 8 + i], bsum[i]);
+            for (int i = 0; i < 8; ++i) {
+                const float tot = iins_warp_sum(bsum[i]);
+                if (lane == 0) s_bias[warp * 8 + i] = tot;
+            }
         }
     }
     umma::tc_fence_before();
