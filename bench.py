@@ -310,9 +310,11 @@ def main():
     kernel_table = None
     # every rank runs the instrumented steps (they contain the gradient all-reduce); rank 0 reports
     eng.use_graph = False
+    eng.set_concurrency(False)              # serial launches: an event pair then brackets exactly one kernel
     prof = []
     for sup in (True, False):
         prof += lib.profile(lambda: eng.step(*dev[0], supervised=sup))
+    eng.set_concurrency(True)
     eng.use_graph = eng_eager
     barrier()
     if rank == 0:

@@ -21,7 +21,7 @@ EXPORTS = [
     "iins_classifier_num_params", "iins_classifier_ws_floats", "iins_classifier_scratch_floats",
     "iins_classifier_forward", "iins_classifier_backward",
     "iins_loss_forward_backward", "iins_adam_step",
-    "iins_adaptive_pool_forward", "iins_adaptive_pool_backward", "iins_accumulate2",
+    "iins_adaptive_pool_forward", "iins_adaptive_pool_backward", "iins_accumulate2", "iins_set_stream_concurrency",
     "iins_launch_count", "iins_profile_begin", "iins_profile_collect",
     "iins_set_compute_mode", "iins_get_compute_mode", "iins_profile_shapes",
 ]

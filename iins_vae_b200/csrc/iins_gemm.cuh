@@ -526,6 +526,215 @@ __global__ void __launch_bounds__(256) iins_row_nt_kernel(const IinsRowParams rp
     iins_epilogue_tile<NT, LD>(p, Cs, st_mean, st_rstd, tile_m, 0);
 }
 
+// ---- one thread per output row ("row2") --------------------------------------------------------------------
+// The small-channel layers are HBM streams (L = 32..128 positions, <= 16 channels): what limits them is the number
+// of instructions per output row, not arithmetic.  One thread owns one GEMM row and all NACC (4 / 8 / 16) output
+// channels in registers: a tap/channel step is NACC/4 16-byte weight loads from shared memory + NACC FFMAs, the
+// InstanceNorm / AdaIN / LayerNorm statistics are warp-shuffle sums (+ one shared-memory exchange between the
+// L/32 warps of a sample), and the row leaves the registers as 16-byte stores -- no staging of the tile in shared
+// memory, no second thread per row.  128 threads = 128 rows = whole samples (L <= 128).
+// Preconditions (host): N <= NACC, K <= IINS_ROW2_KMAX(NACC); with a fused norm: L in {32, 64, 128}.
+#define IINS_ROW2_WMAX 1024            // floats of weights in shared memory: K * NACC <= 1024
+
+template <int NACC>
+IINS_D void iins_row2_fma(float* acc, float a, const float* w) {
+#pragma unroll
+    for (int j = 0; j < NACC; j += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w + j);
+        acc[j] = fmaf(a, w4.x, acc[j]); acc[j + 1] = fmaf(a, w4.y, acc[j + 1]);
+        acc[j + 2] = fmaf(a, w4.z, acc[j + 2]); acc[j + 3] = fmaf(a, w4.w, acc[j + 3]);
+    }
+}
+
+// sum of v over the L rows of this thread's sample (L in {32,64,128}: whole warps); xch: [4] floats per call site
+IINS_D float iins_row2_sample_sum(float v, int nw, int warp, int lane, float* xch) {
+    v = iins_warp_sum(v);
+    if (nw > 1) {                                   // CTA-uniform
+        if (lane == 0) xch[warp] = v;
+        __syncthreads();
+        const int w0 = warp & ~(nw - 1);
+        float t = 0.f;
+        for (int i = 0; i < nw; ++i) t += xch[w0 + i];
+        v = t;
+        __syncthreads();                            // xch is reused by the next reduction
+    }
+    return v;
+}
+
+template <int NACC, int AKIND, int EPI>      // EPI: 0 plain, 1 InstanceNorm / AdaIN, 2 LayerNorm
+__global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowParams rp) {
+    constexpr int BM = 128;
+    __shared__ __align__(16) float Ws[IINS_ROW2_WMAX];       // [k][NACC]
+    __shared__ float s_bias[16];
+    __shared__ float xch[4];
+    const IinsNTParams& p = rp.nt;
+    const IinsGeom& g = p.g;
+    const IinsEpilogue& ep = p.ep;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_m = blockIdx.x * BM;
+    const int Cdim = AKIND == 0 ? g.Cin : g.Cout;
+    for (int e = tid; e < p.K * NACC; e += BM) {
+        const int k = e / NACC, n = e - k * NACC;
+        float v = 0.f;
+        if (n < p.N) {
+            const int t = k / Cdim, c = k - t * Cdim;
+            v = __ldg(p.w + (AKIND == 0 ? iins_w_index(g, n, c, t) : iins_w_index(g, c, n, t)));
+        }
+        Ws[e] = v;
+    }
+    if (tid < 16) s_bias[tid] = (ep.bias != nullptr && tid < p.N) ? __ldg(ep.bias + tid) : 0.f;
+    __syncthreads();
+
+    const int grow = tile_m + tid;
+    const bool ok = grow < p.M;
+    const int b = ok ? grow >> p.lshift : 0, l = ok ? grow & (p.Lrow - 1) : 0;
+    float acc[NACC];
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) acc[j] = s_bias[j & 15];
+    if (ok) {
+        if (AKIND == 0) {
+            for (int t = 0; t < g.ks; ++t) {
+                const int pos = iins_src_pos(g, l, t);
+                if (pos < 0) continue;
+                const float* xr = p.x + iins_in_index(g, b, pos, 0);
+                const float* wr = Ws + t * Cdim * NACC;
+                if (g.in_layout == IINS_NLC && (Cdim & 3) == 0) {
+                    for (int c = 0; c < Cdim; c += 4) {
+                        const float4 a4 = __ldg(reinterpret_cast<const float4*>(xr + c));
+                        iins_row2_fma<NACC>(acc, a4.x, wr + c * NACC);
+                        iins_row2_fma<NACC>(acc, a4.y, wr + (c + 1) * NACC);
+                        iins_row2_fma<NACC>(acc, a4.z, wr + (c + 2) * NACC);
+                        iins_row2_fma<NACC>(acc, a4.w, wr + (c + 3) * NACC);
+                    }
+                } else {
+                    const long cstride = g.in_layout == IINS_NCL ? g.Lin : 1;
+                    for (int c = 0; c < Cdim; ++c) iins_row2_fma<NACC>(acc, __ldg(xr + c * cstride), wr + c * NACC);
+                }
+            }
+        } else {
+            // data gradient: output rows whose tap t reads this input position (<= 3 candidates)
+            int q[3] = {l + g.pad, -1, -1};
+            if (g.mode == IINS_PAD_REFLECT) {
+                if (l >= 1 && l <= g.pad) q[1] = g.pad - l;
+                if (l <= g.Lin - 2 && l >= g.Lin - 1 - g.pad) q[2] = g.pad + 2 * (g.Lin - 1) - l;
+            } else if (g.mode == IINS_PAD_UP2) {
+                q[0] = 2 * l + g.pad;
+                q[1] = q[0] + 1;
+            }
+            const bool vec = g.out_layout == IINS_NLC && (Cdim & 3) == 0 && !p.dz.dy_bcast;
+            const bool masked = p.dz.y != nullptr && p.dz.act != IINS_ACT_NONE;
+            const float sc = p.dz.dy_scale;
+            for (int t = 0; t < g.ks; ++t) {
+                const float* wr = Ws + t * Cdim * NACC;
+#pragma unroll
+                for (int jq = 0; jq < 3; ++jq) {
+                    if (q[jq] < 0) continue;
+                    const int r = q[jq] - t;
+                    if (r < 0) continue;
+                    const int lo = r / g.stride;
+                    if (lo * g.stride != r || lo >= g.Lout) continue;
+                    if (vec) {
+                        const long base = ((long)b * g.Lout + lo) * g.Cout;
+                        for (int c = 0; c < Cdim; c += 4) {
+                            float4 a4 = __ldg(reinterpret_cast<const float4*>(p.dz.dy + base + c));
+                            if (masked) {
+                                const float4 y4 = __ldg(reinterpret_cast<const float4*>(p.dz.y + base + c));
+                                a4.x *= iins_dact_from_y(y4.x, p.dz.act, p.dz.slope); a4.y *= iins_dact_from_y(y4.y, p.dz.act, p.dz.slope);
+                                a4.z *= iins_dact_from_y(y4.z, p.dz.act, p.dz.slope); a4.w *= iins_dact_from_y(y4.w, p.dz.act, p.dz.slope);
+                            }
+                            iins_row2_fma<NACC>(acc, a4.x * sc, wr + c * NACC);
+                            iins_row2_fma<NACC>(acc, a4.y * sc, wr + (c + 1) * NACC);
+                            iins_row2_fma<NACC>(acc, a4.z * sc, wr + (c + 2) * NACC);
+                            iins_row2_fma<NACC>(acc, a4.w * sc, wr + (c + 3) * NACC);
+                        }
+                    } else {
+                        for (int c = 0; c < Cdim; ++c) iins_row2_fma<NACC>(acc, iins_dz_at(g, p.dz, b, lo, c), wr + c * NACC);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- epilogue in registers
+    const int L = p.Lrow;
+    const int nw = L >> 5;                               // warps per sample (1, 2 or 4) when a norm is fused
+    float xh[NACC];                                      // normalised pre-affine values (dead when EPI == 0)
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) xh[j] = 0.f;
+    if (EPI == 1) {
+        const float invL = 1.0f / (float)L;
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+            const float mean = iins_row2_sample_sum(acc[j], nw, warp, lane, xch) * invL;
+            const float d = acc[j] - mean;
+            const float vpe = fmaf(iins_row2_sample_sum(d * d, nw, warp, lane, xch), invL, IINS_EPS);
+            float r = rsqrtf(vpe);
+            r = r * fmaf(-0.5f * vpe, r * r, 1.5f);
+            xh[j] = d * r;
+            if (ok && l == 0 && j < p.N && ep.rstd != nullptr) ep.rstd[(long)b * p.N + j] = r;
+            acc[j] = xh[j];
+            if (ep.norm == IINS_NORM_ADAIN && j < p.N) {
+                const float* ab = ep.adain + (long)b * ep.adain_ld;
+                acc[j] = fmaf(xh[j], __ldg(ab + ep.adain_off_w + j), __ldg(ab + ep.adain_off_b + j));
+            }
+        }
+    } else if (EPI == 2) {
+        // per-sample mean and UNBIASED std over (C*L), eps added to std (models.py:976-981)
+        const float nel = (float)(L * p.N);
+        float part = 0.f;
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) part += j < p.N ? acc[j] : 0.f;
+        const float mean = iins_row2_sample_sum(part, nw, warp, lane, xch) / nel;
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) { const float d = acc[j] - mean; sq += j < p.N ? d * d : 0.f; }
+        sq = iins_row2_sample_sum(sq, nw, warp, lane, xch);
+        const float rs = 1.0f / (sqrtf(sq / (nel - 1.f)) + IINS_EPS);
+        if (ok && l == 0 && ep.rstd != nullptr) ep.rstd[b] = rs;
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+            xh[j] = (acc[j] - mean) * rs;
+            acc[j] = j < p.N ? fmaf(xh[j], __ldg(ep.gamma + j), __ldg(ep.beta + j)) : 0.f;
+        }
+    }
+    if (ep.act == IINS_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    } else if (ep.act != IINS_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) acc[j] = iins_act(acc[j], ep.act, ep.slope);
+    }
+    if (!ok) return;
+    if (p.out_layout == IINS_NLC && p.N == NACC) {
+        const long oi = (long)grow * NACC;
+        if (EPI != 0 && ep.xhat != nullptr) {
+#pragma unroll
+            for (int j = 0; j < NACC; j += 4)
+                *reinterpret_cast<float4*>(ep.xhat + oi + j) = make_float4(xh[j], xh[j + 1], xh[j + 2], xh[j + 3]);
+        }
+        if (ep.add != nullptr) {
+#pragma unroll
+            for (int j = 0; j < NACC; j += 4) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(ep.add + oi + j));
+                acc[j] += a4.x; acc[j + 1] += a4.y; acc[j + 2] += a4.z; acc[j + 3] += a4.w;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NACC; j += 4)
+            *reinterpret_cast<float4*>(ep.y + oi + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+            if (j >= p.N) continue;
+            const long oi = p.out_layout == IINS_NCL ? (((long)b * p.N + j) << p.lshift) + l : (long)grow * p.N + j;
+            if (EPI != 0 && ep.xhat != nullptr) ep.xhat[oi] = xh[j];
+            float o = acc[j];
+            if (ep.add != nullptr) o += ep.add[oi];
+            ep.y[oi] = o;
+        }
+    }
+}
+
 // Weight gradient for the same small layers: dW[n][k] (N <= 16, K <= 64) = sum_rows dz[row][n] * A[row][k].
 // Persistent CTAs: each stages 64 rows of dz and of the im2col'd input in shared memory, thread (n, k-quad)
 // accumulates in registers over the CTA's row range and flushes once with atomics.

@@ -192,7 +192,26 @@ void launch_nt(Ctx& c, IinsNTParams p) {
         if (p.cshift < 0 && p.g.ks == 1 && cdim % 8 == 0) p.cshift = 31;
     }
     if (p.lshift < 0) { c.err = 2; return; }
-    if (p.N <= 16 && p.K <= 64) {                     // small-channel layer: direct SIMT conv + fused epilogue
+    {   // small-channel layer: direct SIMT conv, one thread per output row, register epilogue (iins_row2_nt_kernel)
+        const int nacc = p.N <= 4 ? 4 : (p.N <= 8 ? 8 : 16);
+        const bool norm_ok = p.ep.norm == IINS_NORM_NONE || (p.a_kind == 0 && (p.Lrow == 32 || p.Lrow == 64 || p.Lrow == 128));
+        static int row2_on = -1;
+        if (row2_on < 0) { const char* e = getenv("IINS_ROW2"); row2_on = e ? atoi(e) : 1; }
+        if (row2_on && p.N <= 16 && p.K * nacc <= IINS_ROW2_WMAX && p.K <= 128 && norm_ok) {
+            if (c.phase == 1) return;
+            IinsRowParams rp;
+            rp.nt = p;
+            const int epi = p.ep.norm == IINS_NORM_NONE ? 0 : (p.ep.norm == IINS_NORM_LN ? 2 : 1);
+            const int grid = (p.M + 127) / 128;
+            IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K); IINS_SET_SHAPE(p.M, p.N, p.K);
+#define IINS_R2(NA_, AK_, EP_) \
+            if (nacc == NA_ && p.a_kind == AK_ && epi == EP_) { auto iins_row2_nt_kernel_ = iins_row2_nt_kernel<NA_, AK_, EP_>; IINS_LAUNCH(iins_row2_nt_kernel_, grid, 128, 0, c.st, rp); return; }
+            IINS_R2(4, 0, 0) IINS_R2(8, 0, 0) IINS_R2(16, 0, 0) IINS_R2(4, 1, 0) IINS_R2(8, 1, 0) IINS_R2(16, 1, 0)
+            IINS_R2(4, 0, 1) IINS_R2(8, 0, 1) IINS_R2(16, 0, 1) IINS_R2(4, 0, 2) IINS_R2(8, 0, 2) IINS_R2(16, 0, 2)
+#undef IINS_R2
+        }
+    }
+    if (p.N <= 16 && p.K <= 64) {                     // (previous two-threads-per-row kernel: fallback for other geometries)
         if (c.phase == 1) return;
         IinsRowParams rp;
         rp.nt = p;
@@ -986,6 +1005,15 @@ int iins_set_compute_mode(int mode) {
 int iins_get_compute_mode(void) { return g_mode; }
 void iins_debug_set_timeline(void*, int) {}   /* the per-phase clock trace was removed with the lean kernel variants */
 const char* iins_last_error(void) { return g_err; }
+int iins_set_stream_concurrency(int enable) {
+#ifndef IINS_CPUSIM
+    g_async_wgrad = enable ? 1 : 0;
+    g_branch_streams = enable ? 1 : 0;
+#else
+    (void)enable;
+#endif
+    return IINS_OK;
+}
 int iins_validate_config(const iins_config* cfg) { Shapes s; return make_shapes(cfg, s); }
 
 int iins_encoder_num_params(const iins_config* cfg) { IINS_SHAPES_OR_RETURN(cfg, s); return enc_num_params(s); }

@@ -130,8 +130,16 @@ class SemiTrainEngine:
         self.lr.fill_(float(lr))
 
     # ------------------------------------------------------------------------------------------------
+    concurrent = True       # False: one stream, no overlap (per-kernel event timing); see set_concurrency()
+
+    def set_concurrency(self, enable: bool):
+        """Overlap of independent work on helper streams (heads next to the decoder here; weight gradients and the env
+        encoder inside the library).  Disable to time individual kernels; captured graphs keep the setting they had."""
+        self.concurrent = bool(enable)
+        self.lib.check(self.lib.iins_set_stream_concurrency(int(enable)), "set_stream_concurrency")
+
     def _heads_concurrent(self, supervised: bool) -> bool:
-        return self.mode == "semi" and supervised
+        return self.concurrent and self.mode == "semi" and supervised
 
     def _forward(self, supervised: bool):
         lib, cfg, st = self.lib, self.cfg, _stream()

@@ -146,6 +146,11 @@ int iins_adaptive_pool_backward(const float* dy, float* dx, int batch, int lin, 
 int iins_accumulate2(float* dst1, const float* src1, size_t n1, float* dst2, const float* src2, size_t n2,
                      iins_stream_t stream);
 
+/* Inside one module pass the library overlaps independent work on helper streams (weight gradients next to the
+ * data-gradient chain, env encoder next to the range encoder); 0 serialises everything on the caller's stream --
+ * used when individual kernels are timed with events (bench.py roofline, tools/step_profile.py). Default 1. */
+int iins_set_stream_concurrency(int enable);
+
 /* ---- launch accounting / in-process kernel timing (used by bench.py; not a profiler replacement) ------ */
 unsigned long long iins_launch_count(void);           /* kernels launched by this library so far */
 int iins_profile_begin(void);                          /* record a CUDA-event pair around every launch */

@@ -21,6 +21,7 @@ for m, p in ((Enc, pe), (Dec, pd), (Res, pr), (Cls, pc)):
     m.load_state_dict(p); m.cuda()
 cir, err, label = orc.synthetic_batch(cfg, B, 1)
 eng = SemiTrainEngine(Enc, Dec, Res, Cls, batch_size=B, use_graph=False)
+eng.set_concurrency(False)          # serial launches: one event pair = one kernel
 for _ in range(3):
     eng.step(cir, err, label, supervised=True)
 torch.cuda.synchronize()
