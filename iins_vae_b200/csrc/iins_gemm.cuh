@@ -807,6 +807,111 @@ __global__ void __launch_bounds__(256) iins_row_tn_kernel(const IinsRowTNParams 
     if (p.db != nullptr && tid < N) atomicAdd(p.db + tid, bsum);
 }
 
+// ---- weight gradient of the small-channel conv layers, one thread per row ("row2") ---------------------------
+// dW[n][k] = sum_rows dz[row][n] * A[row][k] with M = B*L huge (up to 524288) and N*K tiny (28..512): a tall-skinny
+// reduction.  Lane = row: a thread loads dz[row][0..NACC) and the im2col slice A[row][k-slice] (TPS taps x CIN
+// channels, compile-time so everything stays in registers), does the NACC x KS outer-product FMAs into its own
+// accumulators and walks on to its next row; only at the very end the 128 threads of the CTA are summed through
+// shared memory and the CTA issues one atomic per output.  grid = (row parts, k slices).
+struct IinsRow2TNParams {
+    IinsTNParams tn;
+    int lshift;                // log2(Lout)
+};
+
+template <int NACC, int CIN, int TPS>
+__global__ void __launch_bounds__(128) iins_row2_tn_kernel(const IinsRow2TNParams rp) {
+    constexpr int KS = CIN * TPS;              // k entries per thread
+    constexpr int NA = NACC * KS;              // accumulators per thread
+    __shared__ float red[128][33];
+    const IinsTNParams& p = rp.tn;
+    const IinsGeom& g = p.g;
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.y * TPS;           // first tap of this CTA's k slice
+    const bool do_bias = p.db != nullptr && blockIdx.y == 0;
+    float acc[NA], bacc[NACC];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) bacc[i] = 0.f;
+    const int r_begin = blockIdx.x * p.rows_per_part;
+    int r_end = r_begin + p.rows_per_part;
+    if (r_end > p.M) r_end = p.M;
+    const bool zvec = g.out_layout == IINS_NLC && g.Cout == NACC && (NACC & 3) == 0 && !p.dz.dy_bcast;
+    const bool masked = p.dz.y != nullptr && p.dz.act != IINS_ACT_NONE;
+    for (int row = r_begin + tid; row < r_end; row += 128) {
+        const int b = row >> rp.lshift, l = row & (g.Lout - 1);
+        float z[NACC], a[KS];
+        if (zvec) {
+            const long zi = (long)row * NACC;
+#pragma unroll
+            for (int j = 0; j < NACC; j += 4) {
+                float4 d4 = __ldg(reinterpret_cast<const float4*>(p.dz.dy + zi + j));
+                if (masked) {
+                    const float4 y4 = __ldg(reinterpret_cast<const float4*>(p.dz.y + zi + j));
+                    d4.x *= iins_dact_from_y(y4.x, p.dz.act, p.dz.slope); d4.y *= iins_dact_from_y(y4.y, p.dz.act, p.dz.slope);
+                    d4.z *= iins_dact_from_y(y4.z, p.dz.act, p.dz.slope); d4.w *= iins_dact_from_y(y4.w, p.dz.act, p.dz.slope);
+                }
+                z[j] = d4.x * p.dz.dy_scale; z[j + 1] = d4.y * p.dz.dy_scale; z[j + 2] = d4.z * p.dz.dy_scale; z[j + 3] = d4.w * p.dz.dy_scale;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NACC; ++j) z[j] = j < g.Cout ? iins_dz_at(g, p.dz, b, l, j) : 0.f;
+        }
+#pragma unroll
+        for (int tt = 0; tt < TPS; ++tt) {
+            const int t = t0 + tt;
+            const int pos = t < g.ks ? iins_src_pos(g, l, t) : -1;
+            if (CIN >= 4 && g.in_layout == IINS_NLC) {
+                const float* xr = p.x + ((long)b * g.Lin + (pos >= 0 ? pos : 0)) * CIN;
+#pragma unroll
+                for (int c = 0; c < CIN; c += 4) {
+                    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (pos >= 0) a4 = __ldg(reinterpret_cast<const float4*>(xr + c));
+                    a[tt * CIN + c] = a4.x; a[tt * CIN + c + 1] = a4.y; a[tt * CIN + c + 2] = a4.z; a[tt * CIN + c + 3] = a4.w;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) a[tt * CIN + c] = pos >= 0 ? __ldg(p.x + iins_in_index(g, b, pos, c)) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NACC; ++n) {
+#pragma unroll
+            for (int k = 0; k < KS; ++k) acc[n * KS + k] = fmaf(z[n], a[k], acc[n * KS + k]);
+            bacc[n] += z[n];
+        }
+    }
+    // ---- CTA reduction, 32 accumulators at a time: red[thread][value] -> 4 partial sums per value -> one atomic
+    const int col = tid & 31, part = tid >> 5;
+#pragma unroll
+    for (int c0 = 0; c0 < NA + NACC; c0 += 32) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int e = c0 + i;                           // compile-time after unrolling
+            red[tid][i] = e < NA ? acc[e < NA ? e : 0] : (e < NA + NACC ? bacc[e < NA + NACC && e >= NA ? e - NA : 0] : 0.f);
+        }
+        __syncthreads();
+        float sum = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) sum += red[part * 32 + r][col];
+        __syncthreads();
+        red[part][col] = sum;
+        __syncthreads();
+        if (part == 0) {
+            sum = red[0][col] + red[1][col] + red[2][col] + red[3][col];
+            const int e = c0 + col;
+            if (e < NA) {
+                const int n = e / KS, k = e - n * KS;
+                const int tt = k / CIN, c = k - tt * CIN, t = t0 + tt;
+                if (n < g.Cout && t < g.ks) atomicAdd(p.dw + iins_w_index(g, n, c, t), sum);
+            } else if (e < NA + NACC && do_bias) {
+                if (e - NA < g.Cout) atomicAdd(p.db + (e - NA), sum);
+            }
+        }
+    }
+}
+
 // Weight gradient of "thin" layers: one of the two GEMM dims is <= 4 (the 1x1 conv on the 2-channel range code:
 // K = 2; the Restorer's last Linear: N = 1).  dW is then T <= 4 rank-1 accumulations of a W-wide row vector:
 // thread = one wide column, 256 / W row groups per CTA, coalesced reads of the wide operand, T accumulators per
