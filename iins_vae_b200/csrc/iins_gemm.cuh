@@ -23,6 +23,17 @@ struct IinsEpilogue {
     const float* beta;
     const float* adain;        // AdaIN params (B, adain_ld): bias at +off_b, weight at +off_w
     int adain_ld, adain_off_b, adain_off_w;
+    // Fused InstanceNorm / AdaIN BACKWARD of the layer whose output gradient this data-gradient GEMM produces (the
+    // tile holds whole samples, so the per-(sample, channel) sums over L are available in the epilogue):
+    //   dz = rstd * (gx - mean_l(gx) - xhat * mean_l(gx * xhat)),  gx = act'(.) * dy * scale
+    // nb_dz != nullptr switches it on; y (the plain gradient) is then optional (nullptr = not needed afterwards).
+    float* nb_dz;
+    const float* nb_xhat;      // saved normalised values of that layer (same indexing as y)
+    const float* nb_rstd;      // [B*N]
+    int nb_act;                // IINS_ACT_NONE / IINS_ACT_RELU of that layer
+    const float* nb_adain;     // AdaIN params of that layer or nullptr (plain InstanceNorm)
+    float* nb_dadain;          // AdaIN parameter gradients (B, ld): bias grad at +off_b, weight grad at +off_w
+    int nb_ld, nb_off_b, nb_off_w;
 };
 
 struct IinsNTParams {

@@ -34,6 +34,10 @@ struct Ctx {
     int njobs = 0, job_i = 0;
     size_t arena = 0;           // bytes of the arena handed out so far
     cudaStream_t st2 = nullptr; // side stream: weight gradients run here, concurrently with the dgrad chain
+    // A data-gradient GEMM is held back until the next call: if that call is the InstanceNorm / AdaIN backward of the
+    // tensor it produces, both run as ONE kernel (fused epilogue); any other call launches it unchanged first.
+    bool has_pending = false;
+    IinsNTParams pending;
 #ifndef IINS_CPUSIM
     IinsPackAllParams jobs;
 #endif
@@ -116,6 +120,7 @@ bool launch_tc_nt_variant(Ctx& c, const IinsTCParams& tp, dim3 grid, int nt, int
     IINS_V(16, 1, IINS_EPI_PLAIN, 1) IINS_V(32, 1, IINS_EPI_PLAIN, 1) IINS_V(64, 1, IINS_EPI_PLAIN, 1)
     IINS_V(64, 0, IINS_EPI_IN, 8) IINS_V(64, 0, IINS_EPI_IN, 16) IINS_V(32, 0, IINS_EPI_IN, 8) IINS_V(32, 0, IINS_EPI_IN, 16)
     IINS_V(32, 0, IINS_EPI_LN, 16) IINS_V(16, 0, IINS_EPI_LN, 32)
+    IINS_V(64, 1, IINS_EPI_NBWD, 8) IINS_V(32, 1, IINS_EPI_NBWD, 16) IINS_V(16, 1, IINS_EPI_NBWD, 32)
     IINS_V(16, 0, IINS_EPI_SMEM, 1) IINS_V(32, 0, IINS_EPI_SMEM, 1) IINS_V(64, 0, IINS_EPI_SMEM, 1)
     IINS_V(16, 1, IINS_EPI_SMEM, 1) IINS_V(32, 1, IINS_EPI_SMEM, 1) IINS_V(64, 1, IINS_EPI_SMEM, 1)
 #undef IINS_V
@@ -161,7 +166,8 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
         const IinsEpilogue& ep = p.ep;
         auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
         bool ok = ep_regs_on && p.out_layout == IINS_NLC && p.N % nt == 0 && al16(ep.y) && al16(ep.add) && ep.act != IINS_ACT_TANH;
-        if (ok && ep.norm == IINS_NORM_NONE) epi = IINS_EPI_PLAIN;
+        if (ok && ep.nb_dz != nullptr) { epi = IINS_EPI_NBWD; ll = p.Lrow; }       // preconditions checked by nbwd_fusable()
+        else if (ok && ep.norm == IINS_NORM_NONE) epi = IINS_EPI_PLAIN;
         else if (ok && p.a_kind == 0 && al16(ep.xhat)) {
             if (ep.norm == IINS_NORM_LN) {
                 if (p.N == nt && ep.gamma != nullptr && ep.beta != nullptr && ((nt == 32 && p.Lrow == 16) || (nt == 16 && p.Lrow == 32))) {
@@ -182,6 +188,41 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     if (!launched) c.err = 4;
 }
 #endif
+
+void launch_nt(Ctx& c, IinsNTParams p);
+void flush_pending(Ctx& c) {
+    if (!c.has_pending) return;
+    c.has_pending = false;
+    launch_nt(c, c.pending);
+}
+
+// Can the held-back data-gradient GEMM take the norm backward of its own output into its epilogue?  Mirrors the
+// conditions of launch_nt / launch_nt_tc for the IINS_EPI_NBWD instances (tile width x rows per sample).
+bool nbwd_fusable(const Ctx& c, const IinsNTParams& p, int L, int C, const float* dy, const float* xhat, const float* rstd,
+                  const float* adain, const float* dadain, int ld, int off_b, int off_w, const float* dz) {
+#ifdef IINS_CPUSIM
+    return false;
+#else
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("IINS_FUSE_NBWD"); on = e ? atoi(e) : 1; }
+    if (!on || g_mode == 2 || p.a_kind != 1 || p.ep.y != dy || p.N != C || p.Lrow != L) return false;
+    {   // row kernel territory (same routing as launch_nt) or the SMEM epilogue forced by IINS_EP_REGS=0
+        const int nacc = p.N <= 4 ? 4 : (p.N <= 8 ? 8 : 16);
+        if (p.N <= 16 && ((p.K * nacc <= IINS_ROW2_WMAX && p.K <= 128) || p.K <= 64)) return false;
+        const char* e = getenv("IINS_EP_REGS");
+        if (e && atoi(e) == 0) return false;
+    }
+    const int cs = ilog2_exact(p.g.Cout);
+    if (cs < 3 || p.g.out_layout != IINS_NLC || p.out_layout != IINS_NLC) return false;
+    const int nt = p.N <= 16 ? 16 : (p.N <= 32 ? 32 : 64);
+    if (p.N % nt != 0 || !((nt == 64 && L == 8) || (nt == 32 && L == 16) || (nt == 16 && L == 32))) return false;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (!al16(p.ep.y) || !al16(p.ep.add) || !al16(xhat) || !al16(rstd) || !al16(dz) || !al16(adain) || !al16(dadain)) return false;
+    if (adain != nullptr && ((ld & 3) || (off_b & 3) || (off_w & 3))) return false;
+    (void)c;
+    return true;
+#endif
+}
 
 void launch_nt(Ctx& c, IinsNTParams p) {
     p.lshift = ilog2_exact(p.Lrow);
@@ -236,6 +277,7 @@ void conv_forward(Ctx& c, const IinsGeom& g, const float* x, const float* w, con
     p.g = g; p.a_kind = 0; p.x = x; p.w = w; p.ep = ep;
     p.M = g.B * g.Lout; p.N = g.Cout; p.K = g.ks * g.Cin;
     p.Lrow = g.Lout; p.out_layout = g.out_layout;
+    flush_pending(c);
     launch_nt(c, p);
 }
 
@@ -248,7 +290,10 @@ void conv_dgrad(Ctx& c, const IinsGeom& g, const IinsDz& dz, const float* w, flo
     p.ep.add = add;
     p.M = g.B * g.Lin; p.N = g.Cin; p.K = g.ks * g.Cout;
     p.Lrow = g.Lin; p.out_layout = g.in_layout;
-    launch_nt(c, p);
+    flush_pending(c);
+    if (c.phase == 1) { launch_nt(c, p); return; }     // collect: only the weight-pack job is recorded
+    c.pending = p;                                     // launched by the next call (possibly fused with a norm backward)
+    c.has_pending = true;
 }
 
 // ---- side stream for the weight gradients --------------------------------------------------------------
@@ -301,11 +346,12 @@ cudaStream_t branch_stream(cudaStream_t) { return nullptr; }
 void fork_to(cudaStream_t, cudaStream_t) {}
 #endif
 void begin_async_wgrad(Ctx& c) { if (c.phase != 1) c.st2 = side_stream(c.st); }
-void end_async_wgrad(Ctx& c) { if (c.phase != 1 && c.st2 != nullptr) { fork_to(c.st2, c.st); c.st2 = nullptr; } }
+void end_async_wgrad(Ctx& c) { flush_pending(c); if (c.phase != 1 && c.st2 != nullptr) { fork_to(c.st2, c.st); c.st2 = nullptr; } }
 // Run an independent part of a module pass on the branch stream: begin_branch() redirects the launches of `c`,
 // end_branch() restores the main stream; join_branch() makes the main stream wait for the branch.
 struct Branch { cudaStream_t main = nullptr, br = nullptr; };
 void begin_branch(Ctx& c, Branch& b) {
+    flush_pending(c);
     if (c.phase == 1) return;
     b.main = c.st;
     if (b.br == nullptr) b.br = branch_stream(c.st);
@@ -313,8 +359,8 @@ void begin_branch(Ctx& c, Branch& b) {
     fork_to(c.st, b.br);
     c.st = b.br;
 }
-void end_branch(Ctx& c, Branch& b) { if (c.phase != 1 && b.br != nullptr) c.st = b.main; }
-void join_branch(Ctx& c, Branch& b) { if (c.phase != 1 && b.br != nullptr) fork_to(b.br, c.st); }
+void end_branch(Ctx& c, Branch& b) { flush_pending(c); if (c.phase != 1 && b.br != nullptr) c.st = b.main; }
+void join_branch(Ctx& c, Branch& b) { flush_pending(c); if (c.phase != 1 && b.br != nullptr) fork_to(b.br, c.st); }
 
 #ifndef IINS_CPUSIM
 template <int NT, int PIECES>
@@ -337,6 +383,7 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
     memset(&p, 0, sizeof(p));
     p.g = g; p.x = x; p.dz = dz; p.dw = dw; p.db = db;
     if (c.phase == 1) return;
+    flush_pending(c);
     cudaStream_t wst = c.st;
     if (c.st2 != nullptr) { fork_to(c.st, c.st2); wst = c.st2; }
     p.M = g.B * g.Lout;
@@ -448,8 +495,19 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
 
 void norm_backward(Ctx& c, int B, int L, int C, int norm, int act, const float* dy, const float* xhat,
                    const float* rstd, const float* gamma, const float* beta, float* dgamma, float* dbeta,
-                   const float* adain, float* dadain, int ld, int off_b, int off_w, float* dz) {
+                   const float* adain, float* dadain, int ld, int off_b, int off_w, float* dz, bool dy_dead = false) {
     if (c.phase == 1) return;
+    if (c.has_pending && (norm == IINS_NORM_IN || norm == IINS_NORM_ADAIN) && (act == IINS_ACT_NONE || act == IINS_ACT_RELU) &&
+        nbwd_fusable(c, c.pending, L, C, dy, xhat, rstd, adain, dadain, ld, off_b, off_w, dz)) {
+        IinsEpilogue& ep = c.pending.ep;
+        ep.nb_dz = dz; ep.nb_xhat = xhat; ep.nb_rstd = rstd; ep.nb_act = act;
+        ep.nb_adain = norm == IINS_NORM_ADAIN ? adain : nullptr; ep.nb_dadain = norm == IINS_NORM_ADAIN ? dadain : nullptr;
+        ep.nb_ld = ld; ep.nb_off_b = off_b; ep.nb_off_w = off_w;
+        if (dy_dead) ep.y = nullptr;                   // the plain gradient is not read by anyone else
+        flush_pending(c);
+        return;
+    }
+    flush_pending(c);
     IinsNormBwdParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.L = L; p.C = C; p.norm = norm; p.act = act; p.dy = dy; p.xhat = xhat; p.rstd = rstd;
@@ -476,12 +534,14 @@ void run_phases(Ctx& c, F&& body) {
         }
         c.phase = 2; c.job_i = 0;
         body();
+        flush_pending(c);
         c.phase = 0;
         return;
     }
 #endif
     c.phase = 0;
     body();
+    flush_pending(c);
 }
 #define IINS_SKIP_IN_COLLECT(c) if ((c).phase == 1) {} else
 
@@ -722,7 +782,7 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
             // first conv: t = relu(IN(conv1(h_in)))
             dzb = fresh();
             norm_backward(c, B, L, C, IINS_NORM_IN, IINS_ACT_RELU, tmp, pl.res1[i].xhat, pl.res1[i].rstd,
-                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, dzb);
+                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, dzb, true);
             conv_wgrad(c, gr, h_in, plain_dz(dzb), G[pi], G[pi + 1]);
             tmp = fresh();
             conv_dgrad(c, gr, plain_dz(dzb), P[pi], tmp, dh);       // + skip gradient
@@ -905,7 +965,7 @@ int decoder_backward(const Shapes& s, const float* const* P, const float* rc, co
         conv_dgrad(c, gr, plain_dz(dzb), P[pi + 2], tmp, nullptr);
         dzb = fresh();
         norm_backward(c, B, s.Lt, s.D, IINS_NORM_ADAIN, IINS_ACT_RELU, tmp, pl.res1[i].xhat, pl.res1[i].rstd, nullptr, nullptr,
-                      nullptr, nullptr, pl.adain, dadain, s.n_adain, off, off + s.D, dzb);
+                      nullptr, nullptr, pl.adain, dadain, s.n_adain, off, off + s.D, dzb, true);
         conv_wgrad(c, gr, h_in, plain_dz(dzb), G[pi], G[pi + 1]);
         tmp = fresh();
         conv_dgrad(c, gr, plain_dz(dzb), P[pi], tmp, dh);

@@ -294,7 +294,8 @@ __device__ __forceinline__ void iins_act_vec(float* v, int act, float slope) {
 enum { IINS_EPI_PLAIN = 0,     // bias, ReLU / LeakyReLU, residual / accumulate operand
        IINS_EPI_IN = 1,        // + InstanceNorm or AdaIN over the LL rows of a sample
        IINS_EPI_LN = 2,        // + the reference's custom LayerNorm over a whole sample (LL rows x NT channels)
-       IINS_EPI_SMEM = 3 };    // anything else: SMEM-staged generic tile epilogue (iins_epilogue_tile)
+       IINS_EPI_SMEM = 3,      // anything else: SMEM-staged generic tile epilogue (iins_epilogue_tile)
+       IINS_EPI_NBWD = 4 };    // data gradient + fused InstanceNorm / AdaIN backward of the producing layer (LL rows / sample)
 
 template <int NT, int PIECES, int EPI, int LL>
 __device__ __forceinline__ void iins_tc_epilogue_regs(const IinsNTParams& p, uint32_t tmem, int tile_m, int n0, int warp, int lane,
@@ -366,6 +367,12 @@ __device__ __forceinline__ void iins_tc_epilogue_regs(const IinsNTParams& p, uin
 #pragma unroll
             for (int j = 0; j < 4; ++j) a4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        float4 x4[EPI == IINS_EPI_NBWD ? 4 : 1];            // fused norm backward: saved x-hat of the producing layer
+        if (EPI == IINS_EPI_NBWD) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                x4[j] = row_ok ? __ldg(reinterpret_cast<const float4*>(ep.nb_xhat + orow + c0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float v[16];
         iins_tmem_chunk16<NT, PIECES>(tl, cbeg + c0, v);
         if (ep.bias != nullptr) {
@@ -373,7 +380,7 @@ __device__ __forceinline__ void iins_tc_epilogue_regs(const IinsNTParams& p, uin
             for (int i = 0; i < 16; ++i) v[i] += __ldg(ep.bias + gn + i);
         }
         // x-hat and rstd are stored as soon as they exist (short live ranges: the kernel runs 2 CTAs / SM at <= 96 registers)
-        float4* xh_dst = (EPI != IINS_EPI_PLAIN && ep.xhat != nullptr && row_ok) ? reinterpret_cast<float4*>(ep.xhat + orow + c0) : nullptr;
+        float4* xh_dst = ((EPI == IINS_EPI_IN || EPI == IINS_EPI_LN) && ep.xhat != nullptr && row_ok) ? reinterpret_cast<float4*>(ep.xhat + orow + c0) : nullptr;
         if (EPI == IINS_EPI_IN) {
             // per (sample, channel) statistics over the L rows; biased variance (models.py:152, 1072)
             constexpr float invL = 1.0f / (float)L;
@@ -413,6 +420,48 @@ __device__ __forceinline__ void iins_tc_epilogue_regs(const IinsNTParams& p, uin
 #pragma unroll
                 for (int i = 0; i < 4; ++i) v[4 * j + i] = fmaf(v[4 * j + i], __ldg(ep.gamma + gn + 4 * j + i), __ldg(ep.beta + gn + 4 * j + i));
             }
+        }
+        if (EPI == IINS_EPI_NBWD) {
+            // v (+ residual operand) = gradient w.r.t. the previous layer's output; that layer's norm backward follows here
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { v[4 * j] += a4[j].x; v[4 * j + 1] += a4[j].y; v[4 * j + 2] += a4[j].z; v[4 * j + 3] += a4[j].w; }
+            if (ep.y != nullptr && row_ok) {
+                float4* dst = reinterpret_cast<float4*>(ep.y + orow + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            constexpr float invL = 1.0f / (float)L;
+            const bool relu = ep.nb_act == IINS_ACT_RELU;
+            const long sb = (long)(row_ok ? b : 0);
+            const bool lead = row_ok && l == 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 r4 = __ldg(reinterpret_cast<const float4*>(ep.nb_rstd + sb * p.N + gn) + j);
+                float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ep.nb_adain != nullptr) {
+                    w4 = __ldg(reinterpret_cast<const float4*>(ep.nb_adain + sb * ep.nb_ld + ep.nb_off_w + gn) + j);
+                    b4 = __ldg(reinterpret_cast<const float4*>(ep.nb_adain + sb * ep.nb_ld + ep.nb_off_b + gn) + j);
+                }
+                const float4 xq = x4[EPI == IINS_EPI_NBWD ? j : 0];
+                const float xv[4] = {xq.x, xq.y, xq.z, xq.w}, rv[4] = {r4.x, r4.y, r4.z, r4.w};
+                const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+                float sr[4], srx[4], o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float u = fmaf(xv[i], wv[i], bv[i]);
+                    const float raw = (relu && !(u > 0.f)) ? 0.f : v[4 * j + i];
+                    sr[i] = iins_lanes_sum<LL>(raw);                 // sum_l raw       (= d bias of AdaIN)
+                    srx[i] = iins_lanes_sum<LL>(raw * xv[i]);        // sum_l raw * xhat (= d weight of AdaIN)
+                    // gx = raw * scale with scale constant over l: mean_l(gx) = scale * sr / L, mean_l(gx * xhat) = scale * srx / L
+                    o[i] = rv[i] * wv[i] * (raw - sr[i] * invL - xv[i] * srx[i] * invL);
+                }
+                if (row_ok) reinterpret_cast<float4*>(ep.nb_dz + orow + c0)[j] = make_float4(o[0], o[1], o[2], o[3]);
+                if (lead && ep.nb_dadain != nullptr) {
+                    *reinterpret_cast<float4*>(ep.nb_dadain + sb * ep.nb_ld + ep.nb_off_b + gn + 4 * j) = make_float4(sr[0], sr[1], sr[2], sr[3]);
+                    *reinterpret_cast<float4*>(ep.nb_dadain + sb * ep.nb_ld + ep.nb_off_w + gn + 4 * j) = make_float4(srx[0], srx[1], srx[2], srx[3]);
+                }
+            }
+            continue;
         }
         iins_act_vec<16>(v, ep.act, ep.slope);
         if (row_ok) {
