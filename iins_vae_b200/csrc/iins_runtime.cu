@@ -105,7 +105,7 @@ void launch_nt_simt(const Ctx& c, const IinsNTParams& p) {
 #ifndef IINS_CPUSIM
 template <int NT, int PIECES, int AKIND, int EPI, int LL>
 void launch_tc_nt_v(Ctx& c, const IinsTCParams& tp, dim3 grid) {
-    constexpr int smem = 2 * (3 * 8192 + 3 * 4 * NT * 16) + 8192;
+    constexpr int smem = 2 * (3 * 4 * (128 * 16 + 64) + 3 * 4 * NT * 16) + 8192;      // A stages use the padded chunk stride
     static bool attr = false;
     auto iins_tc_nt_kernel_ = iins_tc_nt_kernel<NT, PIECES, AKIND, EPI, LL>;
     if (!attr) { cudaFuncSetAttribute(iins_tc_nt_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }

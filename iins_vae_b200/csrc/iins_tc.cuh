@@ -97,6 +97,76 @@ __device__ __forceinline__ void iins_gather8_dgrad_fast(const IinsGeom& g, const
     }
 }
 
+// ---- quad gathers for the forward / data-gradient kernel -----------------------------------------------------
+// A thread fetches 4 consecutive k (one 16-byte load) of one row; the 8 lanes that share a row cover one whole
+// 32-wide K block of it (128 contiguous bytes when the block lies in one tap), so a warp-level load touches 4 rows x
+// 128 B instead of 32 rows x 16 B: ~5x fewer L1 wavefronts than the lane-per-row mapping (measured: the L1 data
+// pipe was the busiest unit of these kernels).
+__device__ __forceinline__ float4 iins_ld4(const float* __restrict__ src, bool ok) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) a = __ldg(reinterpret_cast<const float4*>(src));
+    return a;
+}
+__device__ __forceinline__ float4 iins_gather4_fwd(const IinsGeom& g, const float* __restrict__ x, int K, int cs, int b, int l, int k0) {
+    const int t = k0 >> cs, c0 = k0 & (int)((1u << cs) - 1u);
+    const int pos = iins_src_pos(g, l, t);
+    const bool ok = k0 < K && pos >= 0;
+    return iins_ld4(x + ((long)b * g.Lin + (ok ? pos : 0)) * g.Cin + c0, ok);
+}
+__device__ __forceinline__ float4 iins_dz4(const IinsGeom& g, const IinsDz& d, int b, int l, int n0, bool ok) {
+    const long idx = ((long)b * g.Lout + (ok ? l : 0)) * g.Cout + n0;
+    float4 v = iins_ld4(d.dy_bcast ? d.dy + (long)b * g.Cout + n0 : d.dy + idx, ok);
+    if (d.y != nullptr && d.act != IINS_ACT_NONE) {
+        const float4 y = iins_ld4(d.y + idx, ok);
+        v.x *= iins_dact_from_y(y.x, d.act, d.slope); v.y *= iins_dact_from_y(y.y, d.act, d.slope);
+        v.z *= iins_dact_from_y(y.z, d.act, d.slope); v.w *= iins_dact_from_y(y.w, d.act, d.slope);
+    }
+    if (d.dy_scale != 1.f) { v.x *= d.dy_scale; v.y *= d.dy_scale; v.z *= d.dy_scale; v.w *= d.dy_scale; }
+    return v;
+}
+__device__ __forceinline__ float4 iins_gather4_dgrad(const IinsGeom& g, const IinsDz& d, int K, int cs, int b, int pos, int k0) {
+    const int t = k0 >> cs, c0 = k0 & (int)((1u << cs) - 1u);
+    int q0 = pos + g.pad, q1 = -1, q2 = -1;
+    if (g.mode == IINS_PAD_REFLECT) {
+        if (pos >= 1 && pos <= g.pad) q1 = g.pad - pos;
+        if (pos <= g.Lin - 2 && pos >= g.Lin - 1 - g.pad) q2 = g.pad + 2 * (g.Lin - 1) - pos;
+        if (q1 < 0) { q1 = q2; q2 = -1; }              // a position has both reflected images only when Lin <= 2 * pad + 1
+    } else if (g.mode == IINS_PAD_UP2) {
+        q0 = 2 * pos + g.pad;
+        q1 = q0 + 1;
+    }
+    const int sh = g.stride - 1;                       // stride is 1 or 2
+    auto cand = [&](int q) {
+        const int r = q - t;
+        const int l = r >> sh;
+        const bool ok = k0 < K && q >= 0 && r >= 0 && (r & sh) == 0 && l < g.Lout;
+        return iins_dz4(g, d, b, l, c0, ok);
+    };
+    float4 v = cand(q0);
+    if (g.mode != IINS_PAD_ZERO) {                     // warp-uniform
+        const float4 u = cand(q1);
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        if (q2 >= 0) {                                 // per-lane (no warp collective here: the caller may be divergent)
+            const float4 w = cand(q2);
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+    }
+    return v;
+}
+// split 4 floats into bf16 pieces and store one 8-byte half of a 16-byte K chunk per piece
+__device__ __forceinline__ void iins_store4_split(const float4 v, unsigned char* base, uint32_t piece_stride, int pieces) {
+    if (pieces == 3) {
+        uint32_t a0, a1, a2, b0, b1, b2;
+        umma::split3_pair(v.x, v.y, a0, a1, a2);
+        umma::split3_pair(v.z, v.w, b0, b1, b2);
+        *reinterpret_cast<uint2*>(base) = make_uint2(a0, b0);
+        *reinterpret_cast<uint2*>(base + piece_stride) = make_uint2(a1, b1);
+        *reinterpret_cast<uint2*>(base + 2 * piece_stride) = make_uint2(a2, b2);
+    } else {
+        *reinterpret_cast<uint2*>(base) = make_uint2(umma::cvt_bf16x2(v.x, v.y), umma::cvt_bf16x2(v.z, v.w));
+    }
+}
+
 // split 8 floats into bf16 pieces and store one 16-byte vector per piece
 __device__ __forceinline__ void iins_store8_split(const float* v, unsigned char* base, uint32_t piece_stride, int pieces) {
     uint32_t w[3][4];
@@ -491,7 +561,10 @@ struct IinsTCParams {
 template <int NT, int PIECES, int AKIND, int EPI, int LL>
 __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCParams tp) {
     constexpr int BM = 128;
-    constexpr uint32_t A_PIECE = 4 * BM * 16;            // 8192 B : [chunk][row][16 B]
+    // A stage: [chunk of 8 k][row][16 B] per piece.  The chunk stride (the descriptor's LBO) is padded by 64 bytes so that
+    // the 8-byte stores of a warp (4 rows x 8 quads) spread over all banks: 2 wavefronts for 256 bytes, the minimum.
+    constexpr uint32_t A_LBO = BM * 16 + 64;
+    constexpr uint32_t A_PIECE = 4 * A_LBO;              // 8448 B
     constexpr uint32_t B_TILE = 4 * PIECES * NT * 16;    // [chunk][piece * NT + n][16 B]
     constexpr uint32_t STAGE = 3 * A_PIECE + 3 * 4 * NT * 16;
     constexpr int TCOLS = IinsTmemCols<NT, PIECES>::value;
@@ -513,23 +586,44 @@ __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCParams t
     // ---- producer set-up and the first two K blocks' loads are issued BEFORE the barrier / TMEM set-up, so the first
     // global-load latency overlaps the CTA prologue
     const bool is_prod = warp < 8;
-    const int a_row = tid & 127, a_half = (tid >> 7) & 1;
-    const int grow = tile_m + a_row;
-    const bool a_ok = is_prod && grow < p.M;
-    const int a_b = a_ok ? grow >> p.lshift : 0;
-    const int a_l = a_ok ? grow & (p.Lrow - 1) : 0;
     const int cs = p.cshift;
+    // FORWARD gathers (AKIND 0): producer warp w owns rows 16w .. 16w+15 of the tile; instruction jj covers rows
+    // 16w + 4jj + (lane >> 3) and the 8 lanes of a row take the 8 quads of the K block (coalesced: 4 rows x 128 B per
+    // warp-level load).  DATA-GRADIENT gathers (AKIND 1) keep one row per lane and two 8-wide chunks per thread: their
+    // per-row candidate arithmetic (reflected / strided taps) would be done four times per thread otherwise, and that
+    // kernel is bound by instruction issue, not by L1 wavefronts (measured both ways).
+    const int a_quad = lane & 7;
+    const int a_row0 = AKIND == 0 ? (warp & 7) * 16 + (lane >> 3) : (tid & 127);
+    const int a_half = (tid >> 7) & 1;
+    int a_b[4], a_l[4];
+    bool a_ok[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const int grow = tile_m + a_row0 + (AKIND == 0 ? 4 * jj : 0);
+        a_ok[jj] = is_prod && grow < p.M;
+        a_b[jj] = a_ok[jj] ? grow >> p.lshift : 0;
+        a_l[jj] = a_ok[jj] ? grow & (p.Lrow - 1) : 0;
+    }
     // raw operand data of TWO K blocks ahead lives in registers (the loads of block kb+2 are issued right after
     // block kb is handed to the MMA warp), so a K block costs its convert/store work, not a global-load latency
-    float raw[2][2][8];
-    auto load_raw = [&](int kb, float (*dst)[8]) {
+    float4 raw[2][4];
+    auto load_raw = [&](int kb, float4* dst) {
+        // the host routes layers without 16-byte gathers (< 8 channels, NCL operand) to the SIMT kernels
+        if (AKIND == 0) {
+            const int k0 = kb * 32 + a_quad * 4;
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-            const int k0 = kb * 32 + (a_half * 2 + jj) * 8;
-            // the host routes layers without 16-byte gathers (< 8 channels, NCL operand) to the SIMT kernels
-            if (!a_ok) iins_zero8(dst[jj]);
-            else if (AKIND == 0) iins_gather8_fwd_fast(g, p.x, p.K, cs, a_b, a_l, k0, dst[jj]);
-            else iins_gather8_dgrad_fast(g, p.dz, p.K, cs, a_b, a_l, k0, dst[jj]);
+            for (int jj = 0; jj < 4; ++jj)
+                dst[jj] = a_ok[jj] ? iins_gather4_fwd(g, p.x, p.K, cs, a_b[jj], a_l[jj], k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int k0 = kb * 32 + (a_half * 2 + jj) * 8;
+                float v[8];
+                if (!a_ok[0]) iins_zero8(v);
+                else iins_gather8_dgrad_fast(g, p.dz, p.K, cs, a_b[0], a_l[0], k0, v);
+                dst[2 * jj] = make_float4(v[0], v[1], v[2], v[3]);
+                dst[2 * jj + 1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
         }
     };
     if (is_prod) {
@@ -568,23 +662,32 @@ __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCParams t
             umma::mbar_wait(umma::smem_u32(&mbar_b[s]), (uint32_t)((kb >> 1) & 1));
             umma::tc_fence_after();
             // K-major, no swizzle: LBO = distance between 8-wide k chunks, SBO = 128 B between 8-row groups
-            const uint64_t ad = umma::make_desc(umma::smem_u32(sA), BM * 16, 128);
+            const uint64_t ad = umma::make_desc(umma::smem_u32(sA), A_LBO, 128);
             const uint64_t bd = umma::make_desc(umma::smem_u32(sB), PIECES * NT * 16, 128);
             iins_issue_kstep<NT, PIECES, 0, 0>(tmem, ad, bd, A_PIECE >> 4, leader, kb > 0 ? 1u : 0u);
-            iins_issue_kstep<NT, PIECES, 0, 0>(tmem, ad + ((2 * BM * 16) >> 4), bd + ((2 * PIECES * NT * 16) >> 4), A_PIECE >> 4,
+            iins_issue_kstep<NT, PIECES, 0, 0>(tmem, ad + ((2 * A_LBO) >> 4), bd + ((2 * PIECES * NT * 16) >> 4), A_PIECE >> 4,
                                                leader, 1u);
             if (leader) umma::commit(umma::smem_u32(&mbar_done[s]));
             __syncwarp();
         }
     } else {
         // ------------------------------------------------------------------ producers
-        auto produce = [&](int kb, float (*src)[8]) {
+        auto produce = [&](int kb, float4* src) {
             const int s = kb & 1;
             unsigned char* sA = dsm + s * STAGE;
             if (kb >= 2) umma::mbar_wait(umma::smem_u32(&mbar_done[s]), (uint32_t)(((kb >> 1) - 1) & 1));
+            if (AKIND == 0) {
+                unsigned char* dst = sA + (a_quad >> 1) * A_LBO + a_row0 * 16 + (a_quad & 1) * 8;
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj)
-                iins_store8_split(src[jj], sA + ((a_half * 2 + jj) * BM + a_row) * 16, A_PIECE, PIECES);
+                for (int jj = 0; jj < 4; ++jj) iins_store4_split(src[jj], dst + jj * 64, A_PIECE, PIECES);
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const float v[8] = {src[2 * jj].x, src[2 * jj].y, src[2 * jj].z, src[2 * jj].w,
+                                        src[2 * jj + 1].x, src[2 * jj + 1].y, src[2 * jj + 1].z, src[2 * jj + 1].w};
+                    iins_store8_split(v, sA + (a_half * 2 + jj) * A_LBO + a_row0 * 16, A_PIECE, PIECES);
+                }
+            }
             umma::fence_async_smem();
             umma::mbar_arrive(umma::smem_u32(&mbar_full[s]));
             if (kb + 2 < nkb) load_raw(kb + 2, src);      // in flight while the next block is converted
