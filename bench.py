@@ -131,6 +131,56 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------------
+def hbm_kernel_rooflines(lib, peaks):
+    """The path's pure-streaming kernels (fused loss + seed gradients, fused Adam) timed ALONE at a size that leaves
+    the 126 MB L2 (at the bench batch they move 8-18 MB and are launch-bound): achieved = algorithmic bytes / CUDA-event
+    time, peak = measured HBM copy bandwidth (burst figure: kernel timed alone).  SURVEY.md 8(d): loss 2.07 KB/sample,
+    Adam 28 B/parameter."""
+    import ctypes as C
+    from iins_vae_b200._capi import ptr
+    out = []
+    peak = float(peaks.get("hbm_gbs", 6548.8))
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    Bb, L, NC = 1 << 19, 157, 5                      # 524288 windows: x + xrec + d_xrec = 3 x 329 MB
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(Bb, L, device="cuda", generator=g); xr = torch.randn(Bb, L, device="cuda", generator=g)
+    err = torch.rand(Bb, 1, device="cuda", generator=g); ee = torch.rand(Bb, 1, device="cuda", generator=g)
+    lg = torch.randn(Bb, NC, device="cuda", generator=g); lab = torch.randint(0, NC, (Bb, 1), device="cuda", generator=g).float()
+    o = torch.zeros(8, device="cuda"); dx = torch.empty_like(x); de = torch.empty_like(ee); dl = torch.empty_like(lg)
+    pred = torch.zeros(Bb, dtype=torch.int32, device="cuda")
+    ms = timed(lambda: lib.check(lib.iins_loss_forward_backward(Bb, L, NC, ptr(x), ptr(xr), ptr(err), ptr(ee), ptr(lg), ptr(lab), None,
+                                                                1.0, 10.0, 1.0, ptr(o), ptr(dx), ptr(de), ptr(dl), ptr(pred), st), "loss"))
+    nbytes = Bb * (3 * L * 4 + 2 * 4 + 4 + 4 + NC * 4 + 4 + 4 + NC * 4 + 4)
+    out.append({"kernel": "iins_loss_kernel", "workload": f"{Bb} windows (fused L1 recon + L1 err + CE + seed gradients + metrics)",
+                "bytes": nbytes, "ms": ms, "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": nbytes / (ms * 1e-3) / 1e9 / peak})
+    del x, xr, dx
+    P = 1 << 26                                      # 64 Mi parameters: 7 x 4 B x P = 1.9 GB per update
+    w = torch.randn(P, device="cuda", generator=g); gr = torch.randn(P, device="cuda", generator=g)
+    m = torch.zeros(P, device="cuda"); v = torch.zeros(P, device="cuda")
+    steps = torch.zeros(8, dtype=torch.int32, device="cuda"); lr = torch.full((1,), 1e-4, device="cuda")
+    gb, ge, ga = (C.c_int64 * 1)(0), (C.c_int64 * 1)(P), (C.c_int32 * 1)(1)
+    ms = timed(lambda: lib.check(lib.iins_adam_step(ptr(w), ptr(gr), ptr(m), ptr(v), gb, ge, ga, 1, ptr(steps), ptr(lr), 0.5, 0.999,
+                                                    1e-8, st), "adam"))
+    nbytes = 28 * P
+    out.append({"kernel": "iins_adam_kernel", "workload": f"{P} parameters (read p,g,m,v; write p,m,v)", "bytes": nbytes, "ms": ms,
+                "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / peak})
+    return out
+
+
 def cpu_reference_run(cfg, batch, steps, warmup, threads):
     """The reference algorithm (oracle port: torch CPU ops + autograd + torch.optim.Adam semantics restated in
     oracle/iins_oracle.py) on the host cores; returns samples/s."""
@@ -347,6 +397,13 @@ def main():
         kernel_table = {k: {"ms": round(v[0], 4), "launches": v[2], "tflops": round(v[1] / max(v[0], 1e-9) / 1e9, 3)}
                         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
 
+    hbm_rooflines = None
+    if rank == 0 and world == 1:
+        try:
+            hbm_rooflines = hbm_kernel_rooflines(lib, measured_peaks()[0])
+        except Exception as e:                      # never let the side measurement take the headline down
+            hbm_rooflines = [{"error": repr(e)}]
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -365,7 +422,7 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": int(n_launch), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernels": kernel_table,
+            "kernels": kernel_table, "roofline_hbm": hbm_rooflines,
             "final_loss_terms": {k: float(v) for k, v in zip(("l1_recon", "l1_err", "ce", "weighted_sum"), out_host[:4].tolist())},
         }
         print(json.dumps(line))

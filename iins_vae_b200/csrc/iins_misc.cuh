@@ -307,7 +307,19 @@ __global__ void __launch_bounds__(256) iins_loss_kernel(const IinsLossParams p) 
     if (p.x != nullptr) {
         const long n = (long)p.B * p.L;
         const float ginv = p.lam_ae / (float)n;
-        for (long i = gtid; i < n; i += stride) {
+        // 128-bit accesses over the flattened (B*L) stream whenever the three buffers are 16-byte aligned
+        const bool vec = ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.xrec) | reinterpret_cast<uintptr_t>(p.d_xrec)) & 15) == 0;
+        const long n4 = vec ? n >> 2 : 0;
+#pragma unroll 4
+        for (long i = gtid; i < n4; i += stride) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p.xrec) + i), b = __ldg(reinterpret_cast<const float4*>(p.x) + i);
+            const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+            acc_ae += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
+            if (p.d_xrec != nullptr)
+                reinterpret_cast<float4*>(p.d_xrec)[i] = make_float4(d0 > 0.f ? ginv : (d0 < 0.f ? -ginv : 0.f), d1 > 0.f ? ginv : (d1 < 0.f ? -ginv : 0.f),
+                                                                     d2 > 0.f ? ginv : (d2 < 0.f ? -ginv : 0.f), d3 > 0.f ? ginv : (d3 < 0.f ? -ginv : 0.f));
+        }
+        for (long i = 4 * n4 + gtid; i < n; i += stride) {
             float d = __ldg(p.xrec + i) - __ldg(p.x + i);
             acc_ae += fabsf(d);
             if (p.d_xrec != nullptr) p.d_xrec[i] = d > 0.f ? ginv : (d < 0.f ? -ginv : 0.f);
@@ -392,22 +404,44 @@ __global__ void iins_adam_tick_kernel(int* steps, int n_groups, unsigned active_
 }
 
 __global__ void __launch_bounds__(256) iins_adam_kernel(const IinsAdamParams a) {
-    const long stride = (long)gridDim.x * blockDim.x;
+    // the bias corrections are double-precision pow() like torch's Python scalars: evaluated by ONE thread per CTA
+    // and group (they cost hundreds of fp64 instructions), then shared
+    __shared__ float s_step[8], s_isb2[8];
     const float lr = __ldg(a.lr);
-    for (int gi = 0; gi < a.n_groups; ++gi) {
-        if (!a.groups[gi].active) continue;
-        const int t = a.steps[gi];
+    if (threadIdx.x < a.n_groups && a.groups[threadIdx.x].active) {
+        const int t = a.steps[threadIdx.x];
         const double bc1 = 1.0 - pow(a.beta1, (double)t);
         const double bc2 = 1.0 - pow(a.beta2, (double)t);
-        const float step_size = (float)((double)lr / bc1);
-        const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-        const float b1 = (float)a.beta1, b2 = (float)a.beta2;
-        for (long i = a.groups[gi].begin + (long)blockIdx.x * blockDim.x + threadIdx.x; i < a.groups[gi].end; i += stride) {
-            float g = __ldg(a.g + i);
-            float m = a.m[i] = b1 * a.m[i] + (1.f - b1) * g;
-            float v = a.v[i] = b2 * a.v[i] + (1.f - b2) * g * g;
-            float denom = sqrtf(v) * inv_sqrt_bc2 + a.eps;
-            a.p[i] -= step_size * (m / denom);
+        s_step[threadIdx.x] = (float)((double)lr / bc1);
+        s_isb2[threadIdx.x] = (float)(1.0 / sqrt(bc2));
+    }
+    __syncthreads();
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const float b1 = (float)a.beta1, b2 = (float)a.beta2;
+    for (int gi = 0; gi < a.n_groups; ++gi) {
+        if (!a.groups[gi].active) continue;
+        const float step_size = s_step[gi], inv_sqrt_bc2 = s_isb2[gi];
+        const long begin = a.groups[gi].begin, end = a.groups[gi].end;
+        auto upd = [&](float g, float& m, float& v, float& w) {
+            m = b1 * m + (1.f - b1) * g;
+            v = b2 * v + (1.f - b2) * g * g;
+            const float denom = sqrtf(v) * inv_sqrt_bc2 + a.eps;
+            w -= step_size * (m / denom);
+        };
+        // head up to the first 16-byte boundary, 128-bit body, scalar tail (the four flat buffers share their alignment
+        // only if they were allocated alike: checked)
+        const bool vec = ((reinterpret_cast<uintptr_t>(a.p) | reinterpret_cast<uintptr_t>(a.g) | reinterpret_cast<uintptr_t>(a.m) |
+                           reinterpret_cast<uintptr_t>(a.v)) & 15) == 0;
+        long vb = vec ? (begin + 3) & ~3L : end, ve = vec ? end & ~3L : end;
+        if (vb > ve) { vb = end; ve = end; }
+        for (long i = begin + gtid; i < vb; i += stride) { float m = a.m[i], v = a.v[i], w = a.p[i]; upd(__ldg(a.g + i), m, v, w); a.m[i] = m; a.v[i] = v; a.p[i] = w; }
+        for (long i = (vb >> 2) + gtid; i < (ve >> 2); i += stride) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.g) + i);
+            float4 m4 = reinterpret_cast<float4*>(a.m)[i], v4 = reinterpret_cast<float4*>(a.v)[i], w4 = reinterpret_cast<float4*>(a.p)[i];
+            upd(g4.x, m4.x, v4.x, w4.x); upd(g4.y, m4.y, v4.y, w4.y); upd(g4.z, m4.z, v4.z, w4.z); upd(g4.w, m4.w, v4.w, w4.w);
+            reinterpret_cast<float4*>(a.m)[i] = m4; reinterpret_cast<float4*>(a.v)[i] = v4; reinterpret_cast<float4*>(a.p)[i] = w4;
         }
+        for (long i = ve + gtid; i < end; i += stride) { float m = a.m[i], v = a.v[i], w = a.p[i]; upd(__ldg(a.g + i), m, v, w); a.m[i] = m; a.v[i] = v; a.p[i] = w; }
     }
 }

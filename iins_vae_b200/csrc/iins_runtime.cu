@@ -1220,8 +1220,9 @@ int iins_loss_forward_backward(int batch, int cir_len, int num_classes, const fl
     p.lam_ae = lam_ae; p.lam_res = lam_res; p.lam_env = lam_env; p.out = out;
     p.d_xrec = d_x_recon; p.d_err_est = d_err_est; p.d_logits = d_logits; p.pred = (int*)pred;
     cudaMemsetAsync(out, 0, 8 * sizeof(float), st);
-    long n = x ? (long)batch * cir_len : batch;
-    IINS_LAUNCH(iins_loss_kernel, grid_for(n), 256, 0, st, p);
+    long n = x ? (long)batch * cir_len / 4 : batch;       // 128-bit accesses over the reconstruction stream
+    int lg = grid_for(n / 8);                             // >= 8 iterations per thread: every CTA ends with 5 atomics on the same 32 bytes of `out`
+    IINS_LAUNCH(iins_loss_kernel, lg, 256, 0, st, p);
     return check_cuda("loss");
 }
 
@@ -1244,7 +1245,7 @@ int iins_adam_step(float* params, const float* grads, float* exp_avg, float* exp
     }
     if (mask == 0) return IINS_OK;
     IINS_LAUNCH(iins_adam_tick_kernel, 1, 32, 0, st, (int*)steps, n_groups, mask);
-    IINS_LAUNCH(iins_adam_kernel, grid_for(total), 256, 0, st, a);
+    IINS_LAUNCH(iins_adam_kernel, grid_for(total / 4), 256, 0, st, a);
     return check_cuda("adam");
 }
 
