@@ -98,9 +98,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample: brackets the timed region inside a sampler that was started well before it
+        (nvidia-smi needs ~100 ms to produce its first line; the timed region of the default run is ~50 ms)."""
+        return len(self.rows)
+
+    def stop(self, first=0, last=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)                            # let the last in-region sample arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -108,7 +114,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        last = len(self.rows) if last is None else min(len(self.rows), last + 2)   # + the samples straddling the end
+        window = self.rows[first:last]
+        where = "timed region"
+        if not window:                              # region shorter than one sampling period: nearest samples under the same load
+            window, where = self.rows[max(0, first - 3):last + 3], "timed region +/- 3 samples (same load: warm-up / e2e steps)"
+        self.where = where
+        for r in window:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -118,7 +130,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": where, "period_ms": 20}
 
 
 def measured_peaks():
@@ -266,6 +278,7 @@ def main():
     torch.cuda.set_device(local)
     pg = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL banners off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         pg = dist.group.WORLD
     lib = get_lib()
@@ -293,6 +306,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                             # long before the timed region: nvidia-smi needs ~100 ms to start
     # launches per step, counted from eager passes of both branches (also captures both CUDA graphs)
     launches = {}
     for sup in (True, False):
@@ -313,10 +329,8 @@ def main():
         step_i += 1
 
     # ---------------- timed region 1: inputs resident in HBM
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
+    mark0 = sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_launch = 0
     flops = 0.0
@@ -330,8 +344,8 @@ def main():
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
+    mark1 = sampler.mark()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- timed region 2 (e2e): pinned host inputs, H2D inside, loss read back every step
     out_host = torch.empty(8, dtype=torch.float32).pin_memory()
@@ -349,6 +363,7 @@ def main():
     ms_e2e = e0.elapsed_time(e1)
     barrier()
     assert np.isfinite(out_host.numpy()).all(), "non-finite loss"
+    clocks = sampler.stop(mark0, mark1) if rank == 0 else None      # stopped after the e2e region (same load)
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
@@ -379,7 +394,7 @@ def main():
         achieved = top[1][1] / (top[1][0] * 1e-3) / 1e12 if top[1][0] > 0 else 0.0
         # DRAM traffic per launch of that kernel from the committed ncu --set full capture (profiles/), if present
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_tc_ncu_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r01b_ncu_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 rows = [r for r in json.load(f) if top[0].rstrip("_") in r["kernel"]]
