@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 // Launch bookkeeping: a launch counter (bench.py reports it as gpu_launches) and an optional per-launch
 // CUDA-event profile (iins_profile_begin / iins_profile_collect) used to time individual kernels inside
 // a real step without an external profiler.
@@ -41,11 +42,29 @@ static inline void iins_prof_post(cudaStream_t st) {
     g_iins_prof.cur_flops = 0.0;
     g_iins_prof.cur_shape[0] = g_iins_prof.cur_shape[1] = g_iins_prof.cur_shape[2] = 0;
 }
-#define IINS_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
-    do {                                                                    \
-        iins_prof_pre(#kernel, (stream));                                   \
-        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);         \
-        iins_prof_post((stream));                                           \
+// Every kernel of the library is launched with programmatic dependent launch allowed: it becomes resident while its
+// predecessor in the stream is still draining, runs its prologue (index math, barrier / TMEM set-up, weight staging
+// address arithmetic) and then blocks in iins_pdl_wait() (griddepcontrol.wait = the predecessor grid has completed
+// and its memory is visible) before it touches global memory.  The step is a chain of ~100 dependent 10-30 us
+// kernels: this hides the launch gap and the prologue of each.  IINS_PDL=0 turns the attribute off.
+static int g_iins_pdl = -1;
+static inline int iins_pdl_enabled() {
+    if (g_iins_pdl < 0) { const char* e = getenv("IINS_PDL"); g_iins_pdl = e ? atoi(e) : 1; }
+    return g_iins_pdl;
+}
+#define IINS_LAUNCH(kernel, grid_, block_, smem_, stream_, ...)                                    \
+    do {                                                                                            \
+        iins_prof_pre(#kernel, (stream_));                                                          \
+        cudaLaunchConfig_t cfg_;                                                                    \
+        memset(&cfg_, 0, sizeof(cfg_));                                                             \
+        cfg_.gridDim = dim3(grid_); cfg_.blockDim = dim3(block_);                                   \
+        cfg_.dynamicSmemBytes = (size_t)(smem_); cfg_.stream = (stream_);                           \
+        cudaLaunchAttribute attr_[1];                                                               \
+        attr_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                           \
+        attr_[0].val.programmaticStreamSerializationAllowed = iins_pdl_enabled();                   \
+        cfg_.attrs = attr_; cfg_.numAttrs = 1;                                                      \
+        cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                                             \
+        iins_prof_post((stream_));                                                                  \
     } while (0)
 #define IINS_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
 #define IINS_SET_FLOPS(f) (g_iins_prof.cur_flops = (f))
@@ -54,6 +73,21 @@ static inline void iins_prof_post(cudaStream_t st) {
 
 #define IINS_HD __host__ __device__ __forceinline__
 #define IINS_D __device__ __forceinline__
+
+// Programmatic dependent launch, device side (see IINS_LAUNCH): let the next kernel in the stream start launching, then
+// wait until everything before this kernel has completed.  Called at the top of EVERY kernel (before the first global
+// access); the tensor-core kernels call iins_pdl_wait() after their prologue instead.
+IINS_D void iins_pdl_launch_dependents() {
+#ifndef IINS_CPUSIM
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+IINS_D void iins_pdl_wait() {
+#ifndef IINS_CPUSIM
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+IINS_D void iins_pdl_enter() { iins_pdl_launch_dependents(); iins_pdl_wait(); }
 
 enum { IINS_PAD_ZERO = 0, IINS_PAD_REFLECT = 1, IINS_PAD_UP2 = 2 };
 enum { IINS_ACT_NONE = 0, IINS_ACT_RELU = 1, IINS_ACT_LRELU = 2, IINS_ACT_TANH = 3 };

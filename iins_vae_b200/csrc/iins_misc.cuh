@@ -31,6 +31,7 @@ struct IinsNormBwdParams {
 //   pass 2: reload (L1-resident) and write dz
 // Requires C a power of two, 4 <= C <= 128, and L*C a multiple of 128.
 __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNormBwdParams p) {
+    iins_pdl_enter();
     // LayerNorm's dgamma / dbeta are sums over the whole batch: every warp keeps a running per-channel total over the
     // samples it visits (persistent grid), the CTA combines its 8 warps in shared memory and issues ONE atomic per
     // channel -- one atomic per (sample, channel) serialised 4096 deep on the same few L2 sectors.
@@ -152,6 +153,7 @@ IINS_HD void iins_pool_window(int i, int Lin, int Lout, int& s, int& e) {
 
 __global__ void __launch_bounds__(256) iins_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                             int B, int Lin, int Lout) {
+    iins_pdl_enter();
     long n = (long)B * Lout;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         int b = (int)(i / Lout), o = (int)(i - (long)b * Lout);
@@ -166,6 +168,7 @@ __global__ void __launch_bounds__(256) iins_pool_fwd_kernel(const float* __restr
 // dx[b,j] = sum over windows containing j of dy[b,o]/len(o); optionally times (1 - t^2) with t = tanh output
 __global__ void __launch_bounds__(256) iins_pool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ tanh_y,
                                                             float* __restrict__ dx, int B, int Lin, int Lout) {
+    iins_pdl_enter();
     long n = (long)B * Lin;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         int b = (int)(i / Lin), j = (int)(i - (long)b * Lin);
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(256) iins_pool_bwd_kernel(const float* __restr
 // mean over L of an NLC tensor: (B,L,C) -> (B,C)   (AdaptiveAvgPool1d(1), models.py:279)
 __global__ void __launch_bounds__(256) iins_mean_l_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                           int B, int L, int C) {
+    iins_pdl_enter();
     long n = (long)B * C;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         int b = (int)(i / C), c = (int)(i - (long)b * C);
@@ -231,6 +235,7 @@ IINS_HD float iins_noise_at(unsigned long long seed, unsigned long long offset, 
 __global__ void __launch_bounds__(256) iins_reparam_kl_kernel(const float* __restrict__ cat, const float* __restrict__ noise,
                                                               float* __restrict__ latent, float* __restrict__ kl,
                                                               int B, int E, unsigned long long seed, unsigned long long offset) {
+    iins_pdl_enter();
     const int H = E / 2;
     float part = 0.f;
     long n = (long)B * H;
@@ -253,6 +258,7 @@ __global__ void __launch_bounds__(256) iins_reparam_kl_bwd_kernel(const float* _
                                                                   const float* __restrict__ d_cat_in, const float* __restrict__ d_latent,
                                                                   const float* __restrict__ d_kl, float* __restrict__ dcat,
                                                                   int B, int E, unsigned long long seed, unsigned long long offset) {
+    iins_pdl_enter();
     const int H = E / 2;
     const float gk = d_kl != nullptr ? __ldg(d_kl) / (float)B : 0.f;
     long n = (long)B * H;
@@ -299,6 +305,7 @@ struct IinsLossParams {
 };
 
 __global__ void __launch_bounds__(256) iins_loss_kernel(const IinsLossParams p) {
+    iins_pdl_enter();
     __shared__ float s_part[8][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float acc_ae = 0.f, acc_res = 0.f, acc_ce = 0.f, acc_sq = 0.f, acc_ok = 0.f;
@@ -377,6 +384,7 @@ __global__ void __launch_bounds__(256) iins_loss_kernel(const IinsLossParams p) 
 // into the decoder's when the engine runs the heads concurrently with the decoder (engine.py)
 __global__ void __launch_bounds__(256) iins_accumulate2_kernel(float* __restrict__ dst1, const float* __restrict__ src1, long n1,
                                                                float* __restrict__ dst2, const float* __restrict__ src2, long n2) {
+    iins_pdl_enter();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += (long)gridDim.x * blockDim.x) {
         if (i < n1) dst1[i] += __ldg(src1 + i);
         else dst2[i - n1] += __ldg(src2 + i - n1);
@@ -399,11 +407,13 @@ struct IinsAdamParams {
 };
 
 __global__ void iins_adam_tick_kernel(int* steps, int n_groups, unsigned active_mask) {
+    iins_pdl_enter();
     int i = threadIdx.x;
     if (i < n_groups && ((active_mask >> i) & 1u)) steps[i] += 1;
 }
 
 __global__ void __launch_bounds__(256) iins_adam_kernel(const IinsAdamParams a) {
+    iins_pdl_enter();
     // the bias corrections are double-precision pow() like torch's Python scalars: evaluated by ONE thread per CTA
     // and group (they cost hundreds of fp64 instructions), then shared
     __shared__ float s_step[8], s_isb2[8];

@@ -197,6 +197,7 @@ struct IinsPackParams {
 };
 
 __global__ void __launch_bounds__(256) iins_pack_kernel(const IinsPackParams p) {
+    iins_pdl_enter();
     // one thread per 16-byte destination chunk (n block, k block, chunk, row)
     const long total = (long)p.nblk * p.nkb * 4 * p.NT;
     const int Cdim = p.kind == 0 ? p.g.Cin : p.g.Cout;
@@ -241,6 +242,7 @@ struct IinsPackAllParams {
 };
 
 __global__ void __launch_bounds__(256) iins_pack_all_kernel(const IinsPackAllParams pp) {
+    iins_pdl_enter();
     int j = 0;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < pp.total; e += (long)gridDim.x * blockDim.x) {
         while (j + 1 < pp.njobs && e >= pp.jobs[j + 1].chunk_begin) ++j;
@@ -583,8 +585,7 @@ __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCParams t
     float* st_rstd = st_mean + 1024;
     const int nkb = tp.nkb;
 
-    // ---- producer set-up and the first two K blocks' loads are issued BEFORE the barrier / TMEM set-up, so the first
-    // global-load latency overlaps the CTA prologue
+    // ---- producer set-up (index arithmetic only: no global access before iins_pdl_wait())
     const bool is_prod = warp < 8;
     const int cs = p.cshift;
     // FORWARD gathers (AKIND 0): producer warp w owns rows 16w .. 16w+15 of the tile; instruction jj covers rows
@@ -626,11 +627,7 @@ __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCParams t
             }
         }
     };
-    if (is_prod) {
-        load_raw(0, raw[0]);
-        if (nkb > 1) load_raw(1, raw[1]);
-    }
-
+    iins_pdl_launch_dependents();
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             umma::mbar_init(umma::smem_u32(&mbar_done[i]), 1);
@@ -644,6 +641,12 @@ __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCParams t
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    // everything above overlapped the tail of the previous kernel in the stream; its results are needed from here on
+    iins_pdl_wait();
+    if (is_prod) {
+        load_raw(0, raw[0]);
+        if (nkb > 1) load_raw(1, raw[1]);
+    }
 
     if (warp == 8) {
         // ------------------------------------------------------------------ MMA warp (warp-uniform code)
@@ -746,6 +749,7 @@ struct IinsTCTNParams {
 // grid = (row parts, ceil(K/128), ceil(Cout/NT)).  D^T[k][n] accumulated in TMEM (128 lanes = 128 k entries).
 template <int NT, int PIECES>
 __global__ void __launch_bounds__(288, 2) iins_tc_tn_kernel(const IinsTCTNParams tp) {
+    iins_pdl_launch_dependents();
     constexpr int BR = 32;                               // rows per stage (2 MMA k-steps of 16)
     constexpr uint32_t A_PIECE = 16 * BR * 16;           // [k group of 8][row][16 B] = 8192 B
     constexpr uint32_t B_PIECE = (NT / 8) * BR * 16;     // [n group of 8][row][16 B]; pieces stacked = more n groups
@@ -778,6 +782,7 @@ __global__ void __launch_bounds__(288, 2) iins_tc_tn_kernel(const IinsTCTNParams
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    iins_pdl_wait();                                   // prologue overlapped the previous kernel's tail
     const bool do_bias = p.db != nullptr && blockIdx.y == 0;
     const bool has_z = warp < NT / 8;
     float bsum[8];
