@@ -282,6 +282,54 @@ class SemiTrainEngine:
         d["loss"] = o[3] + (LAMBDA_RANGE * kl if self.mode == "semi" else 0.0)
         return d
 
+    # ---- optimizer state (the reference saves only the four module state_dicts, so a resumed
+    # run restarts Adam from zero moments -- train_semi.py:281-286; these two methods make the resume exact) -------------
+    def optimizer_state_dict(self):
+        """``torch.optim.Adam(itertools.chain(Enc, Dec, Res, Cls parameters)).state_dict()`` layout (train_semi.py:118-122):
+        ``state[i] = {step, exp_avg, exp_avg_sq}`` for parameter i in chain order, ``param_groups`` with lr / betas / eps.
+        Parameters that never received a gradient (restorer.linear_layer2; Res / Cls before the first supervised batch)
+        have no entry, exactly like torch's lazily created state.  Loads into a stock torch.optim.Adam."""
+        fl = self.flat
+        steps = self.steps.tolist()
+        state, o = {}, 0
+        for i, p in enumerate(fl.params):
+            n = p.numel()
+            gi = next((g for g, (b, e) in enumerate(self.groups) if b <= o < e), None)
+            if gi is not None and steps[gi] > 0:
+                state[i] = {"step": torch.tensor(float(steps[gi])), "exp_avg": fl.exp_avg[o:o + n].view(p.shape).clone(),
+                            "exp_avg_sq": fl.exp_avg_sq[o:o + n].view(p.shape).clone()}
+            o += n
+        group = {"lr": float(self.lr.item()), "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(fl.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd):
+        """Inverse of ``optimizer_state_dict`` (also accepts the state_dict of a torch.optim.Adam built over the same
+        parameter chain).  Step counters are per Adam group here: the parameters of a group must agree."""
+        fl = self.flat
+        fl.exp_avg.zero_(); fl.exp_avg_sq.zero_()
+        steps = [0] * len(self.groups)
+        o = 0
+        for i, p in enumerate(fl.params):
+            n = p.numel()
+            st = sd["state"].get(i)
+            if st is not None:
+                gi = next((g for g, (b, e) in enumerate(self.groups) if b <= o < e), None)
+                if gi is None:
+                    raise ValueError(f"parameter {i} has optimizer state but belongs to no Adam group of this engine")
+                step = int(st["step"])
+                if steps[gi] not in (0, step):
+                    raise ValueError("parameters of one Adam group carry different step counts")
+                steps[gi] = step
+                fl.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                fl.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            o += n
+        self.steps.zero_()
+        self.steps[:len(steps)] = torch.tensor(steps, dtype=torch.int32)
+        g = sd["param_groups"][0]
+        self.set_lr(g["lr"])
+
     def named_grads(self):
         """{module-prefixed parameter name: gradient view} of the last step (for tests / inspection)."""
         out = {}

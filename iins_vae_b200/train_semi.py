@@ -80,6 +80,9 @@ def run(opt, dataloader=None, max_steps=None, quiet=False):
                 eng = engines[B] = SemiTrainEngine(Enc, Dec, Res, Cls, batch_size=B, cir_len=cir.shape[1], lr=lr,
                                                    betas=(opt.b1, opt.b2), mode="semi", process_group=pg,
                                                    shared_state=next(iter(engines.values()), None))
+                opt_file = os.path.join(model_path, "Opt_%d.pth" % opt.epoch)
+                if opt.epoch != 0 and len(engines) == 1 and os.path.exists(opt_file):
+                    eng.load_optimizer_state_dict(torch.load(opt_file))   # exact resume (the reference restarts Adam)
             eng.set_lr(lr)
             supervised = bool(mask_stream())
             eng.step(cir, err, label, supervised=supervised)
@@ -103,6 +106,8 @@ def run(opt, dataloader=None, max_steps=None, quiet=False):
         if rank == 0 and opt.checkpoint_interval != -1 and epoch % opt.checkpoint_interval == 0:
             for m, n in ((Enc, "Enc"), (Dec, "Dec"), (Res, "Res"), (Cls, "Cls")):
                 torch.save(m.state_dict(), os.path.join(model_path, "%s_%d.pth" % (n, epoch)))
+            if engines:                                                    # beyond the reference: Adam moments + step counters
+                torch.save(next(iter(engines.values())).optimizer_state_dict(), os.path.join(model_path, "Opt_%d.pth" % epoch))
     return last
 
 

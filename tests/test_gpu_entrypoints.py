@@ -73,3 +73,88 @@ def test_checkpoint_roundtrip_with_reference_key_names(tmp_path):
     sd = torch.load(tmp_path / "Dec_0.pth")
     assert list(sd.keys()) == list(orc.decoder_param_shapes(cfg).keys())
     assert torch.equal(sd["decoder.model.2.block.2.running_var"], torch.ones(64))
+
+
+def _engine(seed, batch):
+    from iins_vae_b200 import models as M
+    from iins_vae_b200.engine import SemiTrainEngine
+    cfg = orc.PathConfig()
+    pe, pd, pr, pc = orc.init_all(cfg, seed)
+    Enc = M.Encoder(1, cfg.dim, cfg.n_residual, cfg.n_downsample, cfg.env_dim, cfg.range_dim)
+    Dec = M.Decoder(1, cfg.dim, cfg.n_residual, cfg.n_downsample, cfg.env_dim, cfg.cir_len, cfg.range_dim)
+    Res = M.Restorer((cfg.range_dim, cfg.code_len))
+    Cls = M.Classifier(cfg.env_dim, cfg.num_classes)
+    for m, p in ((Enc, pe), (Dec, pd), (Res, pr), (Cls, pc)):
+        m.load_state_dict(p)
+        m.cuda()
+    return cfg, (Enc, Dec, Res, Cls), SemiTrainEngine(Enc, Dec, Res, Cls, batch_size=batch, lr=1e-3, use_graph=False)
+
+
+def test_optimizer_state_roundtrip_and_torch_adam_compat(tmp_path):
+    """the engine's Adam state saves in torch.optim.Adam's own layout over the reference's parameter
+    chain (train_semi.py:118-122), loads into a stock torch optimizer, and one stock torch step from it equals one fused
+    step on the same gradients; a fresh engine that loads it continues exactly where the first one stopped."""
+    import itertools
+    B = 64
+    cfg, mods, eng = _engine(21, B)
+    batches = [orc.synthetic_batch(cfg, B, 900 + j) for j in range(4)]
+    for j, sup in enumerate((True, False, True)):
+        eng.step(*batches[j], supervised=sup)
+    sd = eng.optimizer_state_dict()
+    torch.save(sd, tmp_path / "Opt_3.pth")
+    sd = torch.load(tmp_path / "Opt_3.pth")
+    params = list(itertools.chain(*(m.parameters() for m in mods)))
+    assert sd["param_groups"][0]["params"] == list(range(len(params)))
+    # restorer.linear_layer2 never gets a gradient -> no state, like torch's lazily created state
+    names = [n for m in mods for n, _ in m.named_parameters()]
+    missing = [names[i] for i in range(len(params)) if i not in sd["state"]]
+    assert missing == ["restorer.linear_layer2.weight", "restorer.linear_layer2.bias"], missing
+    enc_idx, res_idx = 0, names.index("restorer.layers.0.weight")
+    assert int(sd["state"][enc_idx]["step"]) == 3 and int(sd["state"][res_idx]["step"]) == 2      # Res/Cls skip the unsupervised step
+
+    # (1) a stock torch Adam over detached copies of the parameters, fed the engine's next gradients
+    ref_params = [torch.nn.Parameter(p.detach().clone()) for p in params]
+    topt = torch.optim.Adam(ref_params, lr=1e-3, betas=(0.5, 0.999))
+    topt.load_state_dict(sd)
+    eng.step(*batches[3], supervised=True, update=False)            # gradients only
+    grads = [g.clone() for g in eng.flat.grad_views]
+    for p, g, n in zip(ref_params, grads, names):
+        p.grad = None if "linear_layer2" in n else g
+    topt.step()
+    eng._adam(True)                                                   # the fused update on the same gradients
+    torch.cuda.synchronize()
+    for p_ref, p, n in zip(ref_params, params, names):
+        assert torch.allclose(p_ref, p.detach(), rtol=0, atol=2e-7), n
+
+    # (2) exact resume: a fresh engine on the same weights + loaded state reproduces the moments and counters
+    cfg2, mods2, eng2 = _engine(21, B)
+    for m2, m in zip(mods2, mods):
+        m2.load_state_dict(m.state_dict())
+    eng2.load_optimizer_state_dict(eng.optimizer_state_dict())
+    assert torch.equal(eng2.flat.exp_avg, eng.flat.exp_avg) and torch.equal(eng2.flat.exp_avg_sq, eng.flat.exp_avg_sq)
+    assert eng2.steps.tolist()[:3] == eng.steps.tolist()[:3] == [4, 3, 3]
+    assert abs(float(eng2.lr) - 1e-3) < 1e-9          # the learning rate lives in an fp32 device scalar
+
+
+def test_test_gem_device_side_accumulation_matches_per_batch_path():
+    """test.py:55-107 tail on the device: one host sync, preallocated output arrays -- same numbers as summing per batch."""
+    from iins_vae_b200 import models as M
+    from iins_vae_b200.data import SyntheticCIR
+    from iins_vae_b200.engine import InferenceEngine
+    from iins_vae_b200.test import test_gem
+    from iins_vae_b200.utils import get_args
+    opt = get_args(None).parse_args(["--dataset_env", "nlos"])
+    torch.manual_seed(5)
+    net = M.EMNet(cir_len=157, num_classes=2, env_dim=16).cuda()
+    val = SyntheticCIR(1000, 250, 157, 2, seed=8)
+    res = test_gem(opt, torch.device("cuda"), torch.cuda.FloatTensor, "/tmp", "/tmp", val, net, 0, None)
+    eng = InferenceEngine(net.encoder, net.restorer, net.classifier, batch_size=250)
+    rm, ab, ac, errs = [], [], [], []
+    for batch in val:
+        err_est, pred, out = eng.run(batch["CIR"], batch["Err"], batch["Label"])
+        o = out.tolist()
+        rm.append(max(o[4], 0.0) ** 0.5); ab.append(o[1]); ac.append(o[5] / 250)
+        errs.append(err_est.clone())
+    assert abs(res["rmse"] - np.mean(rm)) < 1e-6 and abs(res["abs"] - np.mean(ab)) < 1e-6 and abs(res["accuracy"] - np.mean(ac)) < 1e-9
+    assert res["err_est"].shape == (1000, 1) and torch.equal(res["err_est"], torch.cat(errs))
+    assert res["pred"].shape == (1000,) and res["env_latent"].shape == (1000, 16)
