@@ -32,6 +32,26 @@ N_BATCHES = 8            # distinct synthetic batches cycled through (no step se
 
 
 # ----------------------------------------------------------------------------------------------------
+class PathShape:
+    """Shape options of the benchmarked 1-D path (models.py:33,68,97,118; train_semi.py:77-82 with the SURVEY 8(d)
+    defaults).  The product arm takes nothing from oracle/: parameters come from the modules' own reference-style
+    initialisation (train_semi.py:104-107), batches from iins_vae_b200.data.SyntheticCIR, the supervision mask from
+    iins_vae_b200.parallel.SupervisionMask."""
+    cir_len, dim, n_residual, n_downsample, env_dim, range_dim, num_classes, pooled_len = 157, 4, 3, 4, 16, 2, 5, 128
+
+    @property
+    def trunk_dim(self):
+        return self.dim * 2 ** self.n_downsample
+
+    @property
+    def code_len(self):
+        return self.pooled_len // (2 ** self.n_downsample)
+
+    @property
+    def n_adain(self):
+        return 2 * self.n_residual * 2 * self.trunk_dim
+
+
 def algorithmic_flops(cfg, supervised: bool) -> float:
     """2*MACs of every Conv1d / Linear executed per SAMPLE in one train step:
     forward + dgrad + wgrad, no data gradient into the two stem convs (their input is the data)."""
@@ -193,10 +213,11 @@ def hbm_kernel_rooflines(lib, peaks):
     return out
 
 
-def cpu_reference_run(cfg, batch, steps, warmup, threads):
+def cpu_reference_run(batch, steps, warmup, threads):
     """The reference algorithm (oracle port: torch CPU ops + autograd + torch.optim.Adam semantics restated in
-    oracle/iins_oracle.py) on the host cores; returns samples/s."""
+    oracle/iins_oracle.py) on the host cores; returns samples/s.  The ONLY code in this file that touches oracle/."""
     from oracle import iins_oracle as orc
+    cfg = orc.PathConfig()
     torch.set_num_threads(threads)
     pe, pd, pr, pc = orc.init_all(cfg, 1234)
     flat = {f"{g}.{k}": v for g, d in zip(("enc", "dec", "res", "cls"), (pe, pd, pr, pc)) for k, v in d.items()
@@ -222,13 +243,12 @@ def cpu_reference_run(cfg, batch, steps, warmup, threads):
 
 
 def run_reference(args):
-    from oracle import iins_oracle as orc
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = orc.PathConfig()
+    cfg = PathShape()
     threads = os.cpu_count() or 1
-    val, ms = cpu_reference_run(cfg, args.batch, args.steps, args.warmup, threads)
+    val, ms = cpu_reference_run(args.batch, args.steps, args.warmup, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -239,7 +259,7 @@ def run_reference(args):
                                    f"(oracle port of models.py + train_semi.py:183-228, torch CPU, {threads} threads)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 def workload_config(batch, gpus):
@@ -261,15 +281,28 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): native libraries (NCCL prints its version banner there) and anything
+    # else that writes to fd 1 during the run go to stderr; the original stdout is restored for emit() only
+    sys.stdout.flush()
+    _stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(_stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+    globals()["_emit"] = emit
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args)
         return
 
     import torch.distributed as dist
-    from oracle import iins_oracle as orc          # parameter init + synthetic data + cpu_baseline leg only
     from iins_vae_b200 import models as M
+    from iins_vae_b200.data import SyntheticCIR
     from iins_vae_b200.engine import SemiTrainEngine
+    from iins_vae_b200.parallel import SupervisionMask
     from iins_vae_b200._capi import get_lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -282,24 +315,25 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         pg = dist.group.WORLD
     lib = get_lib()
-    cfg = orc.PathConfig()
+    cfg = PathShape()
     B, K, W = args.batch, args.steps, args.warmup
 
-    pe, pd, pr, pc = orc.init_all(cfg, 1234)
+    torch.manual_seed(1234)                                     # random-init weights of the named architecture, same on every rank
     Enc = M.Encoder(1, cfg.dim, cfg.n_residual, cfg.n_downsample, cfg.env_dim, cfg.range_dim)
     Dec = M.Decoder(1, cfg.dim, cfg.n_residual, cfg.n_downsample, cfg.env_dim, cfg.cir_len, cfg.range_dim)
     Res = M.Restorer((cfg.range_dim, cfg.code_len))
     Cls = M.Classifier(cfg.env_dim, cfg.num_classes)
-    for m, p in ((Enc, pe), (Dec, pd), (Res, pr), (Cls, pc)):
-        m.load_state_dict(p)
+    for m in (Enc, Dec, Res, Cls):
+        m.apply(M.weights_init_normal)                          # train_semi.py:104-107
         m.cuda()
     eng = SemiTrainEngine(Enc, Dec, Res, Cls, batch_size=B, cir_len=cfg.cir_len, lr=1e-4, betas=(0.5, 0.999),
                           use_graph=True, process_group=pg)
 
-    host = [tuple(t.pin_memory() for t in orc.synthetic_batch(cfg, B, 1234 + 100 * rank + j)) for j in range(N_BATCHES)]
+    data = SyntheticCIR(N_BATCHES * B, B, cfg.cir_len, cfg.num_classes, seed=1234 + 100 * rank, pin=True)
+    host = [(b["CIR"], b["Err"], b["Label"]) for b in data]     # pinned host batches of the loader's shape (dataset.py:118-133)
     dev = [tuple(t.cuda() for t in b) for b in host]
-    rng = np.random.RandomState(1234)                           # identical mask sequence on every rank
-    masks = [orc.supervision_mask(rng, 0.1) for _ in range(W + 2 * K + 8)]
+    mask_stream = SupervisionMask(0.1, seed=1234)               # identical mask sequence on every rank (train_semi.py:203)
+    masks = [mask_stream() for _ in range(W + 2 * K + 8)]
 
     def barrier():
         if world > 1:
@@ -422,7 +456,7 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        val, _ = cpu_reference_run(cfg, B, 8, 2, threads)
+        val, _ = cpu_reference_run(B, 8, 2, threads)
         cpu_baseline = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": f"8 timed steps of batch {B} after 2 warm-up (oracle port, torch CPU, {threads} threads)"}
 
@@ -440,7 +474,7 @@ def main():
             "kernels": kernel_table, "roofline_hbm": hbm_rooflines,
             "final_loss_terms": {k: float(v) for k, v in zip(("l1_recon", "l1_err", "ce", "weighted_sum"), out_host[:4].tolist())},
         }
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         # CUDA graphs that captured NCCL kernels keep the communicator busy at teardown (destroy_process_group
         # was observed to hang): synchronise, rendezvous once more, flush and leave without the teardown.
