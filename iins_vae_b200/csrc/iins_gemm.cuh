@@ -580,16 +580,17 @@ __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowParams r
     iins_pdl_enter();
     constexpr int BM = 128;
     __shared__ __align__(16) float Ws[IINS_ROW2_WMAX];       // [k][NACC]
-    __shared__ float s_bias[16];
+    __shared__ float s_bias[NACC < 16 ? 16 : NACC];
     __shared__ float xch[4];
     const IinsNTParams& p = rp.nt;
     const IinsGeom& g = p.g;
     const IinsEpilogue& ep = p.ep;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_m = blockIdx.x * BM;
+    const int n0 = blockIdx.y * NACC;                    // column block (only the wide plain layers use more than one)
     const int Cdim = AKIND == 0 ? g.Cin : g.Cout;
     for (int e = tid; e < p.K * NACC; e += BM) {
-        const int k = e / NACC, n = e - k * NACC;
+        const int k = e / NACC, n = n0 + e - k * NACC;
         float v = 0.f;
         if (n < p.N) {
             const int t = k / Cdim, c = k - t * Cdim;
@@ -597,7 +598,7 @@ __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowParams r
         }
         Ws[e] = v;
     }
-    if (tid < 16) s_bias[tid] = (ep.bias != nullptr && tid < p.N) ? __ldg(ep.bias + tid) : 0.f;
+    if (tid < NACC) s_bias[tid] = (ep.bias != nullptr && n0 + tid < p.N) ? __ldg(ep.bias + n0 + tid) : 0.f;
     __syncthreads();
 
     const int grow = tile_m + tid;
@@ -605,7 +606,7 @@ __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowParams r
     const int b = ok ? grow >> p.lshift : 0, l = ok ? grow & (p.Lrow - 1) : 0;
     float acc[NACC];
 #pragma unroll
-    for (int j = 0; j < NACC; ++j) acc[j] = s_bias[j & 15];
+    for (int j = 0; j < NACC; ++j) acc[j] = s_bias[j];
     if (ok) {
         if (AKIND == 0) {
             for (int t = 0; t < g.ks; ++t) {
@@ -720,8 +721,8 @@ __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowParams r
         for (int j = 0; j < NACC; ++j) acc[j] = iins_act(acc[j], ep.act, ep.slope);
     }
     if (!ok) return;
-    if (p.out_layout == IINS_NLC && p.N == NACC) {
-        const long oi = (long)grow * NACC;
+    if (p.out_layout == IINS_NLC && (p.N % NACC) == 0) {
+        const long oi = (long)grow * p.N + n0;
         if (EPI != 0 && ep.xhat != nullptr) {
 #pragma unroll
             for (int j = 0; j < NACC; j += 4)
@@ -740,8 +741,8 @@ __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowParams r
     } else {
 #pragma unroll
         for (int j = 0; j < NACC; ++j) {
-            if (j >= p.N) continue;
-            const long oi = p.out_layout == IINS_NCL ? (((long)b * p.N + j) << p.lshift) + l : (long)grow * p.N + j;
+            if (n0 + j >= p.N) continue;
+            const long oi = p.out_layout == IINS_NCL ? (((long)b * p.N + n0 + j) << p.lshift) + l : (long)grow * p.N + n0 + j;
             if (EPI != 0 && ep.xhat != nullptr) ep.xhat[oi] = xh[j];
             float o = acc[j];
             if (ep.add != nullptr) o += ep.add[oi];

@@ -234,21 +234,25 @@ void launch_nt(Ctx& c, IinsNTParams p) {
     }
     if (p.lshift < 0) { c.err = 2; return; }
     {   // small-channel layer: direct SIMT conv, one thread per output row, register epilogue (iins_row2_nt_kernel)
-        const int nacc = p.N <= 4 ? 4 : (p.N <= 8 ? 8 : 16);
+        // wide plain layers with a tiny reduction (the 1x1 conv on the 2-channel range code and its data gradient: K = 2;
+        // the data gradient of the Restorer's last Linear: K = 1) take 64 columns per thread, column blocks in grid.y
+        const bool wide = p.N > 16 && p.N % 64 == 0 && p.K <= 16 && p.ep.norm == IINS_NORM_NONE;
+        const int nacc = wide ? 64 : (p.N <= 4 ? 4 : (p.N <= 8 ? 8 : 16));
         const bool norm_ok = p.ep.norm == IINS_NORM_NONE || (p.a_kind == 0 && (p.Lrow == 32 || p.Lrow == 64 || p.Lrow == 128));
         static int row2_on = -1;
         if (row2_on < 0) { const char* e = getenv("IINS_ROW2"); row2_on = e ? atoi(e) : 1; }
-        if (row2_on && p.N <= 16 && p.K * nacc <= IINS_ROW2_WMAX && p.K <= 128 && norm_ok) {
+        if (row2_on && (p.N <= 16 || wide) && p.K * nacc <= IINS_ROW2_WMAX && p.K <= 128 && norm_ok) {
             if (c.phase == 1) return;
             IinsRowParams rp;
             rp.nt = p;
             const int epi = p.ep.norm == IINS_NORM_NONE ? 0 : (p.ep.norm == IINS_NORM_LN ? 2 : 1);
-            const int grid = (p.M + 127) / 128;
+            const dim3 grid((p.M + 127) / 128, (p.N + nacc - 1) / nacc, 1);
             IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K); IINS_SET_SHAPE(p.M, p.N, p.K);
 #define IINS_R2(NA_, AK_, EP_) \
             if (nacc == NA_ && p.a_kind == AK_ && epi == EP_) { auto iins_row2_nt_kernel_ = iins_row2_nt_kernel<NA_, AK_, EP_>; IINS_LAUNCH(iins_row2_nt_kernel_, grid, 128, 0, c.st, rp); return; }
             IINS_R2(4, 0, 0) IINS_R2(8, 0, 0) IINS_R2(16, 0, 0) IINS_R2(4, 1, 0) IINS_R2(8, 1, 0) IINS_R2(16, 1, 0)
             IINS_R2(4, 0, 1) IINS_R2(8, 0, 1) IINS_R2(16, 0, 1) IINS_R2(4, 0, 2) IINS_R2(8, 0, 2) IINS_R2(16, 0, 2)
+            IINS_R2(64, 0, 0) IINS_R2(64, 1, 0)
 #undef IINS_R2
         }
     }
