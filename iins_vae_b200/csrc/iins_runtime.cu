@@ -1023,7 +1023,6 @@ size_t mlp_ws(const Shapes& s, const MlpSpec& m) {
     for (int i = 1; i < m.n; ++i) n += ((size_t)s.B * m.dims[i] + 3) & ~(size_t)3;
     return n;
 }
-size_t mlp_act_floats(const Shapes& s, const MlpSpec& m) { return mlp_ws(s, m); }
 size_t mlp_scratch(const Shapes& s, const MlpSpec& m) {
     size_t mx = 0;
     for (int i = 1; i < m.n; ++i) if ((size_t)m.dims[i] > mx) mx = m.dims[i];
@@ -1095,7 +1094,6 @@ int iins_set_compute_mode(int mode) {
     return IINS_OK;
 }
 int iins_get_compute_mode(void) { return g_mode; }
-void iins_debug_set_timeline(void*, int) {}   /* the per-phase clock trace was removed with the lean kernel variants */
 const char* iins_last_error(void) { return g_err; }
 int iins_set_stream_concurrency(int enable) {
 #ifndef IINS_CPUSIM

@@ -4,21 +4,24 @@
 //       channels-last activations (im2col on the fly: reflection / zero padding, stride, nearest x2
 //       upsampling, or the transposed tap map for dgrad), split into bf16 pieces and written to shared
 //       memory in the UMMA K-major no-swizzle layout; the weight tile arrives pre-split through a TMA bulk
-//       copy (cp.async.bulk + mbarrier); one elected lane of warp 0 issues tcgen05.mma (M=128, N=16..64,
-//       K=16), the fp32 accumulator lives in TMEM, the epilogue (bias, InstanceNorm / AdaIN / LayerNorm,
-//       activation, residual) runs on the TMEM -> SMEM staged tile.
+//       copy (cp.async.bulk + mbarrier); one elected lane of the MMA warp issues tcgen05.mma (M=128, N=16..64 x
+//       stacked pieces, K=16), the fp32 accumulator lives in TMEM, the epilogue (bias, InstanceNorm / AdaIN /
+//       LayerNorm, activation, residual, or the fused norm BACKWARD of a data gradient) runs in registers straight
+//       out of TMEM (iins_tc_epilogue_regs); a SMEM-staged generic epilogue remains as the fallback variant.
 //   iins_tc_tn_kernel : weight gradient  dW^T[k][n] = sum_rows A[row][k] * dz[row][n]  with both operands
 //       MN-major (the reduction runs over rows), accumulated in TMEM over the CTA's row range and flushed
 //       with atomics.
 //
 // Precision: fp32 parity needs more than TF32/BF16 single-pass products, so each fp32 operand is split into
-// three bf16 pieces (8+8+8 mantissa bits) and the six significant piece products are accumulated in fp32
-// ("bf16x3": error ~2^-23, same class as an fp32 FMA chain).  pieces == 1 is the plain bf16 mode.
+// three bf16 pieces (8+8+8 mantissa bits) and eight of the nine piece products are accumulated in fp32
+// ("bf16x3": operand error ~2^-31; the fp32 accumulation inside the tensor core remains measurably noisier than an
+// FMA chain).  pieces == 1 is the plain bf16 mode.
 //
-// Latency notes (measured with the IINS_TL clock trace, tools/timeline.py): the MMA issue path must be
-// warp-uniform (descriptors in uniform registers; a divergent `if (tid == 0)` costs ~170 cycles per MMA in
-// R2UR traffic), the raw operand data of K block kb+1 is prefetched into registers before the barrier of
-// block kb, and the row / k index splits are shifts (every L and channel count on the path is a power of 2).
+// Latency notes (measured with in-kernel clock traces during bring-up and with ncu): the MMA
+// issue path must be warp-uniform (descriptors in uniform registers; a divergent `if (tid == 0)` costs ~170 cycles per
+// MMA in R2UR traffic), the raw operand data of the next TWO K blocks is prefetched into registers, the row / k index
+// splits are shifts (every L and channel count on the path is a power of 2), and every (tile width, operand kind,
+// epilogue kind, rows per sample) combination is its own template instance (instruction-fetch stalls otherwise).
 #pragma once
 #include "iins_gemm.cuh"
 #ifndef IINS_CPUSIM
