@@ -386,9 +386,14 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(K):
+    # one H2D copy of a pinned host batch per step, issued inside the region: batch i+1 is copied by the engine's
+    # copy stream while step i computes (SemiTrainEngine.prefetch: the repo's input pipeline)
+    eng.prefetch(*host[step_i % N_BATCHES])
+    for k in range(K):
         sup = bool(masks[step_i])
-        out = eng.step(*host[step_i % N_BATCHES], supervised=sup)
+        out = eng.step(supervised=sup, prefetched=True)
+        if k + 1 < K:
+            eng.prefetch(*host[(step_i + 1) % N_BATCHES])
         out_host.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()              # the reference loop reads loss.item() every step
         step_i += 1

@@ -241,12 +241,41 @@ class SemiTrainEngine:
         self.label.copy_(label.view(self.B, 1).to(torch.float32) if label.dtype != torch.float32 else label.view(self.B, 1),
                          non_blocking=True)
 
-    def step(self, cir=None, err=None, label=None, supervised=True, update=True):
+    def prefetch(self, cir, err, label):
+        """Input pipeline: start the host->device copy of the NEXT batch on a copy stream into
+        staging buffers while the current step computes; ``step(prefetched=True)`` then only moves 2.6 MB device to
+        device.  The reference does a synchronous pageable ``.cuda()`` per tensor per step (train_semi.py:174-180)."""
+        if not hasattr(self, "_stage"):
+            self._stage = (torch.empty_like(self.cir), torch.empty_like(self.err), torch.empty_like(self.label))
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._copy_done = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream())
+        self._copy_stream.wait_event(self._stage_free)          # the previous consumer has read the staging buffers
+        with torch.cuda.stream(self._copy_stream):
+            self._stage[0].copy_(cir.view(self.B, self.L), non_blocking=True)
+            self._stage[1].copy_(err.view(self.B, 1), non_blocking=True)
+            lab = label.view(self.B, 1)
+            self._stage[2].copy_(lab if lab.dtype == torch.float32 else lab.to(torch.float32), non_blocking=True)
+            self._copy_done.record(self._copy_stream)
+
+    def _consume_prefetch(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._copy_done)
+        self.cir.copy_(self._stage[0], non_blocking=True)
+        self.err.copy_(self._stage[1], non_blocking=True)
+        self.label.copy_(self._stage[2], non_blocking=True)
+        self._stage_free.record(cur)
+
+    def step(self, cir=None, err=None, label=None, supervised=True, update=True, prefetched=False):
         """One optimisation step.  Returns the device tensor ``out`` (8 floats, see iins_b200.h) -- nothing
-        synchronises; read ``loss_terms()`` when a host value is needed."""
+        synchronises; read ``loss_terms()`` when a host value is needed.  ``prefetched=True`` consumes the batch
+        staged by ``prefetch()`` instead of copying ``cir / err / label`` now."""
         if self.mode == "supervised":
             supervised = True
-        if cir is not None:
+        if prefetched:
+            self._consume_prefetch()
+        elif cir is not None:
             self.load_batch(cir, err, label)
         key = (bool(supervised), bool(update))
         if self.use_graph:

@@ -23,6 +23,26 @@ from .parallel import SupervisionMask, broadcast_parameters, init_distributed
 from .utils import get_args, num_classes_for
 
 
+class _Lookahead:
+    """Iterate a loader one batch ahead so that the next batch can be handed to ``SemiTrainEngine.prefetch``."""
+
+    def __init__(self, it):
+        self.it = iter(it)
+        self.nxt = next(self.it, None)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.nxt is None:
+            raise StopIteration
+        cur, self.nxt = self.nxt, next(self.it, None)
+        return cur
+
+    def peek(self):
+        return self.nxt
+
+
 def build_modules(opt, device):
     """train_semi.py:43-82."""
     len_cir = 157
@@ -72,7 +92,9 @@ def run(opt, dataloader=None, max_steps=None, quiet=False):
         lr = opt.lr * sched.step(epoch - opt.epoch)                        # LambdaLR(optimizer, lr_lambda=...) semantics
         rmse_sum = abs_sum = acc_sum = 0.0
         n_sup = 0
-        for i, batch in enumerate(dataloader):
+        lookahead = _Lookahead(dataloader)
+        pending = None
+        for i, batch in enumerate(lookahead):
             cir, err, label = batch["CIR"], batch["Err"], batch["Label"]
             B = cir.shape[0]
             eng = engines.get(B)
@@ -85,7 +107,15 @@ def run(opt, dataloader=None, max_steps=None, quiet=False):
                     eng.load_optimizer_state_dict(torch.load(opt_file))   # exact resume (the reference restarts Adam)
             eng.set_lr(lr)
             supervised = bool(mask_stream())
-            eng.step(cir, err, label, supervised=supervised)
+            if pending is eng:                                             # this batch was prefetched during the previous step
+                eng.step(supervised=supervised, prefetched=True)
+            else:
+                eng.step(cir, err, label, supervised=supervised)
+            pending = None
+            nxt = lookahead.peek()
+            if nxt is not None and nxt["CIR"].shape[0] == B and nxt["CIR"].is_pinned():
+                eng.prefetch(nxt["CIR"], nxt["Err"], nxt["Label"])        # H2D of the next batch overlaps this step
+                pending = eng
             steps_done += 1
             if supervised and (i % opt.log_every == 0 or max_steps is not None):
                 t = eng.loss_terms()                                       # the only host sync

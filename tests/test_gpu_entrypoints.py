@@ -158,3 +158,24 @@ def test_test_gem_device_side_accumulation_matches_per_batch_path():
     assert abs(res["rmse"] - np.mean(rm)) < 1e-6 and abs(res["abs"] - np.mean(ab)) < 1e-6 and abs(res["accuracy"] - np.mean(ac)) < 1e-6
     assert res["err_est"].shape == (1000, 1) and torch.equal(res["err_est"], torch.cat(errs))
     assert res["pred"].shape == (1000,) and res["env_latent"].shape == (1000, 16)
+
+
+def test_prefetched_batch_gives_the_same_step():
+    """the copy-stream input pipeline (prefetch + step(prefetched=True)) feeds the step the same
+    tensors as the direct path."""
+    B = 128
+    cfg, mods, eng = _engine(33, B)
+    a, b = (tuple(t.pin_memory() for t in orc.synthetic_batch(cfg, B, 70 + j)) for j in range(2))
+    eng.step(*a, supervised=True, update=False)
+    ref_a = eng.out.clone()
+    eng.step(*b, supervised=True, update=False)
+    ref_b = eng.out.clone()
+    eng.prefetch(*a)
+    eng.step(supervised=True, update=False, prefetched=True)
+    eng.prefetch(*b)                                   # overlaps the step above
+    got_a = eng.out.clone()
+    eng.step(supervised=True, update=False, prefetched=True)
+    got_b = eng.out.clone()
+    torch.cuda.synchronize()
+    assert torch.allclose(got_a, ref_a, rtol=1e-6, atol=1e-7) and torch.allclose(got_b, ref_b, rtol=1e-6, atol=1e-7)
+    assert not torch.allclose(ref_a, ref_b)
