@@ -38,14 +38,20 @@ __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNormBwdPar
     __shared__ float s_dg[8][128], s_db[8][128];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = p.C, L = p.L;
-    const int CG = C >> 2;                          // float4 column groups per row (<= 32)
+    // C >= 4: a lane's float4 covers 4 channels of one row (CG column groups per row); C < 4 (dim < 4 configurations): a
+    // float4 covers 4/C rows and element j has channel j & (C-1)
+    const int CG = C >= 4 ? C >> 2 : 1;             // float4 column groups per row (<= 32)
     const int nstep = (L * C) >> 7;                 // float4 steps of 32 lanes
     const bool relu = p.act == IINS_ACT_RELU;
     const int cg = lane & (CG - 1), c0 = cg * 4;    // CG <= 32 and nstep*32 is a multiple of CG: the lane's channels are fixed
+    int ch[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ch[j] = C >= 4 ? c0 + j : (j & (C - 1));
+    const int nch = C >= 4 ? 4 : C;                 // distinct channels held by a lane
     float scale[4] = {1.f, 1.f, 1.f, 1.f}, shift[4] = {0.f, 0.f, 0.f, 0.f};
     if (p.norm == IINS_NORM_LN) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { scale[j] = __ldg(p.gamma + c0 + j); shift[j] = __ldg(p.beta + c0 + j); }
+        for (int j = 0; j < 4; ++j) { scale[j] = __ldg(p.gamma + ch[j]); shift[j] = __ldg(p.beta + ch[j]); }
     }
     float tot_dg[4] = {0.f, 0.f, 0.f, 0.f}, tot_db[4] = {0.f, 0.f, 0.f, 0.f};
     const float invL = 1.0f / (float)L;
@@ -53,8 +59,8 @@ __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNormBwdPar
         if (p.norm == IINS_NORM_ADAIN) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                scale[j] = __ldg(p.adain + (long)b * p.adain_ld + p.adain_off_w + c0 + j);
-                shift[j] = __ldg(p.adain + (long)b * p.adain_ld + p.adain_off_b + c0 + j);
+                scale[j] = __ldg(p.adain + (long)b * p.adain_ld + p.adain_off_w + ch[j]);
+                shift[j] = __ldg(p.adain + (long)b * p.adain_ld + p.adain_off_b + ch[j]);
             }
         }
         const float4* dy4 = reinterpret_cast<const float4*>(p.dy + (long)b * L * C);
@@ -78,6 +84,22 @@ __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNormBwdPar
             tot_g = iins_warp_sum(sg[0] + sg[1] + sg[2] + sg[3]);
             tot_gx = iins_warp_sum(sgx[0] + sgx[1] + sgx[2] + sgx[3]);
         }
+        if (C < 4) {                                    // fold the elements of a lane that share a channel (uniform branch)
+            // elements j < nch hold distinct channels and their index sets {i : ch[i] == ch[j]} are disjoint: in place is safe
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j >= nch) continue;
+                float a = 0.f, b2 = 0.f, c2 = 0.f, d2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (ch[i] == ch[j]) { a += sg[i]; b2 += sgx[i]; c2 += sr[i]; d2 += srx[i]; }
+                sg[j] = a; sgx[j] = b2; sr[j] = c2; srx[j] = d2;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < nch) continue;
+                sg[j] = sg[j & (C - 1)]; sgx[j] = sgx[j & (C - 1)]; sr[j] = sr[j & (C - 1)]; srx[j] = srx[j & (C - 1)];
+            }
+        }
         // per-channel totals: combine the lanes that share this lane's column group (lane bits >= log2(CG))
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -95,8 +117,9 @@ __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNormBwdPar
             if (lane < CG) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    p.dadain[(long)b * p.adain_ld + p.adain_off_b + c0 + j] = sr[j];
-                    p.dadain[(long)b * p.adain_ld + p.adain_off_w + c0 + j] = srx[j];
+                    if (j >= nch) continue;
+                    p.dadain[(long)b * p.adain_ld + p.adain_off_b + ch[j]] = sr[j];
+                    p.dadain[(long)b * p.adain_ld + p.adain_off_w + ch[j]] = srx[j];
                 }
             }
         }
@@ -112,7 +135,7 @@ __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNormBwdPar
             mean_g = tot_g / (float)nel;
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) rs[j] = __ldg(p.rstd + (long)b * C + c0 + j);
+            for (int j = 0; j < 4; ++j) rs[j] = __ldg(p.rstd + (long)b * C + ch[j]);
         }
         for (int i = 0; i < nstep; ++i) {
             const float4 d = __ldg(dy4 + lane + 32 * i), x = __ldg(xh4 + lane + 32 * i);
@@ -131,7 +154,7 @@ __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNormBwdPar
     if (p.norm == IINS_NORM_LN) {               // uniform for the whole CTA
         if (lane < CG) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { s_dg[warp][c0 + j] = tot_dg[j]; s_db[warp][c0 + j] = tot_db[j]; }
+            for (int j = 0; j < 4; ++j) { if (j < nch) { s_dg[warp][ch[j]] = tot_dg[j]; s_db[warp][ch[j]] = tot_db[j]; } }
         }
         __syncthreads();
         if (threadIdx.x < C) {

@@ -43,6 +43,16 @@ struct Ctx {
 #endif
 };
 
+// launch-plan errors recorded in Ctx::err
+int plan_error(int err, const char* where) {
+    const char* what = err == 1 ? "packed weight tiles exceed the scratch arena" :
+                       err == 2 ? "positions per sample must be a power of two" :
+                       err == 3 ? "norm backward: channel count must be a power of two <= 128 and L*C a multiple of 128" :
+                       err == 4 ? "tensor-core kernel variant not built for this (tile width, epilogue, rows per sample)" : "launch plan error";
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, what);
+    return IINS_ERR_BAD_CONFIG;
+}
+
 int check_cuda(const char* where) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -225,6 +235,7 @@ bool nbwd_fusable(const Ctx& c, const IinsNTParams& p, int L, int C, const float
 }
 
 void launch_nt(Ctx& c, IinsNTParams p) {
+    if (p.M <= 0 || p.N <= 0 || p.K <= 0) return;          // empty layer (e.g. n_residual = 0: no AdaIN parameters)
     p.lshift = ilog2_exact(p.Lrow);
     {   // k -> (tap, channel) split of the tensor-core gathers: a shift for power-of-two channel counts; a Linear layer has
         // one tap, so any channel count that is a multiple of 8 works with the "infinite" shift 31 (t = 0, c = k)
@@ -388,6 +399,7 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
     p.g = g; p.x = x; p.dz = dz; p.dw = dw; p.db = db;
     if (c.phase == 1) return;
     flush_pending(c);
+    if (g.B <= 0 || g.Cout <= 0 || g.Cin <= 0) return;      // empty layer
     cudaStream_t wst = c.st;
     if (c.st2 != nullptr) { fork_to(c.st, c.st2); wst = c.st2; }
     p.M = g.B * g.Lout;
@@ -517,8 +529,8 @@ void norm_backward(Ctx& c, int B, int L, int C, int norm, int act, const float* 
     p.B = B; p.L = L; p.C = C; p.norm = norm; p.act = act; p.dy = dy; p.xhat = xhat; p.rstd = rstd;
     p.gamma = gamma; p.beta = beta; p.dgamma = dgamma; p.dbeta = dbeta;
     p.adain = adain; p.dadain = dadain; p.adain_ld = ld; p.adain_off_b = off_b; p.adain_off_w = off_w; p.dz = dz;
-    // one warp per sample: C power of two in [4,128], L*C a multiple of 128
-    if (ilog2_exact(C) < 2 || C > 128 || ((L * C) & 127) != 0) { c.err = 3; return; }
+    // one warp per sample: C power of two in [1,128], L*C a multiple of 128
+    if (ilog2_exact(C) < 0 || C > 128 || ((L * C) & 127) != 0) { c.err = 3; return; }
     int nb = (B + 7) / 8;
     if (nb > 148 * 4) nb = 148 * 4;                 // persistent: the kernel strides over the samples
     IINS_LAUNCH(iins_norm_bwd_kernel, nb, 256, 0, c.st, p);
@@ -569,6 +581,8 @@ int make_shapes(const iins_config* cfg, Shapes& s) {
     if (s.ndown < 4 || s.ndown > 4) return fail(IINS_ERR_BAD_CONFIG, "n_downsample must be 4 (code length 8)");
     if (s.d < 1 || s.d * (1 << s.ndown) > 64)
         return fail(IINS_ERR_BAD_CONFIG, "dim * 2^n_downsample must be <= 64 in this build (norm epilogue tile)");
+    if ((s.d & (s.d - 1)) != 0)
+        return fail(IINS_ERR_BAD_CONFIG, "dim must be a power of two in this build (1, 2 or 4: channel counts are shifts in the gathers and norm kernels)");
     if (s.nres < 0 || s.nres > 16) return fail(IINS_ERR_BAD_CONFIG, "n_residual out of range");
     if (s.E < 2 || (s.E & 1)) return fail(IINS_ERR_BAD_CONFIG, "env_dim must be even");
     if (s.R < 1 || s.R > 64) return fail(IINS_ERR_BAD_CONFIG, "range_dim out of range");
@@ -691,7 +705,7 @@ int encoder_forward(const Shapes& s, const float* const* P, const float* x, cons
     }
     join_branch(c, br);
     });
-    if (c.err) return fail(IINS_ERR_BAD_CONFIG, "encoder_forward: packed weight tile exceeds the scratch");
+    if (c.err) return plan_error(c.err, "encoder_forward");
     return check_cuda("encoder_forward");
 }
 
@@ -815,7 +829,7 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
     join_branch(c, br);
     end_async_wgrad(c);
     });
-    if (c.err) return fail(IINS_ERR_BAD_CONFIG, "encoder_backward: packed weight tile exceeds the scratch");
+    if (c.err) return plan_error(c.err, "encoder_backward");
     return check_cuda("encoder_backward");
 }
 
@@ -899,7 +913,7 @@ int decoder_forward(const Shapes& s, const float* const* P, const float* rc, con
     }
     IINS_SKIP_IN_COLLECT(c) IINS_LAUNCH(iins_pool_fwd_kernel, grid_for((long)B * s.Lc), 256, 0, st, pl.yt, xrec, B, s.P, s.Lc);
     });
-    if (c.err) return fail(IINS_ERR_BAD_CONFIG, "decoder_forward: packed weight tile exceeds the scratch");
+    if (c.err) return plan_error(c.err, "decoder_forward");
     return check_cuda("decoder_forward");
 }
 
@@ -997,7 +1011,7 @@ int decoder_backward(const Shapes& s, const float* const* P, const float* rc, co
     }
     end_async_wgrad(c);
     });
-    if (c.err) return fail(IINS_ERR_BAD_CONFIG, "decoder_backward: packed weight tile exceeds the scratch");
+    if (c.err) return plan_error(c.err, "decoder_backward");
     return check_cuda("decoder_backward");
 }
 
@@ -1043,7 +1057,7 @@ int mlp_forward(const Shapes& s, const MlpSpec& m, const float* const* P, const 
         h = y;
     }
     });
-    if (c.err) return fail(IINS_ERR_BAD_CONFIG, "mlp_forward: packed weight tile exceeds the scratch");
+    if (c.err) return plan_error(c.err, "mlp_forward");
     return check_cuda("mlp_forward");
 }
 
@@ -1076,7 +1090,7 @@ int mlp_backward(const Shapes& s, const MlpSpec& m, const float* const* P, const
     }
     end_async_wgrad(c);
     });
-    if (c.err) return fail(IINS_ERR_BAD_CONFIG, "mlp_backward: packed weight tile exceeds the scratch");
+    if (c.err) return plan_error(c.err, "mlp_backward");
     return check_cuda("mlp_backward");
 }
 

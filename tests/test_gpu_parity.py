@@ -328,3 +328,13 @@ def test_bf16_mode_is_close_and_stated_tolerance():
     assert np.array_equal(eng.pred.cpu().numpy()[safe], ref["label_fake"].argmax(1).numpy()[safe])
     g = eng.named_grads()["dec.decoder.mlp.model.4.weight"]
     assert torch.isfinite(g).all() and float(g.abs().max()) > 0
+
+
+def test_shape_option_sweep_matches_oracle():
+    """One train step for the other shape options of the path (dim 1 / 2, n_residual 0 / 1, num_classes 2 / 10, env_dim 8,
+    range_dim 4, mixed) at a ragged and a multi-tile batch, against the CPU oracle; dim=3 must be refused, not mis-computed."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("config_sweep", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "config_sweep.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run_sweep() == 0
