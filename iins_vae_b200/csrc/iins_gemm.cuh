@@ -679,11 +679,40 @@ __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowParams r
     for (int j = 0; j < NACC; ++j) xh[j] = 0.f;
     if (EPI == 1) {
         const float invL = 1.0f / (float)L;
+        // all NACC columns share ONE shared-memory exchange per statistic (mean, then centred sum of squares) when a
+        // sample spans several warps: 4 CTA barriers instead of 4 per column
+        __shared__ float xchv[4][NACC];
+        float tot[NACC];
+        auto sample_sums = [&](float* v) {               // v[j] -> sum of v[j] over the L rows of this thread's sample
+#pragma unroll
+            for (int j = 0; j < NACC; ++j) v[j] = iins_warp_sum(v[j]);
+            if (nw > 1) {                                // CTA-uniform
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < NACC; ++j) xchv[warp][j] = v[j];
+                }
+                __syncthreads();
+                const int w0 = warp & ~(nw - 1);
+#pragma unroll
+                for (int j = 0; j < NACC; ++j) {
+                    float t = 0.f;
+                    for (int i = 0; i < nw; ++i) t += xchv[w0 + i][j];
+                    v[j] = t;
+                }
+                __syncthreads();
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) tot[j] = acc[j];
+        sample_sums(tot);
+        float dev[NACC];
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) { dev[j] = acc[j] - tot[j] * invL; tot[j] = dev[j] * dev[j]; }
+        sample_sums(tot);
 #pragma unroll
         for (int j = 0; j < NACC; ++j) {
-            const float mean = iins_row2_sample_sum(acc[j], nw, warp, lane, xch) * invL;
-            const float d = acc[j] - mean;
-            const float vpe = fmaf(iins_row2_sample_sum(d * d, nw, warp, lane, xch), invL, IINS_EPS);
+            const float d = dev[j];
+            const float vpe = fmaf(tot[j], invL, IINS_EPS);
             float r = rsqrtf(vpe);
             r = r * fmaf(-0.5f * vpe, r * r, 1.5f);
             xh[j] = d * r;

@@ -322,7 +322,7 @@ void conv_dgrad(Ctx& c, const IinsGeom& g, const IinsDz& dz, const float* w, flo
 // the module (the env encoder next to the range encoder).  IINS_ASYNC_WGRAD=0 / IINS_BRANCH_STREAMS=0 serialise.
 int g_async_wgrad = -1, g_branch_streams = -1;
 struct HelperStreams { cudaStream_t main; cudaStream_t helper[2]; };
-HelperStreams g_helpers[8];
+HelperStreams g_helpers[32];
 int g_n_helpers = 0;
 cudaEvent_t g_fork_events[256];
 int g_fork_i = 0;
@@ -334,7 +334,7 @@ cudaStream_t helper_stream(cudaStream_t main_st, int which) {
         g_fork_events_ready = true;
     }
     for (int i = 0; i < g_n_helpers; ++i) if (g_helpers[i].main == main_st) return g_helpers[i].helper[which];
-    if (g_n_helpers >= 8) return nullptr;
+    if (g_n_helpers >= 32) return nullptr;              // more caller streams than slots: that caller runs serially
     HelperStreams& h = g_helpers[g_n_helpers];
     h.main = main_st;
     for (int k = 0; k < 2; ++k)

@@ -20,6 +20,22 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_SHARED_STREAMS = {}
+
+
+def _shared_stream(device, role):
+    """Side streams are shared by all engines of a device: the library keeps a helper-stream pair per caller stream."""
+    key = (torch.device(device).index, role)
+    if key not in _SHARED_STREAMS:
+        _SHARED_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SHARED_STREAMS[key]
+
+
+def _warmup_stream(device):
+    """The side stream on which a step is run once eagerly before it is captured."""
+    return _shared_stream(device, "warmup")
+
+
 class _Flat:
     """Flatten the parameters of several modules into one buffer (module order, named_parameters order)."""
 
@@ -88,7 +104,7 @@ class SemiTrainEngine:
         # the two heads run on their own stream next to the decoder (independent consumers of the encoder outputs):
         # their range_code / env_code gradients land in separate buffers and are summed once both sides are done
         self.d_rc_heads, self.d_cat_heads = torch.zeros_like(self.rc), torch.zeros_like(self.cat)
-        self.head_stream = torch.cuda.Stream(device=self.device)
+        self.head_stream = _shared_stream(self.device, "heads")     # shared by all engines of the device (one host thread drives them)
         self.d_kl = torch.full((1,), LAMBDA_RANGE, dtype=torch.float32, device=dev)
         if shared_state is not None:
             self.lr, self.steps = shared_state.lr, shared_state.steps
@@ -283,7 +299,7 @@ class SemiTrainEngine:
             if g is None:
                 # warm up once eagerly on a side stream (also validates every call), then capture
                 state = (self.flat.flat.clone(), self.flat.exp_avg.clone(), self.flat.exp_avg_sq.clone(), self.steps.clone())
-                s = torch.cuda.Stream()
+                s = _warmup_stream(self.device)            # one per device: the library keeps helper streams per caller stream
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
                     self._step_body(*key)
@@ -414,7 +430,7 @@ class InferenceEngine:
             self.label.copy_(label.view(self.B, 1).float(), non_blocking=True)
         if self.use_graph:
             if self._graph is None:
-                s = torch.cuda.Stream()
+                s = _warmup_stream(self.device)
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
                     self._body(True)
