@@ -575,7 +575,7 @@ IINS_D float iins_row2_sample_sum(float v, int nw, int warp, int lane, float* xc
     return v;
 }
 
-template <int NACC, int AKIND, int EPI>      // EPI: 0 plain, 1 InstanceNorm / AdaIN, 2 LayerNorm
+template <int NACC, int AKIND, int EPI>      // EPI: 0 plain, 1 InstanceNorm / AdaIN, 2 LayerNorm, 3 data gradient + fused IN backward
 __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowParams rp) {
     iins_pdl_enter();
     constexpr int BM = 128;
@@ -742,6 +742,57 @@ __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowParams r
             acc[j] = j < p.N ? fmaf(xh[j], __ldg(ep.gamma + j), __ldg(ep.beta + j)) : 0.f;
         }
     }
+    if (EPI == 3) {
+        // acc = gradient w.r.t. the previous layer's output (this kernel is that layer's consumer's data gradient); the
+        // InstanceNorm backward of the previous layer follows in registers (same fusion as IINS_EPI_NBWD of the tensor-core
+        // kernel):  dz = rstd * (raw - mean_l(raw) - xhat * mean_l(raw * xhat)),  raw = relu'(xhat) * dy.  Needs N == NACC.
+        __shared__ float xchn[4][2 * NACC];
+        const float invL = 1.0f / (float)L;
+        const long oi = (long)grow * NACC;
+        float xv[NACC], s1[NACC], s2[NACC];
+#pragma unroll
+        for (int j = 0; j < NACC; j += 4) {
+            const float4 x4 = ok ? __ldg(reinterpret_cast<const float4*>(ep.nb_xhat + oi + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xv[j] = x4.x; xv[j + 1] = x4.y; xv[j + 2] = x4.z; xv[j + 3] = x4.w;
+        }
+        if (ep.y != nullptr && ok) {
+#pragma unroll
+            for (int j = 0; j < NACC; j += 4)
+                *reinterpret_cast<float4*>(ep.y + oi + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        }
+        const bool relu = ep.nb_act == IINS_ACT_RELU;
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+            if (relu && !(xv[j] > 0.f)) acc[j] = 0.f;                // raw
+            s1[j] = iins_warp_sum(acc[j]);
+            s2[j] = iins_warp_sum(acc[j] * xv[j]);
+        }
+        if (nw > 1) {                                                // CTA-uniform: the sample spans nw warps
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < NACC; ++j) { xchn[warp][j] = s1[j]; xchn[warp][NACC + j] = s2[j]; }
+            }
+            __syncthreads();
+            const int w0 = warp & ~(nw - 1);
+#pragma unroll
+            for (int j = 0; j < NACC; ++j) {
+                float a = 0.f, c2 = 0.f;
+                for (int i = 0; i < nw; ++i) { a += xchn[w0 + i][j]; c2 += xchn[w0 + i][NACC + j]; }
+                s1[j] = a; s2[j] = c2;
+            }
+        }
+        if (!ok) return;
+#pragma unroll
+        for (int j = 0; j < NACC; j += 4) {
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(ep.nb_rstd + (long)b * NACC + j));
+            const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = rv[i] * (acc[j + i] - s1[j + i] * invL - xv[j + i] * s2[j + i] * invL);
+            *reinterpret_cast<float4*>(ep.nb_dz + oi + j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        return;
+    }
     if (ep.act == IINS_ACT_RELU) {
 #pragma unroll
         for (int j = 0; j < NACC; ++j) acc[j] = fmaxf(acc[j], 0.f);
@@ -752,7 +803,7 @@ __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowParams r
     if (!ok) return;
     if (p.out_layout == IINS_NLC && (p.N % NACC) == 0) {
         const long oi = (long)grow * p.N + n0;
-        if (EPI != 0 && ep.xhat != nullptr) {
+        if ((EPI == 1 || EPI == 2) && ep.xhat != nullptr) {
 #pragma unroll
             for (int j = 0; j < NACC; j += 4)
                 *reinterpret_cast<float4*>(ep.xhat + oi + j) = make_float4(xh[j], xh[j + 1], xh[j + 2], xh[j + 3]);
@@ -772,7 +823,7 @@ __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowParams r
         for (int j = 0; j < NACC; ++j) {
             if (n0 + j >= p.N) continue;
             const long oi = p.out_layout == IINS_NCL ? (((long)b * p.N + n0 + j) << p.lshift) + l : (long)grow * p.N + n0 + j;
-            if (EPI != 0 && ep.xhat != nullptr) ep.xhat[oi] = xh[j];
+            if ((EPI == 1 || EPI == 2) && ep.xhat != nullptr) ep.xhat[oi] = xh[j];
             float o = acc[j];
             if (ep.add != nullptr) o += ep.add[oi];
             ep.y[oi] = o;

@@ -234,6 +234,19 @@ bool nbwd_fusable(const Ctx& c, const IinsNTParams& p, int L, int C, const float
 #endif
 }
 
+// Same question for a data gradient that runs on the one-thread-per-row kernel (small-channel layers): plain InstanceNorm
+// (no AdaIN) over L in {32, 64, 128} rows, all N == NACC channels in one thread, NLC, 16-byte aligned, no residual operand.
+bool row2_nbwd_fusable(const IinsNTParams& p, int L, int C, int norm, const float* dy, const float* xhat, const float* rstd, const float* dz) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("IINS_FUSE_NBWD"); on = e ? atoi(e) : 1; }
+    const char* r2 = getenv("IINS_ROW2");
+    if (!on || (r2 && atoi(r2) == 0) || norm != IINS_NORM_IN || p.a_kind != 1 || p.ep.y != dy || p.N != C || p.Lrow != L) return false;
+    if (!(C == 4 || C == 8 || C == 16) || !(L == 32 || L == 64 || L == 128)) return false;
+    if (p.K * C > IINS_ROW2_WMAX || p.K > 128 || p.ep.add != nullptr || p.out_layout != IINS_NLC) return false;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    return al16(p.ep.y) && al16(xhat) && al16(rstd) && al16(dz);
+}
+
 void launch_nt(Ctx& c, IinsNTParams p) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) return;          // empty layer (e.g. n_residual = 0: no AdaIN parameters)
     p.lshift = ilog2_exact(p.Lrow);
@@ -256,14 +269,14 @@ void launch_nt(Ctx& c, IinsNTParams p) {
             if (c.phase == 1) return;
             IinsRowParams rp;
             rp.nt = p;
-            const int epi = p.ep.norm == IINS_NORM_NONE ? 0 : (p.ep.norm == IINS_NORM_LN ? 2 : 1);
+            const int epi = p.ep.nb_dz != nullptr ? 3 : (p.ep.norm == IINS_NORM_NONE ? 0 : (p.ep.norm == IINS_NORM_LN ? 2 : 1));
             const dim3 grid((p.M + 127) / 128, (p.N + nacc - 1) / nacc, 1);
             IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K); IINS_SET_SHAPE(p.M, p.N, p.K);
 #define IINS_R2(NA_, AK_, EP_) \
             if (nacc == NA_ && p.a_kind == AK_ && epi == EP_) { auto iins_row2_nt_kernel_ = iins_row2_nt_kernel<NA_, AK_, EP_>; IINS_LAUNCH(iins_row2_nt_kernel_, grid, 128, 0, c.st, rp); return; }
             IINS_R2(4, 0, 0) IINS_R2(8, 0, 0) IINS_R2(16, 0, 0) IINS_R2(4, 1, 0) IINS_R2(8, 1, 0) IINS_R2(16, 1, 0)
             IINS_R2(4, 0, 1) IINS_R2(8, 0, 1) IINS_R2(16, 0, 1) IINS_R2(4, 0, 2) IINS_R2(8, 0, 2) IINS_R2(16, 0, 2)
-            IINS_R2(64, 0, 0) IINS_R2(64, 1, 0)
+            IINS_R2(64, 0, 0) IINS_R2(64, 1, 0) IINS_R2(4, 1, 3) IINS_R2(8, 1, 3) IINS_R2(16, 1, 3)
 #undef IINS_R2
         }
     }
@@ -520,6 +533,13 @@ void norm_backward(Ctx& c, int B, int L, int C, int norm, int act, const float* 
         ep.nb_adain = norm == IINS_NORM_ADAIN ? adain : nullptr; ep.nb_dadain = norm == IINS_NORM_ADAIN ? dadain : nullptr;
         ep.nb_ld = ld; ep.nb_off_b = off_b; ep.nb_off_w = off_w;
         if (dy_dead) ep.y = nullptr;                   // the plain gradient is not read by anyone else
+        flush_pending(c);
+        return;
+    }
+    if (c.has_pending && (act == IINS_ACT_NONE || act == IINS_ACT_RELU) && row2_nbwd_fusable(c.pending, L, C, norm, dy, xhat, rstd, dz)) {
+        IinsEpilogue& ep = c.pending.ep;
+        ep.nb_dz = dz; ep.nb_xhat = xhat; ep.nb_rstd = rstd; ep.nb_act = act; ep.nb_adain = nullptr; ep.nb_dadain = nullptr;
+        if (dy_dead) ep.y = nullptr;
         flush_pending(c);
         return;
     }
