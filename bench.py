@@ -272,6 +272,27 @@ def workload_config(batch, gpus):
 
 
 # ----------------------------------------------------------------------------------------------------
+_STDOUT_FD = None
+
+
+def _capture_stdout():
+    """stdout carries exactly ONE line (the JSON): native libraries (NCCL prints its version banner there) and anything
+    else that writes to fd 1 during the run go to stderr; the original stdout is restored by _emit() only."""
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+    if _STDOUT_FD is not None:
+        os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -281,18 +302,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    # stdout carries exactly ONE line (the JSON): native libraries (NCCL prints its version banner there) and anything
-    # else that writes to fd 1 during the run go to stderr; the original stdout is restored for emit() only
-    sys.stdout.flush()
-    _stdout_fd = os.dup(1)
-    os.dup2(2, 1)
-
-    def emit(line):
-        sys.stdout.flush()
-        os.dup2(_stdout_fd, 1)
-        print(json.dumps(line), flush=True)
-        os.dup2(2, 1)
-    globals()["_emit"] = emit
+    _capture_stdout()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args)
