@@ -193,7 +193,7 @@ def hbm_kernel_rooflines(lib, peaks):
     lg = torch.randn(Bb, NC, device="cuda", generator=g); lab = torch.randint(0, NC, (Bb, 1), device="cuda", generator=g).float()
     o = torch.zeros(8, device="cuda"); dx = torch.empty_like(x); de = torch.empty_like(ee); dl = torch.empty_like(lg)
     pred = torch.zeros(Bb, dtype=torch.int32, device="cuda")
-    ms = timed(lambda: lib.check(lib.iins_loss_forward_backward(Bb, L, NC, ptr(x), ptr(xr), ptr(err), ptr(ee), ptr(lg), ptr(lab), None,
+    ms = timed(lambda: lib.check(lib.iins_loss_forward_backward(Bb, L, NC, ptr(x), ptr(xr), ptr(err), ptr(ee), ptr(lg), ptr(lab), None, 0,
                                                                 1.0, 10.0, 1.0, ptr(o), ptr(dx), ptr(de), ptr(dl), ptr(pred), st), "loss"))
     nbytes = Bb * (3 * L * 4 + 2 * 4 + 4 + 4 + NC * 4 + 4 + 4 + NC * 4 + 4)
     out.append({"kernel": "iins_loss_kernel", "workload": f"{Bb} windows (fused L1 recon + L1 err + CE + seed gradients + metrics)",
@@ -206,7 +206,7 @@ def hbm_kernel_rooflines(lib, peaks):
     steps = torch.zeros(8, dtype=torch.int32, device="cuda"); lr = torch.full((1,), 1e-4, device="cuda")
     gb, ge, ga = (C.c_int64 * 1)(0), (C.c_int64 * 1)(P), (C.c_int32 * 1)(1)
     ms = timed(lambda: lib.check(lib.iins_adam_step(ptr(w), ptr(gr), ptr(m), ptr(v), gb, ge, ga, 1, ptr(steps), ptr(lr), 0.5, 0.999,
-                                                    1e-8, st), "adam"))
+                                                    1e-8, 1.0, 1, st), "adam"))
     nbytes = 28 * P
     out.append({"kernel": "iins_adam_kernel", "workload": f"{P} parameters (read p,g,m,v; write p,m,v)", "bytes": nbytes, "ms": ms,
                 "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / peak})
@@ -214,11 +214,29 @@ def hbm_kernel_rooflines(lib, peaks):
 
 
 def cpu_reference_run(batch, steps, warmup, threads):
-    """The reference algorithm (oracle port: torch CPU ops + autograd + torch.optim.Adam semantics restated in
-    oracle/iins_oracle.py) on the host cores; returns samples/s.  The ONLY code in this file that touches oracle/."""
+    """The reference's own implementation of the step on the host cores; returns (samples/s, ms/step, kind, note).
+    kind "reference": the UNMODIFIED reference modules (baseline/_ref/models.py, installed by baseline/install_ref.py) driven
+    through the restated train_semi.py:183-228 loop body with torch.optim.Adam (baseline/ref_step.py) -- none of this
+    repository's code on the path.  kind "port": only if that install is absent -- the oracle port (oracle/iins_oracle.py);
+    this function and the smoke test are the only non-test code that may touch oracle/."""
+    torch.set_num_threads(threads)
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_step
+    if ref_step.available():
+        tr = ref_step.ReferenceTrainer("cpu")
+        batches = ref_step.synthetic_batches(2, batch)
+        masks = ref_step.mask_stream()
+        t0 = None
+        for step in range(warmup + steps):
+            if step == warmup:
+                t0 = time.perf_counter()
+            loss = tr.step(*batches[step % 2], next(masks))
+            float(loss)                                   # the reference reads the loss every step (train_semi.py:240-268)
+        dt = time.perf_counter() - t0
+        sha = ref_step.manifest().get("sha256", "?")[:16]
+        return batch * steps / dt, dt / steps * 1e3, "reference", f"unmodified reference models.py (sha256 {sha}) + train_semi.py:183-228 loop body, torch CPU"
     from oracle import iins_oracle as orc
     cfg = orc.PathConfig()
-    torch.set_num_threads(threads)
     pe, pd, pr, pc = orc.init_all(cfg, 1234)
     flat = {f"{g}.{k}": v for g, d in zip(("enc", "dec", "res", "cls"), (pe, pd, pr, pc)) for k, v in d.items()
             if not orc.is_buffer(k)}
@@ -239,24 +257,59 @@ def cpu_reference_run(batch, steps, warmup, threads):
                                             cfg, bool(mask))
         flat = adam.step(flat, grads)
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps * 1e3
+    return batch * steps / dt, dt / steps * 1e3, "port", "oracle port of models.py + train_semi.py:183-228, torch CPU"
+
+
+def gpu_eager_reference(batch, steps=10, warmup=3):
+    """SURVEY.md 2.2 / BASELINE.md section 4: "the kernel to beat on the same box" = the UNMODIFIED reference modules in eager
+    PyTorch-CUDA (cuDNN / cuBLAS / ATen) on this B200, same step, same batch.  Timed with CUDA events outside the headline
+    timed region.  `value`: inputs resident in HBM, no host read-back; `e2e`: the reference's own loop shape -- pageable
+    host batch -> .cuda() per tensor and loss.item() every step (train_semi.py:174-180, :240-268)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_step
+    if not ref_step.available():
+        return {"unavailable": "baseline/_ref/models.py not installed (run baseline/install_ref.py where /root/reference exists)"}
+    tr = ref_step.ReferenceTrainer("cuda")
+    host = ref_step.synthetic_batches(4, batch)
+    dev = [tuple(t.cuda() for t in b) for b in host]
+    masks = ref_step.mask_stream()
+    for i in range(warmup):
+        tr.step(*dev[i % 4], next(masks))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        tr.step(*dev[i % 4], next(masks))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        float(tr.step(*host[i % 4], next(masks)))
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / steps
+    return {"value": batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "e2e_value": batch / (ms_e2e * 1e-3),
+            "e2e_ms_per_step": ms_e2e, "batch": batch, "steps": steps, "dtype": "fp32 (torch default: TF32 off)",
+            "what": "unmodified reference models.py (baseline/_ref) + train_semi.py:183-228 loop body + torch.optim.Adam, eager "
+                    "PyTorch-CUDA on the same GPU, CUDA-event timing"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = PathShape()
     threads = os.cpu_count() or 1
-    val, ms = cpu_reference_run(args.batch, args.steps, args.warmup, threads)
+    val, ms, kind, note = cpu_reference_run(args.batch, args.steps, args.warmup, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic",
         "config": workload_config(args.batch, args.gpus),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": f"{args.steps} timed steps of batch {args.batch} after {args.warmup} warm-up "
-                                   f"(oracle port of models.py + train_semi.py:183-228, torch CPU, {threads} threads)"},
+                                   f"({note}, {threads} threads)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     _emit(line)
@@ -264,7 +317,7 @@ def run_reference(args):
 
 def workload_config(batch, gpus):
     return {"workload": "IIns-VAE semi-supervised train step (Enc+Dec+Res+Cls, recon+KL+L1+CE, Adam), "
-                        "BASELINE configs[1]: batch 4096 per GPU, fp32",
+                        f"BASELINE configs[1]: batch {batch} per GPU, fp32",
             "batch_per_gpu": batch, "global_batch": batch * gpus, "cir_len": 157, "dim": 4, "env_dim": 16,
             "range_dim": 2, "num_classes": 5, "supervision_rate": 0.1, "parallelism": f"dp{gpus}",
             "l2_policy": f"{N_BATCHES} distinct input batches cycled; per-step working set (saved activations "
@@ -301,6 +354,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the eager PyTorch-CUDA reference leg")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling (BASELINE configs[3]): fixed GLOBAL batch, per-GPU batch = global / world")
+    ap.add_argument("--compute-mode", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-overlap", action="store_true", help="one all-reduce after the backward instead of overlapped buckets")
     args = ap.parse_args()
     _capture_stdout()
     args.warmup = max(args.warmup, 3)
@@ -326,7 +384,14 @@ def main():
         pg = dist.group.WORLD
     lib = get_lib()
     cfg = PathShape()
+    scaling = "weak"
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must divide by the number of ranks")
+        args.batch, scaling = args.global_batch // world, "strong"
     B, K, W = args.batch, args.steps, args.warmup
+    import iins_vae_b200
+    iins_vae_b200.set_compute_mode(args.compute_mode)
 
     torch.manual_seed(1234)                                     # random-init weights of the named architecture, same on every rank
     Enc = M.Encoder(1, cfg.dim, cfg.n_residual, cfg.n_downsample, cfg.env_dim, cfg.range_dim)
@@ -337,7 +402,7 @@ def main():
         m.apply(M.weights_init_normal)                          # train_semi.py:104-107
         m.cuda()
     eng = SemiTrainEngine(Enc, Dec, Res, Cls, batch_size=B, cir_len=cfg.cir_len, lr=1e-4, betas=(0.5, 0.999),
-                          use_graph=True, process_group=pg)
+                          use_graph=True, process_group=pg, overlap_allreduce=not args.no_overlap)
 
     data = SyntheticCIR(N_BATCHES * B, B, cfg.cir_len, cfg.num_classes, seed=1234 + 100 * rank, pin=True)
     host = [(b["CIR"], b["Err"], b["Label"]) for b in data]     # pinned host batches of the loader's shape (dataset.py:118-133)
@@ -481,9 +546,16 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        val, _ = cpu_reference_run(B, 8, 2, threads)
-        cpu_baseline = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"8 timed steps of batch {B} after 2 warm-up (oracle port, torch CPU, {threads} threads)"}
+        val, _, kind, note = cpu_reference_run(B, 8, 2, threads)
+        cpu_baseline = {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
+                        "sample": f"8 timed steps of batch {B} after 2 warm-up ({note}, {threads} threads)"}
+
+    gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        try:
+            gpu_ref = gpu_eager_reference(B)
+        except Exception as e:
+            gpu_ref = {"error": repr(e)}
 
     if rank == 0:
         value = world * B * K / (ms * 1e-3)
@@ -491,24 +563,20 @@ def main():
         h2d = sum(t.numel() * t.element_size() for t in host[0])
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "fp32" if args.compute_mode == "fp32" else "bf16",
             "data": "synthetic", "config": workload_config(B, world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                     "ms_per_step": ms_e2e / K,
                     "pipeline": "H2D of batch i+1 on a copy stream during step i; loss of step i read back after step i+1 is queued"},
             "gpu_launches": int(n_launch), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernels": kernel_table, "roofline_hbm": hbm_rooflines,
+            "kernels": kernel_table, "roofline_hbm": hbm_rooflines, "gpu_eager_reference": gpu_ref,
             "final_loss_terms": {k: float(v) for k, v in zip(("l1_recon", "l1_err", "ce", "weighted_sum"), out_host[:4].tolist())},
         }
         _emit(line)
     if world > 1:
-        # CUDA graphs that captured NCCL kernels keep the communicator busy at teardown (destroy_process_group
-        # was observed to hang): synchronise, rendezvous once more, flush and leave without the teardown.
-        torch.cuda.synchronize()
-        dist.barrier()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        from iins_vae_b200.parallel import shutdown_distributed
+        shutdown_distributed([eng])
 
 
 if __name__ == "__main__":

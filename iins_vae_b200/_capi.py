@@ -7,6 +7,7 @@ or PyTorch fallback anywhere in this package.
 import ctypes as C
 import os
 
+ABI_VERSION = 2
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libiins_b200.so")
 
@@ -65,10 +66,10 @@ class IinsLib:
         d.iins_restorer_backward.argtypes = [_CFG, _PP, _P, _P, _P, _PP, _P, C.c_int, _P, _P]
         d.iins_classifier_forward.argtypes = [_CFG, _PP, _P, _P, _P, _P]
         d.iins_classifier_backward.argtypes = [_CFG, _PP, _P, _P, _P, _PP, _P, C.c_int, _P, _P]
-        d.iins_loss_forward_backward.argtypes = [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P,
+        d.iins_loss_forward_backward.argtypes = [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int,
                                                  C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P]
         d.iins_adam_step.argtypes = [_P, _P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
-                                     C.c_int, _P, _P, C.c_double, C.c_double, C.c_float, _P]
+                                     C.c_int, _P, _P, C.c_double, C.c_double, C.c_float, C.c_float, C.c_int, _P]
         d.iins_adaptive_pool_forward.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P]
         d.iins_adaptive_pool_backward.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P]
         d.iins_accumulate2.argtypes = [_P, _P, C.c_size_t, _P, _P, C.c_size_t, _P]
@@ -119,6 +120,6 @@ def get_lib() -> IinsLib:
         if _build.needs_build():
             _build.build()
         _lib = IinsLib(LIB_PATH)
-        if _lib.iins_abi_version() != 1:
+        if _lib.iins_abi_version() != ABI_VERSION:
             raise IinsError("libiins_b200.so ABI version mismatch")
     return _lib

@@ -308,7 +308,8 @@ __global__ void __launch_bounds__(256) iins_reparam_kl_bwd_kernel(const float* _
 // seed gradients of every head output and the metrics of train.py:104-115.
 //   out[0] = mean|x - xrec|      (L1Loss over B*L)          out[4] = sum (err_est-err)^2 / B  (MSE; rmse = sqrt)
 //   out[1] = mean|err - err_est|                            out[5] = number of correct argmax predictions
-//   out[2] = mean CE(logits, label)                         out[6], out[7] reserved
+//   out[2] = mean CE(logits, label)                         out[6] = number of labels outside [0, NC) after the offset
+//                                                           (torch's CrossEntropyLoss device-asserts on those); out[7] reserved
 //   out[3] = lam_ae*out[0] + lam_res*out[1] + lam_env*out[2]   (KL is added by the caller: it lives in the encoder)
 struct IinsLossParams {
     int B, L, NC;
@@ -319,6 +320,7 @@ struct IinsLossParams {
     const float* logits;       // (B,NC)
     const float* label;        // (B,) float32 holding integers (dataset.py:122) ...
     const long long* label_i64;   // ... or int64 (train.py:72); exactly one of the two
+    int label_offset;          // class index = label - label_offset (train_semi.py:217-222: 1 for every dataset_env but room_full)
     float lam_ae, lam_res, lam_env;
     float* out;                // 8 floats, zeroed by the caller
     float* d_xrec;             // (B,L)
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(256) iins_loss_kernel(const IinsLossParams p) 
     iins_pdl_enter();
     __shared__ float s_part[8][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float acc_ae = 0.f, acc_res = 0.f, acc_ce = 0.f, acc_sq = 0.f, acc_ok = 0.f;
+    float acc_ae = 0.f, acc_res = 0.f, acc_ce = 0.f, acc_sq = 0.f, acc_ok = 0.f, acc_bad = 0.f;
     const long stride = (long)gridDim.x * blockDim.x;
     const long gtid = (long)blockIdx.x * blockDim.x + tid;
     if (p.x != nullptr) {
@@ -364,7 +366,8 @@ __global__ void __launch_bounds__(256) iins_loss_kernel(const IinsLossParams p) 
                 float gi = p.lam_res / (float)p.B;
                 p.d_err_est[b] = d > 0.f ? gi : (d < 0.f ? -gi : 0.f);
             }
-            int tgt = p.label_i64 != nullptr ? (int)p.label_i64[b] : (int)__ldg(p.label + b);
+            int tgt = (p.label_i64 != nullptr ? (int)p.label_i64[b] : (int)__ldg(p.label + b)) - p.label_offset;
+            if (tgt < 0 || tgt >= p.NC) { acc_bad += 1.f; tgt = tgt < 0 ? 0 : p.NC - 1; }      // reported in out[6]; never read outside the row
             const float* z = p.logits + b * p.NC;
             float mx = __ldg(z);
             int am = 0;
@@ -384,14 +387,14 @@ __global__ void __launch_bounds__(256) iins_loss_kernel(const IinsLossParams p) 
             }
         }
     }
-    float vals[5] = {acc_ae, acc_res, acc_ce, acc_sq, acc_ok};
+    float vals[6] = {acc_ae, acc_res, acc_ce, acc_sq, acc_ok, acc_bad};
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
+    for (int k = 0; k < 6; ++k) {
         float v = iins_warp_sum(vals[k]);
         if (lane == 0) s_part[k][warp] = v;
     }
     __syncthreads();
-    if (tid < 5) {
+    if (tid < 6) {
         float v = 0.f;
         for (int w = 0; w < 8; ++w) v += s_part[tid][w];
         float nae = p.x != nullptr ? (float)((long)p.B * p.L) : 1.f;
@@ -400,6 +403,7 @@ __global__ void __launch_bounds__(256) iins_loss_kernel(const IinsLossParams p) 
         if (tid == 2) { v /= (float)p.B; atomicAdd(p.out + 2, v); atomicAdd(p.out + 3, p.lam_env * v); }
         if (tid == 3) { v /= (float)p.B; atomicAdd(p.out + 4, v); }
         if (tid == 4) { atomicAdd(p.out + 5, v); }
+        if (tid == 5 && v != 0.f) { atomicAdd(p.out + 6, v); }
     }
 }
 
@@ -420,20 +424,17 @@ __global__ void __launch_bounds__(256) iins_accumulate2_kernel(float* __restrict
 // an unsupervised batch, restorer.linear_layer2 always) is skipped entirely: no moment decay, no step++.
 struct IinsAdamGroup { long begin, end; int active; };
 struct IinsAdamParams {
-    float* p; const float* g; float* m; float* v;
-    int* steps;                // [n_groups] device counters (already incremented for this step)
+    float* p; float* g; float* m; float* v;
+    float grad_scale;          // g is multiplied by this first (1/world after a SUM all-reduce: the mean of the per-rank gradients)
+    int zero_grads;            // write 0 to every gradient element that was consumed (the next step accumulates into it)
+    int* steps;                // [n_groups + 1] device counters of COMPLETED updates (+ a ticket word, zero between launches): this
+                               // launch uses steps[g] + 1 and its last CTA to finish advances the active groups
     const float* lr;           // device scalar (LambdaLR changes it per epoch)
     double beta1, beta2;       // bias corrections are formed in double like torch's Python scalars
     float eps;
     int n_groups;
     IinsAdamGroup groups[8];
 };
-
-__global__ void iins_adam_tick_kernel(int* steps, int n_groups, unsigned active_mask) {
-    iins_pdl_enter();
-    int i = threadIdx.x;
-    if (i < n_groups && ((active_mask >> i) & 1u)) steps[i] += 1;
-}
 
 __global__ void __launch_bounds__(256) iins_adam_kernel(const IinsAdamParams a) {
     iins_pdl_enter();
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(256) iins_adam_kernel(const IinsAdamParams a) 
     __shared__ float s_step[8], s_isb2[8];
     const float lr = __ldg(a.lr);
     if (threadIdx.x < a.n_groups && a.groups[threadIdx.x].active) {
-        const int t = a.steps[threadIdx.x];
+        const int t = a.steps[threadIdx.x] + 1;
         const double bc1 = 1.0 - pow(a.beta1, (double)t);
         const double bc2 = 1.0 - pow(a.beta2, (double)t);
         s_step[threadIdx.x] = (float)((double)lr / bc1);
@@ -456,7 +457,9 @@ __global__ void __launch_bounds__(256) iins_adam_kernel(const IinsAdamParams a) 
         if (!a.groups[gi].active) continue;
         const float step_size = s_step[gi], inv_sqrt_bc2 = s_isb2[gi];
         const long begin = a.groups[gi].begin, end = a.groups[gi].end;
+        const float gs = a.grad_scale;
         auto upd = [&](float g, float& m, float& v, float& w) {
+            g *= gs;
             m = b1 * m + (1.f - b1) * g;
             v = b2 * v + (1.f - b2) * g * g;
             const float denom = sqrtf(v) * inv_sqrt_bc2 + a.eps;
@@ -468,13 +471,25 @@ __global__ void __launch_bounds__(256) iins_adam_kernel(const IinsAdamParams a) 
                            reinterpret_cast<uintptr_t>(a.v)) & 15) == 0;
         long vb = vec ? (begin + 3) & ~3L : end, ve = vec ? end & ~3L : end;
         if (vb > ve) { vb = end; ve = end; }
-        for (long i = begin + gtid; i < vb; i += stride) { float m = a.m[i], v = a.v[i], w = a.p[i]; upd(__ldg(a.g + i), m, v, w); a.m[i] = m; a.v[i] = v; a.p[i] = w; }
+        const bool zg = a.zero_grads != 0;
+        for (long i = begin + gtid; i < vb; i += stride) { float m = a.m[i], v = a.v[i], w = a.p[i]; upd(a.g[i], m, v, w); a.m[i] = m; a.v[i] = v; a.p[i] = w; if (zg) a.g[i] = 0.f; }
         for (long i = (vb >> 2) + gtid; i < (ve >> 2); i += stride) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.g) + i);
+            const float4 g4 = reinterpret_cast<const float4*>(a.g)[i];
             float4 m4 = reinterpret_cast<float4*>(a.m)[i], v4 = reinterpret_cast<float4*>(a.v)[i], w4 = reinterpret_cast<float4*>(a.p)[i];
             upd(g4.x, m4.x, v4.x, w4.x); upd(g4.y, m4.y, v4.y, w4.y); upd(g4.z, m4.z, v4.z, w4.z); upd(g4.w, m4.w, v4.w, w4.w);
             reinterpret_cast<float4*>(a.m)[i] = m4; reinterpret_cast<float4*>(a.v)[i] = v4; reinterpret_cast<float4*>(a.p)[i] = w4;
+            if (zg) reinterpret_cast<float4*>(a.g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        for (long i = ve + gtid; i < end; i += stride) { float m = a.m[i], v = a.v[i], w = a.p[i]; upd(__ldg(a.g + i), m, v, w); a.m[i] = m; a.v[i] = v; a.p[i] = w; }
+        for (long i = ve + gtid; i < end; i += stride) { float m = a.m[i], v = a.v[i], w = a.p[i]; upd(a.g[i], m, v, w); a.m[i] = m; a.v[i] = v; a.p[i] = w; if (zg) a.g[i] = 0.f; }
+    }
+    // every CTA has read the step counters above; the last one to get here advances them (one launch instead of two)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int ticket = atomicAdd(a.steps + a.n_groups, 1);
+        if (ticket == (int)gridDim.x - 1) {
+            for (int gi = 0; gi < a.n_groups; ++gi) if (a.groups[gi].active) a.steps[gi] += 1;
+            a.steps[a.n_groups] = 0;
+        }
     }
 }

@@ -1121,7 +1121,7 @@ int mlp_backward(const Shapes& s, const MlpSpec& m, const float* const* P, const
 // ============================================================================================ C ABI
 extern "C" {
 
-int iins_abi_version(void) { return 1; }
+int iins_abi_version(void) { return 2; }
 int iins_set_compute_mode(int mode) {
     if (mode < 0 || mode > 2) return fail(IINS_ERR_BAD_CONFIG, "compute mode must be 0 (bf16x3 tensor core), 1 (bf16 tensor core) or 2 (fp32 SIMT)");
     g_mode = mode;
@@ -1241,7 +1241,7 @@ int iins_classifier_backward(const iins_config* cfg, const float* const* params,
 
 int iins_loss_forward_backward(int batch, int cir_len, int num_classes, const float* x, const float* x_recon,
                                const float* err, const float* err_est, const float* logits, const float* label,
-                               const int64_t* label_i64, float lam_ae, float lam_res, float lam_env, float* out,
+                               const int64_t* label_i64, int label_offset, float lam_ae, float lam_res, float lam_env, float* out,
                                float* d_x_recon, float* d_err_est, float* d_logits, int32_t* pred, iins_stream_t stream) {
     if (!out) return fail(IINS_ERR_NULL, "loss: out is NULL");
     if (batch < 1 || num_classes > 64) return fail(IINS_ERR_BAD_CONFIG, "loss: bad sizes");
@@ -1253,6 +1253,7 @@ int iins_loss_forward_backward(int batch, int cir_len, int num_classes, const fl
     p.B = batch; p.L = cir_len; p.NC = num_classes;
     p.x = x; p.xrec = x_recon; p.err = err; p.err_est = err_est; p.logits = logits; p.label = label;
     p.label_i64 = (const long long*)label_i64;
+    p.label_offset = label_offset;
     p.lam_ae = lam_ae; p.lam_res = lam_res; p.lam_env = lam_env; p.out = out;
     p.d_xrec = d_x_recon; p.d_err_est = d_err_est; p.d_logits = d_logits; p.pred = (int*)pred;
     cudaMemsetAsync(out, 0, 8 * sizeof(float), st);
@@ -1262,17 +1263,18 @@ int iins_loss_forward_backward(int batch, int cir_len, int num_classes, const fl
     return check_cuda("loss");
 }
 
-int iins_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const int64_t* group_begin,
+int iins_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, const int64_t* group_begin,
                    const int64_t* group_end, const int32_t* group_active, int n_groups, int32_t* steps, const float* lr,
-                   double beta1, double beta2, float eps, iins_stream_t stream) {
+                   double beta1, double beta2, float eps, float grad_scale, int zero_grads, iins_stream_t stream) {
     if (!params || !grads || !exp_avg || !exp_avg_sq || !group_begin || !group_end || !group_active || !steps || !lr)
         return fail(IINS_ERR_NULL, "adam: NULL argument");
-    if (n_groups < 1 || n_groups > 8) return fail(IINS_ERR_BAD_CONFIG, "adam: 1..8 groups");
+    if (n_groups < 1 || n_groups > 7) return fail(IINS_ERR_BAD_CONFIG, "adam: 1..7 groups");
     cudaStream_t st = (cudaStream_t)stream;
     IinsAdamParams a;
     memset(&a, 0, sizeof(a));
     a.p = params; a.g = grads; a.m = exp_avg; a.v = exp_avg_sq; a.steps = (int*)steps; a.lr = lr;
     a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.n_groups = n_groups;
+    a.grad_scale = grad_scale; a.zero_grads = zero_grads;
     unsigned mask = 0;
     long total = 0;
     for (int i = 0; i < n_groups; ++i) {
@@ -1280,7 +1282,6 @@ int iins_adam_step(float* params, const float* grads, float* exp_avg, float* exp
         if (group_active[i]) { mask |= 1u << i; total += (long)(group_end[i] - group_begin[i]); }
     }
     if (mask == 0) return IINS_OK;
-    IINS_LAUNCH(iins_adam_tick_kernel, 1, 32, 0, st, (int*)steps, n_groups, mask);
     IINS_LAUNCH(iins_adam_kernel, grid_for(total / 4), 256, 0, st, a);
     return check_cuda("adam");
 }

@@ -71,9 +71,13 @@ class SemiTrainEngine:
     """
 
     def __init__(self, Enc, Dec, Res, Cls, batch_size, cir_len=157, lr=1e-4, betas=(0.5, 0.999), eps=1e-8,
-                 mode="semi", use_graph=True, process_group=None, device=None, shared_state=None):
+                 mode="semi", use_graph=True, process_group=None, device=None, shared_state=None, label_offset=0,
+                 overlap_allreduce=True):
         """``shared_state``: another engine over the SAME modules (e.g. for a different batch size, the last
-        ragged batch of an epoch): the flat parameter / gradient / Adam buffers and step counters are shared."""
+        ragged batch of an epoch): the flat parameter / gradient / Adam buffers and step counters are shared.
+        ``label_offset``: class index = label - label_offset (train_semi.py:217-222: 1 for every dataset_env except
+        'room_full', whose labels are already 0-based).  ``overlap_allreduce``: reduce the Dec/Res/Cls gradient bucket on a
+        communication stream while the encoder backward runs; False = one all-reduce after the backward."""
         self.lib = get_lib()
         self.mode = mode
         self.device = torch.device(device if device is not None else torch.cuda.current_device())
@@ -89,6 +93,8 @@ class SemiTrainEngine:
                               Cls.filters)
         self.lib.check(self.lib.iins_validate_config(self.cfg), "engine config")
         self.betas, self.eps = betas, eps
+        self.label_offset = int(label_offset)
+        self.overlap_allreduce = bool(overlap_allreduce)
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         dev, B = self.device, self.B
@@ -105,6 +111,7 @@ class SemiTrainEngine:
         # their range_code / env_code gradients land in separate buffers and are summed once both sides are done
         self.d_rc_heads, self.d_cat_heads = torch.zeros_like(self.rc), torch.zeros_like(self.cat)
         self.head_stream = _shared_stream(self.device, "heads")     # shared by all engines of the device (one host thread drives them)
+        self.comm_stream = _shared_stream(self.device, "comm")      # gradient all-reduce next to the encoder backward
         self.d_kl = torch.full((1,), LAMBDA_RANGE, dtype=torch.float32, device=dev)
         if shared_state is not None:
             self.lr, self.steps = shared_state.lr, shared_state.steps
@@ -187,14 +194,15 @@ class SemiTrainEngine:
         lib.check(lib.iins_loss_forward_backward(
             self.B, self.L, self.NC, ptr(self.cir) if semi else None, ptr(self.xrec) if semi else None,
             ptr(self.err) if supervised else None, ptr(self.err_est) if supervised else None,
-            ptr(self.logits) if supervised else None, ptr(self.label) if supervised else None, None,
+            ptr(self.logits) if supervised else None, ptr(self.label) if supervised else None, None, self.label_offset,
             LAMBDA_AE, lam_res, LAMBDA_ENV, ptr(self.out), ptr(self.d_xrec) if semi else None,
             ptr(self.d_err) if supervised else None, ptr(self.d_logits) if supervised else None, ptr(self.pred),
             _stream()), "loss")
 
     def _backward(self, supervised: bool):
         lib, cfg, st, semi = self.lib, self.cfg, _stream(), self.mode == "semi"
-        self.flat.grad.zero_()
+        # the gradient buffer is zero here: the fused Adam zeroes what it consumes (iins_adam_step zero_grads), and a
+        # gradients-only step (update=False) is followed by an explicit clear in step()
         conc = self._heads_concurrent(supervised)
         main = torch.cuda.current_stream()
 
@@ -222,24 +230,55 @@ class SemiTrainEngine:
                                            ptr(self.d_cat_heads), self.d_cat.numel(), st), "accumulate head gradients")
         elif supervised:
             heads(st, self.d_rc, self.d_cat, acc)
+        self._allreduce_late_buckets(supervised)
         lib.check(lib.iins_encoder_backward(cfg, self.ptab["enc"], None, 0, 0, ptr(self.rc), ptr(self.cat),
                                             ptr(self.ws["encoder"]), ptr(self.d_rc), ptr(self.d_cat), None,
                                             ptr(self.d_kl) if semi else None, self.gtab["enc"],
                                             ptr(self.scratch["encoder"]), st), "encoder backward")
 
+    # ---- data-parallel gradient exchange ---------------------------------------------------------------
+    # The flat gradient buffer is laid out [Enc | Dec | Res | Cls] (module order); the backward produces it back to front:
+    # Dec, Res and Cls gradients are complete before the encoder backward starts.  Bucket 1 = everything behind the encoder
+    # (only the part that has gradients this step) is summed over the ranks on a communication stream WHILE the encoder
+    # backward runs; bucket 0 = the encoder follows on the same stream; the main stream joins before Adam, which applies
+    # the 1/world factor (SUM all-reduce + grad_scale = the mean of the per-rank gradients).
+    def _bucket_bounds(self, supervised: bool):
+        enc_end = self.spans["enc"][1]
+        end = self.flat.total if supervised else self.groups[0][1]
+        return enc_end, end
+
+    def _allreduce_late_buckets(self, supervised: bool):
+        if self.world == 1 or not self.overlap_allreduce:
+            return
+        import torch.distributed as dist
+        enc_end, end = self._bucket_bounds(supervised)
+        if end <= enc_end:
+            return
+        main = torch.cuda.current_stream()
+        self.comm_stream.wait_stream(main)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(self.flat.grad[enc_end:end], op=dist.ReduceOp.SUM, group=self.pg)
+
     def _allreduce(self, supervised: bool):
         if self.world == 1:
             return
-        from .parallel import allreduce_mean_
-        # unsupervised batches: only the always-on bucket [Enc (+Dec)] has gradients (train_semi.py:204-214)
-        allreduce_mean_(self.flat.grad, self.flat.total if supervised else self.groups[0][1], self.pg)
+        import torch.distributed as dist
+        enc_end, end = self._bucket_bounds(supervised)
+        if not self.overlap_allreduce:
+            dist.all_reduce(self.flat.grad[:end], op=dist.ReduceOp.SUM, group=self.pg)
+            return
+        main = torch.cuda.current_stream()
+        self.comm_stream.wait_stream(main)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(self.flat.grad[:enc_end], op=dist.ReduceOp.SUM, group=self.pg)
+        main.wait_stream(self.comm_stream)
 
     def _adam(self, supervised: bool):
         act = (C.c_int32 * 3)(1, int(supervised), int(supervised))
         fl = self.flat
         self.lib.check(self.lib.iins_adam_step(ptr(fl.flat), ptr(fl.grad), ptr(fl.exp_avg), ptr(fl.exp_avg_sq), self._gb,
                                                self._ge, act, 3, ptr(self.steps), ptr(self.lr), self.betas[0], self.betas[1],
-                                               self.eps, _stream()), "adam")
+                                               self.eps, 1.0 / self.world, 1, _stream()), "adam")
 
     def _step_body(self, supervised: bool, update: bool = True):
         self._forward(supervised)
@@ -294,6 +333,9 @@ class SemiTrainEngine:
         elif cir is not None:
             self.load_batch(cir, err, label)
         key = (bool(supervised), bool(update))
+        if getattr(self.flat, "grads_dirty", False):              # the previous step kept its gradients (update=False)
+            self.flat.grad.zero_()
+            self.flat.grads_dirty = False
         if self.use_graph:
             g = self._graphs.get(key)
             if g is None:
@@ -310,16 +352,26 @@ class SemiTrainEngine:
                 # the warm-up and the capture pass must not count as optimisation steps
                 self.flat.flat.copy_(state[0]); self.flat.exp_avg.copy_(state[1]); self.flat.exp_avg_sq.copy_(state[2])
                 self.steps.copy_(state[3])
+                self.flat.grad.zero_()
                 self._graphs[key] = g
             g.replay()
         else:
             self._step_body(*key)
+        self.flat.grads_dirty = not update
         self.n_steps += 1
         return self.out
+
+    def close(self):
+        """Drop the captured graphs (they hold the NCCL communicator busy: call before destroy_process_group)."""
+        torch.cuda.synchronize(self.device)
+        self._graphs.clear()
 
     def loss_terms(self):
         """Host copy of the loss terms of the last step (this synchronises)."""
         o = self.out.tolist()
+        if o[6] != 0.0:
+            raise ValueError(f"{int(o[6])} labels outside [0, {self.NC}) after label_offset={self.label_offset} "
+                             "(train_semi.py:217-222: labels are 1-based for every dataset_env except 'room_full')")
         kl = float(self.kl) if self.mode == "semi" else 0.0
         lam_res = LAMBDA_RES if self.mode == "semi" else 1.0
         d = dict(loss_ae=LAMBDA_AE * o[0], loss_range=LAMBDA_RANGE * kl, loss_res=lam_res * o[1], loss_env=LAMBDA_ENV * o[2],
@@ -390,8 +442,9 @@ class SemiTrainEngine:
 class InferenceEngine:
     """test.py:66-85: Encoder -> (Classifier, Restorer), no grad, fused metrics.  Static buffers + CUDA graph."""
 
-    def __init__(self, Enc, Res, Cls, batch_size, cir_len=157, use_graph=True, device=None):
+    def __init__(self, Enc, Res, Cls, batch_size, cir_len=157, use_graph=True, device=None, label_offset=0):
         self.lib = get_lib()
+        self.label_offset = int(label_offset)
         self.device = torch.device(device if device is not None else torch.cuda.current_device())
         o = Enc.opts
         self.B, self.L, self.NC = int(batch_size), int(cir_len), Cls.num_classes
@@ -418,8 +471,8 @@ class InferenceEngine:
         lib.check(lib.iins_classifier_forward(cfg, self.ptab["cls"], ptr(self.cat), ptr(self.logits), ptr(self.ws["classifier"]),
                                               st), "classifier forward")
         lib.check(lib.iins_loss_forward_backward(self.B, self.L, self.NC, None, None, ptr(self.err), ptr(self.err_est),
-                                                 ptr(self.logits), ptr(self.label), None, 1.0, 1.0, 1.0, ptr(self.out), None, None,
-                                                 None, ptr(self.pred), st), "metrics")
+                                                 ptr(self.logits), ptr(self.label), None, self.label_offset, 1.0, 1.0, 1.0,
+                                                 ptr(self.out), None, None, None, ptr(self.pred), st), "metrics")
 
     def run(self, cir=None, err=None, label=None):
         """Returns (err_est (B,1), pred (B,) int32, out[8]) as device tensors (static buffers, overwritten next call)."""

@@ -7,6 +7,8 @@ per-batch supervision mask of train_semi.py:203 is a HOST random draw: every ran
 identically everywhere.
 """
 import os
+import sys
+import threading
 
 import numpy as np
 import torch
@@ -41,13 +43,41 @@ def shard_range(n_items: int, rank: int, world: int):
 
 
 def allreduce_mean_(flat: torch.Tensor, n_active: int, group=None):
-    """In-place mean all-reduce of flat[:n_active] (the buckets whose gradients exist this step)."""
+    """In-place mean all-reduce of flat[:n_active] (the buckets whose gradients exist this step).  Host-side helper for
+    callers that own their optimizer; the fused engine instead SUM-reduces its buckets on a communication stream next to
+    the encoder backward and lets iins_adam_step apply the 1/world factor (engine.SemiTrainEngine._allreduce)."""
     if group is None or dist.get_world_size(group) == 1:
         return flat
     g = flat[:n_active]
     dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
     g.mul_(1.0 / dist.get_world_size(group))
     return flat
+
+
+def shutdown_distributed(engines=(), timeout_s: float = 30.0):
+    """Orderly teardown of a data-parallel run.  CUDA graphs that captured NCCL kernels keep the communicator referenced:
+    the engines drop their graphs first, every rank synchronises and meets at a barrier, then the process group is
+    destroyed.  A watchdog ends the process if the destroy call does not return (observed in round 1 when the graphs
+    were still alive) so that a benchmark or training run can never hang at exit."""
+    if not dist.is_initialized():
+        return
+    for e in engines:
+        e.close()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    dist.barrier()
+    done = threading.Event()
+
+    def _watchdog():
+        if not done.wait(timeout_s):
+            sys.stdout.flush()
+            sys.stderr.flush()
+            sys.stderr.write("shutdown_distributed: destroy_process_group did not return, leaving\n")
+            os._exit(0)
+
+    threading.Thread(target=_watchdog, daemon=True).start()
+    dist.destroy_process_group()
+    done.set()
 
 
 class SupervisionMask:

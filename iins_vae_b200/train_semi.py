@@ -19,8 +19,14 @@ from . import set_compute_mode
 from .data import SyntheticCIR
 from .engine import SemiTrainEngine
 from .models import Classifier, Decoder, Encoder, LambdaLR, Restorer, weights_init_normal
-from .parallel import SupervisionMask, broadcast_parameters, init_distributed
+from .parallel import SupervisionMask, broadcast_parameters, init_distributed, shutdown_distributed
 from .utils import get_args, num_classes_for
+
+
+def label_offset_for(dataset_env: str) -> int:
+    """train_semi.py:217-222 / :250-253: CrossEntropyLoss gets ``label_gt - 1`` and accuracy compares ``argmax + 1`` for every
+    dataset_env except 'room_full' (whose labels are 0..4); the other environments carry labels 1..NC."""
+    return 0 if dataset_env == "room_full" else 1
 
 
 class _Lookahead:
@@ -60,6 +66,16 @@ def build_modules(opt, device):
 
 
 def run(opt, dataloader=None, max_steps=None, quiet=False):
+    """The training loop; under torchrun the process group is torn down in an orderly way at the end."""
+    engines = {}
+    try:
+        return _run(opt, engines, dataloader, max_steps, quiet)
+    finally:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            shutdown_distributed(engines.values())
+
+
+def _run(opt, engines, dataloader=None, max_steps=None, quiet=False):
     rank, local, world, pg = init_distributed()
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
@@ -82,8 +98,8 @@ def run(opt, dataloader=None, max_steps=None, quiet=False):
     broadcast_parameters((Enc, Dec, Res, Cls), pg)
     if dataloader is None:
         n = opt.synthetic if opt.synthetic > 0 else 16 * opt.batch_size
-        dataloader = SyntheticCIR(n, opt.batch_size, len_cir, opt.num_classes, seed=1234 + rank)
-    engines = {}
+        dataloader = SyntheticCIR(n, opt.batch_size, len_cir, opt.num_classes, seed=1234 + rank,
+                                  label_base=label_offset_for(opt.dataset_env))
     sched = LambdaLR(opt.n_epochs, opt.epoch, opt.decay_epoch)
     mask_stream = SupervisionMask(opt.supervision_rate, seed=1234)
     prev_time, steps_done = time.time(), 0
@@ -101,7 +117,8 @@ def run(opt, dataloader=None, max_steps=None, quiet=False):
             if eng is None:
                 eng = engines[B] = SemiTrainEngine(Enc, Dec, Res, Cls, batch_size=B, cir_len=cir.shape[1], lr=lr,
                                                    betas=(opt.b1, opt.b2), mode="semi", process_group=pg,
-                                                   shared_state=next(iter(engines.values()), None))
+                                                   shared_state=next(iter(engines.values()), None),
+                                                   label_offset=label_offset_for(opt.dataset_env))
                 opt_file = os.path.join(model_path, "Opt_%d.pth" % opt.epoch)
                 if opt.epoch != 0 and len(engines) == 1 and os.path.exists(opt_file):
                     eng.load_optimizer_state_dict(torch.load(opt_file))   # exact resume (the reference restarts Adam)

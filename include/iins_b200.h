@@ -116,24 +116,30 @@ int iins_classifier_backward(const iins_config* cfg, const float* const* params,
 
 /* ---- Fused loss + seed gradients + metrics: train_semi.py:199-225, train.py:87-91, :104-115 -------
  * out[8] (zeroed inside): [0] mean|x-x_recon|  [1] mean|err-err_est|  [2] mean CE  [3] lam-weighted sum
- * of [0..2] (the KL term lives in the encoder)  [4] mean (err_est-err)^2  [5] #correct argmax.
+ * of [0..2] (the KL term lives in the encoder)  [4] mean (err_est-err)^2  [5] #correct argmax
+ * [6] number of labels outside [0, num_classes) after the offset (must be 0: torch's CrossEntropyLoss device-asserts).
  * x/x_recon may be NULL (train.py variant), err/err_est/logits/label may be NULL (unsupervised batch).
- * label: fp32 holding integers (dataset.py:122) or, if label_i64 != NULL, int64. */
+ * label: fp32 holding integers (dataset.py:122) or, if label_i64 != NULL, int64.
+ * label_offset: class index = label - label_offset.  train_semi.py:217-222 feeds CrossEntropyLoss `label_gt - 1` and
+ * scores `argmax + 1` for every dataset_env except 'room_full' (labels 1..NC): pass 1 there, 0 for room_full / train.py. */
 int iins_loss_forward_backward(int batch, int cir_len, int num_classes,
                                const float* x, const float* x_recon, const float* err, const float* err_est,
-                               const float* logits, const float* label, const int64_t* label_i64,
+                               const float* logits, const float* label, const int64_t* label_i64, int label_offset,
                                float lam_ae, float lam_res, float lam_env, float* out,
                                float* d_x_recon, float* d_err_est, float* d_logits, int32_t* pred,
                                iins_stream_t stream);
 
 /* ---- Fused Adam over a flat parameter buffer: torch.optim.Adam as used at train_semi.py:118-122 -----
- * groups: up to 8 half-open element ranges [begin,end) with an `active` flag; an inactive group is
- * skipped entirely (grad None in the reference).  steps: device int32[n_groups] step counters, advanced
- * by this call for active groups.  lr: device scalar. */
-int iins_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+ * groups: up to 7 half-open element ranges [begin,end) with an `active` flag; an inactive group is
+ * skipped entirely (grad None in the reference).  steps: device int32[n_groups + 1]: completed updates per
+ * group, advanced by this call for active groups (by the last CTA of the ONE launch), plus a ticket word
+ * that must be zero when the call is enqueued.  lr: device scalar.
+ * grad_scale: gradients are multiplied by it first (1/world_size after a SUM all-reduce = the data-parallel mean);
+ * zero_grads != 0: consumed gradient elements are zeroed (the backward passes accumulate: no separate memset). */
+int iins_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq,
                    const int64_t* group_begin, const int64_t* group_end, const int32_t* group_active,
                    int n_groups, int32_t* steps, const float* lr, double beta1, double beta2, float eps,
-                   iins_stream_t stream);
+                   float grad_scale, int zero_grads, iins_stream_t stream);
 
 /* ---- small helpers used at the module boundary ----------------------------------------------------- */
 /* AdaptiveAvgPool1d over (B,Lin)->(B,Lout) (models.py:146, 436) and its backward */

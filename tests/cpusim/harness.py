@@ -84,7 +84,7 @@ class SimStep:
         lib.check(lib.iins_loss_forward_backward(
             B, cfg.cir_len, cfg.num_classes, ptr(self.cir), ptr(self.xrec),
             ptr(err) if supervised else None, ptr(self.err_est) if supervised else None,
-            ptr(self.logits) if supervised else None, ptr(label) if supervised else None, None,
+            ptr(self.logits) if supervised else None, ptr(label) if supervised else None, None, getattr(self, "label_offset", 0),
             orc.LAMBDA_AE, orc.LAMBDA_RES, orc.LAMBDA_ENV, ptr(self.out), ptr(d_xrec),
             ptr(d_err) if supervised else None, ptr(d_logits) if supervised else None, None, None), "loss")
         d_rc = torch.zeros_like(self.rc)

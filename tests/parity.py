@@ -129,7 +129,16 @@ def grad_report(got, truth, ref32, gscale, ref_factor=REF_FACTOR):
     return rows
 
 
-def assert_grads(rows, batch, require_strict, label=""):
+MAX_FLIP_TENSORS = 3       # at most this many tensors of a step may use the kink-flip band instead of the strict bound
+STRICT_BATCH = 16          # batches up to this size must be strict on every tensor
+
+
+def assert_grads(rows, batch, require_strict=None, label="", max_flip=MAX_FLIP_TENSORS):
+    """Every tensor within the strict bound; at most ``max_flip`` tensors may instead sit in the kink-flip band
+    FLIP_C / batch (one ReLU / LeakyReLU / sign() kink decided differently by two correct fp32 evaluations moves every
+    upstream tensor by O(1/B)); batches <= STRICT_BATCH must be strict throughout.  Returns the band count."""
+    if require_strict is None:
+        require_strict = batch <= STRICT_BATCH
     bad_strict = [r for r in rows if not r[3]]
     if require_strict:
         assert not bad_strict, f"{label}: {len(bad_strict)} tensors beyond the strict bound, e.g. {bad_strict[0]}"
@@ -137,6 +146,8 @@ def assert_grads(rows, batch, require_strict, label=""):
     flip = FLIP_C / batch
     beyond = [r for r in bad_strict if r[1] > flip]
     assert not beyond, f"{label}: {len(beyond)} tensors beyond even the kink-flip bound {flip:.1e}, e.g. {beyond[0]}"
+    assert len(bad_strict) <= max_flip, (f"{label}: {len(bad_strict)} tensors need the kink-flip band (cap {max_flip}): "
+                                         f"{[r[0] for r in bad_strict]}")
     return len(bad_strict)
 
 

@@ -118,6 +118,9 @@ def test_modules_autograd_match_golden(golden):
         assert abs(rmse - golden[pre + "metrics"][0]) < 1e-3
     for row in summary:
         print("golden case %s (B=%d): %d tensors beyond the strict bound, worst rel-L2 %.2e" % row)
+    for case, batch, n_fail, worst in summary:
+        if batch > parity.STRICT_BATCH:
+            assert n_fail <= parity.MAX_FLIP_TENSORS, f"{case}: {n_fail} tensors in the kink-flip band (cap {parity.MAX_FLIP_TENSORS})"
     small = [r for r in summary if r[1] <= 4]
     clean = [r for r in small if r[2] == 0]
     assert len(clean) * 2 >= len(small), f"fewer than half of the B<=4 golden cases are kink-free on this device: {summary}"
@@ -125,7 +128,7 @@ def test_modules_autograd_match_golden(golden):
 
 @pytest.mark.parametrize("batch,supervised,graph,mode", [
     (64, True, False, "fp32"), (130, False, False, "fp32"), (1, True, False, "fp32"), (2, True, False, "fp32"),
-    (4096, True, True, "fp32"), (4096, False, True, "fp32"),
+    (4096, True, True, "fp32"), (4096, False, True, "fp32"), (8192, True, True, "fp32"),
     (2, True, False, "simt"), (130, True, False, "simt"), (4096, True, True, "simt")])
 def test_engine_step_matches_oracle(batch, supervised, graph, mode):
     """Fused engine (fused loss, flat gradient buffer) vs the CPU oracle, up to BASELINE's batch 4096, for the
@@ -139,7 +142,7 @@ def test_engine_step_matches_oracle(batch, supervised, graph, mode):
     cir, err, label = orc.synthetic_batch(cfg, batch, 500 + batch)
     eng = SemiTrainEngine(*mods, batch_size=batch, cir_len=cfg.cir_len, use_graph=graph)
     eng.step(cir, err, label, supervised=supervised, update=False)
-    if graph:                                   # replay must give the same numbers as the capture pass
+    if graph:                                   # a second replay (compared with the eager pass in test_graph_replay_*)
         eng.step(cir, err, label, supervised=supervised, update=False)
     torch.cuda.synchronize()
     ref, ref_grads = orc.semi_step_with_grads(*pdicts, cir, err, label, cfg, supervised,
@@ -170,7 +173,7 @@ def test_engine_step_matches_oracle(batch, supervised, graph, mode):
                                         supervised, torch.zeros(batch, cfg.env_dim // 2, 1).double())
     rows = parity.grad_report(got, truth, ref_grads, gscale,
                               parity.REF_FACTOR_TC if mode == "fp32" else parity.REF_FACTOR)
-    n_flip = parity.assert_grads(rows, batch, require_strict=(batch <= 2), label=f"B={batch}")
+    n_flip = parity.assert_grads(rows, batch, label=f"B={batch}")       # strict for B <= 16, at most 3 tensors in the band
     rel = sorted(r[1] for r in rows if not orc.grad_is_structurally_zero(r[0]))
     ref = sorted(r[2] for r in rows if not orc.grad_is_structurally_zero(r[0]))
     print(f"[{mode}] B={batch} sup={supervised}: gradient rel-L2 error vs fp64 oracle: median {rel[len(rel) // 2]:.2e} max {rel[-1]:.2e}"
@@ -338,3 +341,123 @@ def test_shape_option_sweep_matches_oracle():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.run_sweep() == 0
+
+
+@pytest.mark.parametrize("supervised", [True, False])
+def test_graph_replay_matches_eager_and_is_reproducible(supervised):
+    """The CUDA-graph replay of a step must produce what the eager pass of the same engine produces, and five replays
+    must agree with each other: the only run-to-run freedom is the order of the fp32 atomics that flush the weight
+    gradients (a gradient tensor is never read again inside the step, so the noise cannot propagate).  Stated bounds:
+    forward tensors and losses bit-identical; every gradient tensor within 2e-6 rel-L2 of the eager pass and of the
+    first replay."""
+    from iins_vae_b200.engine import SemiTrainEngine
+    cfg = orc.PathConfig()
+    batch = 4096
+    mods, _ = _mods(cfg, 23)
+    cir, err, label = orc.synthetic_batch(cfg, batch, 623)
+    eng = SemiTrainEngine(*mods, batch_size=batch, cir_len=cfg.cir_len, use_graph=False)
+    eng.step(cir, err, label, supervised=supervised, update=False)
+    torch.cuda.synchronize()
+    eager = {k: v.clone() for k, v in eng.named_grads().items()}
+    eager_out = (eng.out.clone(), eng.kl.clone(), eng.xrec.clone(), eng.rc.clone(), eng.cat.clone())
+    eng.use_graph = True
+    runs = []
+    for _ in range(5):
+        eng.step(cir, err, label, supervised=supervised, update=False)
+        torch.cuda.synchronize()
+        runs.append({k: v.clone() for k, v in eng.named_grads().items()})
+        for a, b in zip(eager_out[1:], (eng.kl, eng.xrec, eng.rc, eng.cat)):
+            assert torch.equal(a, b), "forward tensors of a replay differ from the eager pass"
+        assert torch.allclose(eager_out[0], eng.out, rtol=1e-6, atol=0), "loss terms (atomic sums) differ beyond 1e-6"
+    worst_eager = worst_replay = 0.0
+    for k, e in eager.items():
+        n = float(e.norm())
+        if n == 0.0:
+            assert all(float(r[k].abs().max()) == 0.0 for r in runs), k
+            continue
+        worst_eager = max(worst_eager, max(float((r[k] - e).norm()) / n for r in runs))
+        worst_replay = max(worst_replay, max(float((r[k] - runs[0][k]).norm()) / n for r in runs[1:]))
+    print(f"sup={supervised}: replay vs eager worst rel-L2 {worst_eager:.2e}; replay vs replay {worst_replay:.2e}")
+    assert worst_eager <= 2e-6 and worst_replay <= 2e-6
+
+
+# BASELINE configs[2]: bf16 operands (8 mantissa bits: unit round-off 2^-9 = 2e-3), fp32 accumulation and statistics.
+# Stated tolerances, per tensor class, rel-L2 against the fp64 oracle at B=8192 (measured values are printed by the test and
+# recorded in profiles/; the bounds are ~3x the measured worst of the class):
+BF16_GRAD_TOL = {"cls": 2e-2, "res": 2e-2, "dec": 5e-2, "enc.env_encoder": 5e-2, "enc.range_encoder": 1.5e-1}
+
+
+def _bf16_class(name):
+    for k in ("enc.range_encoder", "enc.env_encoder", "dec", "res", "cls"):
+        if name.startswith(k):
+            return k
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("batch", [8192])
+def test_bf16_mode_full_gradient_parity(batch):
+    """configs[2] (semi-supervised step, bf16, B=8192): loss within 1e-2, every forward tensor within 3e-2 of its scale,
+    EVERY parameter-gradient tensor within the per-class rel-L2 bound BF16_GRAD_TOL of the fp64 oracle, both mask
+    branches, graph replay on."""
+    import iins_vae_b200
+    from iins_vae_b200.engine import SemiTrainEngine
+    cfg = orc.PathConfig()
+    mods, pdicts = _mods(cfg, 31)
+    cir, err, label = orc.synthetic_batch(cfg, batch, 831)
+    iins_vae_b200.set_compute_mode("bf16")
+    eng = SemiTrainEngine(*mods, batch_size=batch, cir_len=cfg.cir_len, use_graph=True)
+    dbl = lambda d: {k: v.double() for k, v in d.items()}
+    for supervised in (True, False):
+        eng.step(cir, err, label, supervised=supervised, update=False)
+        torch.cuda.synchronize()
+        ref, truth = orc.semi_step_with_grads(*(dbl(p) for p in pdicts), cir.double(), err.double(), label.double(), cfg,
+                                              supervised, torch.zeros(batch, cfg.env_dim // 2, 1).double())
+        t = eng.loss_terms()
+        np.testing.assert_allclose(t["loss"], float(ref["loss"]), rtol=1e-2)
+        for name, got, want in (("range_code", eng.rc, ref["range_code"]), ("env_code", eng.cat, ref["env_code"].view(batch, -1)),
+                                ("cir_gen", eng.xrec, ref["cir_gen"].view(batch, -1))):
+            scale = float(want.abs().max())
+            assert float((got.cpu().double() - want).abs().max()) <= 3e-2 * scale, name
+        got = eng.named_grads()
+        worst = {}
+        for name, g64 in truth.items():
+            if g64 is None:
+                assert float(got[name].abs().max()) == 0.0, name
+                continue
+            if orc.grad_is_structurally_zero(name):
+                continue
+            rel = float((got[name].cpu().double() - g64).norm() / (g64.norm() + 1e-300))
+            c = _bf16_class(name)
+            if rel > worst.get(c, ("", 0.0))[1]:
+                worst[c] = (name, rel)
+        print(f"[bf16] B={batch} sup={supervised}: worst rel-L2 per class " +
+              ", ".join(f"{c}: {r:.2e} ({n})" for c, (n, r) in sorted(worst.items())))
+        for c, (n, r) in worst.items():
+            assert r <= BF16_GRAD_TOL[c], f"{n}: rel-L2 {r:.2e} beyond the stated bf16 bound {BF16_GRAD_TOL[c]:.1e} of class {c}"
+
+
+def test_one_based_labels_match_reference_shift():
+    """train_semi.py:217-222: with any dataset_env but 'room_full' the labels are 1..NC and the reference feeds
+    CrossEntropyLoss `label - 1`: the engine with label_offset=1 on 1-based labels must equal label_offset=0 on the
+    shifted labels, and raw 1-based labels without the offset must fail loudly instead of reading out of the row."""
+    from iins_vae_b200.engine import SemiTrainEngine
+    cfg = orc.PathConfig(num_classes=4)
+    batch = 96
+    mods, pdicts = _mods(cfg, 41)
+    cir, err, label = orc.synthetic_batch(cfg, batch, 141)            # labels in [0, NC)
+    e0 = SemiTrainEngine(*mods, batch_size=batch, use_graph=False)
+    e0.step(cir, err, label, supervised=True, update=False)
+    t0, g0 = e0.loss_terms(), {k: v.clone() for k, v in e0.named_grads().items()}
+    e1 = SemiTrainEngine(*mods, batch_size=batch, use_graph=False, shared_state=e0, label_offset=1)
+    e1.step(cir, err, label + 1, supervised=True, update=False)
+    t1 = e1.loss_terms()
+    np.testing.assert_allclose(t0["loss_env"], t1["loss_env"], rtol=1e-6)
+    assert t0["accuracy"] == t1["accuracy"]
+    for k, v in e1.named_grads().items():
+        if k.startswith("cls."):
+            assert torch.allclose(v, g0[k], rtol=1e-5, atol=1e-9), k
+    ref = orc.semi_forward(*pdicts, cir, err, label, cfg, True, torch.zeros(batch, cfg.env_dim // 2, 1))
+    np.testing.assert_allclose(t1["loss_env"], float(ref["loss_env"]), rtol=1e-4)
+    e0.step(cir, err, label + 1, supervised=True, update=False)       # 1-based labels, no offset: label == NC is invalid
+    with pytest.raises(ValueError):
+        e0.loss_terms()
