@@ -24,7 +24,14 @@ struct IinsProfState {
     cudaEvent_t ev0[4096], ev1[4096];
     int ev_ready;
 };
-static IinsProfState g_iins_prof;
+// one instance for the whole library (defined in iins_runtime.cu; the kernel-instance translation units share it)
+#ifdef IINS_DEFINE_GLOBALS
+IinsProfState g_iins_prof;
+int g_iins_pdl = -1;
+#else
+extern IinsProfState g_iins_prof;
+extern int g_iins_pdl;
+#endif
 static inline void iins_prof_pre(const char* name, cudaStream_t st) {
     g_iins_prof.launches++;
     if (g_iins_prof.enabled && g_iins_prof.n < 4096) {
@@ -47,7 +54,6 @@ static inline void iins_prof_post(cudaStream_t st) {
 // address arithmetic) and then blocks in iins_pdl_wait() (griddepcontrol.wait = the predecessor grid has completed
 // and its memory is visible) before it touches global memory.  The step is a chain of ~100 dependent 10-30 us
 // kernels: this hides the launch gap and the prologue of each.  IINS_PDL=0 turns the attribute off.
-static int g_iins_pdl = -1;
 static inline int iins_pdl_enabled() {
     if (g_iins_pdl < 0) { const char* e = getenv("IINS_PDL"); g_iins_pdl = e ? atoi(e) : 1; }
     return g_iins_pdl;

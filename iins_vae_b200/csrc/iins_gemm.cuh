@@ -210,7 +210,7 @@ __device__ __forceinline__ void iins_epilogue_tile(const IinsNTParams& p, const 
 }
 
 template <int BN>
-__global__ void __launch_bounds__(256) iins_nt_kernel(const IinsNTParams p) {
+static __global__ void __launch_bounds__(256) iins_nt_kernel(const IinsNTParams p) {
     iins_pdl_enter();
     constexpr int BM = 128, BK = 16, TN = 4;
     constexpr int CT = BN / TN;            // threads along n
@@ -339,7 +339,7 @@ struct IinsTNParams {
 
 // grid = (row parts, ceil(K/64), ceil(N/64)); each CTA owns a 64(n) x 64(k) block of dW, reduces its
 // row range in registers (4x4 per thread) and flushes once with atomicAdd.
-__global__ void __launch_bounds__(256) iins_tn_kernel(const IinsTNParams p) {
+static __global__ void __launch_bounds__(256) iins_tn_kernel(const IinsTNParams p) {
     iins_pdl_enter();
     constexpr int BR = 32, BNK = 64;
     __shared__ __align__(16) float Ds[BR * BNK];
@@ -425,7 +425,7 @@ struct IinsRowParams {
     IinsNTParams nt;           // geometry, operands, epilogue, M/N/K, Lrow, lshift
 };
 
-__global__ void __launch_bounds__(256) iins_row_nt_kernel(const IinsRowParams rp) {
+static __global__ void __launch_bounds__(256) iins_row_nt_kernel(const IinsRowParams rp) {
     iins_pdl_enter();
     constexpr int BM = 128, NT = 16, LD = NT + 1, KMAX = 64;
     __shared__ __align__(16) float Ws[KMAX * NT];            // [k][n]
@@ -576,7 +576,7 @@ IINS_D float iins_row2_sample_sum(float v, int nw, int warp, int lane, float* xc
 }
 
 template <int NACC, int AKIND, int EPI>      // EPI: 0 plain, 1 InstanceNorm / AdaIN, 2 LayerNorm, 3 data gradient + fused IN backward
-__global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowParams rp) {
+static __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowParams rp) {
     iins_pdl_enter();
     constexpr int BM = 128;
     __shared__ __align__(16) float Ws[IINS_ROW2_WMAX];       // [k][NACC]
@@ -840,7 +840,7 @@ struct IinsRowTNParams {
     int lshift;
 };
 
-__global__ void __launch_bounds__(256) iins_row_tn_kernel(const IinsRowTNParams rp) {
+static __global__ void __launch_bounds__(256) iins_row_tn_kernel(const IinsRowTNParams rp) {
     iins_pdl_enter();
     constexpr int BR = 64, NT = 16, KMAX = 64;
     __shared__ float Zs[BR * (NT + 1)];        // [r][n]
@@ -916,7 +916,7 @@ struct IinsRow2TNParams {
 };
 
 template <int NACC, int CIN, int TPS>
-__global__ void __launch_bounds__(128) iins_row2_tn_kernel(const IinsRow2TNParams rp) {
+static __global__ void __launch_bounds__(128) iins_row2_tn_kernel(const IinsRow2TNParams rp) {
     iins_pdl_enter();
     constexpr int KS = CIN * TPS;              // k entries per thread
     constexpr int NA = NACC * KS;              // accumulators per thread
@@ -1022,7 +1022,7 @@ struct IinsThinTNParams {
     int thin_is_k;             // 1: K <= 4 (wide = output channels), 0: Cout <= 4 (wide = k)
 };
 
-__global__ void __launch_bounds__(256) iins_thin_tn_kernel(const IinsThinTNParams tp) {
+static __global__ void __launch_bounds__(256) iins_thin_tn_kernel(const IinsThinTNParams tp) {
     iins_pdl_enter();
     const IinsTNParams& p = tp.tn;
     const IinsGeom& g = p.g;

@@ -30,7 +30,7 @@ struct IinsNormBwdParams {
 //   pass 1: accumulate sum_l g and sum_l g*xhat per channel (IN / AdaIN) or over the whole sample (LN)
 //   pass 2: reload (L1-resident) and write dz
 // Requires C a power of two, 4 <= C <= 128, and L*C a multiple of 128.
-__global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNormBwdParams p) {
+static __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNormBwdParams p) {
     iins_pdl_enter();
     // LayerNorm's dgamma / dbeta are sums over the whole batch: every warp keeps a running per-channel total over the
     // samples it visits (persistent grid), the CTA combines its 8 warps in shared memory and issues ONE atomic per
@@ -174,7 +174,7 @@ IINS_HD void iins_pool_window(int i, int Lin, int Lout, int& s, int& e) {
     e = ((i + 1) * Lin + Lout - 1) / Lout;
 }
 
-__global__ void __launch_bounds__(256) iins_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+static __global__ void __launch_bounds__(256) iins_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                             int B, int Lin, int Lout) {
     iins_pdl_enter();
     long n = (long)B * Lout;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) iins_pool_fwd_kernel(const float* __restr
 }
 
 // dx[b,j] = sum over windows containing j of dy[b,o]/len(o); optionally times (1 - t^2) with t = tanh output
-__global__ void __launch_bounds__(256) iins_pool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ tanh_y,
+static __global__ void __launch_bounds__(256) iins_pool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ tanh_y,
                                                             float* __restrict__ dx, int B, int Lin, int Lout) {
     iins_pdl_enter();
     long n = (long)B * Lin;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) iins_pool_bwd_kernel(const float* __restr
 }
 
 // mean over L of an NLC tensor: (B,L,C) -> (B,C)   (AdaptiveAvgPool1d(1), models.py:279)
-__global__ void __launch_bounds__(256) iins_mean_l_kernel(const float* __restrict__ x, float* __restrict__ y,
+static __global__ void __launch_bounds__(256) iins_mean_l_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                           int B, int L, int C) {
     iins_pdl_enter();
     long n = (long)B * C;
@@ -255,7 +255,7 @@ IINS_HD float iins_noise_at(unsigned long long seed, unsigned long long offset, 
 // --------------------------------------------------------------- reparameterisation + KL
 // cat (B,E) = [mu | log_sigma];  latent = noise*exp(ls)+mu;  kl = mean_b 0.5*sum(exp(2ls)+mu^2-1-2ls)
 // (models.py:285-298).  noise: explicit (B,E/2) tensor if given, else Philox(seed, offset).
-__global__ void __launch_bounds__(256) iins_reparam_kl_kernel(const float* __restrict__ cat, const float* __restrict__ noise,
+static __global__ void __launch_bounds__(256) iins_reparam_kl_kernel(const float* __restrict__ cat, const float* __restrict__ noise,
                                                               float* __restrict__ latent, float* __restrict__ kl,
                                                               int B, int E, unsigned long long seed, unsigned long long offset) {
     iins_pdl_enter();
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) iins_reparam_kl_kernel(const float* __res
 }
 
 // dcat = d_cat_in + d_kl * dkl/dcat + latent-path terms
-__global__ void __launch_bounds__(256) iins_reparam_kl_bwd_kernel(const float* __restrict__ cat, const float* __restrict__ noise,
+static __global__ void __launch_bounds__(256) iins_reparam_kl_bwd_kernel(const float* __restrict__ cat, const float* __restrict__ noise,
                                                                   const float* __restrict__ d_cat_in, const float* __restrict__ d_latent,
                                                                   const float* __restrict__ d_kl, float* __restrict__ dcat,
                                                                   int B, int E, unsigned long long seed, unsigned long long offset) {
@@ -329,7 +329,7 @@ struct IinsLossParams {
     int* pred;                 // (B,) argmax or nullptr
 };
 
-__global__ void __launch_bounds__(256) iins_loss_kernel(const IinsLossParams p) {
+static __global__ void __launch_bounds__(256) iins_loss_kernel(const IinsLossParams p) {
     iins_pdl_enter();
     __shared__ float s_part[8][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(256) iins_loss_kernel(const IinsLossParams p) 
 
 // dst1 += src1, dst2 += src2 in one launch: sums the head gradients (Restorer -> d range_code, Classifier -> d env_code)
 // into the decoder's when the engine runs the heads concurrently with the decoder (engine.py)
-__global__ void __launch_bounds__(256) iins_accumulate2_kernel(float* __restrict__ dst1, const float* __restrict__ src1, long n1,
+static __global__ void __launch_bounds__(256) iins_accumulate2_kernel(float* __restrict__ dst1, const float* __restrict__ src1, long n1,
                                                                float* __restrict__ dst2, const float* __restrict__ src2, long n2) {
     iins_pdl_enter();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += (long)gridDim.x * blockDim.x) {
@@ -436,7 +436,7 @@ struct IinsAdamParams {
     IinsAdamGroup groups[8];
 };
 
-__global__ void __launch_bounds__(256) iins_adam_kernel(const IinsAdamParams a) {
+static __global__ void __launch_bounds__(256) iins_adam_kernel(const IinsAdamParams a) {
     iins_pdl_enter();
     // the bias corrections are double-precision pow() like torch's Python scalars: evaluated by ONE thread per CTA
     // and group (they cost hundreds of fp64 instructions), then shared

@@ -1,7 +1,10 @@
 // Host-side sequencing of the IIns-VAE path and the C ABI declared in include/iins_b200.h.
 // One translation unit: kernels (iins_gemm.cuh, iins_misc.cuh) + the module-level launch plans.
+#define IINS_DEFINE_GLOBALS
 #include "iins_gemm.cuh"
 #include "iins_tc.cuh"
+#include "iins_launchers.h"
+#include "iins_trunk.h"
 #include "iins_misc.cuh"
 #include "../../include/iins_b200.h"
 
@@ -113,30 +116,6 @@ void launch_nt_simt(const Ctx& c, const IinsNTParams& p) {
 }
 
 #ifndef IINS_CPUSIM
-template <int NT, int PIECES, int AKIND, int EPI, int LL>
-void launch_tc_nt_v(Ctx& c, const IinsTCParams& tp, dim3 grid) {
-    constexpr int smem = 2 * (3 * 4 * (128 * 16 + 64) + 3 * 4 * NT * 16) + 8192;      // A stages use the padded chunk stride
-    static bool attr = false;
-    auto iins_tc_nt_kernel_ = iins_tc_nt_kernel<NT, PIECES, AKIND, EPI, LL>;
-    if (!attr) { cudaFuncSetAttribute(iins_tc_nt_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    IINS_LAUNCH(iins_tc_nt_kernel_, grid, 288, smem, c.st, tp);
-}
-// (tile width, operand kind, epilogue kind, rows per sample) -> kernel instance; false if that instance is not built
-template <int PIECES>
-bool launch_tc_nt_variant(Ctx& c, const IinsTCParams& tp, dim3 grid, int nt, int akind, int epi, int ll) {
-#define IINS_V(NT_, AK_, EPI_, LL_) \
-    if (nt == NT_ && akind == AK_ && epi == EPI_ && ll == LL_) { launch_tc_nt_v<NT_, PIECES, AK_, EPI_, LL_>(c, tp, grid); return true; }
-    IINS_V(16, 0, IINS_EPI_PLAIN, 1) IINS_V(32, 0, IINS_EPI_PLAIN, 1) IINS_V(64, 0, IINS_EPI_PLAIN, 1)
-    IINS_V(16, 1, IINS_EPI_PLAIN, 1) IINS_V(32, 1, IINS_EPI_PLAIN, 1) IINS_V(64, 1, IINS_EPI_PLAIN, 1)
-    IINS_V(64, 0, IINS_EPI_IN, 8) IINS_V(64, 0, IINS_EPI_IN, 16) IINS_V(32, 0, IINS_EPI_IN, 8) IINS_V(32, 0, IINS_EPI_IN, 16)
-    IINS_V(32, 0, IINS_EPI_LN, 16) IINS_V(16, 0, IINS_EPI_LN, 32)
-    IINS_V(64, 1, IINS_EPI_NBWD, 8) IINS_V(32, 1, IINS_EPI_NBWD, 16) IINS_V(16, 1, IINS_EPI_NBWD, 32)
-    IINS_V(16, 0, IINS_EPI_SMEM, 1) IINS_V(32, 0, IINS_EPI_SMEM, 1) IINS_V(64, 0, IINS_EPI_SMEM, 1)
-    IINS_V(16, 1, IINS_EPI_SMEM, 1) IINS_V(32, 1, IINS_EPI_SMEM, 1) IINS_V(64, 1, IINS_EPI_SMEM, 1)
-#undef IINS_V
-    return false;
-}
-
 void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     static int nt_max = 0;                 // tuning knob: cap the tile width (more, smaller CTAs); env IINS_NT_MAX
     if (nt_max == 0) { const char* e = getenv("IINS_NT_MAX"); nt_max = e ? atoi(e) : 64; if (nt_max != 16 && nt_max != 32) nt_max = 64; }
@@ -193,8 +172,8 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     }
     dim3 grid((p.M + 127) / 128, pk.nblk, 1);
     IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K); IINS_SET_SHAPE(p.M, p.N, p.K);
-    const bool launched = tp.pieces == 3 ? launch_tc_nt_variant<3>(c, tp, grid, nt, p.a_kind, epi, ll)
-                                         : launch_tc_nt_variant<1>(c, tp, grid, nt, p.a_kind, epi, ll);
+    const bool launched = tp.pieces == 3 ? iins_launch_tc_nt_p3(c.st, tp, grid, nt, p.a_kind, epi, ll)
+                                         : iins_launch_tc_nt_p1(c.st, tp, grid, nt, p.a_kind, epi, ll);
     if (!launched) c.err = 4;
 }
 #endif
@@ -390,22 +369,6 @@ void begin_branch(Ctx& c, Branch& b) {
 void end_branch(Ctx& c, Branch& b) { flush_pending(c); if (c.phase != 1 && b.br != nullptr) c.st = b.main; }
 void join_branch(Ctx& c, Branch& b) { flush_pending(c); if (c.phase != 1 && b.br != nullptr) fork_to(b.br, c.st); }
 
-#ifndef IINS_CPUSIM
-template <int NT, int PIECES>
-void launch_tc_tn_tp(cudaStream_t st, const IinsTCTNParams& tp, dim3 grid) {
-    constexpr int smem = 2 * (3 * 8192 + 3 * (NT / 8) * 32 * 16);
-    static bool attr = false;
-    auto iins_tc_tn_kernel_ = iins_tc_tn_kernel<NT, PIECES>;
-    if (!attr) { cudaFuncSetAttribute(iins_tc_tn_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    IINS_LAUNCH(iins_tc_tn_kernel_, grid, 288, smem, st, tp);
-}
-template <int NT>
-void launch_tc_tn_t(cudaStream_t st, const IinsTCTNParams& tp, dim3 grid) {
-    if (tp.pieces == 3) launch_tc_tn_tp<NT, 3>(st, tp, grid);
-    else launch_tc_tn_tp<NT, 1>(st, tp, grid);
-}
-#endif
-
 void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, float* dw, float* db) {
     IinsTNParams p;
     memset(&p, 0, sizeof(p));
@@ -483,9 +446,7 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
         if (tp.lshift < 0) { c.err = 2; return; }
         dim3 grid(parts, ky, nz);
         IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K); IINS_SET_SHAPE(p.M, g.Cout, K);
-        if (nt == 16) launch_tc_tn_t<16>(wst, tp, grid);
-        else if (nt == 32) launch_tc_tn_t<32>(wst, tp, grid);
-        else launch_tc_tn_t<64>(wst, tp, grid);
+        iins_launch_tc_tn(wst, tp, grid, nt);
         return;
     }
 #endif
@@ -581,6 +542,38 @@ void run_phases(Ctx& c, F&& body) {
 }
 #define IINS_SKIP_IN_COLLECT(c) if ((c).phase == 1) {} else
 
+struct EncLayerRef { float* y; float* xhat; float* rstd; };
+#ifndef IINS_CPUSIM
+// The L = 8 residual trunk (2 * n_residual k3 convolutions over (B, 8, 64)) as ONE persistent kernel (iins_trunk.cu).  Called
+// in the EXECUTE phase in place of the per-layer launches; the collect phase has recorded one weight-pack job per
+// convolution (forward kind, 64-wide tiles), whose outputs are consecutive in the arena.  Returns false -> per-layer path.
+bool trunk_forward_fused(Ctx& c, int B, int D, int Lt, int nres, const float* x, const float* const* P, int pi,
+                         const EncLayerRef* res1, const EncLayerRef* res2, const float* adain, int adain_ld) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("IINS_FUSED_TRUNK"); on = e ? atoi(e) : 1; }
+    if (!on || c.phase != 2 || g_mode == 2 || D != 64 || Lt != 8 || nres < 1 || 2 * nres > IINS_TRUNK_MAX_CONVS) return false;
+    if (c.job_i + 2 * nres > c.njobs) return false;
+    const int pieces = g_mode == 1 ? 1 : 3;
+    const size_t conv_bytes = (size_t)64 * 192 * pieces * 2;
+    IinsTrunkFwdParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.B = B; tp.nconv = 2 * nres; tp.pieces = pieces; tp.x = x; tp.adain = adain; tp.adain_ld = adain_ld;
+    tp.wpack = c.jobs.jobs[c.job_i].out;
+    for (int k = 0; k < 2 * nres; ++k) {
+        const IinsPackJob& j = c.jobs.jobs[c.job_i + k];
+        if (j.kind != 0 || j.NT != 64 || j.N != 64 || j.K != 192 ||
+            reinterpret_cast<const unsigned char*>(j.out) != reinterpret_cast<const unsigned char*>(tp.wpack) + k * conv_bytes) return false;
+        const EncLayerRef& l = (k & 1) ? res2[k >> 1] : res1[k >> 1];
+        tp.layer[k].bias = P[pi + 2 * k + 1]; tp.layer[k].y = l.y; tp.layer[k].xhat = l.xhat; tp.layer[k].rstd = l.rstd;
+        tp.layer[k].adain_off_b = 4 * D * (k >> 1) + ((k & 1) ? 2 * D : 0);       // assign_adain_params: [bias1 | weight1 | bias2 | weight2]
+        tp.layer[k].adain_off_w = tp.layer[k].adain_off_b + D;
+    }
+    if (!iins_trunk_forward_launch(c.st, tp)) return false;
+    c.job_i += 2 * nres;
+    return true;
+}
+#endif
+
 // ------------------------------------------------------------------------------ shape helpers
 struct Shapes {
     int B, Lc, d, nres, ndown, E, R, NC, F;
@@ -623,7 +616,7 @@ struct Bump {
 };
 
 // ===================================================================================== Encoder
-struct EncLayer { float* y; float* xhat; float* rstd; };
+typedef EncLayerRef EncLayer;
 struct EncPlan {
     float* xp;
     EncLayer stem;
@@ -706,7 +699,12 @@ int encoder_forward(const Shapes& s, const float* const* P, const float* x, cons
         pi += 2;
         h = pl.down[i].y; L /= 2; C *= 2;
     }
-    for (int i = 0; i < s.nres; ++i) {
+    bool trunk_done = false;
+#ifndef IINS_CPUSIM
+    trunk_done = trunk_forward_fused(c, B, C, L, s.nres, h, P, pi, pl.res1, pl.res2, nullptr, 0);
+    if (trunk_done) { pi += 4 * s.nres; h = pl.res2[s.nres - 1].y; }
+#endif
+    for (int i = 0; i < s.nres && !trunk_done; ++i) {
         IinsGeom g = conv_geom(B, L, L, C, C, 3, 1, 1, IINS_PAD_REFLECT);
         IinsEpilogue e1 = plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, pl.res1[i].y);
         e1.norm = IINS_NORM_IN; e1.xhat = pl.res1[i].xhat; e1.rstd = pl.res1[i].rstd;
@@ -905,7 +903,12 @@ int decoder_forward(const Shapes& s, const float* const* P, const float* rc, con
     }
     const float* h = pl.d0;
     IinsGeom gr = conv_geom(B, s.Lt, s.Lt, s.D, s.D, 3, 1, 1, IINS_PAD_REFLECT);
-    for (int i = 0; i < s.nres; ++i) {
+    bool trunk_done = false;
+#ifndef IINS_CPUSIM
+    trunk_done = trunk_forward_fused(c, B, s.D, s.Lt, s.nres, h, P, ix.res0, pl.res1, pl.res2, pl.adain, s.n_adain);
+    if (trunk_done) h = pl.res2[s.nres - 1].y;
+#endif
+    for (int i = 0; i < s.nres && !trunk_done; ++i) {
         int pi = ix.res0 + 4 * i;
         int off = 4 * s.D * i;         // assign_adain_params: [bias1 | weight1 | bias2 | weight2] (models.py:457-464)
         IinsEpilogue e1 = plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, pl.res1[i].y);

@@ -199,7 +199,7 @@ struct IinsPackParams {
     int pieces;          // 3 or 1: the pieces are STACKED along the tile's row (n) dimension
 };
 
-__global__ void __launch_bounds__(256) iins_pack_kernel(const IinsPackParams p) {
+static __global__ void __launch_bounds__(256) iins_pack_kernel(const IinsPackParams p) {
     iins_pdl_enter();
     // one thread per 16-byte destination chunk (n block, k block, chunk, row)
     const long total = (long)p.nblk * p.nkb * 4 * p.NT;
@@ -244,7 +244,7 @@ struct IinsPackAllParams {
     IinsPackJob jobs[IINS_PACK_MAX_JOBS];
 };
 
-__global__ void __launch_bounds__(256) iins_pack_all_kernel(const IinsPackAllParams pp) {
+static __global__ void __launch_bounds__(256) iins_pack_all_kernel(const IinsPackAllParams pp) {
     iins_pdl_enter();
     int j = 0;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < pp.total; e += (long)gridDim.x * blockDim.x) {
@@ -564,7 +564,7 @@ struct IinsTCParams {
 //   bready[s] (tx bytes)   TMA       -> MMA warp : stage s holds the weight tile
 //   done[s]   (tcgen05.commit) MMA   -> everyone : the MMAs reading stage s have completed (stage reusable)
 template <int NT, int PIECES, int AKIND, int EPI, int LL>
-__global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCParams tp) {
+static __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCParams tp) {
     constexpr int BM = 128;
     // A stage: [chunk of 8 k][row][16 B] per piece.  The chunk stride (the descriptor's LBO) is padded by 64 bytes so that
     // the 8-byte stores of a warp (4 rows x 8 quads) spread over all banks: 2 wavefronts for 256 bytes, the minimum.
@@ -751,7 +751,7 @@ struct IinsTCTNParams {
 
 // grid = (row parts, ceil(K/128), ceil(Cout/NT)).  D^T[k][n] accumulated in TMEM (128 lanes = 128 k entries).
 template <int NT, int PIECES>
-__global__ void __launch_bounds__(288, 2) iins_tc_tn_kernel(const IinsTCTNParams tp) {
+static __global__ void __launch_bounds__(288, 2) iins_tc_tn_kernel(const IinsTCTNParams tp) {
     iins_pdl_launch_dependents();
     constexpr int BR = 32;                               // rows per stage (2 MMA k-steps of 16)
     constexpr uint32_t A_PIECE = 16 * BR * 16;           // [k group of 8][row][16 B] = 8192 B

@@ -233,6 +233,81 @@ def synthetic_batch(cfg: PathConfig, batch: int, seed: int):
 
 
 # ------------------------------------------------------------------------ primitives
+# ---------------------------------------------------------------------------------------------------
+# Operand rounding (test infrastructure for the bf16 compute mode, BASELINE configs[2]).
+# With ``operand_rounding("bf16")`` active every Conv1d / Linear of the restatement rounds its two GEMM operands to
+# bfloat16 (round-to-nearest-even) and accumulates in the working precision -- forward (x, W), data gradient (dy, W) and
+# weight gradient (x, dy) -- which is the arithmetic the reference would see with bf16 tensor-core operands and fp32
+# accumulation / statistics.  Its distance from the fp64 evaluation is the yardstick the bf16 parity test uses
+# (tests/test_gpu_parity.py::test_bf16_mode_full_gradient_parity): the CUDA path must not be further from exact
+# arithmetic than a small multiple of what ANY bf16-operand evaluation of the reference is.
+_OPERAND_ROUNDING = None
+
+
+class operand_rounding:
+    def __init__(self, kind):
+        assert kind in (None, "bf16")
+        self.kind = kind
+
+    def __enter__(self):
+        global _OPERAND_ROUNDING
+        self.prev, _OPERAND_ROUNDING = _OPERAND_ROUNDING, self.kind
+        return self
+
+    def __exit__(self, *exc):
+        global _OPERAND_ROUNDING
+        _OPERAND_ROUNDING = self.prev
+
+
+def _rnd(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+class _RoundedConv1d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, stride, padding):
+        xr, wr = _rnd(x), _rnd(w)
+        ctx.save_for_backward(xr, wr)
+        ctx.conf = (stride, padding, b is not None)
+        return F.conv1d(xr, wr, b, stride=stride, padding=padding)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xr, wr = ctx.saved_tensors
+        stride, padding, has_bias = ctx.conf
+        gr = _rnd(gy)
+        gx = torch.nn.grad.conv1d_input(xr.shape, wr, gr, stride=stride, padding=padding)
+        gw = torch.nn.grad.conv1d_weight(xr, wr.shape, gr, stride=stride, padding=padding)
+        return gx, gw, (gy.sum((0, 2)) if has_bias else None), None, None
+
+
+class _RoundedLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xr, wr = _rnd(x), _rnd(w)
+        ctx.save_for_backward(xr, wr)
+        ctx.has_bias = b is not None
+        return F.linear(xr, wr, b)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xr, wr = ctx.saved_tensors
+        gr = _rnd(gy)
+        return gr @ wr, gr.t() @ xr, (gy.sum(0) if ctx.has_bias else None)
+
+
+def _conv1d(x, w, b=None, stride=1, padding=0):
+    if _OPERAND_ROUNDING is None:
+        return F.conv1d(x, w, b, stride=stride, padding=padding)
+    return _RoundedConv1d.apply(x, w, b, stride, padding)
+
+
+def _linear(x, w, b=None):
+    if _OPERAND_ROUNDING is None:
+        return F.linear(x, w, b)
+    return _RoundedLinear.apply(x, w, b)
+
+
 def adaptive_pool_windows(lin: int, lout: int):
     """AdaptiveAvgPool1d window table: start=floor(i*lin/lout), end=ceil((i+1)*lin/lout)
     (torch semantics; used at models.py:146, 264, 279, 436)."""
@@ -309,27 +384,27 @@ def range_encoder(p, x1, cfg: PathConfig, taps=None):
     pre = "range_encoder.model."
     h = adaptive_avg_pool1d(x1, cfg.pooled_len)
     idx = 2
-    h = F.conv1d(reflection_pad1d(h, 3), p[f"{pre}{idx}.weight"], p[f"{pre}{idx}.bias"])
+    h = _conv1d(reflection_pad1d(h, 3), p[f"{pre}{idx}.weight"], p[f"{pre}{idx}.bias"])
     h = torch.relu(instance_norm1d(h))
     if taps is not None:
         taps["r0"] = h
     idx += 3
     for i in range(cfg.n_downsample):
-        h = F.conv1d(h, p[f"{pre}{idx}.weight"], p[f"{pre}{idx}.bias"], stride=2, padding=1)
+        h = _conv1d(h, p[f"{pre}{idx}.weight"], p[f"{pre}{idx}.bias"], stride=2, padding=1)
         h = torch.relu(instance_norm1d(h))
         if taps is not None:
             taps[f"r{i + 1}"] = h
         idx += 3
     for i in range(cfg.n_residual):                                  # models.py:988-1005
         q = f"{pre}{idx}.block."
-        t = F.conv1d(reflection_pad1d(h, 1), p[q + "1.weight"], p[q + "1.bias"])
+        t = _conv1d(reflection_pad1d(h, 1), p[q + "1.weight"], p[q + "1.bias"])
         t = torch.relu(instance_norm1d(t))
-        t = F.conv1d(reflection_pad1d(t, 1), p[q + "5.weight"], p[q + "5.bias"])
+        t = _conv1d(reflection_pad1d(t, 1), p[q + "5.weight"], p[q + "5.bias"])
         h = h + instance_norm1d(t)
         if taps is not None:
             taps[f"rres{i}"] = h
         idx += 1
-    h = torch.relu(F.conv1d(h, p[f"{pre}{idx}.weight"], p[f"{pre}{idx}.bias"]))
+    h = torch.relu(_conv1d(h, p[f"{pre}{idx}.weight"], p[f"{pre}{idx}.bias"]))
     return h
 
 
@@ -338,19 +413,19 @@ def env_encoder(p, x1, cfg: PathConfig, noise=None, taps=None):
     pre = "env_encoder.model."
     h = adaptive_avg_pool1d(x1, cfg.pooled_len)
     idx = 2
-    h = torch.relu(F.conv1d(reflection_pad1d(h, 3), p[f"{pre}{idx}.weight"], p[f"{pre}{idx}.bias"]))
+    h = torch.relu(_conv1d(reflection_pad1d(h, 3), p[f"{pre}{idx}.weight"], p[f"{pre}{idx}.bias"]))
     if taps is not None:
         taps["e0"] = h
     idx += 2
     n_conv = 2 + max(0, cfg.n_downsample - 2 - 2)
     for i in range(n_conv):
-        h = torch.relu(F.conv1d(h, p[f"{pre}{idx}.weight"], p[f"{pre}{idx}.bias"], stride=2, padding=1))
+        h = torch.relu(_conv1d(h, p[f"{pre}{idx}.weight"], p[f"{pre}{idx}.bias"], stride=2, padding=1))
         if taps is not None:
             taps[f"e{i + 1}"] = h
         idx += 2
     h = h.mean(dim=-1, keepdim=True)                                  # AdaptiveAvgPool1d(1)
     idx += 1
-    cat = F.conv1d(h, p[f"{pre}{idx}.weight"], p[f"{pre}{idx}.bias"])
+    cat = _conv1d(h, p[f"{pre}{idx}.weight"], p[f"{pre}{idx}.bias"])
     half = cat.shape[1] // 2
     mu, log_sigma = cat[:, :half], cat[:, half:]
     if noise is None:
@@ -373,13 +448,13 @@ def decoder(p, range_code, env_code, cfg: PathConfig, taps=None):
     b = range_code.shape[0]
     D = cfg.trunk_dim
     s = env_code.reshape(b, -1)                                       # MLP.forward :961
-    s = torch.relu(F.linear(s, p["decoder.mlp.model.0.weight"], p["decoder.mlp.model.0.bias"]))
-    s = torch.relu(F.linear(s, p["decoder.mlp.model.2.weight"], p["decoder.mlp.model.2.bias"]))
-    adain = F.linear(s, p["decoder.mlp.model.4.weight"], p["decoder.mlp.model.4.bias"])
+    s = torch.relu(_linear(s, p["decoder.mlp.model.0.weight"], p["decoder.mlp.model.0.bias"]))
+    s = torch.relu(_linear(s, p["decoder.mlp.model.2.weight"], p["decoder.mlp.model.2.bias"]))
+    adain = _linear(s, p["decoder.mlp.model.4.weight"], p["decoder.mlp.model.4.bias"])
     if taps is not None:
         taps["adain"] = adain
     pre = "decoder.model."
-    h = torch.relu(F.conv1d(range_code, p[pre + "0.weight"], p[pre + "0.bias"]))
+    h = torch.relu(_conv1d(range_code, p[pre + "0.weight"], p[pre + "0.bias"]))
     idx = 2
     off = 0
     for i in range(cfg.n_residual):
@@ -388,20 +463,20 @@ def decoder(p, range_code, env_code, cfg: PathConfig, taps=None):
         b1, w1 = adain[:, off:off + D], adain[:, off + D:off + 2 * D]
         b2, w2 = adain[:, off + 2 * D:off + 3 * D], adain[:, off + 3 * D:off + 4 * D]
         off += 4 * D
-        t = F.conv1d(reflection_pad1d(h, 1), p[q + "1.weight"], p[q + "1.bias"])
+        t = _conv1d(reflection_pad1d(h, 1), p[q + "1.weight"], p[q + "1.bias"])
         t = torch.relu(adaptive_instance_norm1d(t, w1, b1))
-        t = F.conv1d(reflection_pad1d(t, 1), p[q + "5.weight"], p[q + "5.bias"])
+        t = _conv1d(reflection_pad1d(t, 1), p[q + "5.weight"], p[q + "5.bias"])
         h = h + adaptive_instance_norm1d(t, w2, b2)
         if taps is not None:
             taps[f"dres{i}"] = h
         idx += 1
     for i in range(cfg.n_downsample):
-        h = F.conv1d(upsample_nearest2(h), p[f"{pre}{idx + 1}.weight"], p[f"{pre}{idx + 1}.bias"], padding=2)
+        h = _conv1d(upsample_nearest2(h), p[f"{pre}{idx + 1}.weight"], p[f"{pre}{idx + 1}.bias"], padding=2)
         h = torch.relu(custom_layer_norm(h, p[f"{pre}{idx + 2}.gamma"], p[f"{pre}{idx + 2}.beta"]))
         if taps is not None:
             taps[f"u{i + 1}"] = h
         idx += 4
-    h = torch.tanh(F.conv1d(reflection_pad1d(h, 3), p[f"{pre}{idx + 1}.weight"], p[f"{pre}{idx + 1}.bias"]))
+    h = torch.tanh(_conv1d(reflection_pad1d(h, 3), p[f"{pre}{idx + 1}.weight"], p[f"{pre}{idx + 1}.bias"]))
     h = adaptive_avg_pool1d(h, cfg.cir_len)
     return h.squeeze()                                                # models.py:90
 
@@ -410,15 +485,15 @@ def restorer(p, range_code):
     """RestorerLinear.forward, soft=False branch (models.py:642-658)."""
     h = range_code.reshape(range_code.size(0), -1)
     for i in (0, 2, 4):
-        h = F.leaky_relu(F.linear(h, p[f"restorer.layers.{i}.weight"], p[f"restorer.layers.{i}.bias"]), 0.2)
-    return F.linear(h, p["restorer.linear_layer1.weight"], p["restorer.linear_layer1.bias"])
+        h = F.leaky_relu(_linear(h, p[f"restorer.layers.{i}.weight"], p[f"restorer.layers.{i}.bias"]), 0.2)
+    return _linear(h, p["restorer.linear_layer1.weight"], p["restorer.linear_layer1.bias"])
 
 
 def classifier(p, env_code):
     """ClassifierLinear.forward (models.py:858-862); note LeakyReLU(0.2) on the logits (:854)."""
     h = env_code.reshape(env_code.size(0), -1)
     for i, slope in zip((0, 2, 4, 6), (0.01, 0.01, 0.01, 0.2)):
-        h = F.leaky_relu(F.linear(h, p[f"classifier.layers.{i}.weight"], p[f"classifier.layers.{i}.bias"]), slope)
+        h = F.leaky_relu(_linear(h, p[f"classifier.layers.{i}.weight"], p[f"classifier.layers.{i}.bias"]), slope)
     return h
 
 
