@@ -23,6 +23,11 @@ struct IinsNormBwdParams {
     float* dadain;             // AdaIN grads  (B, ld), written (each entry owned by one (b,c))
     int adain_ld, adain_off_b, adain_off_w;
     float* dz;                 // out (NLC)
+    // column blocks: the kernel handles C <= 128 channels per launch; a wider InstanceNorm / AdaIN layer (per-channel
+    // statistics are independent) is processed as blocks of 128 channels: the host offsets dy / xhat / dz / rstd and the
+    // AdaIN offsets by the block's first channel and passes the full row stride here
+    int ldc;                   // floats between consecutive rows (positions) of dy / xhat / dz: the layer's full channel count
+    int rstd_ld;               // floats between consecutive samples of rstd (IN / AdaIN)
 };
 
 // One WARP per sample (the per-sample tensors are 2 KB: L*C = 512 on this path): two passes over the sample's
@@ -44,6 +49,10 @@ static __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNor
     const int nstep = (L * C) >> 7;                 // float4 steps of 32 lanes
     const bool relu = p.act == IINS_ACT_RELU;
     const int cg = lane & (CG - 1), c0 = cg * 4;    // CG <= 32 and nstep*32 is a multiple of CG: the lane's channels are fixed
+    // float4 index of this lane's element in step i: contiguous when the rows are dense (ldc == C); otherwise row * ldc/4 + cg
+    const int cgs = 31 - __clz(CG), ld4 = p.ldc >> 2;
+    const bool dense = p.ldc == C;
+    auto idx4 = [&](int i) { const int f = lane + 32 * i; return dense ? f : (f >> cgs) * ld4 + (f & (CG - 1)); };
     int ch[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) ch[j] = C >= 4 ? c0 + j : (j & (C - 1));
@@ -63,12 +72,12 @@ static __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNor
                 shift[j] = __ldg(p.adain + (long)b * p.adain_ld + p.adain_off_b + ch[j]);
             }
         }
-        const float4* dy4 = reinterpret_cast<const float4*>(p.dy + (long)b * L * C);
-        const float4* xh4 = reinterpret_cast<const float4*>(p.xhat + (long)b * L * C);
+        const float4* dy4 = reinterpret_cast<const float4*>(p.dy + (long)b * L * p.ldc);
+        const float4* xh4 = reinterpret_cast<const float4*>(p.xhat + (long)b * L * p.ldc);
         float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};        // grad wrt xhat
         float sr[4] = {0.f, 0.f, 0.f, 0.f}, srx[4] = {0.f, 0.f, 0.f, 0.f};        // grad wrt the affine output
         for (int i = 0; i < nstep; ++i) {
-            const float4 d = __ldg(dy4 + lane + 32 * i), x = __ldg(xh4 + lane + 32 * i);
+            const float4 d = __ldg(dy4 + idx4(i)), x = __ldg(xh4 + idx4(i));
             const float dv[4] = {d.x, d.y, d.z, d.w}, xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -123,7 +132,7 @@ static __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNor
                 }
             }
         }
-        float4* dz4 = reinterpret_cast<float4*>(p.dz + (long)b * L * C);
+        float4* dz4 = reinterpret_cast<float4*>(p.dz + (long)b * L * p.ldc);
         float rs[4];
         float coef = 0.f, mean_g = 0.f;
         if (p.norm == IINS_NORM_LN) {
@@ -135,10 +144,10 @@ static __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNor
             mean_g = tot_g / (float)nel;
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) rs[j] = __ldg(p.rstd + (long)b * C + ch[j]);
+            for (int j = 0; j < 4; ++j) rs[j] = __ldg(p.rstd + (long)b * p.rstd_ld + ch[j]);
         }
         for (int i = 0; i < nstep; ++i) {
-            const float4 d = __ldg(dy4 + lane + 32 * i), x = __ldg(xh4 + lane + 32 * i);
+            const float4 d = __ldg(dy4 + idx4(i)), x = __ldg(xh4 + idx4(i));
             const float dv[4] = {d.x, d.y, d.z, d.w}, xv[4] = {x.x, x.y, x.z, x.w};
             float o[4];
 #pragma unroll
@@ -148,7 +157,7 @@ static __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNor
                 if (p.norm == IINS_NORM_LN) o[j] = rs[j] * (gx - mean_g) - xv[j] * coef;
                 else o[j] = rs[j] * (gx - sg[j] * invL - xv[j] * sgx[j] * invL);
             }
-            dz4[lane + 32 * i] = make_float4(o[0], o[1], o[2], o[3]);
+            dz4[idx4(i)] = make_float4(o[0], o[1], o[2], o[3]);
         }
     }
     if (p.norm == IINS_NORM_LN) {               // uniform for the whole CTA
@@ -163,6 +172,53 @@ static __global__ void __launch_bounds__(256) iins_norm_bwd_kernel(const IinsNor
             for (int w = 0; w < 8; ++w) { a += s_dg[w][threadIdx.x]; bsum += s_db[w][threadIdx.x]; }
             atomicAdd(p.dgamma + threadIdx.x, a);
             atomicAdd(p.dbeta + threadIdx.x, bsum);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------ LayerNorm forward (split path)
+// The reference's custom LayerNorm (models.py:976-985) normalises over ALL (C, L) of a sample.  When the convolution that
+// feeds it is wider than one GEMM column block (C > 64: dim >= 8) the statistics span several CTAs of the GEMM, so the
+// GEMM writes z = conv + bias and this kernel finishes the layer: per-sample mean, UNBIASED std, xhat = (z - mean) / (std + eps),
+// y = relu(xhat * gamma[c] + beta[c]).  One warp per sample, three passes over the (L2-resident) sample; z may alias xhat.
+struct IinsLnFwdParams {
+    int B, L, C;               // C a power of two in [4, 128], L * C a multiple of 128
+    const float* z;            // (B, L, C) pre-norm values
+    const float* gamma; const float* beta;
+    float* y; float* xhat; float* rstd;     // rstd: [B] = 1 / (std + eps)
+    int relu;
+};
+
+static __global__ void __launch_bounds__(256) iins_ln_fwd_kernel(const IinsLnFwdParams p) {
+    iins_pdl_enter();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nel = p.L * p.C, nstep = nel >> 7;
+    const int c0 = (lane & ((p.C >> 2) - 1)) * 4;            // C/4 <= 32 column groups: the lane's 4 channels are fixed
+    float g[4], bt[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { g[j] = __ldg(p.gamma + c0 + j); bt[j] = __ldg(p.beta + c0 + j); }
+    for (int b = blockIdx.x * 8 + warp; b < p.B; b += gridDim.x * 8) {
+        const float4* z4 = reinterpret_cast<const float4*>(p.z + (long)b * nel);
+        float sum = 0.f;
+        for (int i = 0; i < nstep; ++i) { const float4 v = z4[lane + 32 * i]; sum += (v.x + v.y) + (v.z + v.w); }
+        const float mean = iins_warp_sum(sum) / (float)nel;
+        float sq = 0.f;
+        for (int i = 0; i < nstep; ++i) {
+            const float4 v = z4[lane + 32 * i];
+            const float a = v.x - mean, c = v.y - mean, d = v.z - mean, e = v.w - mean;
+            sq = fmaf(a, a, sq); sq = fmaf(c, c, sq); sq = fmaf(d, d, sq); sq = fmaf(e, e, sq);
+        }
+        const float rs = 1.0f / (sqrtf(iins_warp_sum(sq) / (float)(nel - 1)) + IINS_EPS);
+        if (lane == 0) p.rstd[b] = rs;
+        float4* xh4 = reinterpret_cast<float4*>(p.xhat + (long)b * nel);
+        float4* y4 = reinterpret_cast<float4*>(p.y + (long)b * nel);
+        for (int i = 0; i < nstep; ++i) {
+            const float4 v = z4[lane + 32 * i];
+            const float4 xh = make_float4((v.x - mean) * rs, (v.y - mean) * rs, (v.z - mean) * rs, (v.w - mean) * rs);
+            float4 o = make_float4(fmaf(xh.x, g[0], bt[0]), fmaf(xh.y, g[1], bt[1]), fmaf(xh.z, g[2], bt[2]), fmaf(xh.w, g[3], bt[3]));
+            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            xh4[lane + 32 * i] = xh;
+            y4[lane + 32 * i] = o;
         }
     }
 }

@@ -25,13 +25,17 @@ int fail(int code, const char* msg) {
 //   1  tcgen05 tensor cores, plain bf16 operands, fp32 accumulate (looser tolerance, BASELINE configs[2])
 //   2  fp32 SIMT (FFMA) kernels -- the bring-up / cross-check path
 int g_mode = 0;
-#define IINS_WPACK_FLOATS ((size_t)1 << 21)       // 8 MB arena: the packed weight tiles of every layer of one module pass
+// arena for the packed weight tiles of every layer of one module pass: 8 MB up to a 64-channel trunk (dim <= 4), 32 MB for
+// the wider configurations (dim = 16: a 256-channel k3 trunk convolution alone packs to 1.2 MB in fp32-grade mode)
+#define IINS_WPACK_FLOATS_SMALL ((size_t)1 << 21)
+#define IINS_WPACK_FLOATS_LARGE ((size_t)1 << 23)
 
 // A module pass runs its launch plan twice when the tensor-core path is on: phase 1 only COLLECTS the weight
 // packing jobs (no launch), one kernel then packs every layer's weights, phase 2 launches the layers.
 struct Ctx {
     cudaStream_t st;
-    float* wpack = nullptr;     // IINS_WPACK_FLOATS floats of scratch for the tensor-core weight tiles
+    float* wpack = nullptr;     // wpack_floats(shapes) floats of scratch for the tensor-core weight tiles
+    size_t wpack_cap = IINS_WPACK_FLOATS_SMALL * sizeof(float);   // its size in bytes
     int err = 0;
     int phase = 0;              // 0 = pack inline per layer, 1 = collect, 2 = execute with pre-packed tiles
     int njobs = 0, job_i = 0;
@@ -50,7 +54,7 @@ struct Ctx {
 int plan_error(int err, const char* where) {
     const char* what = err == 1 ? "packed weight tiles exceed the scratch arena" :
                        err == 2 ? "positions per sample must be a power of two" :
-                       err == 3 ? "norm backward: channel count must be a power of two <= 128 and L*C a multiple of 128" :
+                       err == 3 ? "norm kernels: channel count must be a power of two (<= 128, or a multiple of 128 for InstanceNorm / AdaIN) and L*C a multiple of 128" :
                        err == 4 ? "tensor-core kernel variant not built for this (tile width, epilogue, rows per sample)" : "launch plan error";
     snprintf(g_err, sizeof(g_err), "%s: %s", where, what);
     return IINS_ERR_BAD_CONFIG;
@@ -129,7 +133,7 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     size_t bytes = (size_t)pk.nblk * pk.nkb * pk.pieces * 4 * nt * 16;
     long chunks = (long)pk.nblk * pk.nkb * 4 * nt;
     if (c.phase == 1) {                                // collect
-        if (c.wpack == nullptr || c.arena + bytes > IINS_WPACK_FLOATS * sizeof(float) || c.njobs >= IINS_PACK_MAX_JOBS) { c.err = 1; return; }
+        if (c.wpack == nullptr || c.arena + bytes > c.wpack_cap || c.njobs >= IINS_PACK_MAX_JOBS) { c.err = 1; return; }
         IinsPackJob& j = c.jobs.jobs[c.njobs++];
         j.w = p.w; j.out = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(c.wpack) + c.arena);
         j.Cin = p.g.Cin; j.Cout = p.g.Cout; j.ks = p.g.ks; j.kind = p.a_kind; j.N = p.N; j.K = p.K; j.NT = nt;
@@ -140,7 +144,7 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     }
     if (c.phase == 2) pk.out = c.jobs.jobs[c.job_i++].out;
     else {
-        if (c.wpack == nullptr || bytes > IINS_WPACK_FLOATS * sizeof(float)) { c.err = 1; return; }
+        if (c.wpack == nullptr || bytes > c.wpack_cap) { c.err = 1; return; }
         IINS_LAUNCH(iins_pack_kernel, grid_for(chunks), 256, 0, c.st, pk);
     }
     IinsTCParams tp;
@@ -505,16 +509,22 @@ void norm_backward(Ctx& c, int B, int L, int C, int norm, int act, const float* 
         return;
     }
     flush_pending(c);
-    IinsNormBwdParams p;
-    memset(&p, 0, sizeof(p));
-    p.B = B; p.L = L; p.C = C; p.norm = norm; p.act = act; p.dy = dy; p.xhat = xhat; p.rstd = rstd;
-    p.gamma = gamma; p.beta = beta; p.dgamma = dgamma; p.dbeta = dbeta;
-    p.adain = adain; p.dadain = dadain; p.adain_ld = ld; p.adain_off_b = off_b; p.adain_off_w = off_w; p.dz = dz;
-    // one warp per sample: C power of two in [1,128], L*C a multiple of 128
-    if (ilog2_exact(C) < 0 || C > 128 || ((L * C) & 127) != 0) { c.err = 3; return; }
-    int nb = (B + 7) / 8;
-    if (nb > 148 * 4) nb = 148 * 4;                 // persistent: the kernel strides over the samples
-    IINS_LAUNCH(iins_norm_bwd_kernel, nb, 256, 0, c.st, p);
+    // one warp per sample and at most 128 channels per launch; a wider InstanceNorm / AdaIN layer (independent per-channel
+    // statistics) runs as column blocks of 128 channels
+    const bool blocked = C > 128 && norm != IINS_NORM_LN && C % 128 == 0;
+    const int Cb = blocked ? 128 : C;
+    if (ilog2_exact(Cb) < 0 || Cb > 128 || ((L * Cb) & 127) != 0) { c.err = 3; return; }
+    for (int cb = 0; cb < C; cb += Cb) {
+        IinsNormBwdParams p;
+        memset(&p, 0, sizeof(p));
+        p.B = B; p.L = L; p.C = Cb; p.norm = norm; p.act = act; p.dy = dy + cb; p.xhat = xhat + cb; p.rstd = rstd + cb;
+        p.gamma = gamma; p.beta = beta; p.dgamma = dgamma; p.dbeta = dbeta;
+        p.adain = adain; p.dadain = dadain; p.adain_ld = ld; p.adain_off_b = off_b + cb; p.adain_off_w = off_w + cb; p.dz = dz + cb;
+        p.ldc = C; p.rstd_ld = C;
+        int nb = (B + 7) / 8;
+        if (nb > 148 * 4) nb = 148 * 4;                 // persistent: the kernel strides over the samples
+        IINS_LAUNCH(iins_norm_bwd_kernel, nb, 256, 0, c.st, p);
+    }
 }
 
 template <class F>
@@ -572,6 +582,39 @@ bool trunk_forward_fused(Ctx& c, int B, int D, int Lt, int nres, const float* x,
     c.job_i += 2 * nres;
     return true;
 }
+
+// Backward of the same trunk: the data-gradient chain (+ the norm backward between the convolutions) as ONE kernel; the
+// collect phase has recorded the 2 * n_residual data-gradient pack jobs in DESCENDING convolution order.  dz[k] receives
+// the gradient w.r.t. convolution k's pre-norm output (the weight gradients, launched by the caller, read it).
+bool trunk_backward_fused(Ctx& c, int B, int D, int Lt, int nres, const float* dh, float* dx, float* dh_scratch, float* const* dz,
+                          const EncLayerRef* res1, const EncLayerRef* res2, const float* adain, float* dadain, int adain_ld,
+                          const EncLayerRef* pre, float* pre_dz) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("IINS_FUSED_TRUNK_BWD"); on = e ? atoi(e) : 1; }
+    if (!on || c.phase != 2 || g_mode == 2 || D != 64 || Lt != 8 || nres < 1 || 2 * nres > IINS_TRUNK_MAX_CONVS) return false;
+    flush_pending(c);              // `dh` may be the output of a held-back data gradient (which consumes ITS pack job first)
+    if (c.job_i + 2 * nres > c.njobs) return false;
+    const int pieces = g_mode == 1 ? 1 : 3, nconv = 2 * nres;
+    const size_t conv_bytes = (size_t)64 * 192 * pieces * 2;
+    IinsTrunkBwdParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.B = B; tp.nconv = nconv; tp.pieces = pieces; tp.dh = dh; tp.dx = dx; tp.dh_scratch = dh_scratch;
+    tp.adain = adain; tp.dadain = dadain; tp.adain_ld = adain_ld;
+    tp.wpack = c.jobs.jobs[c.job_i].out;
+    for (int k = 0; k < nconv; ++k) {
+        const IinsPackJob& j = c.jobs.jobs[c.job_i + k];          // job k packs convolution nconv - 1 - k
+        if (j.kind != 1 || j.NT != 64 || j.N != 64 || j.K != 192 ||
+            reinterpret_cast<const unsigned char*>(j.out) != reinterpret_cast<const unsigned char*>(tp.wpack) + k * conv_bytes) return false;
+        const EncLayerRef& l = (k & 1) ? res2[k >> 1] : res1[k >> 1];
+        tp.layer[k].xhat = l.xhat; tp.layer[k].rstd = l.rstd; tp.layer[k].dz = dz[k];
+        tp.layer[k].adain_off_b = 4 * D * (k >> 1) + ((k & 1) ? 2 * D : 0);
+        tp.layer[k].adain_off_w = tp.layer[k].adain_off_b + D;
+    }
+    if (pre != nullptr) { tp.pre.xhat = pre->xhat; tp.pre.rstd = pre->rstd; tp.pre.dz = pre_dz; tp.pre_relu = 1; }
+    if (!iins_trunk_backward_launch(c.st, tp)) return false;
+    c.job_i += nconv;
+    return true;
+}
 #endif
 
 // ------------------------------------------------------------------------------ shape helpers
@@ -592,10 +635,10 @@ int make_shapes(const iins_config* cfg, Shapes& s) {
     if (s.B < 1) return fail(IINS_ERR_BAD_CONFIG, "batch must be >= 1");
     if (s.Lc < 8 || s.Lc > 4096) return fail(IINS_ERR_BAD_CONFIG, "cir_len out of range");
     if (s.ndown < 4 || s.ndown > 4) return fail(IINS_ERR_BAD_CONFIG, "n_downsample must be 4 (code length 8)");
-    if (s.d < 1 || s.d * (1 << s.ndown) > 64)
-        return fail(IINS_ERR_BAD_CONFIG, "dim * 2^n_downsample must be <= 64 in this build (norm epilogue tile)");
+    if (s.d < 1 || s.d * (1 << s.ndown) > 256)
+        return fail(IINS_ERR_BAD_CONFIG, "dim * 2^n_downsample must be <= 256 in this build (dim <= 16)");
     if ((s.d & (s.d - 1)) != 0)
-        return fail(IINS_ERR_BAD_CONFIG, "dim must be a power of two in this build (1, 2 or 4: channel counts are shifts in the gathers and norm kernels)");
+        return fail(IINS_ERR_BAD_CONFIG, "dim must be a power of two in this build (1, 2, 4, 8 or 16: channel counts are shifts in the gathers and norm kernels)");
     if (s.nres < 0 || s.nres > 16) return fail(IINS_ERR_BAD_CONFIG, "n_residual out of range");
     if (s.E < 2 || (s.E & 1)) return fail(IINS_ERR_BAD_CONFIG, "env_dim must be even");
     if (s.R < 1 || s.R > 64) return fail(IINS_ERR_BAD_CONFIG, "range_dim out of range");
@@ -607,6 +650,8 @@ int make_shapes(const iins_config* cfg, Shapes& s) {
     s.n_adain = 4 * s.nres * s.D;
     return IINS_OK;
 }
+
+size_t wpack_floats(const Shapes& s) { return s.D <= 64 ? IINS_WPACK_FLOATS_SMALL : IINS_WPACK_FLOATS_LARGE; }
 
 // bump allocator over a float workspace (same walk in forward and backward)
 struct Bump {
@@ -651,6 +696,7 @@ int encoder_forward(const Shapes& s, const float* const* P, const float* x, cons
     Ctx c{st};
     EncPlan pl;
     c.wpack = ws + plan_encoder(s, ws, pl);
+    c.wpack_cap = wpack_floats(s) * sizeof(float);
     const int B = s.B;
     run_phases(c, [&]() {
     IINS_SKIP_IN_COLLECT(c) IINS_LAUNCH(iins_pool_fwd_kernel, grid_for((long)B * s.P), 256, 0, st, x, pl.xp, B, s.Lc, s.P);
@@ -732,7 +778,7 @@ size_t encoder_scratch(const Shapes& s) {
     size_t act = (size_t)128 * 4 * s.d;                 // largest activation per sample (env stem: 128 x 4d)
     if ((size_t)s.Lt * s.D > act) act = (size_t)s.Lt * s.D;
     size_t n_fresh = 4 + 2 + 4 * (size_t)s.nres + 2 * (size_t)s.ndown + 2;      // one buffer per gradient tensor
-    return n_fresh * (B * act + 4) + B * (16 * (size_t)s.d + 4) + B * ((size_t)s.E + 4) + IINS_WPACK_FLOATS;
+    return n_fresh * (B * act + 4) + B * (16 * (size_t)s.d + 4) + B * ((size_t)s.E + 4) + wpack_floats(s);
 }
 
 int encoder_backward(const Shapes& s, const float* const* P, const float* noise, uint64_t seed, uint64_t offset,
@@ -747,7 +793,8 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
     Bump b{scratch, 0};
     float* dpooled = b.take((size_t)B * 16 * s.d);
     float* dcat = b.take((size_t)B * s.E);
-    c.wpack = b.take(IINS_WPACK_FLOATS);
+    c.wpack = b.take(wpack_floats(s));
+    c.wpack_cap = wpack_floats(s) * sizeof(float);
     const size_t fresh_base = b.off;
     const int n_range = 2 * (1 + s.ndown + 2 * s.nres + 1);
 
@@ -805,7 +852,30 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
         float* tmp = nullptr;
         conv_dgrad(c, go, dzo, P[pi], dh, nullptr);
         IinsGeom gr = conv_geom(B, L, L, C, C, 3, 1, 1, IINS_PAD_REFLECT);
-        for (int i = s.nres - 1; i >= 0; --i) {
+        bool trunk_done = false, pre_done = false;
+#ifndef IINS_CPUSIM
+        if (c.phase == 2 && s.nres >= 1 && s.nres <= 16 && s.ndown >= 1) {
+            const size_t fb_save = fb.off;
+            float* dzs[IINS_TRUNK_MAX_CONVS];
+            for (int k = 0; k < 2 * s.nres; ++k) dzs[k] = fresh();
+            float* scr = fresh();
+            float* pre_dz = fresh();
+            trunk_done = trunk_backward_fused(c, B, C, L, s.nres, dh, nullptr, scr, dzs, pl.res1, pl.res2, nullptr, nullptr, 0,
+                                              &pl.down[s.ndown - 1], pre_dz);
+            if (trunk_done) {
+                for (int k = 2 * s.nres - 1; k >= 0; --k) {           // weight gradients (side stream): input of conv k, dz of conv k
+                    const float* a_in = (k & 1) ? pl.res1[k >> 1].y : (k >= 2 ? pl.res2[(k >> 1) - 1].y : pl.down[s.ndown - 1].y);
+                    conv_wgrad(c, gr, a_in, plain_dz(dzs[k]), G[pi - 4 * s.nres + 2 * k], G[pi - 4 * s.nres + 2 * k + 1]);
+                }
+                pi -= 4 * s.nres;
+                dzb = pre_dz;
+                pre_done = true;
+            } else {
+                fb.off = fb_save;                                      // hand the buffers back
+            }
+        }
+#endif
+        for (int i = s.nres - 1; i >= 0 && !trunk_done; --i) {
             pi -= 4;
             const float* h_in = i > 0 ? pl.res2[i - 1].y : pl.down[s.ndown - 1].y;
             // second conv of the block: out = h_in + IN(conv2(t))
@@ -828,9 +898,11 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
             pi -= 2;
             const float* h_in = i > 0 ? pl.down[i - 1].y : pl.stem.y;
             IinsGeom g = conv_geom(B, 2 * L, L, C / 2, C, 4, 2, 1, IINS_PAD_ZERO);
-            dzb = fresh();
-            norm_backward(c, B, L, C, IINS_NORM_IN, IINS_ACT_RELU, dh, pl.down[i].xhat, pl.down[i].rstd,
-                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, dzb);
+            if (!(pre_done && i == s.ndown - 1)) {
+                dzb = fresh();
+                norm_backward(c, B, L, C, IINS_NORM_IN, IINS_ACT_RELU, dh, pl.down[i].xhat, pl.down[i].rstd,
+                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, dzb);
+            }
             conv_wgrad(c, g, h_in, plain_dz(dzb), G[pi], G[pi + 1]);
             tmp = fresh();
             conv_dgrad(c, g, plain_dz(dzb), P[pi], tmp, nullptr);
@@ -888,6 +960,7 @@ int decoder_forward(const Shapes& s, const float* const* P, const float* rc, con
     Ctx c{st};
     DecPlan pl;
     c.wpack = ws + plan_decoder(s, ws, pl);
+    c.wpack_cap = wpack_floats(s) * sizeof(float);
     DecIdx ix = dec_idx(s);
     const int B = s.B;
     run_phases(c, [&]() {
@@ -925,9 +998,26 @@ int decoder_forward(const Shapes& s, const float* const* P, const float* rc, con
     for (int i = 0; i < s.ndown; ++i) {
         int pi = ix.up0 + 4 * i;
         IinsGeom g = conv_geom(B, L, 2 * L, C, C / 2, 5, 1, 2, IINS_PAD_UP2);
-        IinsEpilogue ep = plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, pl.up[i].y);
-        ep.norm = IINS_NORM_LN; ep.xhat = pl.up[i].xhat; ep.rstd = pl.up[i].rstd; ep.gamma = P[pi + 2]; ep.beta = P[pi + 3];
-        conv_forward(c, g, h, P[pi], ep);
+        if (C / 2 > 64) {
+            // wider than one GEMM column block: the LayerNorm statistics span several CTAs -> conv + bias, then the LN kernel
+            conv_forward(c, g, h, P[pi], plain_epilogue(P[pi + 1], IINS_ACT_NONE, 0.f, pl.up[i].xhat));
+            IINS_SKIP_IN_COLLECT(c) {
+                IinsLnFwdParams lp;
+                memset(&lp, 0, sizeof(lp));
+                lp.B = B; lp.L = 2 * L; lp.C = C / 2; lp.z = pl.up[i].xhat; lp.gamma = P[pi + 2]; lp.beta = P[pi + 3];
+                lp.y = pl.up[i].y; lp.xhat = pl.up[i].xhat; lp.rstd = pl.up[i].rstd; lp.relu = 1;
+                if (ilog2_exact(lp.C) < 2 || lp.C > 128 || ((lp.L * lp.C) & 127) != 0) c.err = 3;
+                else {
+                    int nb = (B + 7) / 8;
+                    if (nb > 148 * 4) nb = 148 * 4;
+                    IINS_LAUNCH(iins_ln_fwd_kernel, nb, 256, 0, c.st, lp);
+                }
+            }
+        } else {
+            IinsEpilogue ep = plain_epilogue(P[pi + 1], IINS_ACT_RELU, 0.f, pl.up[i].y);
+            ep.norm = IINS_NORM_LN; ep.xhat = pl.up[i].xhat; ep.rstd = pl.up[i].rstd; ep.gamma = P[pi + 2]; ep.beta = P[pi + 3];
+            conv_forward(c, g, h, P[pi], ep);
+        }
         h = pl.up[i].y; L *= 2; C /= 2;
     }
     {
@@ -944,7 +1034,7 @@ size_t decoder_scratch(const Shapes& s) {
     size_t B = s.B;
     size_t act = (size_t)s.Lt * s.D;
     size_t n_fresh = 2 + 2 * (size_t)s.ndown + 4 * (size_t)s.nres + 2;
-    return n_fresh * (B * act + 4) + B * ((size_t)s.n_adain + 4) + 2 * (B * 256 + 4) + B * ((size_t)s.P + 4) + IINS_WPACK_FLOATS;
+    return n_fresh * (B * act + 4) + B * ((size_t)s.n_adain + 4) + 2 * (B * 256 + 4) + B * ((size_t)s.P + 4) + wpack_floats(s);
 }
 
 int decoder_backward(const Shapes& s, const float* const* P, const float* rc, const float* cat, const float* ws,
@@ -961,7 +1051,8 @@ int decoder_backward(const Shapes& s, const float* const* P, const float* rc, co
     float* dm2 = b.take((size_t)B * 256);
     float* dm1 = b.take((size_t)B * 256);
     float* dyt = b.take((size_t)B * s.P);
-    c.wpack = b.take(IINS_WPACK_FLOATS);
+    c.wpack = b.take(wpack_floats(s));
+    c.wpack_cap = wpack_floats(s) * sizeof(float);
     const size_t fresh_base = b.off;
 
     run_phases(c, [&]() {
@@ -994,7 +1085,28 @@ int decoder_backward(const Shapes& s, const float* const* P, const float* rc, co
         L /= 2; C *= 2;
     }
     IinsGeom gr = conv_geom(B, s.Lt, s.Lt, s.D, s.D, 3, 1, 1, IINS_PAD_REFLECT);
-    for (int i = s.nres - 1; i >= 0; --i) {
+    bool trunk_done = false;
+#ifndef IINS_CPUSIM
+    if (c.phase == 2 && s.nres >= 1 && s.nres <= 16) {
+        const size_t fb_save = fb.off;
+        float* dzs[IINS_TRUNK_MAX_CONVS];
+        for (int k = 0; k < 2 * s.nres; ++k) dzs[k] = fresh();
+        float* scr = fresh();
+        float* dx = fresh();
+        trunk_done = trunk_backward_fused(c, B, s.D, s.Lt, s.nres, dh, dx, scr, dzs, pl.res1, pl.res2, pl.adain, dadain, s.n_adain,
+                                          nullptr, nullptr);
+        if (trunk_done) {
+            for (int k = 2 * s.nres - 1; k >= 0; --k) {               // weight gradients (side stream): input of conv k, dz of conv k
+                const float* a_in = (k & 1) ? pl.res1[k >> 1].y : (k >= 2 ? pl.res2[(k >> 1) - 1].y : pl.d0);
+                conv_wgrad(c, gr, a_in, plain_dz(dzs[k]), G[ix.res0 + 2 * k], G[ix.res0 + 2 * k + 1]);
+            }
+            dh = dx;
+        } else {
+            fb.off = fb_save;
+        }
+    }
+#endif
+    for (int i = s.nres - 1; i >= 0 && !trunk_done; --i) {
         int pi = ix.res0 + 4 * i;
         int off = 4 * s.D * i;
         const float* h_in = i > 0 ? pl.res2[i - 1].y : pl.d0;
@@ -1063,13 +1175,14 @@ size_t mlp_ws(const Shapes& s, const MlpSpec& m) {
 size_t mlp_scratch(const Shapes& s, const MlpSpec& m) {
     size_t mx = 0;
     for (int i = 1; i < m.n; ++i) if ((size_t)m.dims[i] > mx) mx = m.dims[i];
-    return 4 * (((size_t)s.B * mx + 3) & ~(size_t)3) + IINS_WPACK_FLOATS;
+    return 4 * (((size_t)s.B * mx + 3) & ~(size_t)3) + wpack_floats(s);
 }
 
 int mlp_forward(const Shapes& s, const MlpSpec& m, const float* const* P, const float* in, float* out, float* ws,
                 float* wpack, cudaStream_t st) {
     Ctx c{st};
     c.wpack = wpack;
+    c.wpack_cap = wpack_floats(s) * sizeof(float);
     run_phases(c, [&]() {
     Bump b{ws, 0};
     const float* h = in;
@@ -1093,9 +1206,10 @@ int mlp_backward(const Shapes& s, const MlpSpec& m, const float* const* P, const
     acts[0] = in;
     for (int i = 1; i < m.n; ++i) acts[i] = b.take((size_t)s.B * m.dims[i]);
     acts[m.n] = out_saved;
-    size_t quarter = (mlp_scratch(s, m) - IINS_WPACK_FLOATS) / 4;
+    size_t quarter = (mlp_scratch(s, m) - wpack_floats(s)) / 4;
     float* bufs[4] = {scratch, scratch + quarter, scratch + 2 * quarter, scratch + 3 * quarter};   // one per layer (n <= 4)
     c.wpack = scratch + 4 * quarter;
+    c.wpack_cap = wpack_floats(s) * sizeof(float);
     run_phases(c, [&]() {
     begin_async_wgrad(c);
     const float* dy = d_out;
@@ -1146,7 +1260,7 @@ int iins_validate_config(const iins_config* cfg) { Shapes s; return make_shapes(
 int iins_encoder_num_params(const iins_config* cfg) { IINS_SHAPES_OR_RETURN(cfg, s); return enc_num_params(s); }
 size_t iins_encoder_ws_floats(const iins_config* cfg) {
     Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0;
-    EncPlan pl; return plan_encoder(s, nullptr, pl) + IINS_WPACK_FLOATS;
+    EncPlan pl; return plan_encoder(s, nullptr, pl) + wpack_floats(s);
 }
 size_t iins_encoder_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return encoder_scratch(s); }
 
@@ -1171,7 +1285,7 @@ int iins_encoder_backward(const iins_config* cfg, const float* const* params, co
 int iins_decoder_num_params(const iins_config* cfg) { IINS_SHAPES_OR_RETURN(cfg, s); return dec_num_params(s); }
 size_t iins_decoder_ws_floats(const iins_config* cfg) {
     Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0;
-    DecPlan pl; return plan_decoder(s, nullptr, pl) + IINS_WPACK_FLOATS;
+    DecPlan pl; return plan_decoder(s, nullptr, pl) + wpack_floats(s);
 }
 size_t iins_decoder_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return decoder_scratch(s); }
 
@@ -1193,7 +1307,7 @@ int iins_decoder_backward(const iins_config* cfg, const float* const* params, co
 }
 
 int iins_restorer_num_params(const iins_config* cfg) { IINS_SHAPES_OR_RETURN(cfg, s); return 10; }
-size_t iins_restorer_ws_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return mlp_ws(s, restorer_spec(s)) + IINS_WPACK_FLOATS; }
+size_t iins_restorer_ws_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return mlp_ws(s, restorer_spec(s)) + wpack_floats(s); }
 size_t iins_restorer_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return mlp_scratch(s, restorer_spec(s)); }
 int iins_restorer_forward(const iins_config* cfg, const float* const* params, const float* range_code, float* err_est,
                           float* ws, iins_stream_t stream) {
@@ -1215,7 +1329,7 @@ int iins_restorer_backward(const iins_config* cfg, const float* const* params, c
 int iins_classifier_num_params(const iins_config* cfg) { IINS_SHAPES_OR_RETURN(cfg, s); return 8; }
 size_t iins_classifier_ws_floats(const iins_config* cfg) {
     Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0;
-    return mlp_ws(s, classifier_spec(s)) + (((size_t)s.B * s.NC + 3) & ~(size_t)3) + IINS_WPACK_FLOATS;
+    return mlp_ws(s, classifier_spec(s)) + (((size_t)s.B * s.NC + 3) & ~(size_t)3) + wpack_floats(s);
 }
 size_t iins_classifier_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return mlp_scratch(s, classifier_spec(s)); }
 int iins_classifier_forward(const iins_config* cfg, const float* const* params, const float* env_code, float* logits,

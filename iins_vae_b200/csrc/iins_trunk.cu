@@ -23,12 +23,26 @@
 namespace {
 
 constexpr int TR_SAMPLES = 16;                       // samples per tile (128 GEMM rows)
-constexpr int TR_ROWS = TR_SAMPLES * 10;             // operand rows incl. the reflected edge rows
-constexpr uint32_t TR_LBO = TR_ROWS * 16;            // bytes between 8-channel chunks
+constexpr int TR_ROWS = TR_SAMPLES * 10;             // operand rows incl. the edge rows
+constexpr uint32_t TR_LBO = TR_ROWS * 16 + 16;       // bytes between 8-channel chunks (+16: the epilogue's 8-byte stores of the
+                                                     // 8 chunks of a row then fall into different banks)
 constexpr uint32_t TR_SBO = 160;                     // bytes between 8-row groups (= samples)
-constexpr uint32_t TR_APIECE = 8 * TR_LBO;           // one piece of the operand: 20480 B
+constexpr uint32_t TR_APIECE = 8 * TR_LBO;           // one piece of the operand: 20608 B
 constexpr int TR_NSLOT = 8;                          // weight ring slots
 constexpr int TR_KS = 12;                            // k-steps of 16 per convolution: 3 taps x 4
+constexpr int TR_STG_LD = 68;                        // floats per row of the accumulator staging tile (64 + 4: conflict-free)
+constexpr uint32_t TR_STG_BYTES = 128 * TR_STG_LD * 4;
+
+template <int PIECES>
+struct TrunkSmem {
+    static constexpr uint32_t SLICE = PIECES * 64 * 16 * 2;       // one (tap, 16-channel) weight slice: [2 chunks][PIECES*64 rows][16 B]
+    static constexpr uint32_t A_BYTES = PIECES * TR_APIECE;
+    static constexpr uint32_t RING = TR_NSLOT * SLICE;
+    // the fp32 staging tile of the epilogue aliases the operand (dead once the MMAs of a convolution have completed) when
+    // the operand is large enough (3 pieces); the 1-piece operand is smaller than the tile, which then gets its own space
+    static constexpr bool STG_ALIAS = A_BYTES >= TR_STG_BYTES;
+    static constexpr uint32_t TOTAL = A_BYTES + RING + (STG_ALIAS ? 0 : TR_STG_BYTES);
+};
 
 __device__ __forceinline__ void tma_tensor_2d(uint32_t dst_saddr, const CUtensorMap* map, int c0, int c1, uint32_t mbar_saddr) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -38,11 +52,58 @@ __device__ __forceinline__ void tma_tensor_2d(uint32_t dst_saddr, const CUtensor
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }     // the 8 epilogue warps
 
+// ---- epilogue plumbing shared by the forward and the backward kernel -------------------------------------------------
+// The accumulator row of TMEM lane r can only be read by thread (r & 31) of a warp with (warp & 3) == r >> 5, i.e. one
+// thread sees ONE position of a sample -- but InstanceNorm and its backward reduce over the 8 positions.  Instead of
+// 6 shuffles per value, the tile is transposed through shared memory once: every thread stages its row (2 x 16 columns),
+// one named barrier, then thread t owns sample (t >> 4), channels 4 * (t & 15) .. +3 at ALL 8 positions (32 values in
+// registers): the statistics are plain in-thread sums, the per-(sample, channel) operands (bias, AdaIN weight / bias, rstd)
+// are loaded once instead of once per position, and every global access is a 16-byte piece of a 256-byte contiguous row.
+template <int PIECES>
+__device__ __forceinline__ void stage_accumulator(uint32_t tmem, int warp, int lane, float* stg) {
+    const int q = warp & 3, hf = warp >> 2;
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    float* dst = stg + (q * 32 + lane) * TR_STG_LD + hf * 32;
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 16) {
+        float v[16];
+        iins_tmem_chunk16<64, PIECES>(tl, hf * 32 + c0, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(dst + c0 + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    }
+}
+__device__ __forceinline__ void load_columns(const float* stg, int s, int cg, float4* x) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) x[l] = *reinterpret_cast<const float4*>(stg + (s * 8 + l) * TR_STG_LD + 4 * cg);
+}
+// 4 channels x 8 positions -> bf16 pieces in the operand tile: rows 1..8 of the sample; the two edge rows are the reflected
+// copies (forward: ReflectionPad1d(1), padded row 0 = x(1), padded row 9 = x(6)) or zeros (backward).  All ten rows are
+// written every time: the staging tile of the epilogue may alias them.
+template <int PIECES, bool REFLECT>
+__device__ __forceinline__ void write_operand_columns(unsigned char* sA, int s, int cg, const float4* x) {
+    unsigned char* base = sA + (cg >> 1) * TR_LBO + (s * 10) * 16 + (cg & 1) * 8;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) iins_store4_split(x[l], base + (l + 1) * 16, TR_APIECE, PIECES);
+    if (REFLECT) {
+        iins_store4_split(x[1], base, TR_APIECE, PIECES);
+        iins_store4_split(x[6], base + 9 * 16, TR_APIECE, PIECES);
+    } else {
+#pragma unroll
+        for (int pc = 0; pc < PIECES; ++pc) {
+            *reinterpret_cast<uint2*>(base + pc * TR_APIECE) = make_uint2(0u, 0u);
+            *reinterpret_cast<uint2*>(base + pc * TR_APIECE + 9 * 16) = make_uint2(0u, 0u);
+        }
+    }
+}
+#define IINS_F4_OP(dst, a, op, b) do { (dst).x = (a).x op (b).x; (dst).y = (a).y op (b).y; (dst).z = (a).z op (b).z; (dst).w = (a).w op (b).w; } while (0)
+
+// ======================================================================================================= forward
 template <int PIECES, bool ADAIN, bool TMAP>
 __global__ void __launch_bounds__(320, 2) iins_trunk_fwd_kernel(const IinsTrunkFwdParams p, const __grid_constant__ CUtensorMap wmap) {
-    constexpr uint32_t SLICE = PIECES * 64 * 16 * 2;             // one (tap, 16-channel) weight slice: [2 chunks][PIECES*64 rows][16 B]
-    constexpr uint32_t A_BYTES = PIECES * TR_APIECE;
+    using SM = TrunkSmem<PIECES>;
+    constexpr uint32_t SLICE = SM::SLICE;
     constexpr int TCOLS = IinsTmemCols<64, PIECES>::value;
     extern __shared__ __align__(1024) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long w_full[TR_NSLOT];
@@ -51,7 +112,8 @@ __global__ void __launch_bounds__(320, 2) iins_trunk_fwd_kernel(const IinsTrunkF
     __shared__ __align__(8) unsigned long long a_ready;
     __shared__ uint32_t tmem_slot;
     unsigned char* sA = dsm;
-    unsigned char* sW = dsm + A_BYTES;
+    unsigned char* sW = dsm + SM::A_BYTES;
+    float* stg = reinterpret_cast<float*>(SM::STG_ALIAS ? dsm : dsm + SM::A_BYTES + SM::RING);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = (p.B + TR_SAMPLES - 1) / TR_SAMPLES;
 
@@ -116,110 +178,84 @@ __global__ void __launch_bounds__(320, 2) iins_trunk_fwd_kernel(const IinsTrunkF
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue warps: thread = one GEMM row, 32 channels
-        const int q = warp & 3, hf = warp >> 2;
-        const int row = q * 32 + lane;
-        const int s = row >> 3, l = row & 7;
-        const int cbeg = hf * 32;
-        const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
-        unsigned char* a_row = sA + (s * 10 + l + 1) * 16;                  // this row inside a chunk (piece 0)
-        // the reflected copies of ReflectionPad1d(1): position 1 also fills row 0, position 6 also fills row 9
-        const int extra = l == 1 ? -2 * 16 : (l == 6 ? 2 * 16 : 0);
-        auto write_operand = [&](const float* v, int c0) {                  // 16 channels starting at cbeg + c0
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                unsigned char* dst = a_row + ((cbeg + c0) / 8 + h) * TR_LBO;
-                iins_store8_split(v + 8 * h, dst, TR_APIECE, PIECES);
-                if (extra != 0) iins_store8_split(v + 8 * h, dst + extra, TR_APIECE, PIECES);
-            }
-        };
+        // ------------------------------------------------------------------ epilogue warps
+        const int s = tid >> 4, cg = tid & 15;                              // after the transpose: sample, 4-channel group
         uint32_t j = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int gb = tile * TR_SAMPLES + s;
-            const bool row_ok = gb < p.B;
-            const long orow = ((long)(row_ok ? gb : 0) * 8 + l) * 64 + cbeg;
+            const bool ok = gb < p.B;
+            const long sb = ok ? gb : 0;
+            const long o0 = sb * 512 + 4 * cg;                              // element (sample, position 0, channel 4 cg) of a (B, 8, 64) tensor
+            float4 x[8];
             // ---- stage 0: the trunk input (fp32, channels-last) -> bf16 pieces in A
 #pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 16) {
-                float v[16];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float4 t = row_ok ? __ldg(reinterpret_cast<const float4*>(p.x + orow + c0) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
-                }
-                write_operand(v, c0);
-            }
+            for (int l = 0; l < 8; ++l) x[l] = ok ? __ldg(reinterpret_cast<const float4*>(p.x + o0 + l * 64)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            write_operand_columns<PIECES, true>(sA, s, cg, x);
             umma::fence_async_smem();
             umma::mbar_arrive(umma::smem_u32(&a_ready));
             for (int c = 0; c < p.nconv; ++c, ++j) {
                 const IinsTrunkLayer& ly = p.layer[c];
                 const bool second = (c & 1) != 0;                           // second convolution of a block: no ReLU, + skip
-                const float* skip = !second ? nullptr : (c == 1 ? p.x : p.layer[c - 2].y);
                 umma::mbar_wait(umma::smem_u32(&acc_full), j & 1);
                 umma::tc_fence_after();
-#pragma unroll 1
-                for (int c0 = 0; c0 < 32; c0 += 16) {
-                    const int gn = cbeg + c0;
-                    float4 a4[4];
+                stage_accumulator<PIECES>(tmem, warp, lane, stg);
+                umma::tc_fence_before();
+                epi_bar();
+                load_columns(stg, s, cg, x);
+                epi_bar();                                                  // staging (aliasing A) may be overwritten from here on
+                // (the bias is a parameter tensor inside the caller's flat buffer: 4-byte aligned only)
+                const float4 b4 = make_float4(__ldg(ly.bias + 4 * cg), __ldg(ly.bias + 4 * cg + 1), __ldg(ly.bias + 4 * cg + 2), __ldg(ly.bias + 4 * cg + 3));
+                // InstanceNorm over the 8 positions: biased variance, eps inside the square root (models.py:152, 1072)
+                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        // plain (coherent) load: for c >= 3 this thread wrote these very values earlier in the kernel
-                        a4[k] = (second && row_ok) ? *(reinterpret_cast<const float4*>(skip + orow + c0) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float v[16];
-                    iins_tmem_chunk16<64, PIECES>(tl, gn, v);
+                for (int l = 0; l < 8; ++l) { IINS_F4_OP(x[l], x[l], +, b4); IINS_F4_OP(sum, sum, +, x[l]); }
+                const float4 mean = make_float4(sum.x * 0.125f, sum.y * 0.125f, sum.z * 0.125f, sum.w * 0.125f);
+                float4 sq = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) v[k] += __ldg(ly.bias + gn + k);
-                    // InstanceNorm statistics over the 8 positions of the sample = the 8 lanes of this lane group;
-                    // biased variance, eps inside the square root (models.py:152, 1072)
-                    float4* xh_dst = row_ok ? reinterpret_cast<float4*>(ly.xhat + orow + c0) : nullptr;
-                    float4* rs_dst = (row_ok && l == 0) ? reinterpret_cast<float4*>(ly.rstd + (long)gb * 64 + gn) : nullptr;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float rs[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float mean = iins_lanes_sum<8>(v[4 * k + e]) * 0.125f;
-                            const float d = v[4 * k + e] - mean;
-                            const float vpe = fmaf(iins_lanes_sum<8>(d * d), 0.125f, IINS_EPS);
-                            float r = rsqrtf(vpe);
-                            r = r * fmaf(-0.5f * vpe, r * r, 1.5f);          // one Newton step: full fp32 accuracy
-                            rs[e] = r;
-                            v[4 * k + e] = d * r;
-                        }
-                        if (rs_dst != nullptr) rs_dst[k] = make_float4(rs[0], rs[1], rs[2], rs[3]);
-                        if (xh_dst != nullptr) xh_dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                    }
-                    if (ADAIN) {
-                        const float* ab = p.adain + (long)(row_ok ? gb : 0) * p.adain_ld + gn;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(ab + ly.adain_off_w) + k);
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ab + ly.adain_off_b) + k);
-                            v[4 * k] = fmaf(v[4 * k], w4.x, b4.x); v[4 * k + 1] = fmaf(v[4 * k + 1], w4.y, b4.y);
-                            v[4 * k + 2] = fmaf(v[4 * k + 2], w4.z, b4.z); v[4 * k + 3] = fmaf(v[4 * k + 3], w4.w, b4.w);
-                        }
-                    }
-                    if (!second) {
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) { v[4 * k] += a4[k].x; v[4 * k + 1] += a4[k].y; v[4 * k + 2] += a4[k].z; v[4 * k + 3] += a4[k].w; }
-                    }
-                    if (row_ok) {
-                        float4* dst = reinterpret_cast<float4*>(ly.y + orow + c0);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                    }
-                    if (c + 1 < p.nconv) write_operand(v, c0);              // the next convolution reads it in place
+                for (int l = 0; l < 8; ++l) {
+                    IINS_F4_OP(x[l], x[l], -, mean);
+                    sq.x = fmaf(x[l].x, x[l].x, sq.x); sq.y = fmaf(x[l].y, x[l].y, sq.y); sq.z = fmaf(x[l].z, x[l].z, sq.z); sq.w = fmaf(x[l].w, x[l].w, sq.w);
                 }
-                if (c + 1 < p.nconv) {
-                    umma::tc_fence_before();                               // TMEM reads done before the next MMAs overwrite it
+                auto rstd_of = [](float ssq) {
+                    const float vpe = fmaf(ssq, 0.125f, IINS_EPS);
+                    const float r = rsqrtf(vpe);
+                    return r * fmaf(-0.5f * vpe, r * r, 1.5f);              // one Newton step: full fp32 accuracy
+                };
+                const float4 rs = make_float4(rstd_of(sq.x), rstd_of(sq.y), rstd_of(sq.z), rstd_of(sq.w));
+                if (ok) *reinterpret_cast<float4*>(ly.rstd + sb * 64 + 4 * cg) = rs;
+#pragma unroll
+                for (int l = 0; l < 8; ++l) {
+                    IINS_F4_OP(x[l], x[l], *, rs);
+                    if (ok) *reinterpret_cast<float4*>(ly.xhat + o0 + l * 64) = x[l];
+                }
+                if (ADAIN) {
+                    const float* ab = p.adain + sb * p.adain_ld + 4 * cg;
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(ab + ly.adain_off_w));
+                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(ab + ly.adain_off_b));
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) {
+                        x[l].x = fmaf(x[l].x, w4.x, a4.x); x[l].y = fmaf(x[l].y, w4.y, a4.y); x[l].z = fmaf(x[l].z, w4.z, a4.z); x[l].w = fmaf(x[l].w, w4.w, a4.w);
+                    }
+                }
+                if (!second) {
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) { x[l].x = fmaxf(x[l].x, 0.f); x[l].y = fmaxf(x[l].y, 0.f); x[l].z = fmaxf(x[l].z, 0.f); x[l].w = fmaxf(x[l].w, 0.f); }
+                } else if (ok) {
+                    // plain (coherent) loads: for c >= 3 this thread wrote these very values earlier in the kernel
+                    const float* skip = (c == 1 ? p.x : p.layer[c - 2].y) + o0;
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) { const float4 h4 = *reinterpret_cast<const float4*>(skip + l * 64); IINS_F4_OP(x[l], x[l], +, h4); }
+                }
+                if (ok) {
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) *reinterpret_cast<float4*>(ly.y + o0 + l * 64) = x[l];
+                }
+                if (c + 1 < p.nconv) {                                      // the next convolution reads it in place
+                    write_operand_columns<PIECES, true>(sA, s, cg, x);
                     umma::fence_async_smem();
                     umma::mbar_arrive(umma::smem_u32(&a_ready));
                 }
             }
-            umma::tc_fence_before();
         }
     }
     umma::tc_fence_before();
@@ -238,8 +274,8 @@ __global__ void __launch_bounds__(320, 2) iins_trunk_fwd_kernel(const IinsTrunkF
 // weights on the window at shift 2) into the same TMEM accumulator; the weight ring streams 20 slices per convolution.
 template <int PIECES, bool ADAIN, bool TMAP>
 __global__ void __launch_bounds__(320, 2) iins_trunk_bwd_kernel(const IinsTrunkBwdParams p, const __grid_constant__ CUtensorMap wmap) {
-    constexpr uint32_t SLICE = PIECES * 64 * 16 * 2;
-    constexpr uint32_t A_BYTES = PIECES * TR_APIECE;
+    using SM = TrunkSmem<PIECES>;
+    constexpr uint32_t SLICE = SM::SLICE;
     constexpr int TCOLS = IinsTmemCols<64, PIECES>::value;
     constexpr int NSL = 20;                                        // slices per convolution through the ring
     extern __shared__ __align__(1024) unsigned char dsm[];
@@ -248,7 +284,8 @@ __global__ void __launch_bounds__(320, 2) iins_trunk_bwd_kernel(const IinsTrunkB
     __shared__ __align__(8) unsigned long long acc_full, main_done, a_ready, z_ready;
     __shared__ uint32_t tmem_slot;
     unsigned char* sA = dsm;
-    unsigned char* sW = dsm + A_BYTES;
+    unsigned char* sW = dsm + SM::A_BYTES;
+    float* stg = reinterpret_cast<float*>(SM::STG_ALIAS ? dsm : dsm + SM::A_BYTES + SM::RING);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = (p.B + TR_SAMPLES - 1) / TR_SAMPLES;
 
@@ -264,11 +301,6 @@ __global__ void __launch_bounds__(320, 2) iins_trunk_bwd_kernel(const IinsTrunkB
         umma::mbar_init(umma::smem_u32(&z_ready), 256);
         umma::fence_mbar_init();
         if (TMAP) prefetch_tensormap(&wmap);
-    }
-    // the zero rows 0 and 9 of every sample are written once (nothing overwrites them afterwards)
-    for (int e = tid; e < (int)(A_BYTES / 16); e += 320) {
-        const int r = (e % TR_ROWS) % 10;
-        if (r == 0 || r == 9) *reinterpret_cast<uint4*>(sA + (size_t)e * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
     if (warp == 8) umma::tmem_alloc(umma::smem_u32(&tmem_slot), TCOLS);
     umma::tc_fence_before();
@@ -329,119 +361,102 @@ __global__ void __launch_bounds__(320, 2) iins_trunk_bwd_kernel(const IinsTrunkB
             }
         }
     } else {
-        const int q = warp & 3, hf = warp >> 2;
-        const int row = q * 32 + lane;
-        const int s = row >> 3, l = row & 7;
-        const int cbeg = hf * 32;
-        const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
-        unsigned char* a_row = sA + (s * 10 + l + 1) * 16;
-        auto write_operand = [&](const float* v, int c0) {
+        const int s = tid >> 4, cg = tid & 15;
+        // InstanceNorm / AdaIN backward of layer `ly` applied to the gradient x (w.r.t. that layer's OUTPUT; 8 positions x 4
+        // channels):  dz = rstd * w * (g - mean_l(g) - xhat * mean_l(g * xhat)),  g = x masked by the layer's ReLU;
+        // AdaIN: d bias = sum_l g, d weight = sum_l g * xhat.  x is replaced by dz, which also goes to HBM (weight gradients).
+        auto norm_backward = [&](const IinsTrunkBwdLayer& ly, bool relu, float4* x, long o0, long sb, bool ok, bool adain) {
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(ly.rstd + sb * 64 + 4 * cg));
+            float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (adain) {
+                w4 = __ldg(reinterpret_cast<const float4*>(p.adain + sb * p.adain_ld + ly.adain_off_w + 4 * cg));
+                b4 = __ldg(reinterpret_cast<const float4*>(p.adain + sb * p.adain_ld + ly.adain_off_b + 4 * cg));
+            }
+            float4 xh[8];
+            float4 sr = make_float4(0.f, 0.f, 0.f, 0.f), srx = sr;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) iins_store8_split(v + 8 * h, a_row + ((cbeg + c0) / 8 + h) * TR_LBO, TR_APIECE, PIECES);
-        };
-        // InstanceNorm / AdaIN backward of layer `ly` applied to the 16 gradient values v (w.r.t. that layer's OUTPUT):
-        //   dz = rstd * w * (g - mean_l(g) - xhat * mean_l(g * xhat)),  g = v masked by the layer's ReLU;  AdaIN: d bias = sum_l g,
-        //   d weight = sum_l g * xhat.  v is replaced by dz; dz goes to HBM (the weight-gradient kernels read it).
-        auto norm_backward16 = [&](const IinsTrunkBwdLayer& ly, bool relu, float* v, long orow, int gn, int c0, long sb, bool row_ok, bool lead) {
+            for (int l = 0; l < 8; ++l) {
+                xh[l] = ok ? __ldg(reinterpret_cast<const float4*>(ly.xhat + o0 + l * 64)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (relu) {
+                    if (!(fmaf(xh[l].x, w4.x, b4.x) > 0.f)) x[l].x = 0.f;
+                    if (!(fmaf(xh[l].y, w4.y, b4.y) > 0.f)) x[l].y = 0.f;
+                    if (!(fmaf(xh[l].z, w4.z, b4.z) > 0.f)) x[l].z = 0.f;
+                    if (!(fmaf(xh[l].w, w4.w, b4.w) > 0.f)) x[l].w = 0.f;
+                }
+                IINS_F4_OP(sr, sr, +, x[l]);
+                srx.x = fmaf(x[l].x, xh[l].x, srx.x); srx.y = fmaf(x[l].y, xh[l].y, srx.y); srx.z = fmaf(x[l].z, xh[l].z, srx.z); srx.w = fmaf(x[l].w, xh[l].w, srx.w);
+            }
+            if (adain && ok) {
+                *reinterpret_cast<float4*>(p.dadain + sb * p.adain_ld + ly.adain_off_b + 4 * cg) = sr;
+                *reinterpret_cast<float4*>(p.dadain + sb * p.adain_ld + ly.adain_off_w + 4 * cg) = srx;
+            }
+            const float4 sc = make_float4(r4.x * w4.x, r4.y * w4.y, r4.z * w4.z, r4.w * w4.w);
+            const float4 m = make_float4(sr.x * 0.125f, sr.y * 0.125f, sr.z * 0.125f, sr.w * 0.125f);
+            const float4 mx = make_float4(srx.x * 0.125f, srx.y * 0.125f, srx.z * 0.125f, srx.w * 0.125f);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float4 xq = row_ok ? __ldg(reinterpret_cast<const float4*>(ly.xhat + orow + c0) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 r4 = __ldg(reinterpret_cast<const float4*>(ly.rstd + sb * 64 + gn) + k);
-                float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ADAIN) {
-                    w4 = __ldg(reinterpret_cast<const float4*>(p.adain + sb * p.adain_ld + ly.adain_off_w + gn) + k);
-                    b4 = __ldg(reinterpret_cast<const float4*>(p.adain + sb * p.adain_ld + ly.adain_off_b + gn) + k);
-                }
-                const float xv[4] = {xq.x, xq.y, xq.z, xq.w}, rv[4] = {r4.x, r4.y, r4.z, r4.w};
-                const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
-                float sr[4], srx[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float u = fmaf(xv[e], wv[e], bv[e]);
-                    const float raw = (relu && !(u > 0.f)) ? 0.f : v[4 * k + e];
-                    sr[e] = iins_lanes_sum<8>(raw);
-                    srx[e] = iins_lanes_sum<8>(raw * xv[e]);
-                    v[4 * k + e] = rv[e] * wv[e] * (raw - sr[e] * 0.125f - xv[e] * srx[e] * 0.125f);
-                }
-                if (row_ok) reinterpret_cast<float4*>(ly.dz + orow + c0)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                if (ADAIN && lead) {
-                    *reinterpret_cast<float4*>(p.dadain + sb * p.adain_ld + ly.adain_off_b + gn + 4 * k) = make_float4(sr[0], sr[1], sr[2], sr[3]);
-                    *reinterpret_cast<float4*>(p.dadain + sb * p.adain_ld + ly.adain_off_w + gn + 4 * k) = make_float4(srx[0], srx[1], srx[2], srx[3]);
-                }
+            for (int l = 0; l < 8; ++l) {
+                x[l].x = sc.x * (x[l].x - m.x - xh[l].x * mx.x); x[l].y = sc.y * (x[l].y - m.y - xh[l].y * mx.y);
+                x[l].z = sc.z * (x[l].z - m.z - xh[l].z * mx.z); x[l].w = sc.w * (x[l].w - m.w - xh[l].w * mx.w);
+                if (ok) *reinterpret_cast<float4*>(ly.dz + o0 + l * 64) = x[l];
             }
         };
         uint32_t j = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int gb = tile * TR_SAMPLES + s;
-            const bool row_ok = gb < p.B;
-            const long sb = row_ok ? gb : 0;
-            const long orow = (sb * 8 + l) * 64 + cbeg;
-            const bool lead = row_ok && l == 0;
+            const bool ok = gb < p.B;
+            const long sb = ok ? gb : 0;
+            const long o0 = sb * 512 + 4 * cg;
+            float4 x[8];
             // ---- stage 0: norm backward of the LAST convolution's norm (second conv of the last block: no ReLU)
-#pragma unroll 1
-            for (int c0 = 0; c0 < 32; c0 += 16) {
-                float v[16];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float4 t = row_ok ? __ldg(reinterpret_cast<const float4*>(p.dh + orow + c0) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
-                }
-                norm_backward16(p.layer[p.nconv - 1], false, v, orow, cbeg + c0, c0, sb, row_ok, lead);
-                write_operand(v, c0);
-            }
+            for (int l = 0; l < 8; ++l) x[l] = ok ? __ldg(reinterpret_cast<const float4*>(p.dh + o0 + l * 64)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            norm_backward(p.layer[p.nconv - 1], false, x, o0, sb, ok, ADAIN);
+            write_operand_columns<PIECES, false>(sA, s, cg, x);
             umma::fence_async_smem();
             umma::mbar_arrive(umma::smem_u32(&a_ready));
             for (int c = p.nconv - 1; c >= 0; --c, ++j) {
-                // ---- the 12 main k-steps have read the tile: clear its six middle rows for the two edge terms
+                // ---- the 12 main k-steps have read the tile: clear its six middle rows (positions 1..6) for the two edge terms
                 umma::mbar_wait(umma::smem_u32(&main_done), j & 1);
-                if (l >= 1 && l <= 6) {
+                {
+                    unsigned char* base = sA + (cg >> 1) * TR_LBO + (s * 10) * 16 + (cg & 1) * 8;
 #pragma unroll
-                    for (int h = 0; h < 4; ++h)
+                    for (int l = 1; l <= 6; ++l)
 #pragma unroll
-                        for (int pc = 0; pc < PIECES; ++pc)
-                            *reinterpret_cast<uint4*>(a_row + (cbeg / 8 + h) * TR_LBO + pc * TR_APIECE) = make_uint4(0u, 0u, 0u, 0u);
+                        for (int pc = 0; pc < PIECES; ++pc) *reinterpret_cast<uint2*>(base + pc * TR_APIECE + (l + 1) * 16) = make_uint2(0u, 0u);
                 }
                 umma::fence_async_smem();
                 umma::mbar_arrive(umma::smem_u32(&z_ready));
                 umma::mbar_wait(umma::smem_u32(&acc_full), j & 1);
                 umma::tc_fence_after();
+                stage_accumulator<PIECES>(tmem, warp, lane, stg);
+                umma::tc_fence_before();
+                epi_bar();
+                load_columns(stg, s, cg, x);
+                epi_bar();
                 const bool first = (c & 1) == 0;                            // first convolution of its block: + the skip gradient
-                const float* skip = !first ? nullptr : (c == p.nconv - 2 ? p.dh : p.dh_scratch);
-#pragma unroll 1
-                for (int c0 = 0; c0 < 32; c0 += 16) {
-                    const int gn = cbeg + c0;
-                    float4 a4[4];
+                if (first && ok) {   // plain loads: dh_scratch is written by this very thread two stages earlier
+                    const float* skip = (c == p.nconv - 2 ? p.dh : p.dh_scratch) + o0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)   // plain loads: dh_scratch is written by this very thread two stages earlier
-                        a4[k] = (first && row_ok) ? *(reinterpret_cast<const float4*>(skip + orow + c0) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float v[16];
-                    iins_tmem_chunk16<64, PIECES>(tl, gn, v);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { v[4 * k] += a4[k].x; v[4 * k + 1] += a4[k].y; v[4 * k + 2] += a4[k].z; v[4 * k + 3] += a4[k].w; }
-                    if (c == 0) {
-                        if (p.dx != nullptr && row_ok) {
-                            float4* dst = reinterpret_cast<float4*>(p.dx + orow + c0);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                        }
-                        if (p.pre.xhat != nullptr) norm_backward16(p.pre, p.pre_relu != 0, v, orow, gn, c0, sb, row_ok, false);
-                        continue;
-                    }
-                    if (first && row_ok) {                                  // gradient w.r.t. the previous block's output: the next skip term
-                        float4* dst = reinterpret_cast<float4*>(p.dh_scratch + orow + c0);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                    }
-                    norm_backward16(p.layer[c - 1], ((c - 1) & 1) == 0, v, orow, gn, c0, sb, row_ok, lead);
-                    write_operand(v, c0);
+                    for (int l = 0; l < 8; ++l) { const float4 h4 = *reinterpret_cast<const float4*>(skip + l * 64); IINS_F4_OP(x[l], x[l], +, h4); }
                 }
-                if (c > 0) {
-                    umma::tc_fence_before();
-                    umma::fence_async_smem();
-                    umma::mbar_arrive(umma::smem_u32(&a_ready));
+                if (c == 0) {
+                    if (p.dx != nullptr && ok) {
+#pragma unroll
+                        for (int l = 0; l < 8; ++l) *reinterpret_cast<float4*>(p.dx + o0 + l * 64) = x[l];
+                    }
+                    if (p.pre.xhat != nullptr) norm_backward(p.pre, p.pre_relu != 0, x, o0, sb, ok, false);
+                    break;
                 }
+                if (first && ok) {                                          // gradient w.r.t. the previous block's output: the next skip term
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) *reinterpret_cast<float4*>(p.dh_scratch + o0 + l * 64) = x[l];
+                }
+                norm_backward(p.layer[c - 1], ((c - 1) & 1) == 0, x, o0, sb, ok, ADAIN);
+                write_operand_columns<PIECES, false>(sA, s, cg, x);
+                umma::fence_async_smem();
+                umma::mbar_arrive(umma::smem_u32(&a_ready));
             }
-            umma::tc_fence_before();
+            ++j;                                                            // the `break` at c == 0 skipped the loop increment
         }
     }
     umma::tc_fence_before();
@@ -464,7 +479,7 @@ bool make_weight_map(CUtensorMap* map, const void* base, int pieces, int nconv) 
 
 template <int PIECES, bool ADAIN, bool TMAP>
 void launch_variant(cudaStream_t st, const IinsTrunkFwdParams& p, const CUtensorMap& map, int grid) {
-    constexpr int smem = PIECES * (int)TR_APIECE + TR_NSLOT * PIECES * 64 * 16 * 2;
+    constexpr int smem = (int)TrunkSmem<PIECES>::TOTAL;
     static bool attr = false;
     auto iins_trunk_fwd_kernel_ = iins_trunk_fwd_kernel<PIECES, ADAIN, TMAP>;
     if (!attr) { cudaFuncSetAttribute(iins_trunk_fwd_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
@@ -473,7 +488,7 @@ void launch_variant(cudaStream_t st, const IinsTrunkFwdParams& p, const CUtensor
 
 template <int PIECES, bool ADAIN, bool TMAP>
 void launch_bwd_variant(cudaStream_t st, const IinsTrunkBwdParams& p, const CUtensorMap& map, int grid) {
-    constexpr int smem = PIECES * (int)TR_APIECE + TR_NSLOT * PIECES * 64 * 16 * 2;
+    constexpr int smem = (int)TrunkSmem<PIECES>::TOTAL;
     static bool attr = false;
     auto iins_trunk_bwd_kernel_ = iins_trunk_bwd_kernel<PIECES, ADAIN, TMAP>;
     if (!attr) { cudaFuncSetAttribute(iins_trunk_bwd_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }

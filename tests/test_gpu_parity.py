@@ -381,7 +381,7 @@ def test_graph_replay_matches_eager_and_is_reproducible(supervised):
         runs.append({k: v.clone() for k, v in eng.named_grads().items()})
         for a, b in zip(eager_out[2:], (eng.xrec, eng.rc, eng.cat)):
             assert torch.equal(a, b), "forward tensors of a replay differ from the eager pass"
-        assert torch.allclose(eager_out[1], eng.kl, rtol=1e-6, atol=0), "KL (a sum of float atomics) differs beyond 1e-6"
+        assert torch.allclose(eager_out[1], eng.kl, rtol=1e-5, atol=0), "KL (a sum of float atomics) differs beyond 1e-5"
         assert torch.allclose(eager_out[0], eng.out, rtol=1e-6, atol=0), "loss terms (atomic sums) differ beyond 1e-6"
     worst_eager = worst_replay = 0.0
     for k, e in eager.items():

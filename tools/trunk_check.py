@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 
 
 def run(fused: str, out: str):
-    env = dict(os.environ, IINS_FUSED_TRUNK=fused, IINS_TRUNK_TMAP=os.environ.get("IINS_TRUNK_TMAP", "1"))
+    env = dict(os.environ, IINS_FUSED_TRUNK=fused, IINS_FUSED_TRUNK_BWD=fused, IINS_TRUNK_TMAP=os.environ.get("IINS_TRUNK_TMAP", "1"))
     subprocess.run([sys.executable, __file__, "--child", out], env=env, check=True)
 
 
@@ -33,7 +33,7 @@ def child(out):
             res[f"{mode}.{B}.xrec"] = eng.xrec.cpu()
             res[f"{mode}.{B}.loss"] = torch.tensor(eng.loss_terms()["loss"])
             for k, v in eng.named_grads().items():
-                if "model.17.block.1.weight" in k or "model.2.block.1.weight" in k or "range_encoder.model.2.weight" in k:
+                if k.startswith("enc.range_encoder") or k.startswith("dec.decoder"):
                     res[f"{mode}.{B}.g.{k}"] = v.cpu().clone()
     torch.save(res, out)
 
@@ -47,11 +47,17 @@ if __name__ == "__main__":
     run("1", "/tmp/trunk_fused.pt")
     a, b = torch.load("/tmp/trunk_ref.pt"), torch.load("/tmp/trunk_fused.pt")
     bad = 0
+    from oracle import iins_oracle as orc
     for k in a:
-        d = float((a[k].double() - b[k].double()).abs().max())
-        sc = float(a[k].double().abs().max()) + 1e-30
-        flag = "" if d <= (1e-5 if k.startswith("fp32") else 2e-2) * sc else "  <<< MISMATCH"
+        if ".g." in k and orc.grad_is_structurally_zero(k.split(".g.")[1]):
+            continue                        # conv biases in front of an InstanceNorm: the true gradient is exactly 0 (rounding noise only)
+        d = float((a[k].double() - b[k].double()).norm())
+        sc = float(a[k].double().norm()) + 1e-30
+        # the two paths differ only in summation order / kink decisions: fp32-grade 2e-3 rel-L2 (a flipped ReLU kink at B = 16..37
+        # moves a tensor by O(1/B)), bf16 operands 5e-2
+        flag = "" if d <= (2e-3 if k.startswith("fp32.4096") else 5e-2) * sc else "  <<< MISMATCH"
         bad += bool(flag)
-        print(f"{k:60s} max|diff| {d:.3e} (scale {sc:.3e}){flag}")
+        if flag or ".g." not in k or "block.1.weight" in k or "mlp.model.4" in k or "model.2.weight" in k:
+            print(f"{k:60s} rel-L2 diff {d / sc:.3e} (norm {sc:.3e}){flag}")
     print("TRUNK_CHECK", "FAILED" if bad else "PASSED")
     sys.exit(1 if bad else 0)
