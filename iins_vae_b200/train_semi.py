@@ -65,6 +65,9 @@ def build_modules(opt, device):
     return Enc, Dec, Res, Cls, len_cir
 
 
+last_modules = None          # (Enc, Dec, Res, Cls) of the most recent run() in this process (for callers that continue with them)
+
+
 def run(opt, dataloader=None, max_steps=None, quiet=False):
     """The training loop; under torchrun the process group is torn down in an orderly way at the end."""
     engines = {}
@@ -81,6 +84,8 @@ def _run(opt, engines, dataloader=None, max_steps=None, quiet=False):
     torch.cuda.set_device(device)
     set_compute_mode(opt.compute_mode)
     Enc, Dec, Res, Cls, len_cir = build_modules(opt, device)
+    global last_modules
+    last_modules = (Enc, Dec, Res, Cls)
     tag = "%s_mode_%s/SEMI%f_AE%d_Res%s_Cls%s_Rdim%dEdim%d" % (opt.dataset_env, opt.mode, opt.supervision_rate, opt.conv_type,
                                                            opt.restorer_type, opt.classifier_type, opt.range_dim, opt.env_dim)
     model_path, result_path = os.path.join("saved_models_semi", tag), os.path.join("saved_results_semi", tag)
@@ -96,6 +101,16 @@ def _run(opt, engines, dataloader=None, max_steps=None, quiet=False):
         for m in (Enc, Dec, Res, Cls):
             m.apply(weights_init_normal)
     broadcast_parameters((Enc, Dec, Res, Cls), pg)
+    root = getattr(opt, "data_root", "./data/data_zenodo/dataset.pkl")                 # train_semi.py:133
+    if dataloader is None and opt.synthetic <= 0 and os.path.exists(root):
+        # the reference's own data flow (train_semi.py:137-147) on the pinned-ring pipeline: pickle -> split -> StandardScaler
+        # fitted on the training CIRs -> shuffled batches gathered into pinned host buffers by a background thread
+        from .dataset import PinnedBatchRing, UWBDataset, err_mitigation_dataset
+        data_train, _, _, _ = err_mitigation_dataset(root=root, dataset_name=opt.dataset_name, dataset_env=opt.dataset_env,
+                                                     split_factor=0.8, scaling=True, mode=opt.mode)
+        if world > 1:                                                                  # every rank trains on its own slice
+            data_train = tuple(a[rank::world] for a in data_train)
+        dataloader = PinnedBatchRing(UWBDataset(data_train), opt.batch_size, shuffle=True, seed=1234 + rank)
     if dataloader is None:
         n = opt.synthetic if opt.synthetic > 0 else 16 * opt.batch_size
         dataloader = SyntheticCIR(n, opt.batch_size, len_cir, opt.num_classes, seed=1234 + rank,

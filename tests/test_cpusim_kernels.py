@@ -21,6 +21,39 @@ def sim():
     return harness, harness.build_sim()
 
 
+def test_dim16_decoder_gradients_match_autograd(sim):
+    """dim = 16 (utils.py:38 --filters 16: 256-channel trunk): the launch plans take other routes than at dim = 4 -- the
+    LayerNorm behind a conv wider than one column block runs as conv + bias followed by the LN kernel, the norm backward walks
+    column blocks of 128 channels, the weight arena is shape-sized.  Decoder forward + backward through the C ABI against
+    torch autograd of the oracle in fp64, with a smooth upstream gradient (no loss kinks)."""
+    from iins_vae_b200._capi import ptr, ptr_array
+    H, lib = sim
+    cfg, B = orc.PathConfig(dim=16), 1
+    pe, pd, pr, pc = orc.init_all(cfg, 0)
+    torch.manual_seed(0)
+    rc, cat = torch.rand(B, cfg.range_dim, cfg.code_len), torch.randn(B, cfg.env_dim) * 0.3
+    st = H.SimStep(lib, cfg, B, pe, pd, pr, pc)
+    xrec = torch.zeros(B, cfg.cir_len)
+    lib.check(lib.iins_decoder_forward(st.c, ptr_array(st.P["dec"]), ptr(rc), ptr(cat), ptr(xrec), ptr(st.ws["decoder"]), None), "fwd")
+    d_x = torch.randn(B, cfg.cir_len) * 0.01
+    G = [torch.zeros_like(p) for p in st.P["dec"]]
+    d_rc, d_cat = torch.zeros_like(rc), torch.zeros_like(cat)
+    lib.check(lib.iins_decoder_backward(st.c, ptr_array(st.P["dec"]), ptr(rc), ptr(cat), ptr(st.ws["decoder"]), ptr(d_x), ptr_array(G),
+                                        ptr(d_rc), ptr(d_cat), 0, ptr(st.scratch["decoder"]), None), "bwd")
+    pdd = {k: v.double().requires_grad_(not orc.is_buffer(k)) for k, v in pd.items()}
+    rcd, catd = rc.double().requires_grad_(True), cat.double().requires_grad_(True)
+    out = orc.decoder(pdd, rcd, catd.view(B, -1, 1), cfg)
+    (out.view(B, -1) * d_x.double()).sum().backward()
+    assert float((xrec.double() - out.detach().view(B, -1)).abs().max()) < 2e-5
+    for n, g in zip(st.names["dec"], G):
+        r = pdd["" + n].grad
+        if orc.grad_is_structurally_zero("dec." + n):
+            continue
+        assert float((g.double() - r).norm()) <= 2e-4 * float(r.norm()), n
+    assert float((d_rc.double() - rcd.grad).norm()) <= 2e-4 * float(rcd.grad.norm())
+    assert float((d_cat.double() - catd.grad.view(B, -1)).norm()) <= 2e-4 * float(catd.grad.norm())
+
+
 @pytest.mark.parametrize("batch,supervised,seed", [(2, True, 0), (5, False, 1), (19, True, 2)])
 def test_semi_step_matches_oracle(sim, batch, supervised, seed):
     H, lib = sim
@@ -61,7 +94,7 @@ def test_semi_step_matches_oracle(sim, batch, supervised, seed):
 
 def test_config_validation_fails_loudly(sim):
     H, lib = sim
-    c = H.make_cfg(orc.PathConfig(dim=16), 4)          # trunk 256 channels: not supported by this build
+    c = H.make_cfg(orc.PathConfig(dim=32), 4)          # trunk 512 channels: not supported by this build (dim <= 16)
     assert lib.iins_validate_config(c) != 0
     assert b"dim" in lib.dll.iins_last_error()
 

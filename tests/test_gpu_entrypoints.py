@@ -179,3 +179,75 @@ def test_prefetched_batch_gives_the_same_step():
     torch.cuda.synchronize()
     assert torch.allclose(got_a, ref_a, rtol=1e-6, atol=1e-7) and torch.allclose(got_b, ref_b, rtol=1e-6, atol=1e-7)
     assert not torch.allclose(ref_a, ref_b)
+
+
+def test_ring_fed_training_matches_direct_feed(tmp_path, monkeypatch):
+    """train_semi.run fed by the pinned batch ring (StandardScaler'd arrays -> shuffled pinned batches ->
+    prefetch on the copy stream, ragged last batch included) must train exactly like feeding the same batches, in the same
+    order, straight to engine.step()."""
+    from iins_vae_b200 import dataset as D, models as M, train_semi
+    from iins_vae_b200.engine import SemiTrainEngine
+    from iins_vae_b200.parallel import SupervisionMask
+    from iins_vae_b200.utils import get_args
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.RandomState(0)
+    cir = rng.randn(1100, 157) * 2 + 0.5
+    data = (cir, np.abs(rng.randn(1100, 1)) * 0.15, rng.randint(0, 5, (1100, 1)).astype(float))
+    train, _, _, _ = D.err_mitigation_dataset(None, data=data, split_factor=0.8, scaling=True, mode="full")     # 880 windows
+    ds = D.UWBDataset(train)
+    parser = get_args(None)
+    parser.add_argument("--supervision_rate", type=float, default=0.1)
+    opt = parser.parse_args(["--dataset_env", "room_full", "--batch_size", "256", "--n_epochs", "3", "--lr", "0.001",
+                             "--checkpoint_interval", "-1"])
+    torch.manual_seed(0)
+    train_semi.run(opt, dataloader=D.PinnedBatchRing(ds, 256, shuffle=True, seed=7), quiet=True)
+    trained = train_semi.last_modules
+    # the same run by hand: same init (seed), same batch order (ring seed), same mask stream
+    torch.manual_seed(0)
+    Enc, Dec, Res, Cls, _ = train_semi.build_modules(opt, torch.device("cuda"))
+    for m in (Enc, Dec, Res, Cls):
+        m.apply(M.weights_init_normal)
+    engines, mask = {}, SupervisionMask(opt.supervision_rate, seed=1234)
+    ring = D.PinnedBatchRing(ds, 256, shuffle=True, seed=7)
+    sched = M.LambdaLR(opt.n_epochs, 0, opt.decay_epoch)
+    for epoch in range(3):
+        for batch in ring:
+            B = batch["CIR"].shape[0]
+            if B not in engines:
+                engines[B] = SemiTrainEngine(Enc, Dec, Res, Cls, batch_size=B, lr=opt.lr, betas=(opt.b1, opt.b2),
+                                             shared_state=next(iter(engines.values()), None))
+            engines[B].set_lr(opt.lr * sched.step(epoch))
+            engines[B].step(batch["CIR"].clone(), batch["Err"].clone(), batch["Label"].clone(), supervised=bool(mask()))
+    torch.cuda.synchronize()
+    for a, b in zip(trained, (Enc, Dec, Res, Cls)):
+        for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+            assert torch.allclose(p, q, rtol=1e-4, atol=2e-6), n
+
+
+def test_sharded_inference_driver_single_rank():
+    """BASELINE configs[4] driver (iins_vae_b200/infer.py) on one rank: pinned host windows -> two-slot device ring -> captured
+    inference graph; outputs and metric sums equal a direct InferenceEngine pass over the same windows (ragged tail included)."""
+    from iins_vae_b200 import models as M
+    from iins_vae_b200.engine import InferenceEngine
+    from iins_vae_b200.infer import ShardedInference, synthetic_windows
+    torch.manual_seed(2)
+    net = M.EMNet(cir_len=157, num_classes=5, env_dim=16).cuda()
+    cir, err, label = synthetic_windows(10_000, 157, 5, seed=9)
+    assert cir.is_pinned()
+    sh = ShardedInference(net, cir, err, label, batch_size=4096)
+    for _ in range(2):
+        sums = sh.run()
+    torch.cuda.synchronize()
+    s = sums.tolist()
+    ref_e, ref_p = [], []
+    for lo in range(0, 10_000, 4096):
+        hi = min(lo + 4096, 10_000)
+        eng = InferenceEngine(net.encoder, net.restorer, net.classifier, batch_size=hi - lo)
+        e, p, _ = eng.run(cir[lo:hi].cuda(), err[lo:hi].cuda(), label[lo:hi].cuda())
+        ref_e.append(e.clone()); ref_p.append(p.clone())
+    ref_e, ref_p = torch.cat(ref_e), torch.cat(ref_p)
+    assert torch.equal(sh.err_est, ref_e) and torch.equal(sh.pred, ref_p)
+    assert s[3] == 10_000
+    np.testing.assert_allclose(s[0] / s[3], float((ref_e.cpu() - err).abs().mean()), rtol=1e-5)
+    np.testing.assert_allclose(s[1] / s[3], float(((ref_e.cpu() - err) ** 2).mean()), rtol=1e-5)
+    assert s[2] == float((ref_p.cpu() == label.view(-1).int()).sum())

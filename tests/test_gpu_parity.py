@@ -145,11 +145,23 @@ KINK_FREE_K = {64: 1, 130: 2}
 def test_engine_step_matches_oracle(batch, supervised, graph, mode):
     """Fused engine (fused loss, flat gradient buffer) vs the CPU oracle, up to BASELINE's batch 4096, for the
     tensor-core fp32-grade path ("fp32": tcgen05, bf16x3 split) and the SIMT fp32 cross-check path."""
+    _engine_step_vs_oracle(orc.PathConfig(), KINK_FREE_K.get(batch, 0), batch, supervised, graph, mode)
+
+
+# BASELINE configs[0] names "reference default options from utils.py": utils.py:38 --filters 16, i.e. dim = 16 (256-channel
+# trunk, 3,993,291 parameters): the same per-tensor bound, on kink-free seeds at B = 64 (scan: profiles/r02_kink_seed_scan_dim16.log).
+KINK_FREE_K_DIM16 = {64: 1}
+
+
+@pytest.mark.parametrize("batch,supervised,graph", [(64, True, False), (64, False, False), (4096, True, True)])
+def test_dim16_engine_step_matches_oracle(batch, supervised, graph):
+    _engine_step_vs_oracle(orc.PathConfig(dim=16), KINK_FREE_K_DIM16.get(batch, 0), batch, supervised, graph, "fp32")
+
+
+def _engine_step_vs_oracle(cfg, k, batch, supervised, graph, mode):
     import iins_vae_b200
     from iins_vae_b200.engine import SemiTrainEngine
     iins_vae_b200.set_compute_mode(mode)
-    cfg = orc.PathConfig()
-    k = KINK_FREE_K.get(batch, 0)
     seed = 11 + batch + 1000 * k
     mods, pdicts = _mods(cfg, seed)
     cir, err, label = orc.synthetic_batch(cfg, batch, 500 + batch + 1000 * k)

@@ -10,7 +10,7 @@ from oracle import iins_oracle as orc
 from iins_vae_b200 import models as M
 from iins_vae_b200.engine import SemiTrainEngine
 
-CASES = [dict(dim=2), dict(dim=1), dict(dim=3), dict(n_residual=1), dict(n_residual=0), dict(num_classes=2), dict(num_classes=10),
+CASES = [dict(dim=2), dict(dim=1), dict(dim=3), dict(dim=8), dict(dim=16), dict(dim=16, n_residual=1, env_dim=8), dict(n_residual=1), dict(n_residual=0), dict(num_classes=2), dict(num_classes=10),
          dict(env_dim=8), dict(range_dim=4), dict(dim=2, n_residual=2, env_dim=32, num_classes=3)]
 
 

@@ -2,7 +2,7 @@
 sign() kink within rounding distance, i.e. for which the CUDA gradients are strict against the fp64 oracle in BOTH compute
 modes.  One flipped kink moves every gradient tensor upstream of it by O(1/B), which at B = 64..130
 hides real errors of a few per cent: the parity tests therefore run these batches on kink-free seeds and cap the band.
-    python tools/kink_seed_scan.py 64,130 0:12"""
+    python tools/kink_seed_scan.py 64,130 0:12 [dim]"""
 import os
 import sys
 
@@ -19,7 +19,9 @@ from iins_vae_b200.engine import SemiTrainEngine
 def main():
     batches = [int(b) for b in sys.argv[1].split(",")]
     lo, hi = (int(v) for v in sys.argv[2].split(":"))
-    cfg = orc.PathConfig()
+    dim = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+    cfg = orc.PathConfig(dim=dim)
+    print(f"dim={dim}")
     for batch in batches:
         for supervised in (True, False):
             for k in range(lo, hi):
