@@ -487,6 +487,50 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
     IINS_LAUNCH(iins_tn_kernel, dim3(parts, ky, nz), 256, 0, wst, p);
 }
 
+// Weight gradients of `n` convolutions of IDENTICAL geometry (plain dz, no activation) as ONE launch of the tensor-core
+// kernel (blockIdx.z = problem): the residual trunk, whose dz tensors all exist once the fused backward kernel has run.
+void conv_wgrad_batch(Ctx& c, const IinsGeom& g, int n, const float* const* xs, const float* const* dzs, float* const* dws,
+                      float* const* dbs) {
+    if (c.phase == 1 || n <= 0) return;
+    flush_pending(c);
+#ifndef IINS_CPUSIM
+    const int K = g.ks * g.Cin;
+    auto chan_ok = [&](int cdim) { return ilog2_exact(cdim) >= 3 || (g.ks == 1 && cdim % 8 == 0); };
+    const bool tc_ok = chan_ok(g.Cin) && g.Cout % 8 == 0 && g.Cout <= 64 && g.in_layout == IINS_NLC && g.out_layout == IINS_NLC;
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("IINS_WGRAD_BATCH"); on = e ? atoi(e) : 1; }
+    if (on && g_mode != 2 && tc_ok && n <= 8 && ilog2_exact(g.Lout) >= 0) {
+        cudaStream_t wst = c.st;
+        if (c.st2 != nullptr) { fork_to(c.st, c.st2); wst = c.st2; }
+        IinsTCTNParams tp;
+        memset(&tp, 0, sizeof(tp));
+        IinsTNParams& p = tp.tn;
+        p.g = g; p.dz = plain_dz(nullptr); p.M = g.B * g.Lout;
+        const int nt = g.Cout <= 16 ? 16 : (g.Cout <= 32 ? 32 : 64);
+        const int ky = (K + 127) / 128;
+        // the batch already fills the grid n times over: aim for ~2 CTAs per SM in TOTAL, i.e. fewer, longer row parts per
+        // problem (the per-CTA prologue, TMEM allocation and the 128 x NT atomic flush are paid once per part)
+        long want = (148L * 2 + (long)ky * n - 1) / ((long)ky * n);
+        const long max_parts = (p.M + 127) / 128;
+        if (want > max_parts) want = max_parts;
+        if (want < 1) want = 1;
+        long rpp = (p.M + want - 1) / want;
+        rpp = (rpp + 31) / 32 * 32;
+        p.rows_per_part = (int)rpp;
+        tp.pieces = g_mode == 1 ? 1 : 3; tp.K = K;
+        tp.lshift = ilog2_exact(g.Lout); tp.cshift_in = ilog2_exact(g.Cin); tp.cshift_out = ilog2_exact(g.Cout);
+        if (tp.cshift_in < 0) tp.cshift_in = 31;
+        tp.nbatch = n;
+        for (int i = 0; i < n; ++i) { tp.bx[i] = xs[i]; tp.bdy[i] = dzs[i]; tp.bdw[i] = dws[i]; tp.bdb[i] = dbs[i]; }
+        dim3 grid((unsigned)((p.M + rpp - 1) / rpp), ky, n);
+        IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K * n); IINS_SET_SHAPE(p.M, g.Cout, K * n);
+        iins_launch_tc_tn(wst, tp, grid, nt);
+        return;
+    }
+#endif
+    for (int i = 0; i < n; ++i) conv_wgrad(c, g, xs[i], plain_dz(dzs[i]), dws[i], dbs[i]);
+}
+
 void norm_backward(Ctx& c, int B, int L, int C, int norm, int act, const float* dy, const float* xhat,
                    const float* rstd, const float* gamma, const float* beta, float* dgamma, float* dbeta,
                    const float* adain, float* dadain, int ld, int off_b, int off_w, float* dz, bool dy_dead = false) {
@@ -863,9 +907,14 @@ int encoder_backward(const Shapes& s, const float* const* P, const float* noise,
             trunk_done = trunk_backward_fused(c, B, C, L, s.nres, dh, nullptr, scr, dzs, pl.res1, pl.res2, nullptr, nullptr, 0,
                                               &pl.down[s.ndown - 1], pre_dz);
             if (trunk_done) {
-                for (int k = 2 * s.nres - 1; k >= 0; --k) {           // weight gradients (side stream): input of conv k, dz of conv k
-                    const float* a_in = (k & 1) ? pl.res1[k >> 1].y : (k >= 2 ? pl.res2[(k >> 1) - 1].y : pl.down[s.ndown - 1].y);
-                    conv_wgrad(c, gr, a_in, plain_dz(dzs[k]), G[pi - 4 * s.nres + 2 * k], G[pi - 4 * s.nres + 2 * k + 1]);
+                for (int k0 = 0; k0 < 2 * s.nres; k0 += 8) {          // weight gradients (side stream), up to 8 convolutions per launch
+                    const float* xs[8]; const float* dzp[8]; float* dws[8]; float* dbs[8];
+                    int nb = 0;
+                    for (int k = k0; k < 2 * s.nres && nb < 8; ++k, ++nb) {   // input of conv k, dz of conv k
+                        xs[nb] = (k & 1) ? pl.res1[k >> 1].y : (k >= 2 ? pl.res2[(k >> 1) - 1].y : pl.down[s.ndown - 1].y);
+                        dzp[nb] = dzs[k]; dws[nb] = G[pi - 4 * s.nres + 2 * k]; dbs[nb] = G[pi - 4 * s.nres + 2 * k + 1];
+                    }
+                    conv_wgrad_batch(c, gr, nb, xs, dzp, dws, dbs);
                 }
                 pi -= 4 * s.nres;
                 dzb = pre_dz;
@@ -1096,9 +1145,14 @@ int decoder_backward(const Shapes& s, const float* const* P, const float* rc, co
         trunk_done = trunk_backward_fused(c, B, s.D, s.Lt, s.nres, dh, dx, scr, dzs, pl.res1, pl.res2, pl.adain, dadain, s.n_adain,
                                           nullptr, nullptr);
         if (trunk_done) {
-            for (int k = 2 * s.nres - 1; k >= 0; --k) {               // weight gradients (side stream): input of conv k, dz of conv k
-                const float* a_in = (k & 1) ? pl.res1[k >> 1].y : (k >= 2 ? pl.res2[(k >> 1) - 1].y : pl.d0);
-                conv_wgrad(c, gr, a_in, plain_dz(dzs[k]), G[ix.res0 + 2 * k], G[ix.res0 + 2 * k + 1]);
+            for (int k0 = 0; k0 < 2 * s.nres; k0 += 8) {              // weight gradients (side stream), up to 8 convolutions per launch
+                const float* xs[8]; const float* dzp[8]; float* dws[8]; float* dbs[8];
+                int nb = 0;
+                for (int k = k0; k < 2 * s.nres && nb < 8; ++k, ++nb) {       // input of conv k, dz of conv k
+                    xs[nb] = (k & 1) ? pl.res1[k >> 1].y : (k >= 2 ? pl.res2[(k >> 1) - 1].y : pl.d0);
+                    dzp[nb] = dzs[k]; dws[nb] = G[ix.res0 + 2 * k]; dbs[nb] = G[ix.res0 + 2 * k + 1];
+                }
+                conv_wgrad_batch(c, gr, nb, xs, dzp, dws, dbs);
             }
             dh = dx;
         } else {

@@ -747,6 +747,11 @@ struct IinsTCTNParams {
     int lshift;          // log2(Lout) (rows per sample)
     int cshift_in;       // log2(Cin) or -1
     int cshift_out;      // log2(Cout) or -1
+    // Batched launch: `nbatch` > 0 problems of IDENTICAL geometry (the 2 * n_residual trunk convolutions, whose dz tensors
+    // the fused backward kernel leaves behind all at once) in ONE grid: blockIdx.z selects the problem (Cout <= NT then),
+    // the operand / output pointers come from these arrays instead of tn.x / tn.dz.dy / tn.dw / tn.db.
+    int nbatch;
+    const float* bx[8]; const float* bdy[8]; float* bdw[8]; float* bdb[8];
 };
 
 // grid = (row parts, ceil(K/128), ceil(Cout/NT)).  D^T[k][n] accumulated in TMEM (128 lanes = 128 k entries).
@@ -766,7 +771,13 @@ static __global__ void __launch_bounds__(288, 2) iins_tc_tn_kernel(const IinsTCT
     const IinsTNParams& p = tp.tn;
     const IinsGeom& g = p.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ktile0 = blockIdx.y * 128, n0 = blockIdx.z * NT;
+    const bool batched = tp.nbatch > 0;
+    const int ktile0 = blockIdx.y * 128, n0 = batched ? 0 : blockIdx.z * NT;
+    const float* const px = batched ? tp.bx[blockIdx.z] : p.x;
+    IinsDz pdz = p.dz;
+    if (batched) pdz.dy = tp.bdy[blockIdx.z];
+    float* const pdw = batched ? tp.bdw[blockIdx.z] : p.dw;
+    float* const pdb = batched ? tp.bdb[blockIdx.z] : p.db;
     const int r_begin = blockIdx.x * p.rows_per_part;
     int r_end = r_begin + p.rows_per_part;
     if (r_end > p.M) r_end = p.M;
@@ -786,7 +797,7 @@ static __global__ void __launch_bounds__(288, 2) iins_tc_tn_kernel(const IinsTCT
     umma::tc_fence_after();
     const uint32_t tmem = tmem_slot;
     iins_pdl_wait();                                   // prologue overlapped the previous kernel's tail
-    const bool do_bias = p.db != nullptr && blockIdx.y == 0;
+    const bool do_bias = pdb != nullptr && blockIdx.y == 0;
     const bool has_z = warp < NT / 8;
     float bsum[8];
     iins_zero8(bsum);
@@ -819,11 +830,11 @@ static __global__ void __launch_bounds__(288, 2) iins_tc_tn_kernel(const IinsTCT
             for (int jj = 0; jj < 2; ++jj) {
                 const int k0 = ktile0 + (warp + 8 * jj) * 8;
                 if (!ok || k0 >= tp.K) iins_zero8(ra[jj]);
-                else iins_gather8_fwd_fast(g, p.x, tp.K, tp.cshift_in, b, l, k0, ra[jj]);
+                else iins_gather8_fwd_fast(g, px, tp.K, tp.cshift_in, b, l, k0, ra[jj]);
             }
             if (has_z) {
                 if (!ok) iins_zero8(rz);
-                else iins_dz8_fast(g, p.dz, b, l, n0 + warp * 8, true, rz);
+                else iins_dz8_fast(g, pdz, b, l, n0 + warp * 8, true, rz);
             }
         };
         auto produce = [&](int it, float (*ra)[8], float* rz) {
@@ -870,7 +881,7 @@ static __global__ void __launch_bounds__(288, 2) iins_tc_tn_kernel(const IinsTCT
             const int t = kok ? k / g.Cin : 0, ci = kok ? k - t * g.Cin : 0;
             // dW[n][ci][t]: this lane's (ci, t) is fixed, n walks the accumulator columns with a constant stride
             const long nstride = (long)g.Cin * g.ks;
-            float* dst0 = p.dw + (long)(n0 + cbeg) * nstride + (long)ci * g.ks + t;
+            float* dst0 = pdw + (long)(n0 + cbeg) * nstride + (long)ci * g.ks + t;
 #pragma unroll
             for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 16) {
                 float v[16];
@@ -894,7 +905,7 @@ static __global__ void __launch_bounds__(288, 2) iins_tc_tn_kernel(const IinsTCT
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (do_bias && tid < NT && n0 + tid < g.Cout && nit >= 1) atomicAdd(p.db + n0 + tid, s_bias[tid]);
+    if (do_bias && tid < NT && n0 + tid < g.Cout && nit >= 1) atomicAdd(pdb + n0 + tid, s_bias[tid]);
     if (warp == 8) umma::tmem_dealloc(tmem, TCOLS);
 }
 

@@ -142,6 +142,8 @@ class PinnedBatchRing:
         order = self.rng.permutation(n) if self.shuffle else np.arange(n)
         nb = len(self)
         free, full = queue.Queue(), queue.Queue(maxsize=self.depth)
+        if self.cuda_fence and torch.cuda.is_available():
+            torch.cuda.synchronize()      # epoch boundary: copies out of the previous epoch's last slots may still be in flight
         for s in range(self.depth):
             free.put(s)
         ds = self.dataset

@@ -497,6 +497,130 @@ def classifier(p, env_code):
     return h
 
 
+
+# ------------------------------------------------------------------ Conv1d heads
+BN_EPS = 0.8                 # ``nn.BatchNorm1d(out_filters, 0.8)``: the second positional argument is eps (models.py:676, 881)
+BN_MOMENTUM = 0.1
+DROPOUT_P = 0.25
+
+
+def restorer_conv1d_param_shapes(cfg: PathConfig) -> "OrderedDict[str, tuple]":
+    """``RestorerConv1d`` (models.py:661-693): state_dict order incl. the BatchNorm buffers."""
+    sh = OrderedDict()
+    sh["restorer.conv_blocks.0.weight"] = (16, cfg.range_dim, 4)
+    sh["restorer.conv_blocks.0.bias"] = (16,)
+    sh["restorer.conv_blocks.3.weight"] = (32, 16, 4)
+    sh["restorer.conv_blocks.3.bias"] = (32,)
+    sh["restorer.conv_blocks.6.weight"] = (32,)
+    sh["restorer.conv_blocks.6.bias"] = (32,)
+    sh["restorer.conv_blocks.6.running_mean"] = (32,)
+    sh["restorer.conv_blocks.6.running_var"] = (32,)
+    sh["restorer.conv_blocks.6.num_batches_tracked"] = ()
+    sh["restorer.linear_layer1.weight"] = (1, 64)
+    sh["restorer.linear_layer1.bias"] = (1,)
+    sh["restorer.linear_layer2.0.weight"] = (2, 64)      # unused when soft=False
+    sh["restorer.linear_layer2.0.bias"] = (2,)
+    return sh
+
+
+def classifier_conv1d_param_shapes(cfg: PathConfig, filters: int = 16) -> "OrderedDict[str, tuple]":
+    """``ClassifierConv1d`` (models.py:865-891)."""
+    sh = OrderedDict()
+    sh["classifier.conv_blocks.0.weight"] = (filters, cfg.env_dim, 1)
+    sh["classifier.conv_blocks.0.bias"] = (filters,)
+    sh["classifier.conv_blocks.3.weight"] = (filters, filters, 1)
+    sh["classifier.conv_blocks.3.bias"] = (filters,)
+    sh["classifier.conv_blocks.6.weight"] = (filters,)
+    sh["classifier.conv_blocks.6.bias"] = (filters,)
+    sh["classifier.conv_blocks.6.running_mean"] = (filters,)
+    sh["classifier.conv_blocks.6.running_var"] = (filters,)
+    sh["classifier.conv_blocks.6.num_batches_tracked"] = ()
+    sh["classifier.linear.0.weight"] = (cfg.num_classes, filters)
+    sh["classifier.linear.0.bias"] = (cfg.num_classes,)
+    return sh
+
+
+def init_conv_head_params(shapes, gen):
+    """Reference init distributions (models.py:8-14 via .apply(weights_init_normal)): Conv weights N(0, 0.02), BatchNorm weight
+    N(1, 0.02) and bias 0, conv biases / Linear torch defaults; buffers at their PyTorch initial values."""
+    out = OrderedDict()
+    fan_in = 1
+    for name, shp in shapes.items():
+        if name.endswith("num_batches_tracked"):
+            out[name] = torch.zeros((), dtype=torch.long)
+            continue
+        if name.endswith("running_mean"):
+            out[name] = torch.zeros(shp)
+            continue
+        if name.endswith("running_var"):
+            out[name] = torch.ones(shp)
+            continue
+        if len(shp) >= 2 and name.endswith("weight"):
+            fan_in = int(np.prod(shp[1:]))
+        if ".6.weight" in name:
+            t = 1.0 + torch.randn(shp, generator=gen) * 0.02
+        elif ".6.bias" in name:
+            t = torch.zeros(shp)
+        elif len(shp) == 3:
+            t = torch.randn(shp, generator=gen) * 0.02
+        else:
+            t = (torch.rand(shp, generator=gen) * 2 - 1) / math.sqrt(fan_in)
+        out[name] = t.float()
+    return out
+
+
+def dropout_apply(x, mask, training: bool):
+    """nn.Dropout(0.25) (models.py:672, 877) with an explicit keep-mask (0 / 1, same shape as x): kept values are scaled by
+    1 / (1 - p); identity in eval mode."""
+    if not training:
+        return x
+    return x * mask.to(x.dtype) / (1.0 - DROPOUT_P)
+
+
+def batch_norm1d(x, weight, bias, running_mean, running_var, training: bool, eps: float = BN_EPS):
+    """nn.BatchNorm1d(C, eps=0.8) on (B, C, L): training -> batch statistics over (B, L), biased variance; returns
+    (y, new_running_mean, new_running_var) with the momentum-0.1 update (unbiased variance) PyTorch applies; eval -> running
+    statistics."""
+    if training:
+        n = x.shape[0] * x.shape[2]
+        mean = x.mean(dim=(0, 2))
+        var = x.var(dim=(0, 2), unbiased=False)
+        new_rm = (1 - BN_MOMENTUM) * running_mean.to(x.dtype) + BN_MOMENTUM * mean.detach()
+        new_rv = (1 - BN_MOMENTUM) * running_var.to(x.dtype) + BN_MOMENTUM * var.detach() * (n / max(n - 1, 1))
+    else:
+        mean, var, new_rm, new_rv = running_mean.to(x.dtype), running_var.to(x.dtype), running_mean, running_var
+    y = (x - mean.view(1, -1, 1)) / torch.sqrt(var.view(1, -1, 1) + eps) * weight.view(1, -1, 1) + bias.view(1, -1, 1)
+    return y, new_rm, new_rv
+
+
+def restorer_conv1d(p, range_code, masks=None, training: bool = True):
+    """RestorerConv1d.forward (models.py:702-716), soft=False.  masks = (m1 (B,16,4), m2 (B,32,2)) dropout keep-masks.
+    Returns (err_est (B,1), (new_running_mean, new_running_var))."""
+    q = "restorer.conv_blocks."
+    m1, m2 = masks if masks is not None else (None, None)
+    h = F.leaky_relu(_conv1d(range_code, p[q + "0.weight"], p[q + "0.bias"], stride=2, padding=1), 0.2)
+    h = dropout_apply(h, m1, training)
+    h = F.leaky_relu(_conv1d(h, p[q + "3.weight"], p[q + "3.bias"], stride=2, padding=1), 0.2)
+    h = dropout_apply(h, m2, training)
+    h, rm, rv = batch_norm1d(h, p[q + "6.weight"], p[q + "6.bias"], p[q + "6.running_mean"], p[q + "6.running_var"], training)
+    flat = h.reshape(h.shape[0], -1)
+    return _linear(flat, p["restorer.linear_layer1.weight"], p["restorer.linear_layer1.bias"]), (rm, rv)
+
+
+def classifier_conv1d(p, env_code, masks=None, training: bool = True):
+    """ClassifierConv1d.forward (models.py:893-902).  masks = (m1 (B,F,1), m2 (B,F,1))."""
+    q = "classifier.conv_blocks."
+    m1, m2 = masks if masks is not None else (None, None)
+    h = env_code.reshape(env_code.shape[0], -1).unsqueeze(2)
+    h = F.leaky_relu(_conv1d(h, p[q + "0.weight"], p[q + "0.bias"]), 0.2)
+    h = dropout_apply(h, m1, training)
+    h = F.leaky_relu(_conv1d(h, p[q + "3.weight"], p[q + "3.bias"]), 0.2)
+    h = dropout_apply(h, m2, training)
+    h, rm, rv = batch_norm1d(h, p[q + "6.weight"], p[q + "6.bias"], p[q + "6.running_mean"], p[q + "6.running_var"], training)
+    logits = F.leaky_relu(_linear(h.reshape(h.shape[0], -1), p["classifier.linear.0.weight"], p["classifier.linear.0.bias"]), 0.2)
+    return logits, (rm, rv)
+
+
 def emnet(pe, pr, pc, cir, cfg: PathConfig, noise=None):
     """The composite ``network(cir) -> (label_est, env_latent, err_est)`` used by
     train.py:82 / test.py:73.  ``EMNet`` is missing from the reference (run.py:59-62 is the

@@ -197,7 +197,7 @@ def test_ring_fed_training_matches_direct_feed(tmp_path, monkeypatch):
     ds = D.UWBDataset(train)
     parser = get_args(None)
     parser.add_argument("--supervision_rate", type=float, default=0.1)
-    opt = parser.parse_args(["--dataset_env", "room_full", "--batch_size", "256", "--n_epochs", "3", "--lr", "0.001",
+    opt = parser.parse_args(["--dataset_env", "room_full", "--batch_size", "256", "--n_epochs", "3", "--decay_epoch", "2", "--lr", "0.001",
                              "--checkpoint_interval", "-1"])
     torch.manual_seed(0)
     train_semi.run(opt, dataloader=D.PinnedBatchRing(ds, 256, shuffle=True, seed=7), quiet=True)
