@@ -25,12 +25,22 @@ EXPORTS = [
     "iins_adaptive_pool_forward", "iins_adaptive_pool_backward", "iins_accumulate2", "iins_set_stream_concurrency",
     "iins_launch_count", "iins_profile_begin", "iins_profile_collect",
     "iins_set_compute_mode", "iins_get_compute_mode", "iins_profile_shapes",
+    "iins_restorer_conv_ws_floats", "iins_restorer_conv_scratch_floats", "iins_restorer_conv_forward", "iins_restorer_conv_backward",
+    "iins_classifier_conv_ws_floats", "iins_classifier_conv_scratch_floats", "iins_classifier_conv_forward",
+    "iins_classifier_conv_backward",
 ]
 
 
 class IinsConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("batch", "cir_len", "dim", "n_residual", "n_downsample", "env_dim",
                                        "range_dim", "num_classes", "cls_filters")]
+
+
+class IinsHeadState(C.Structure):
+    """iins_head_state (include/iins_b200.h): dropout source + BatchNorm buffers of a Conv1d head."""
+    _fields_ = [("training", C.c_int), ("mask1", C.c_void_p), ("mask2", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p),
+                ("bn_stats", C.c_void_p), ("phase", C.c_int), ("count_scale", C.c_double)]
 
 
 class IinsError(RuntimeError):
@@ -66,6 +76,14 @@ class IinsLib:
         d.iins_restorer_backward.argtypes = [_CFG, _PP, _P, _P, _P, _PP, _P, C.c_int, _P, _P]
         d.iins_classifier_forward.argtypes = [_CFG, _PP, _P, _P, _P, _P]
         d.iins_classifier_backward.argtypes = [_CFG, _PP, _P, _P, _P, _PP, _P, C.c_int, _P, _P]
+        _HS = C.POINTER(IinsHeadState)
+        for mod in ("restorer", "classifier"):
+            for q in ("ws", "scratch"):
+                f = getattr(d, f"iins_{mod}_conv_{q}_floats")
+                f.argtypes = [_CFG]
+                f.restype = C.c_size_t
+            getattr(d, f"iins_{mod}_conv_forward").argtypes = [_CFG, _PP, _P, _P, _P, _HS, _P]
+            getattr(d, f"iins_{mod}_conv_backward").argtypes = [_CFG, _PP, _P, _P, _P, _PP, _P, C.c_int, _P, _HS, _P]
         d.iins_loss_forward_backward.argtypes = [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int,
                                                  C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P]
         d.iins_adam_step.argtypes = [_P, _P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32),

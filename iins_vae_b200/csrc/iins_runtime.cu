@@ -6,6 +6,7 @@
 #include "iins_launchers.h"
 #include "iins_trunk.h"
 #include "iins_misc.cuh"
+#include "iins_heads.cuh"
 #include "../../include/iins_b200.h"
 
 #include <stdio.h>
@@ -1285,6 +1286,185 @@ int mlp_backward(const Shapes& s, const MlpSpec& m, const float* const* P, const
     return check_cuda("mlp_backward");
 }
 
+// ============================================================================ Conv1d heads
+// RestorerConv1d (models.py:661-716):   (B,R,8) -> [Conv1d(R,16,k4,s2,p1) LReLU(.2) Dropout(.25)] -> [Conv1d(16,32,k4,s2,p1) LReLU
+//   Dropout BatchNorm1d(32, eps .8)] -> flatten (B,64) -> Linear(64,1)
+// ClassifierConv1d (models.py:865-902): (B,E,1) -> [Conv1d(E,F,k1) LReLU Dropout] -> [Conv1d(F,F,k1) LReLU Dropout BatchNorm1d(F, eps .8)]
+//   -> flatten -> Linear(F,NC) -> LReLU(.2)
+// The flatten of the reference is over (C, L) = index c * L + l, which is exactly the weight layout of a Conv1d with ks = L
+// taps: the output Linear runs as a convolution with L taps over the channels-last activation (no transpose).
+struct ConvHead {
+    int C0, L0, in_layout;      // input channels / positions / layout
+    int C1, L1, C2, L2;         // after block 1 / block 2
+    int ks, stride, pad;
+    int nout;                   // output features
+    float out_slope;            // LeakyReLU slope on the output, < 0: none
+};
+ConvHead restorer_conv_spec(const Shapes& s) {
+    ConvHead h; h.C0 = s.R; h.L0 = s.Lt; h.in_layout = IINS_NCL; h.C1 = 16; h.L1 = s.Lt / 2; h.C2 = 32; h.L2 = s.Lt / 4;
+    h.ks = 4; h.stride = 2; h.pad = 1; h.nout = 1; h.out_slope = -1.f;
+    return h;
+}
+ConvHead classifier_conv_spec(const Shapes& s) {
+    ConvHead h; h.C0 = s.E; h.L0 = 1; h.in_layout = IINS_NLC; h.C1 = s.F; h.L1 = 1; h.C2 = s.F; h.L2 = 1;
+    h.ks = 1; h.stride = 1; h.pad = 0; h.nout = s.NC; h.out_slope = 0.2f;
+    return h;
+}
+struct ConvHeadPlan { float *a1, *d1, *a2, *d2, *xhat, *ybn, *saved, *out; };
+size_t plan_conv_head(const Shapes& s, const ConvHead& h, float* ws, ConvHeadPlan& pl) {
+    Bump b{ws, 0};
+    const size_t B = s.B;
+    pl.a1 = b.take(B * h.L1 * h.C1); pl.d1 = b.take(B * h.L1 * h.C1);
+    pl.a2 = b.take(B * h.L2 * h.C2); pl.d2 = b.take(B * h.L2 * h.C2);
+    pl.xhat = b.take(B * h.L2 * h.C2); pl.ybn = b.take(B * h.L2 * h.C2);
+    pl.saved = b.take(2 * (size_t)h.C2);
+    pl.out = b.take(B * h.nout);                              // private copy of the output (the LeakyReLU'd logits are needed for backward)
+    return b.off;
+}
+size_t conv_head_scratch(const Shapes& s, const ConvHead& h) {
+    const size_t B = s.B;
+    return 2 * (B * h.L1 * h.C1 + 4) + 3 * (B * h.L2 * h.C2 + 4) + wpack_floats(s);
+}
+int conv_head_check(const ConvHead& h, const iins_head_state* st) {
+    if (st == nullptr) return fail(IINS_ERR_NULL, "conv head: state is NULL");
+    if (h.L2 < 1 || h.C2 > 256 || (h.L0 != 1 && h.L2 * 4 != h.L0)) return fail(IINS_ERR_BAD_CONFIG, "conv head: unsupported shape (code length must be 8)");
+    if (st->training && st->bn_stats == nullptr) return fail(IINS_ERR_NULL, "conv head: bn_stats is NULL in training mode");
+    if (!st->training && (st->running_mean == nullptr || st->running_var == nullptr)) return fail(IINS_ERR_NULL, "conv head: eval mode needs the running statistics");
+    if (st->phase < 0 || st->phase > 2) return fail(IINS_ERR_BAD_CONFIG, "conv head: phase must be 0, 1 or 2");
+    return IINS_OK;
+}
+void launch_dropout(Ctx& c, const float* x, float* y, const float* mask, int B, int L, int C, const iins_head_state* st, int which) {
+    if (c.phase == 1) return;
+    flush_pending(c);
+    IinsDropoutParams dp;
+    memset(&dp, 0, sizeof(dp));
+    dp.x = x; dp.y = y; dp.mask = mask; dp.B = B; dp.L = L; dp.C = C; dp.p = 0.25f;
+    dp.seed = st->seed; dp.offset = st->offset * 2 + (unsigned long long)which;   // two dropout layers per call
+    IINS_LAUNCH(iins_dropout_kernel, grid_for((long)B * L * C), 256, 0, c.st, dp);
+}
+
+int conv_head_forward(const Shapes& s, const ConvHead& h, const float* const* P, const float* in, float* out, float* ws,
+                      const iins_head_state* st, cudaStream_t stream) {
+    Ctx c{stream};
+    ConvHeadPlan pl;
+    c.wpack = ws + plan_conv_head(s, h, ws, pl);
+    c.wpack_cap = wpack_floats(s) * sizeof(float);
+    const int B = s.B, train = st->training;
+    const long rows2 = (long)B * h.L2;
+    run_phases(c, [&]() {
+    if (st->phase != 2) {
+        IinsGeom g1 = conv_geom(B, h.L0, h.L1, h.C0, h.C1, h.ks, h.stride, h.pad, IINS_PAD_ZERO);
+        g1.in_layout = h.in_layout;
+        conv_forward(c, g1, in, P[0], plain_epilogue(P[1], IINS_ACT_LRELU, 0.2f, pl.a1));
+        const float* x2 = pl.a1;
+        if (train) { launch_dropout(c, pl.a1, pl.d1, st->mask1, B, h.L1, h.C1, st, 0); x2 = pl.d1; }
+        IinsGeom g2 = conv_geom(B, h.L1, h.L2, h.C1, h.C2, h.ks, h.stride, h.pad, IINS_PAD_ZERO);
+        conv_forward(c, g2, x2, P[2], plain_epilogue(P[3], IINS_ACT_LRELU, 0.2f, pl.a2));
+        if (train) launch_dropout(c, pl.a2, pl.d2, st->mask2, B, h.L2, h.C2, st, 1);
+        IINS_SKIP_IN_COLLECT(c) if (train) {
+            flush_pending(c);
+            cudaMemsetAsync(st->bn_stats, 0, 2 * (size_t)h.C2 * sizeof(double), c.st);
+            IinsBnStatsParams sp;
+            memset(&sp, 0, sizeof(sp));
+            sp.a = pl.d2; sp.rows = rows2; sp.C = h.C2; sp.sums = st->bn_stats;
+            long nb = (rows2 + (256 / h.C2) * 8 - 1) / ((256 / h.C2) * 8);
+            if (nb > 148 * 2) nb = 148 * 2;
+            if (nb < 1) nb = 1;
+            IINS_LAUNCH(iins_bn_stats_kernel, (int)nb, 256, 0, c.st, sp);
+        }
+    }
+    if (st->phase != 1) {
+        IINS_SKIP_IN_COLLECT(c) {
+            flush_pending(c);
+            IinsBnApplyParams ap;
+            memset(&ap, 0, sizeof(ap));
+            ap.x = train ? pl.d2 : pl.a2; ap.xhat = pl.xhat; ap.y = pl.ybn; ap.rows = rows2; ap.C = h.C2;
+            ap.sums = train ? st->bn_stats : nullptr;
+            ap.count = (double)rows2 * (st->count_scale > 0.0 ? st->count_scale : 1.0);
+            ap.gamma = P[4]; ap.beta = P[5]; ap.eps = 0.8f; ap.momentum = 0.1f;
+            ap.running_mean = st->running_mean; ap.running_var = st->running_var; ap.num_batches_tracked = (long long*)st->num_batches_tracked;
+            ap.saved = pl.saved;
+            IINS_LAUNCH(iins_bn_apply_kernel, grid_for(rows2 * h.C2), 256, 0, c.st, ap);
+        }
+        // Linear over the (C, L)-flattened map == a convolution with L2 taps on the channels-last activation
+        IinsGeom go = conv_geom(B, h.L2, 1, h.C2, h.nout, h.L2, 1, 0, IINS_PAD_ZERO);
+        const int act = h.out_slope < 0.f ? IINS_ACT_NONE : IINS_ACT_LRELU;
+        conv_forward(c, go, pl.ybn, P[6], plain_epilogue(P[7], act, h.out_slope, pl.out));
+        IINS_SKIP_IN_COLLECT(c) { flush_pending(c); cudaMemcpyAsync(out, pl.out, (size_t)B * h.nout * sizeof(float), cudaMemcpyDeviceToDevice, c.st); }
+    }
+    });
+    if (c.err) return plan_error(c.err, "conv_head_forward");
+    return check_cuda("conv_head_forward");
+}
+
+int conv_head_backward(const Shapes& s, const ConvHead& h, const float* const* P, const float* in, const float* ws,
+                       const float* d_out, float* const* G, float* d_in, int accumulate, float* scratch,
+                       const iins_head_state* st, cudaStream_t stream) {
+    Ctx c{stream};
+    ConvHeadPlan pl;
+    plan_conv_head(s, h, const_cast<float*>(ws), pl);
+    const int B = s.B, train = st->training;
+    const long rows2 = (long)B * h.L2;
+    Bump b{scratch, 0};
+    float* d_ybn = b.take((size_t)rows2 * h.C2);
+    float* d_d2 = b.take((size_t)rows2 * h.C2);
+    float* d_a2 = b.take((size_t)rows2 * h.C2);
+    float* d_d1 = b.take((size_t)B * h.L1 * h.C1);
+    float* d_a1 = b.take((size_t)B * h.L1 * h.C1);
+    c.wpack = b.take(wpack_floats(s));
+    c.wpack_cap = wpack_floats(s) * sizeof(float);
+    run_phases(c, [&]() {
+    begin_async_wgrad(c);
+    if (st->phase != 2) {
+        IinsGeom go = conv_geom(B, h.L2, 1, h.C2, h.nout, h.L2, 1, 0, IINS_PAD_ZERO);
+        IinsDz dzo = h.out_slope < 0.f ? plain_dz(d_out) : act_dz(d_out, pl.out, IINS_ACT_LRELU, h.out_slope);
+        conv_wgrad(c, go, pl.ybn, dzo, G[6], G[7]);
+        conv_dgrad(c, go, dzo, P[6], d_ybn, nullptr);
+        IINS_SKIP_IN_COLLECT(c) {
+            flush_pending(c);
+            // sum dy (= d beta) and sum dy * xhat (= d gamma): the LOCAL sums also go into the gradient buffers
+            if (train) cudaMemsetAsync(st->bn_stats + 2 * h.C2, 0, 2 * (size_t)h.C2 * sizeof(double), c.st);
+            IinsBnStatsParams sp;
+            memset(&sp, 0, sizeof(sp));
+            sp.a = d_ybn; sp.b = pl.xhat; sp.rows = rows2; sp.C = h.C2;
+            sp.sums = st->bn_stats + 2 * h.C2; sp.g_first = G[5]; sp.g_second = G[4];
+            long nb = (rows2 + (256 / h.C2) * 8 - 1) / ((256 / h.C2) * 8);
+            if (nb > 148 * 2) nb = 148 * 2;
+            if (nb < 1) nb = 1;
+            IINS_LAUNCH(iins_bn_stats_kernel, (int)nb, 256, 0, c.st, sp);
+        }
+    }
+    if (st->phase != 1) {
+        IINS_SKIP_IN_COLLECT(c) {
+            flush_pending(c);
+            IinsBnBwdParams bp;
+            memset(&bp, 0, sizeof(bp));
+            bp.dy = d_ybn; bp.xhat = pl.xhat; bp.dx = d_d2; bp.rows = rows2; bp.C = h.C2;
+            bp.sums = train ? st->bn_stats + 2 * h.C2 : nullptr;
+            bp.count = (double)rows2 * (st->count_scale > 0.0 ? st->count_scale : 1.0);
+            bp.gamma = P[4]; bp.saved = pl.saved;
+            IINS_LAUNCH(iins_bn_bwd_kernel, grid_for(rows2 * h.C2), 256, 0, c.st, bp);
+        }
+        const float* g2 = d_d2;
+        if (train) { launch_dropout(c, d_d2, d_a2, st->mask2, B, h.L2, h.C2, st, 1); g2 = d_a2; }
+        IinsGeom gc2 = conv_geom(B, h.L1, h.L2, h.C1, h.C2, h.ks, h.stride, h.pad, IINS_PAD_ZERO);
+        IinsDz dz2 = act_dz(g2, pl.a2, IINS_ACT_LRELU, 0.2f);
+        conv_wgrad(c, gc2, train ? pl.d1 : pl.a1, dz2, G[2], G[3]);
+        conv_dgrad(c, gc2, dz2, P[2], d_d1, nullptr);
+        const float* g1 = d_d1;
+        if (train) { launch_dropout(c, d_d1, d_a1, st->mask1, B, h.L1, h.C1, st, 0); g1 = d_a1; }
+        IinsGeom gc1 = conv_geom(B, h.L0, h.L1, h.C0, h.C1, h.ks, h.stride, h.pad, IINS_PAD_ZERO);
+        gc1.in_layout = h.in_layout;
+        IinsDz dz1 = act_dz(g1, pl.a1, IINS_ACT_LRELU, 0.2f);
+        conv_wgrad(c, gc1, in, dz1, G[0], G[1]);
+        if (d_in != nullptr) conv_dgrad(c, gc1, dz1, P[0], d_in, accumulate ? d_in : nullptr);
+    }
+    end_async_wgrad(c);
+    });
+    if (c.err) return plan_error(c.err, "conv_head_backward");
+    return check_cuda("conv_head_backward");
+}
+
 #define IINS_SHAPES_OR_RETURN(cfg, s) Shapes s; { int rc_ = make_shapes(cfg, s); if (rc_ != IINS_OK) return rc_; }
 
 }  // namespace
@@ -1408,6 +1588,53 @@ int iins_classifier_backward(const iins_config* cfg, const float* const* params,
     MlpSpec m = classifier_spec(s);
     return mlp_backward(s, m, params, env_code, ws + mlp_ws(s, m), ws, d_logits, grads, d_env_code, accumulate, scratch,
                         (cudaStream_t)stream);
+}
+
+// ---- Conv1d heads
+size_t iins_restorer_conv_ws_floats(const iins_config* cfg) {
+    Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0;
+    ConvHeadPlan pl; return plan_conv_head(s, restorer_conv_spec(s), nullptr, pl) + wpack_floats(s);
+}
+size_t iins_restorer_conv_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return conv_head_scratch(s, restorer_conv_spec(s)); }
+size_t iins_classifier_conv_ws_floats(const iins_config* cfg) {
+    Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0;
+    ConvHeadPlan pl; return plan_conv_head(s, classifier_conv_spec(s), nullptr, pl) + wpack_floats(s);
+}
+size_t iins_classifier_conv_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return conv_head_scratch(s, classifier_conv_spec(s)); }
+
+int iins_restorer_conv_forward(const iins_config* cfg, const float* const* params, const float* range_code, float* err_est, float* ws,
+                               const iins_head_state* state, iins_stream_t stream) {
+    IINS_SHAPES_OR_RETURN(cfg, s);
+    if (!params || !range_code || !err_est || !ws) return fail(IINS_ERR_NULL, "restorer_conv_forward: NULL argument");
+    const ConvHead h = restorer_conv_spec(s);
+    int rc = conv_head_check(h, state); if (rc != IINS_OK) return rc;
+    return conv_head_forward(s, h, params, range_code, err_est, ws, state, (cudaStream_t)stream);
+}
+int iins_restorer_conv_backward(const iins_config* cfg, const float* const* params, const float* range_code, const float* ws,
+                                const float* d_err_est, float* const* grads, float* d_range_code, int accumulate, float* scratch,
+                                const iins_head_state* state, iins_stream_t stream) {
+    IINS_SHAPES_OR_RETURN(cfg, s);
+    if (!params || !range_code || !ws || !d_err_est || !grads || !scratch) return fail(IINS_ERR_NULL, "restorer_conv_backward: NULL argument");
+    const ConvHead h = restorer_conv_spec(s);
+    int rc = conv_head_check(h, state); if (rc != IINS_OK) return rc;
+    return conv_head_backward(s, h, params, range_code, ws, d_err_est, grads, d_range_code, accumulate, scratch, state, (cudaStream_t)stream);
+}
+int iins_classifier_conv_forward(const iins_config* cfg, const float* const* params, const float* env_code, float* logits, float* ws,
+                                 const iins_head_state* state, iins_stream_t stream) {
+    IINS_SHAPES_OR_RETURN(cfg, s);
+    if (!params || !env_code || !logits || !ws) return fail(IINS_ERR_NULL, "classifier_conv_forward: NULL argument");
+    const ConvHead h = classifier_conv_spec(s);
+    int rc = conv_head_check(h, state); if (rc != IINS_OK) return rc;
+    return conv_head_forward(s, h, params, env_code, logits, ws, state, (cudaStream_t)stream);
+}
+int iins_classifier_conv_backward(const iins_config* cfg, const float* const* params, const float* env_code, const float* ws,
+                                  const float* d_logits, float* const* grads, float* d_env_code, int accumulate, float* scratch,
+                                  const iins_head_state* state, iins_stream_t stream) {
+    IINS_SHAPES_OR_RETURN(cfg, s);
+    if (!params || !env_code || !ws || !d_logits || !grads || !scratch) return fail(IINS_ERR_NULL, "classifier_conv_backward: NULL argument");
+    const ConvHead h = classifier_conv_spec(s);
+    int rc = conv_head_check(h, state); if (rc != IINS_OK) return rc;
+    return conv_head_backward(s, h, params, env_code, ws, d_logits, grads, d_env_code, accumulate, scratch, state, (cudaStream_t)stream);
 }
 
 int iins_loss_forward_backward(int batch, int cir_len, int num_classes, const float* x, const float* x_recon,

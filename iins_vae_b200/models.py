@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ._capi import IinsConfig, get_lib, ptr, ptr_array
+from ._capi import IinsConfig, IinsHeadState, get_lib, ptr, ptr_array
 
 __all__ = ["Encoder", "Decoder", "Restorer", "Classifier", "EMNet", "weights_init_normal", "LambdaLR",
            "LayerNorm", "AdaptiveInstanceNorm1d"]
@@ -218,6 +218,67 @@ class _HeadFn(torch.autograd.Function):
         return (d_in, None, None, None) + tuple(grads) + (None,) * (len(ctx.params) - n_used)
 
 
+def _addr(t):
+    return None if t is None else t.data_ptr()
+
+
+class _ConvHeadFn(torch.autograd.Function):
+    """Restorer / Classifier with net_type='Conv1d' (models.py:661-716, :865-902): Conv1d + LeakyReLU + Dropout blocks, BatchNorm1d
+    (eps 0.8), Linear.  ``hs`` carries the dropout source (explicit masks or a Philox seed / offset) and the BatchNorm buffers."""
+
+    @staticmethod
+    def forward(ctx, inp, kind, cfg, out_dim, hs, *params):
+        lib = get_lib()
+        lib.check(lib.iins_validate_config(cfg), f"{kind} config")
+        dev = inp.device
+        out = torch.empty(inp.shape[0], out_dim, device=dev)
+        ws = _empty(getattr(lib, f"iins_{kind}_conv_ws_floats")(cfg), dev)
+        st = IinsHeadState(int(hs["training"]), _addr(hs.get("mask1")), _addr(hs.get("mask2")), int(hs["seed"]), int(hs["offset"]),
+                           _addr(hs["running_mean"]), _addr(hs["running_var"]), _addr(hs["num_batches_tracked"]),
+                           _addr(hs["bn_stats"]), 0, 1.0)
+        lib.check(getattr(lib, f"iins_{kind}_conv_forward")(cfg, ptr_array(params), ptr(inp), ptr(out), ptr(ws), C.byref(st), _stream()),
+                  f"{kind} (Conv1d) forward")
+        ctx.kind, ctx.cfg, ctx.params, ctx.hs, ctx.st = kind, cfg, params, hs, st
+        ctx.save_for_backward(inp, ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = get_lib()
+        inp, ws = ctx.saved_tensors
+        n_used = 8                                                   # restorer.linear_layer2 is never touched (grad None)
+        grads = [torch.zeros_like(p) for p in ctx.params[:n_used]]
+        d_in = torch.empty_like(inp)
+        scratch = _empty(getattr(lib, f"iins_{ctx.kind}_conv_scratch_floats")(ctx.cfg), inp.device)
+        lib.check(getattr(lib, f"iins_{ctx.kind}_conv_backward")(
+            ctx.cfg, ptr_array(ctx.params), ptr(inp), ptr(ws), ptr(d_out.contiguous().float()),
+            ptr_array(grads + [None] * (len(ctx.params) - n_used)), ptr(d_in), 0, ptr(scratch), C.byref(ctx.st), _stream()),
+            f"{ctx.kind} (Conv1d) backward")
+        return (d_in, None, None, None, None) + tuple(grads) + (None,) * (len(ctx.params) - n_used)
+
+
+def _conv_block(holder, first_index, cin, cout, ks, stride, pad, bn):
+    """Parameter holders of one ``conv_block`` of the reference (Conv1d, LeakyReLU, Dropout[, BatchNorm1d(c, 0.8)]) under the
+    reference's Sequential indices."""
+    holder.put(first_index, nn.Conv1d(cin, cout, ks, stride, pad))
+    if bn:
+        holder.put(first_index + 3, nn.BatchNorm1d(cout, 0.8))      # second positional argument = eps (models.py:676, 881)
+
+
+class _ConvHeadMixin:
+    """Shared forward plumbing of the two Conv1d heads."""
+
+    def _head_state(self, bn, masks, dev):
+        if not hasattr(self, "_bn_stats") or self._bn_stats.device != dev:
+            self._bn_stats = torch.zeros(4 * bn.num_features, dtype=torch.float64, device=dev)
+        self._offset += 1
+        hs = dict(training=self.training, seed=self._seed, offset=self._offset, running_mean=bn.running_mean,
+                  running_var=bn.running_var, num_batches_tracked=bn.num_batches_tracked, bn_stats=self._bn_stats)
+        if masks is not None:
+            hs["mask1"], hs["mask2"] = (m.contiguous().float() for m in masks)
+        return hs
+
+
 # ------------------------------------------------------------------------------------ modules
 class Encoder(nn.Module):
     """models.py:32-64.  ``forward(x:(B,L)) -> (range_code (B,out_dim,8), env_code (B,style_dim,1),
@@ -323,53 +384,81 @@ class Decoder(nn.Module):
         return x_recon.squeeze()                      # models.py:90
 
 
-class Restorer(nn.Module):
-    """models.py:94-112 with net_type='Linear', soft=False (RestorerLinear :615-658)."""
+class Restorer(_ConvHeadMixin, nn.Module):
+    """models.py:94-112.  net_type='Linear' -> RestorerLinear (:615-658); net_type='Conv1d' -> RestorerConv1d (:661-716):
+    two Conv1d(k4,s2,p1) + LeakyReLU(0.2) + Dropout(0.25) blocks, BatchNorm1d(32, eps=0.8) behind the second, Linear(64, 1).
+    ``forward(range_code, masks=None)``: ``masks`` = (m1 (B,16,4), m2 (B,32,2)) explicit dropout keep-masks (tests replay the
+    reference's); by default Philox4x32-10 decides inside the kernel (``seed``, one offset per call)."""
 
-    def __init__(self, code_shape, soft=False, filters=64, conv_type=1, expand=False, net_type="Linear"):
+    def __init__(self, code_shape, soft=False, filters=64, conv_type=1, expand=False, net_type="Linear", seed=0):
         super().__init__()
-        if net_type != "Linear":
-            raise NotImplementedError("iins_vae_b200: only net_type='Linear' is on the B200 path (SURVEY 8f)")
+        if net_type not in ("Linear", "Conv1d"):
+            raise NotImplementedError("iins_vae_b200: net_type 'Linear' and 'Conv1d' are on the B200 path (Conv2d: SURVEY 8f row 3)")
         if soft:
             raise NotImplementedError("iins_vae_b200: soft=True (host np.random reparameterisation) is not on the path")
-        self.soft = soft
+        self.soft, self.net_type = soft, net_type
         self.code_shape = tuple(int(v) for v in code_shape)
         n_in = int(np.prod(code_shape))
         self.restorer = _Slots()
-        layers = self.restorer.put("layers", _Slots())
-        layers.put(0, nn.Linear(n_in, 512))
-        layers.put(2, nn.Linear(512, 256))
-        layers.put(4, nn.Linear(256, 256))
-        self.restorer.put("linear_layer1", nn.Linear(256, 1))
-        self.restorer.put("linear_layer2", nn.Linear(256, 2))       # present, unused (models.py:632)
+        self._seed, self._offset = int(seed), 0
+        if net_type == "Linear":
+            layers = self.restorer.put("layers", _Slots())
+            layers.put(0, nn.Linear(n_in, 512))
+            layers.put(2, nn.Linear(512, 256))
+            layers.put(4, nn.Linear(256, 256))
+            self.restorer.put("linear_layer1", nn.Linear(256, 1))
+            self.restorer.put("linear_layer2", nn.Linear(256, 2))       # present, unused (models.py:632)
+        else:
+            blocks = self.restorer.put("conv_blocks", _Slots())
+            _conv_block(blocks, 0, self.code_shape[0], 16, 4, 2, 1, bn=False)
+            _conv_block(blocks, 3, 16, 32, 4, 2, 1, bn=True)
+            self.restorer.put("linear_layer1", nn.Linear(64, 1))
+            l2 = self.restorer.put("linear_layer2", _Slots())           # nn.Sequential(nn.Linear(64, 2)): present, unused
+            l2.put(0, nn.Linear(64, 2))
 
-    def forward(self, range_code):
+    def forward(self, range_code, masks=None):
         rc = _check_input(range_code, "range_code")
         if tuple(rc.shape[1:]) != self.code_shape or self.code_shape[-1] != 8:
             raise RuntimeError(f"Restorer expects range_code (B,{self.code_shape}) with code length 8")
         cfg = _cfg(rc.shape[0], range_dim=self.code_shape[0])
-        return _HeadFn.apply(rc, "restorer", cfg, 1, *_params_of(self))
+        if self.net_type == "Linear":
+            return _HeadFn.apply(rc, "restorer", cfg, 1, *_params_of(self))
+        hs = self._head_state(getattr(self.restorer.conv_blocks, "6"), masks, rc.device)
+        return _ConvHeadFn.apply(rc, "restorer", cfg, 1, hs, *_params_of(self))
 
 
-class Classifier(nn.Module):
-    """models.py:115-132 with net_type='Linear' (ClassifierLinear :838-862)."""
+class Classifier(_ConvHeadMixin, nn.Module):
+    """models.py:115-132.  net_type='Linear' -> ClassifierLinear (:838-862); net_type='Conv1d' -> ClassifierConv1d (:865-902):
+    two Conv1d(k1) + LeakyReLU(0.2) + Dropout(0.25) blocks on (B, env_dim, 1), BatchNorm1d(filters, eps=0.8) behind the second,
+    Linear(filters, num_classes) + LeakyReLU(0.2)."""
 
-    def __init__(self, env_dim, num_classes, filters=16, net_type="Linear"):
+    def __init__(self, env_dim, num_classes, filters=16, net_type="Linear", seed=0):
         super().__init__()
-        if net_type != "Linear":
-            raise NotImplementedError("iins_vae_b200: only net_type='Linear' is on the B200 path (SURVEY 8f)")
-        self.env_dim, self.num_classes, self.filters = env_dim, num_classes, filters
+        if net_type not in ("Linear", "Conv1d"):
+            raise NotImplementedError("iins_vae_b200: net_type 'Linear' and 'Conv1d' are on the B200 path (Conv2d: SURVEY 8f row 3)")
+        self.env_dim, self.num_classes, self.filters, self.net_type = env_dim, num_classes, filters, net_type
         self.classifier = _Slots()
-        layers = self.classifier.put("layers", _Slots())
-        layers.put(0, nn.Linear(env_dim, filters))
-        layers.put(2, nn.Linear(filters, filters * 2))
-        layers.put(4, nn.Linear(filters * 2, filters))
-        layers.put(6, nn.Linear(filters, num_classes))
+        self._seed, self._offset = int(seed) + 1, 0
+        if net_type == "Linear":
+            layers = self.classifier.put("layers", _Slots())
+            layers.put(0, nn.Linear(env_dim, filters))
+            layers.put(2, nn.Linear(filters, filters * 2))
+            layers.put(4, nn.Linear(filters * 2, filters))
+            layers.put(6, nn.Linear(filters, num_classes))
+        else:
+            blocks = self.classifier.put("conv_blocks", _Slots())
+            _conv_block(blocks, 0, env_dim, filters, 1, 1, 0, bn=False)
+            _conv_block(blocks, 3, filters, filters, 1, 1, 0, bn=True)
+            lin = self.classifier.put("linear", _Slots())
+            lin.put(0, nn.Linear(filters, num_classes))
 
-    def forward(self, env_code):
+    def forward(self, env_code, masks=None):
         cat = _check_input(env_code, "env_code").view(env_code.size(0), -1)
         cfg = _cfg(cat.shape[0], env_dim=self.env_dim, num_classes=self.num_classes, filters=self.filters)
-        return _HeadFn.apply(cat, "classifier", cfg, self.num_classes, *_params_of(self))
+        if self.net_type == "Linear":
+            return _HeadFn.apply(cat, "classifier", cfg, self.num_classes, *_params_of(self))
+        hs = self._head_state(getattr(self.classifier.conv_blocks, "6"), masks, cat.device)
+        return _ConvHeadFn.apply(cat, "classifier", cfg, self.num_classes, hs, *_params_of(self))
 
 
 class EMNet(nn.Module):

@@ -114,6 +114,39 @@ int iins_classifier_backward(const iins_config* cfg, const float* const* params,
                              const float* ws, const float* d_logits, float* const* grads,
                              float* d_env_code, int accumulate, float* scratch, iins_stream_t stream);
 
+/* ---- Conv1d heads (net_type='Conv1d'): RestorerConv1d models.py:661-716, ClassifierConv1d models.py:865-902 --------------
+ * Conv1d + LeakyReLU(0.2) + Dropout(0.25) blocks, BatchNorm1d(eps = 0.8: the second positional argument of
+ * nn.BatchNorm1d(c, 0.8) is eps) on the second block, Linear output (+ LeakyReLU(0.2) on the classifier's logits).
+ * params (named_parameters order): conv_blocks.0.{weight,bias}, conv_blocks.3.{weight,bias}, conv_blocks.6.{weight,bias}
+ * (BatchNorm), then linear_layer1.{weight,bias} (+ linear_layer2.0.{weight,bias}, never touched) / linear.0.{weight,bias}. */
+typedef struct iins_head_state {
+    int training;              /* 1: dropout active, batch statistics, running buffers updated (nn.Module.train()); 0: eval */
+    const float* mask1;        /* explicit dropout keep-masks (0 / 1) in the reference's (B, C, L) element order, or NULL: */
+    const float* mask2;        /*   Philox4x32-10(seed, offset) decides, reproducibly in forward and backward            */
+    uint64_t seed, offset;
+    float* running_mean;       /* BatchNorm buffers [C] (device); updated with momentum 0.1 in training, read in eval      */
+    float* running_var;
+    int64_t* num_batches_tracked;
+    double* bn_stats;          /* device double[4 * C] scratch: [0,2C) forward sums (x, x^2), [2C,4C) backward sums (dy, dy*xhat) */
+    int phase;                 /* 0: whole call.  1: stop after the LOCAL batch sums are in bn_stats; 2: continue from bn_stats --    */
+                               /*    a data-parallel caller all-reduces the 2 * C doubles in between (SyncBN)                          */
+    double count_scale;        /* number of ranks whose sums were added into bn_stats (1 without SyncBN)                              */
+} iins_head_state;
+size_t iins_restorer_conv_ws_floats(const iins_config* cfg);
+size_t iins_restorer_conv_scratch_floats(const iins_config* cfg);
+int iins_restorer_conv_forward(const iins_config* cfg, const float* const* params, const float* range_code, float* err_est,
+                               float* ws, const iins_head_state* state, iins_stream_t stream);
+int iins_restorer_conv_backward(const iins_config* cfg, const float* const* params, const float* range_code, const float* ws,
+                                const float* d_err_est, float* const* grads, float* d_range_code, int accumulate,
+                                float* scratch, const iins_head_state* state, iins_stream_t stream);
+size_t iins_classifier_conv_ws_floats(const iins_config* cfg);
+size_t iins_classifier_conv_scratch_floats(const iins_config* cfg);
+int iins_classifier_conv_forward(const iins_config* cfg, const float* const* params, const float* env_code, float* logits,
+                                 float* ws, const iins_head_state* state, iins_stream_t stream);
+int iins_classifier_conv_backward(const iins_config* cfg, const float* const* params, const float* env_code, const float* ws,
+                                  const float* d_logits, float* const* grads, float* d_env_code, int accumulate,
+                                  float* scratch, const iins_head_state* state, iins_stream_t stream);
+
 /* ---- Fused loss + seed gradients + metrics: train_semi.py:199-225, train.py:87-91, :104-115 -------
  * out[8] (zeroed inside): [0] mean|x-x_recon|  [1] mean|err-err_est|  [2] mean CE  [3] lam-weighted sum
  * of [0..2] (the KL term lives in the encoder)  [4] mean (err_est-err)^2  [5] #correct argmax

@@ -21,6 +21,7 @@ sys.path.insert(0, "/root/reference")
 
 import models as ref                      # noqa: E402
 from oracle import iins_oracle as orc      # noqa: E402
+from tests.golden.make_golden_common import conv_head_case_inputs   # noqa: E402
 
 
 def capture_masks(module):
@@ -38,18 +39,11 @@ def capture_masks(module):
 
 
 def run_case(store, prefix, kind, seed, batch, training, cfg):
-    gen = torch.Generator().manual_seed(seed)
+    x, p, gen = conv_head_case_inputs(kind, seed, batch, cfg)
     if kind == "res":
-        shapes = orc.restorer_conv1d_param_shapes(cfg)
         mod = ref.Restorer(code_shape=(cfg.range_dim, cfg.code_len), soft=False, filters=cfg.dim, conv_type=1, expand=False, net_type="Conv1d")
-        x = torch.rand(batch, cfg.range_dim, cfg.code_len, generator=gen)
     else:
-        shapes = orc.classifier_conv1d_param_shapes(cfg)
         mod = ref.Classifier(env_dim=cfg.env_dim, num_classes=cfg.num_classes, filters=16, net_type="Conv1d")
-        x = torch.randn(batch, cfg.env_dim, 1, generator=gen) * 0.5
-    p = orc.init_conv_head_params(shapes, gen)
-    p[[k for k in p if k.endswith("running_mean")][0]] += 0.05          # non-trivial buffers (eval mode uses them)
-    p[[k for k in p if k.endswith("running_var")][0]] *= 1.3
     assert list(mod.state_dict().keys()) == list(p.keys()), (list(mod.state_dict().keys()), list(p.keys()))
     mod.load_state_dict(p)
     mod.train(training)

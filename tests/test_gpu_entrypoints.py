@@ -181,11 +181,13 @@ def test_prefetched_batch_gives_the_same_step():
     assert not torch.allclose(ref_a, ref_b)
 
 
-def test_ring_fed_training_matches_direct_feed(tmp_path, monkeypatch):
+def test_ring_fed_training_sees_exactly_the_ring_batches(tmp_path, monkeypatch):
     """train_semi.run fed by the pinned batch ring (StandardScaler'd arrays -> shuffled pinned batches ->
-    prefetch on the copy stream, ragged last batch included) must train exactly like feeding the same batches, in the same
-    order, straight to engine.step()."""
-    from iins_vae_b200 import dataset as D, models as M, train_semi
+    prefetch on the copy stream, ragged last batch included, several epochs so that ring slots are recycled): the tensors
+    every step actually computes on must be exactly the ring's batches, in order, with the seeded supervision mask -- no
+    stale or half-overwritten pinned buffer.  (Comparing trained parameters would not do: the float atomics of the weight
+    gradients make two identical runs drift by +-lr on noise-dominated entries.)"""
+    from iins_vae_b200 import dataset as D, train_semi
     from iins_vae_b200.engine import SemiTrainEngine
     from iins_vae_b200.parallel import SupervisionMask
     from iins_vae_b200.utils import get_args
@@ -197,31 +199,32 @@ def test_ring_fed_training_matches_direct_feed(tmp_path, monkeypatch):
     ds = D.UWBDataset(train)
     parser = get_args(None)
     parser.add_argument("--supervision_rate", type=float, default=0.1)
-    opt = parser.parse_args(["--dataset_env", "room_full", "--batch_size", "256", "--n_epochs", "3", "--decay_epoch", "2", "--lr", "0.001",
+    opt = parser.parse_args(["--dataset_env", "room_full", "--batch_size", "256", "--n_epochs", "4", "--decay_epoch", "3", "--lr", "0.001",
                              "--checkpoint_interval", "-1"])
+    seen = []
+    orig = SemiTrainEngine.step
+
+    def spy(self, *a, **kw):
+        out = orig(self, *a, **kw)
+        seen.append((self.B, bool(kw.get("supervised", True)), self.cir.double().sum().item(), self.cir[:, 3].double().sum().item(),
+                     self.err.double().sum().item(), self.label.double().sum().item()))
+        return out
+
+    monkeypatch.setattr(SemiTrainEngine, "step", spy)
     torch.manual_seed(0)
-    train_semi.run(opt, dataloader=D.PinnedBatchRing(ds, 256, shuffle=True, seed=7), quiet=True)
-    trained = train_semi.last_modules
-    # the same run by hand: same init (seed), same batch order (ring seed), same mask stream
-    torch.manual_seed(0)
-    Enc, Dec, Res, Cls, _ = train_semi.build_modules(opt, torch.device("cuda"))
-    for m in (Enc, Dec, Res, Cls):
-        m.apply(M.weights_init_normal)
-    engines, mask = {}, SupervisionMask(opt.supervision_rate, seed=1234)
-    ring = D.PinnedBatchRing(ds, 256, shuffle=True, seed=7)
-    sched = M.LambdaLR(opt.n_epochs, 0, opt.decay_epoch)
-    for epoch in range(3):
+    last = train_semi.run(opt, dataloader=D.PinnedBatchRing(ds, 256, shuffle=True, seed=7), quiet=True)
+    assert np.isfinite(last["loss"])
+    mask = SupervisionMask(opt.supervision_rate, seed=1234)
+    ring = D.PinnedBatchRing(ds, 256, shuffle=True, seed=7, pin=False)
+    want = []
+    for epoch in range(4):
         for batch in ring:
-            B = batch["CIR"].shape[0]
-            if B not in engines:
-                engines[B] = SemiTrainEngine(Enc, Dec, Res, Cls, batch_size=B, lr=opt.lr, betas=(opt.b1, opt.b2),
-                                             shared_state=next(iter(engines.values()), None))
-            engines[B].set_lr(opt.lr * sched.step(epoch))
-            engines[B].step(batch["CIR"].clone(), batch["Err"].clone(), batch["Label"].clone(), supervised=bool(mask()))
-    torch.cuda.synchronize()
-    for a, b in zip(trained, (Enc, Dec, Res, Cls)):
-        for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
-            assert torch.allclose(p, q, rtol=1e-4, atol=2e-6), n
+            c, e, l = batch["CIR"].double(), batch["Err"].double(), batch["Label"].double()
+            want.append((c.shape[0], bool(mask()), float(c.sum()), float(c[:, 3].sum()), float(e.sum()), float(l.sum())))
+    assert len(seen) == len(want) == 16
+    for i, (g, w) in enumerate(zip(seen, want)):
+        assert g[:2] == w[:2], (i, g, w)
+        np.testing.assert_allclose(g[2:], w[2:], rtol=1e-9, atol=1e-6, err_msg=f"step {i}: the engine computed on other data than ring batch {i}")
 
 
 def test_sharded_inference_driver_single_rank():
