@@ -40,7 +40,8 @@ class IinsHeadState(C.Structure):
     """iins_head_state (include/iins_b200.h): dropout source + BatchNorm buffers of a Conv1d head."""
     _fields_ = [("training", C.c_int), ("mask1", C.c_void_p), ("mask2", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64),
                 ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p),
-                ("bn_stats", C.c_void_p), ("phase", C.c_int), ("count_scale", C.c_double)]
+                ("bn_stats", C.c_void_p), ("phase", C.c_int), ("count_scale", C.c_double), ("sample_offset", C.c_int64),
+                ("offset_dev", C.c_void_p)]
 
 
 class IinsError(RuntimeError):

@@ -68,7 +68,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write("".join(logs))
         tmp = OUT + f".tmp{os.getpid()}"
         r = subprocess.run([nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a"] + [_obj(s) for s in _sources()] +
-                           ["-o", tmp, "-lcuda"], capture_output=True, text=True)
+                           ["-o", tmp], capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("nvcc failed linking libiins_b200.so")

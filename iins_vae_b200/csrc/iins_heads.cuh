@@ -12,6 +12,8 @@ struct IinsDropoutParams {
     int B, L, C;
     float p;                           // drop probability; kept values are scaled by 1 / (1 - p)
     unsigned long long seed, offset;
+    const int* offset_dev;             // optional device counter added to offset (CUDA-graph replays)
+    long long sample_offset;           // global index of sample 0 (Philox counters only)
 };
 
 IINS_HD float iins_uniform01(unsigned a) { return ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f); }
@@ -20,6 +22,7 @@ static __global__ void __launch_bounds__(256) iins_dropout_kernel(const IinsDrop
     iins_pdl_enter();
     const long n = (long)p.B * p.L * p.C;
     const float scale = 1.0f / (1.0f - p.p);
+    const unsigned long long off = p.offset + (p.offset_dev != nullptr ? 2ull * (unsigned long long)__ldg(p.offset_dev) : 0ull);
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
         const int c = (int)(e % p.C);
         const long r = e / p.C;
@@ -29,8 +32,9 @@ static __global__ void __launch_bounds__(256) iins_dropout_kernel(const IinsDrop
         float keep;
         if (p.mask != nullptr) keep = __ldg(p.mask + ncl);
         else {
-            const IinsPhilox rr = iins_philox(p.seed, (unsigned long long)(ncl >> 2), p.offset);
-            keep = iins_uniform01(rr.c[ncl & 3]) >= p.p ? 1.f : 0.f;
+            const long gl = ncl + p.sample_offset * p.C * p.L;
+            const IinsPhilox rr = iins_philox(p.seed, (unsigned long long)(gl >> 2), off);
+            keep = iins_uniform01(rr.c[gl & 3]) >= p.p ? 1.f : 0.f;
         }
         p.y[e] = __ldg(p.x + e) * keep * scale;
     }

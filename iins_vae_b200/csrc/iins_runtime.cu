@@ -1340,6 +1340,7 @@ void launch_dropout(Ctx& c, const float* x, float* y, const float* mask, int B, 
     memset(&dp, 0, sizeof(dp));
     dp.x = x; dp.y = y; dp.mask = mask; dp.B = B; dp.L = L; dp.C = C; dp.p = 0.25f;
     dp.seed = st->seed; dp.offset = st->offset * 2 + (unsigned long long)which;   // two dropout layers per call
+    dp.offset_dev = (const int*)st->offset_dev; dp.sample_offset = (long long)st->sample_offset;
     IINS_LAUNCH(iins_dropout_kernel, grid_for((long)B * L * C), 256, 0, c.st, dp);
 }
 

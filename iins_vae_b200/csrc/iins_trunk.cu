@@ -464,14 +464,35 @@ __global__ void __launch_bounds__(320, 2) iins_trunk_bwd_kernel(const IinsTrunkB
     if (warp == 8) umma::tmem_dealloc(tmem, TCOLS);
 }
 
+// cuTensorMapEncodeTiled is a DRIVER API entry point: it is resolved through the runtime (cudaGetDriverEntryPoint) so that the
+// library carries no link-time dependency on libcuda.so.1 (it must load on a GPU-less build / CI host as well).
+typedef CUresult (*IinsEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+IinsEncodeTiledFn encode_tiled_fn() {
+    static IinsEncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<IinsEncodeTiledFn>(ptr);
+        else (void)cudaGetLastError();
+    }
+    return fn;
+}
+
 bool make_weight_map(CUtensorMap* map, const void* base, int pieces, int nconv) {
+    IinsEncodeTiledFn encode = encode_tiled_fn();
+    if (encode == nullptr) return false;                      // -> the plain bulk-copy (cp.async.bulk) variant of the kernels
     // the packed weights as a 2-D array of 512-byte rows: one slice = SLICE / 512 consecutive rows (box = the whole slice)
     const unsigned slice = (unsigned)pieces * 64 * 16 * 2;
     const cuuint64_t dims[2] = {256, (cuuint64_t)(slice / 512) * TR_KS * nconv};
     const cuuint64_t strides[1] = {512};
     const cuuint32_t box[2] = {256, slice / 512};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;

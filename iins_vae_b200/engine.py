@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from ._capi import IinsConfig, get_lib, ptr, ptr_array
+from ._capi import IinsConfig, IinsHeadState, get_lib, ptr, ptr_array
 
 LAMBDA_AE, LAMBDA_RES, LAMBDA_RANGE, LAMBDA_ENV = 1.0, 10.0, 1.0, 1.0      # train_semi.py:111-114
 
@@ -97,6 +97,7 @@ class SemiTrainEngine:
         self.overlap_allreduce = bool(overlap_allreduce)
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
         dev, B = self.device, self.B
         f = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
         # static I/O
@@ -120,8 +121,18 @@ class SemiTrainEngine:
             self.steps = torch.zeros(8, dtype=torch.int32, device=dev)
         lib = self.lib
         names = ("encoder", "decoder", "restorer", "classifier")
-        self.ws = {m: f(int(getattr(lib, f"iins_{m}_ws_floats")(self.cfg)) + 16) for m in names}
-        self.scratch = {m: f(int(getattr(lib, f"iins_{m}_scratch_floats")(self.cfg)) + 16) for m in names}
+        # Conv1d heads (net_type='Conv1d') have their own entry points, workspaces and a BatchNorm state
+        self.conv_head = {"restorer": getattr(Res, "net_type", "Linear") == "Conv1d",
+                          "classifier": getattr(Cls, "net_type", "Linear") == "Conv1d"}
+        q = lambda m, what: f"iins_{m}_conv_{what}_floats" if self.conv_head.get(m) else f"iins_{m}_{what}_floats"
+        self.ws = {m: f(int(getattr(lib, q(m, "ws"))(self.cfg)) + 16) for m in names}
+        self.scratch = {m: f(int(getattr(lib, q(m, "scratch"))(self.cfg)) + 16) for m in names}
+        self.head_state = {}
+        for m, mod in (("restorer", Res), ("classifier", Cls)):
+            if self.conv_head[m]:
+                bn = getattr(getattr(mod, m).conv_blocks, "6")
+                stats = torch.zeros(4 * bn.num_features, dtype=torch.float64, device=dev)
+                self.head_state[m] = dict(bn=bn, stats=stats, C=bn.num_features, seed=mod._seed)
         # pointer tables per module
         self._tables(mods)
         self._graphs = {}
@@ -143,7 +154,8 @@ class SemiTrainEngine:
         self.spans = spans
         # Adam groups (half-open element ranges): always-on [Enc (+Dec)], Res without linear_layer2, Cls.
         res_b, res_e = spans["res"]
-        res_used = res_e - (2 * 256 + 2)                 # linear_layer2.{weight,bias} are the last 514 elements
+        # restorer.linear_layer2.* (the soft head, unused when soft=False) are the trailing parameters of the Restorer
+        res_used = res_e - sum(p.numel() for n, p in self.Res.named_parameters() if "linear_layer2" in n)
         always_end = spans["dec"][1] if self.mode == "semi" else spans["enc"][1]
         self.groups = [(0, always_end), (res_b, res_used), spans["cls"]]
         self._gb = (C.c_int64 * 3)(*[g[0] for g in self.groups])
@@ -170,10 +182,12 @@ class SemiTrainEngine:
                                            None, ptr(self.kl), ptr(self.ws["encoder"]), st), "encoder forward")
 
         def heads(hst):
-            lib.check(lib.iins_restorer_forward(cfg, self.ptab["res"], ptr(self.rc), ptr(self.err_est),
-                                                ptr(self.ws["restorer"]), hst), "restorer forward")
-            lib.check(lib.iins_classifier_forward(cfg, self.ptab["cls"], ptr(self.cat), ptr(self.logits),
-                                                  ptr(self.ws["classifier"]), hst), "classifier forward")
+            for m, tab, src, dst in (("restorer", "res", self.rc, self.err_est), ("classifier", "cls", self.cat, self.logits)):
+                if self.conv_head[m]:
+                    self._conv_head_call(m, "forward", hst, lambda st: getattr(lib, f"iins_{m}_conv_forward")(
+                        cfg, self.ptab[tab], ptr(src), ptr(dst), ptr(self.ws[m]), C.byref(st), hst), 0)
+                else:
+                    lib.check(getattr(lib, f"iins_{m}_forward")(cfg, self.ptab[tab], ptr(src), ptr(dst), ptr(self.ws[m]), hst), f"{m} forward")
 
         main = torch.cuda.current_stream()
         if self._heads_concurrent(supervised):
@@ -207,12 +221,14 @@ class SemiTrainEngine:
         main = torch.cuda.current_stream()
 
         def heads(hst, d_rc, d_cat, acc):
-            lib.check(lib.iins_restorer_backward(cfg, self.ptab["res"], ptr(self.rc), ptr(self.ws["restorer"]), ptr(self.d_err),
-                                                 self.gtab["res"], ptr(d_rc), acc, ptr(self.scratch["restorer"]), hst),
-                      "restorer backward")
-            lib.check(lib.iins_classifier_backward(cfg, self.ptab["cls"], ptr(self.cat), ptr(self.ws["classifier"]),
-                                                   ptr(self.d_logits), self.gtab["cls"], ptr(d_cat), acc,
-                                                   ptr(self.scratch["classifier"]), hst), "classifier backward")
+            for m, tab, src, dout, din in (("restorer", "res", self.rc, self.d_err, d_rc), ("classifier", "cls", self.cat, self.d_logits, d_cat)):
+                if self.conv_head[m]:
+                    self._conv_head_call(m, "backward", hst, lambda st: getattr(lib, f"iins_{m}_conv_backward")(
+                        cfg, self.ptab[tab], ptr(src), ptr(self.ws[m]), ptr(dout), self.gtab[tab], ptr(din), acc, ptr(self.scratch[m]),
+                        C.byref(st), hst), 2)
+                else:
+                    lib.check(getattr(lib, f"iins_{m}_backward")(cfg, self.ptab[tab], ptr(src), ptr(self.ws[m]), ptr(dout), self.gtab[tab],
+                                                                 ptr(din), acc, ptr(self.scratch[m]), hst), f"{m} backward")
 
         if conc:
             self.head_stream.wait_stream(main)
@@ -235,6 +251,28 @@ class SemiTrainEngine:
                                             ptr(self.ws["encoder"]), ptr(self.d_rc), ptr(self.d_cat), None,
                                             ptr(self.d_kl) if semi else None, self.gtab["enc"],
                                             ptr(self.scratch["encoder"]), st), "encoder backward")
+
+    def _conv_head_call(self, m, what, hst, call, stats_half):
+        """One pass of a Conv1d head.  Its BatchNorm1d normalises over the BATCH, the one place where the path is not
+        per-sample: on several ranks the pass runs in two phases around an all-reduce of the 2 * C double-precision batch sums
+        (SyncBN), so that N ranks x B/N samples normalise exactly like one rank x B.  The dropout masks come from Philox with the
+        device-side step counter as offset (a captured graph replays fresh masks every step)."""
+        hs = self.head_state[m]
+        bn = hs["bn"]
+
+        def state(phase):
+            return IinsHeadState(1, None, None, hs["seed"], 0, bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                                 bn.num_batches_tracked.data_ptr(), hs["stats"].data_ptr(), phase, float(self.world),
+                                 self.rank * self.B, self.steps.data_ptr())
+
+        if self.world == 1:
+            self.lib.check(call(state(0)), f"{m} (Conv1d) {what}")
+            return
+        import torch.distributed as dist
+        self.lib.check(call(state(1)), f"{m} (Conv1d) {what}, phase 1")
+        n = 2 * hs["C"]
+        dist.all_reduce(hs["stats"][stats_half * hs["C"]:stats_half * hs["C"] + n], op=dist.ReduceOp.SUM, group=self.pg)
+        self.lib.check(call(state(2)), f"{m} (Conv1d) {what}, phase 2")
 
     # ---- data-parallel gradient exchange (SURVEY.md 8(e)) ---------------------------------------------------------------
     # The flat gradient buffer is laid out [Enc | Dec | Res | Cls] (module order); the backward produces it back to front:
@@ -457,7 +495,11 @@ class InferenceEngine:
         self.rc, self.cat, self.kl = f(B, o["range_dim"], 128 >> o["n_downsample"]), f(B, o["env_dim"]), f(1)
         self.err_est, self.logits, self.out = f(B, 1), f(B, self.NC), f(8)
         self.pred = torch.zeros(B, dtype=torch.int32, device=dev)
-        self.ws = {m: f(int(getattr(self.lib, f"iins_{m}_ws_floats")(self.cfg)) + 16) for m in ("encoder", "restorer", "classifier")}
+        self.conv_head = {"restorer": getattr(Res, "net_type", "Linear") == "Conv1d",
+                          "classifier": getattr(Cls, "net_type", "Linear") == "Conv1d"}
+        q = lambda m: f"iins_{m}_conv_ws_floats" if self.conv_head.get(m) else f"iins_{m}_ws_floats"
+        self.ws = {m: f(int(getattr(self.lib, q(m))(self.cfg)) + 16) for m in ("encoder", "restorer", "classifier")}
+        self.bn = {m: getattr(getattr(mod, m).conv_blocks, "6") for m, mod in (("restorer", Res), ("classifier", Cls)) if self.conv_head[m]}
         self.ptab = {n: ptr_array(list(m.parameters())) for n, m in (("enc", Enc), ("res", Res), ("cls", Cls))}
         self._keep = (Enc, Res, Cls)
         self.use_graph, self._graph = use_graph, None
@@ -466,10 +508,14 @@ class InferenceEngine:
         lib, cfg, st = self.lib, self.cfg, _stream()
         lib.check(lib.iins_encoder_forward(cfg, self.ptab["enc"], ptr(self.cir), None, 0, 0, ptr(self.rc), ptr(self.cat), None,
                                            ptr(self.kl), ptr(self.ws["encoder"]), st), "encoder forward")
-        lib.check(lib.iins_restorer_forward(cfg, self.ptab["res"], ptr(self.rc), ptr(self.err_est), ptr(self.ws["restorer"]), st),
-                  "restorer forward")
-        lib.check(lib.iins_classifier_forward(cfg, self.ptab["cls"], ptr(self.cat), ptr(self.logits), ptr(self.ws["classifier"]),
-                                              st), "classifier forward")
+        for m, tab, src, dst in (("restorer", "res", self.rc, self.err_est), ("classifier", "cls", self.cat, self.logits)):
+            if self.conv_head[m]:                       # eval mode (test.py:43-47): no dropout, BatchNorm on the running statistics
+                bn = self.bn[m]
+                hs = IinsHeadState(0, None, None, 0, 0, bn.running_mean.data_ptr(), bn.running_var.data_ptr(), None, None, 0, 1.0, 0, None)
+                lib.check(getattr(lib, f"iins_{m}_conv_forward")(cfg, self.ptab[tab], ptr(src), ptr(dst), ptr(self.ws[m]), C.byref(hs), st),
+                          f"{m} (Conv1d) forward")
+            else:
+                lib.check(getattr(lib, f"iins_{m}_forward")(cfg, self.ptab[tab], ptr(src), ptr(dst), ptr(self.ws[m]), st), f"{m} forward")
         lib.check(lib.iins_loss_forward_backward(self.B, self.L, self.NC, None, None, ptr(self.err), ptr(self.err_est),
                                                  ptr(self.logits), ptr(self.label), None, self.label_offset, 1.0, 1.0, 1.0,
                                                  ptr(self.out), None, None, None, ptr(self.pred), st), "metrics")

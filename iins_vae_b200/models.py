@@ -235,7 +235,7 @@ class _ConvHeadFn(torch.autograd.Function):
         ws = _empty(getattr(lib, f"iins_{kind}_conv_ws_floats")(cfg), dev)
         st = IinsHeadState(int(hs["training"]), _addr(hs.get("mask1")), _addr(hs.get("mask2")), int(hs["seed"]), int(hs["offset"]),
                            _addr(hs["running_mean"]), _addr(hs["running_var"]), _addr(hs["num_batches_tracked"]),
-                           _addr(hs["bn_stats"]), 0, 1.0)
+                           _addr(hs["bn_stats"]), 0, 1.0, 0, None)
         lib.check(getattr(lib, f"iins_{kind}_conv_forward")(cfg, ptr_array(params), ptr(inp), ptr(out), ptr(ws), C.byref(st), _stream()),
                   f"{kind} (Conv1d) forward")
         ctx.kind, ctx.cfg, ctx.params, ctx.hs, ctx.st = kind, cfg, params, hs, st
@@ -470,12 +470,13 @@ class EMNet(nn.Module):
     def __init__(self, cir_len=157, num_classes=2, env_dim=16, filters=16, enet_type=1, mnet_type=1, dim=4,
                  n_residual=3, n_downsample=4, range_dim=2):
         super().__init__()
-        if enet_type != 1 or mnet_type != 1:
-            raise NotImplementedError("iins_vae_b200: only the Linear identifier / regressor heads (type 1)")
+        if enet_type not in (1, 2) or mnet_type not in (1, 2):
+            raise NotImplementedError("iins_vae_b200: identifier / regressor types 1 (Linear) and 2 (Conv1d); 3 (Conv2d) is SURVEY 8f row 3")
         self.cir_len = cir_len
         self.encoder = Encoder(1, dim, n_residual, n_downsample, env_dim, range_dim)
-        self.classifier = Classifier(env_dim, num_classes, filters=16)
-        self.restorer = Restorer((range_dim, 128 // 2 ** n_downsample))
+        kinds = {1: "Linear", 2: "Conv1d"}                  # utils.py:43-44: 1 for linear, 2 for conv1d
+        self.classifier = Classifier(env_dim, num_classes, filters=16, net_type=kinds[enet_type])
+        self.restorer = Restorer((range_dim, 128 // 2 ** n_downsample), net_type=kinds[mnet_type])
 
     def forward(self, cir):
         range_code, env_code, _, _ = self.encoder(cir)

@@ -131,6 +131,10 @@ typedef struct iins_head_state {
     int phase;                 /* 0: whole call.  1: stop after the LOCAL batch sums are in bn_stats; 2: continue from bn_stats --    */
                                /*    a data-parallel caller all-reduces the 2 * C doubles in between (SyncBN)                          */
     double count_scale;        /* number of ranks whose sums were added into bn_stats (1 without SyncBN)                              */
+    int64_t sample_offset;     /* index of this rank's first sample in the global batch: Philox counters use GLOBAL sample indices,  */
+                               /*    so N ranks x B/N samples draw the masks one rank x B would                                        */
+    const int32_t* offset_dev; /* optional DEVICE counter added to `offset` when the Philox masks are drawn: a captured CUDA graph */
+                               /*    replays the same kernel arguments, so the per-step offset has to come from device memory         */
 } iins_head_state;
 size_t iins_restorer_conv_ws_floats(const iins_config* cfg);
 size_t iins_restorer_conv_scratch_floats(const iins_config* cfg);

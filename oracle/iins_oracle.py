@@ -181,7 +181,7 @@ def grad_is_structurally_zero(name: str, cfg: "PathConfig" = None) -> bool:
 
 
 def is_buffer(name: str) -> bool:
-    return name.endswith("running_mean") or name.endswith("running_var")
+    return name.endswith("running_mean") or name.endswith("running_var") or name.endswith("num_batches_tracked")
 
 
 def init_params(shapes: "OrderedDict[str, tuple]", gen: torch.Generator) -> "OrderedDict[str, torch.Tensor]":
@@ -644,12 +644,14 @@ def cross_entropy_mean(logits, target):
     return (lse - logits.gather(1, target.view(-1, 1)).squeeze(1)).mean()
 
 
-def semi_forward(pe, pd, pr, pc, cir, err, label, cfg: PathConfig, supervised: bool, noise=None, taps=None):
-    """One forward of the semi-supervised step (train_semi.py:186-225)."""
+def semi_forward(pe, pd, pr, pc, cir, err, label, cfg: PathConfig, supervised: bool, noise=None, taps=None, head_fns=None):
+    """One forward of the semi-supervised step (train_semi.py:186-225).  ``head_fns`` = dict(res=f(p, range_code) -> err_fake,
+    cls=f(p, env_code) -> logits) selects other heads than the Linear ones (net_type='Conv1d': restorer_conv1d / classifier_conv1d
+    with their dropout masks bound)."""
     rc, cat, latent, kl = encoder(pe, cir, cfg, noise, taps)
     cir_gen = decoder(pd, rc, cat, cfg, taps)
-    err_fake = restorer(pr, rc)
-    label_fake = classifier(pc, cat)
+    err_fake = restorer(pr, rc) if head_fns is None else head_fns["res"](pr, rc)
+    label_fake = classifier(pc, cat) if head_fns is None else head_fns["cls"](pc, cat)
     out = dict(range_code=rc, env_code=cat, env_code_rv=latent, kl=kl,
                cir_gen=cir_gen, err_fake=err_fake, label_fake=label_fake)
     out["loss_ae"] = LAMBDA_AE * l1_mean(cir, cir_gen.reshape(cir.shape))        # :199
@@ -726,7 +728,7 @@ def trainable(params: dict) -> dict:
     return {k: v for k, v in params.items() if not is_buffer(k)}
 
 
-def semi_step_with_grads(pe, pd, pr, pc, cir, err, label, cfg, supervised, noise=None):
+def semi_step_with_grads(pe, pd, pr, pc, cir, err, label, cfg, supervised, noise=None, head_fns=None):
     """Forward + autograd backward of the semi step; returns (out, grads) where grads maps
     'enc.<key>' / 'dec.<key>' / 'res.<key>' / 'cls.<key>' -> tensor or None (None == the
     parameter received no gradient, e.g. restorer.linear_layer2 always, Res/Cls when the
@@ -742,7 +744,7 @@ def semi_step_with_grads(pe, pd, pr, pc, cir, err, label, cfg, supervised, noise
                 t.requires_grad_(True)
                 leaves[f"{g}.{k}"] = t
             work[g][k] = t
-    out = semi_forward(work["enc"], work["dec"], work["res"], work["cls"], cir, err, label, cfg, supervised, noise)
+    out = semi_forward(work["enc"], work["dec"], work["res"], work["cls"], cir, err, label, cfg, supervised, noise, head_fns=head_fns)
     out["loss"].backward()
     grads = {k: (t.grad.detach() if t.grad is not None else None) for k, t in leaves.items()}
     out = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}

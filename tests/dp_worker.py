@@ -105,6 +105,51 @@ def main():
                     o += n
                 print(f"[dp] world={world} B={B} ({hi - lo}/rank) overlap={overlap} supervised={supervised}: worst gradient rel-L2 vs "
                       f"1 rank x {B}: {worst[1]:.2e} ({worst[0]}); loss {float(loss_dp) / world:.7f} vs {loss_one:.7f}", flush=True)
+    # ---- Conv1d heads: BatchNorm over the batch -> SyncBN (2 * C double sums all-reduced between the two
+    # phases of the head's pass), dropout masks drawn from Philox counters over GLOBAL sample indices: N ranks x B/N == 1 rank x B
+    def conv_modules(seed=88):
+        pe, pd, _, _ = orc.init_all(cfg, seed)
+        gen = torch.Generator().manual_seed(seed + 99)
+        pr = orc.init_conv_head_params(orc.restorer_conv1d_param_shapes(cfg), gen)
+        pc = orc.init_conv_head_params(orc.classifier_conv1d_param_shapes(cfg), gen)
+        Enc = M.Encoder(1, cfg.dim, cfg.n_residual, cfg.n_downsample, cfg.env_dim, cfg.range_dim)
+        Dec = M.Decoder(1, cfg.dim, cfg.n_residual, cfg.n_downsample, cfg.env_dim, cfg.cir_len, cfg.range_dim)
+        Res = M.Restorer((cfg.range_dim, cfg.code_len), net_type="Conv1d")
+        Cls = M.Classifier(cfg.env_dim, cfg.num_classes, net_type="Conv1d")
+        for m, p in ((Enc, pe), (Dec, pd), (Res, pr), (Cls, pc)):
+            m.load_state_dict(p)
+            m.cuda()
+        return Enc, Dec, Res, Cls
+
+    mods_dp = conv_modules()
+    dp = SemiTrainEngine(*mods_dp, batch_size=hi - lo, use_graph=True, process_group=pg)
+    engines.append(dp)
+    for _ in range(2):
+        dp.step(cir[lo:hi], err[lo:hi], label[lo:hi], supervised=True, update=False)
+    torch.cuda.synchronize()
+    g_dp = {k: (v / world).cpu() for k, v in dp.named_grads().items()}
+    bn_dp = getattr(mods_dp[2].restorer.conv_blocks, "6").running_var.clone()
+    if rank == 0:
+        mods_one = conv_modules()
+        one = SemiTrainEngine(*mods_one, batch_size=B, use_graph=True)
+        for _ in range(2):
+            one.step(cir, err, label, supervised=True, update=False)
+        torch.cuda.synchronize()
+        worst = ("", 0.0)
+        for k, v in one.named_grads().items():
+            n1 = float(v.norm())
+            if n1 == 0.0 or orc.grad_is_structurally_zero(k):
+                continue
+            rel = float((g_dp[k] - v.cpu()).norm()) / n1
+            if rel > worst[1]:
+                worst = (k, rel)
+            if rel > parity.RTOL_FP32:
+                failures.append(f"conv heads {k}: rel-L2 {rel:.2e} > {parity.RTOL_FP32}")
+        bn_one = getattr(mods_one[2].restorer.conv_blocks, "6").running_var
+        if not torch.allclose(bn_dp, bn_one, rtol=1e-5, atol=1e-7):
+            failures.append("conv heads: BatchNorm running_var differs between 2 ranks (SyncBN) and 1 rank")
+        print(f"[dp] world={world} Conv1d heads (SyncBN, global-index Philox dropout): worst gradient rel-L2 vs 1 rank x {B}: "
+              f"{worst[1]:.2e} ({worst[0]})", flush=True)
     ok = torch.tensor([len(failures)], device="cuda")
     dist.broadcast(ok, src=0)
     if rank == 0:

@@ -217,7 +217,7 @@ def test_conv1d_heads_match_reference_fixtures(sim, kind):
         masks = [torch.from_numpy(golden[pre + f"mask{i}"]).contiguous() for i in range(2)] if training else [None, None]
         stats = torch.zeros(4 * rm.numel(), dtype=torch.float64)
         st = IinsHeadState(training, masks[0].data_ptr() if training else None, masks[1].data_ptr() if training else None, 0, 0,
-                           rm.data_ptr(), rv.data_ptr(), nbt.data_ptr(), stats.data_ptr(), 0, 1.0)
+                           rm.data_ptr(), rv.data_ptr(), nbt.data_ptr(), stats.data_ptr(), 0, 1.0, 0, None)
         xin = x.contiguous() if kind == "res" else x.reshape(batch, -1).contiguous()
         nout = 1 if kind == "res" else cfg.num_classes
         out = torch.zeros(batch, nout)

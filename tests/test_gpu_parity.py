@@ -541,3 +541,82 @@ def test_conv1d_heads_match_reference_fixtures(kind):
     assert not torch.equal(o1, o2), "a new dropout mask per call"
     mod.eval()
     assert torch.equal(mod(x), mod(x)), "eval mode is deterministic"
+
+
+def _conv_mods(cfg, seed):
+    from iins_vae_b200 import models as M
+    pe, pd, _, _ = orc.init_all(cfg, seed)
+    gen = torch.Generator().manual_seed(seed + 99)
+    pr = orc.init_conv_head_params(orc.restorer_conv1d_param_shapes(cfg), gen)
+    pc = orc.init_conv_head_params(orc.classifier_conv1d_param_shapes(cfg), gen)
+    Enc = M.Encoder(1, cfg.dim, cfg.n_residual, cfg.n_downsample, cfg.env_dim, cfg.range_dim)
+    Dec = M.Decoder(1, cfg.dim, cfg.n_residual, cfg.n_downsample, cfg.env_dim, cfg.cir_len, cfg.range_dim)
+    Res = M.Restorer((cfg.range_dim, cfg.code_len), net_type="Conv1d")
+    Cls = M.Classifier(cfg.env_dim, cfg.num_classes, net_type="Conv1d")
+    for m, p in ((Enc, pe), (Dec, pd), (Res, pr), (Cls, pc)):
+        m.load_state_dict(p)
+        m.cuda()
+    return (Enc, Dec, Res, Cls), (pe, pd, pr, pc)
+
+
+def _conv_head_masks(eng, m, B):
+    """The Philox keep-masks the kernels drew, recovered from the saved activations (dropout output vs input) and returned
+    in the reference's (B, C, L) layout."""
+    C1, L1, C2, L2 = (16, 4, 32, 2) if m == "restorer" else (eng.cfg.cls_filters, 1, eng.cfg.cls_filters, 1)
+    ws = eng.ws[m]
+    n1, n2 = B * L1 * C1, B * L2 * C2
+    r4 = lambda n: (n + 3) // 4 * 4
+    a1, d1 = ws[:n1], ws[r4(n1):r4(n1) + n1]
+    o = 2 * r4(n1)
+    a2, d2 = ws[o:o + n2], ws[o + r4(n2):o + r4(n2) + n2]
+    m1 = torch.where(a1 != 0, (d1 != 0).float(), torch.ones_like(a1)).view(B, L1, C1).permute(0, 2, 1).contiguous().cpu()
+    m2 = torch.where(a2 != 0, (d2 != 0).float(), torch.ones_like(a2)).view(B, L2, C2).permute(0, 2, 1).contiguous().cpu()
+    return m1, m2
+
+
+def test_engine_with_conv1d_heads_matches_oracle():
+    """regressor_type / identifier_type = 2 (utils.py:43-44) through the fused engine: the semi-supervised step with
+    RestorerConv1d + ClassifierConv1d (Philox dropout, BatchNorm over the batch) against the oracle replaying the masks the
+    kernels drew; every gradient tensor to the fp32 bound, BatchNorm buffers updated like torch's, keep rate 0.75."""
+    from iins_vae_b200.engine import SemiTrainEngine
+    cfg = orc.PathConfig()
+    batch = 512
+    mods, pdicts = _conv_mods(cfg, 61)
+    cir, err, label = orc.synthetic_batch(cfg, batch, 161)
+    eng = SemiTrainEngine(*mods, batch_size=batch, use_graph=False)
+    eng.step(cir, err, label, supervised=True, update=False)
+    torch.cuda.synchronize()
+    masks_r, masks_c = _conv_head_masks(eng, "restorer", batch), _conv_head_masks(eng, "classifier", batch)
+    keep = float(torch.cat([m.flatten() for m in masks_r + masks_c]).mean())
+    assert abs(keep - 0.75) < 0.02, keep
+    bufs = {}
+    fns = dict(res=lambda p, rc: orc.restorer_conv1d(p, rc, masks_r, True)[0], cls=lambda p, cat: orc.classifier_conv1d(p, cat, masks_c, True)[0])
+    zero = torch.zeros(batch, cfg.env_dim // 2, 1)
+    ref, ref_grads = orc.semi_step_with_grads(*pdicts, cir, err, label, cfg, True, zero, head_fns=fns)
+    dbl = lambda d: {k: (v.double() if v.is_floating_point() else v) for k, v in d.items()}
+    _, truth = orc.semi_step_with_grads(*(dbl(p) for p in pdicts), cir.double(), err.double(), label.double(), cfg, True, zero.double(),
+                                        head_fns=fns)
+    t = eng.loss_terms()
+    for k in ("loss", "loss_res", "loss_env"):
+        np.testing.assert_allclose(t[k], float(ref[k]), rtol=1e-4)
+    gscale = max(float(g.abs().max()) for g in ref_grads.values() if g is not None)
+    got = eng.named_grads()
+    for name, g in ref_grads.items():
+        if g is None:
+            assert float(got[name].abs().max()) == 0.0, name
+    rows = parity.grad_report(got, truth, ref_grads, gscale, parity.REF_FACTOR_TC)
+    n_band = parity.assert_grads(rows, batch, label="conv heads")
+    worst = max(r[1] for r in rows if r[0].startswith(("res.", "cls.")))
+    print(f"[conv1d heads] B={batch}: worst head-gradient rel-L2 vs fp64 oracle {worst:.2e}, {n_band} tensors in the kink band, keep rate {keep:.3f}")
+    # BatchNorm buffers after ONE training pass == torch's momentum update on the oracle's batch statistics
+    _, (rm, rv) = orc.restorer_conv1d(pdicts[2], ref["range_code"], masks_r, True)
+    bn = getattr(mods[2].restorer.conv_blocks, "6")
+    np.testing.assert_allclose(bn.running_mean.cpu().numpy(), rm.numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(bn.running_var.cpu().numpy(), rv.numpy(), rtol=1e-4, atol=1e-6)
+    # a full optimisation step replayed from the graph draws NEW masks every step (device-side Philox offset)
+    eng2 = SemiTrainEngine(*mods, batch_size=batch, use_graph=True, shared_state=eng)
+    outs = []
+    for _ in range(3):
+        eng2.step(cir, err, label, supervised=True)
+        outs.append(_conv_head_masks(eng2, "restorer", batch)[0].clone())
+    assert not torch.equal(outs[1], outs[2])

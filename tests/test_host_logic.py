@@ -39,7 +39,7 @@ def test_config_validation_and_sizes_without_gpu():
     assert lib.iins_encoder_num_params(ok) == 32 and lib.iins_decoder_num_params(ok) == 38
     assert lib.iins_restorer_num_params(ok) == 10 and lib.iins_classifier_num_params(ok) == 8
     assert lib.iins_encoder_ws_floats(ok) > 4096 * 15000          # saved activations, ~18k floats / sample
-    for bad in (IinsConfig(0, 157, 4, 3, 4, 16, 2, 5, 16), IinsConfig(8, 157, 16, 3, 4, 16, 2, 5, 16),
+    for bad in (IinsConfig(0, 157, 4, 3, 4, 16, 2, 5, 16), IinsConfig(8, 157, 32, 3, 4, 16, 2, 5, 16),
                 IinsConfig(8, 157, 4, 3, 3, 16, 2, 5, 16), IinsConfig(8, 157, 4, 3, 4, 15, 2, 5, 16)):
         assert lib.iins_validate_config(bad) != 0
         assert len(lib.dll.iins_last_error()) > 0
@@ -53,7 +53,14 @@ def test_modules_fail_loudly_on_cpu_tensors():
     with pytest.raises(NotImplementedError):
         M.Encoder(conv_type=2)
     with pytest.raises(NotImplementedError):
-        M.Restorer((2, 8), net_type="Conv1d")
+        M.Restorer((2, 8), net_type="Conv2d")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        M.Restorer((2, 8), net_type="Conv1d")(torch.zeros(4, 2, 8))
+    # the Conv1d heads keep the reference's state_dict keys, BatchNorm buffers included (models.py:661-693, 865-891)
+    from oracle import iins_oracle as orc
+    cfg = orc.PathConfig()
+    assert list(M.Restorer((2, 8), net_type="Conv1d").state_dict()) == list(orc.restorer_conv1d_param_shapes(cfg))
+    assert list(M.Classifier(16, 5, net_type="Conv1d").state_dict()) == list(orc.classifier_conv1d_param_shapes(cfg))
 
 
 def test_state_dict_surface_matches_oracle_inventory():
