@@ -28,6 +28,7 @@ EXPORTS = [
     "iins_restorer_conv_ws_floats", "iins_restorer_conv_scratch_floats", "iins_restorer_conv_forward", "iins_restorer_conv_backward",
     "iins_classifier_conv_ws_floats", "iins_classifier_conv_scratch_floats", "iins_classifier_conv_forward",
     "iins_classifier_conv_backward",
+    "iins_restorer_soft_ws_floats", "iins_restorer_soft_scratch_floats", "iins_restorer_soft_forward", "iins_restorer_soft_backward",
 ]
 
 
@@ -85,6 +86,12 @@ class IinsLib:
                 f.restype = C.c_size_t
             getattr(d, f"iins_{mod}_conv_forward").argtypes = [_CFG, _PP, _P, _P, _P, _HS, _P]
             getattr(d, f"iins_{mod}_conv_backward").argtypes = [_CFG, _PP, _P, _P, _P, _PP, _P, C.c_int, _P, _HS, _P]
+        for q in ("ws", "scratch"):
+            f = getattr(d, f"iins_restorer_soft_{q}_floats")
+            f.argtypes = [_CFG]
+            f.restype = C.c_size_t
+        d.iins_restorer_soft_forward.argtypes = [_CFG, _PP, _P, _P, _P, _P, _P]
+        d.iins_restorer_soft_backward.argtypes = [_CFG, _PP, _P, _P, _P, _P, _PP, _P, C.c_int, _P, _P]
         d.iins_loss_forward_backward.argtypes = [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int,
                                                  C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P]
         d.iins_adam_step.argtypes = [_P, _P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32),

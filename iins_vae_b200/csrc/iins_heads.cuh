@@ -149,3 +149,36 @@ static __global__ void __launch_bounds__(256) iins_bn_bwd_kernel(const IinsBnBwd
         p.dx[e] = s_sc[c] * (__ldg(p.dy + e) - s_m1[c] - __ldg(p.xhat + e) * s_m2[c]);
     }
 }
+
+// ---- soft Restorer (RestorerLinear with soft=True, models.py:634-655) --------------------------------------------------
+// ml (B, 2) = linear_layer2 output: mu = ml[:, 0], logvar = ml[:, 1];  std = exp(logvar / 2);  noise (B, 1) ~ N(0, 1).
+// The reference computes ``sampled_z * std + mu`` with sampled_z of shape (B, 1) and std / mu of shape (B,): torch broadcasts
+// that to (B, B):  z[i][j] = noise[i] * std[j] + mu[j].  Reproduced as is (the drop-in contract is the reference's behaviour).
+static __global__ void __launch_bounds__(256) iins_soft_reparam_kernel(const float* __restrict__ ml, const float* __restrict__ noise,
+                                                                      float* __restrict__ z, int B) {
+    iins_pdl_enter();
+    const long n = (long)B * B;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / B), j = (int)(e - (long)i * B);
+        z[e] = fmaf(__ldg(noise + i), expf(0.5f * __ldg(ml + 2 * j + 1)), __ldg(ml + 2 * j));
+    }
+}
+// d_ml[j][0] = sum_i dz[i][j];   d_ml[j][1] = sum_i dz[i][j] * noise[i] * 0.5 * std[j].   One warp per column j.
+static __global__ void __launch_bounds__(256) iins_soft_reparam_bwd_kernel(const float* __restrict__ ml, const float* __restrict__ noise,
+                                                                          const float* __restrict__ dz, float* __restrict__ d_ml, int B) {
+    iins_pdl_enter();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = blockIdx.x * 8 + warp; j < B; j += gridDim.x * 8) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int i = lane; i < B; i += 32) {
+            const float g = __ldg(dz + (long)i * B + j);
+            s0 += g;
+            s1 = fmaf(g, __ldg(noise + i), s1);
+        }
+        s0 = iins_warp_sum(s0); s1 = iins_warp_sum(s1);
+        if (lane == 0) {
+            d_ml[2 * j] = s0;
+            d_ml[2 * j + 1] = s1 * 0.5f * expf(0.5f * __ldg(ml + 2 * j + 1));
+        }
+    }
+}

@@ -1215,6 +1215,12 @@ MlpSpec restorer_spec(const Shapes& s) {
     m.slopes[0] = m.slopes[1] = m.slopes[2] = 0.2f; m.slopes[3] = -1.f;         // models.py:621-631
     return m;
 }
+// soft=True (models.py:649-653): the trunk ends in linear_layer2 (256 -> 2: mu, logvar) instead of linear_layer1
+MlpSpec restorer_soft_spec(const Shapes& s) {
+    MlpSpec m = restorer_spec(s);
+    m.dims[4] = 2;
+    return m;
+}
 MlpSpec classifier_spec(const Shapes& s) {
     MlpSpec m; m.n = 4;
     m.dims[0] = s.E; m.dims[1] = s.F; m.dims[2] = 2 * s.F; m.dims[3] = s.F; m.dims[4] = s.NC;
@@ -1589,6 +1595,44 @@ int iins_classifier_backward(const iins_config* cfg, const float* const* params,
     MlpSpec m = classifier_spec(s);
     return mlp_backward(s, m, params, env_code, ws + mlp_ws(s, m), ws, d_logits, grads, d_env_code, accumulate, scratch,
                         (cudaStream_t)stream);
+}
+
+// ---- soft Restorer
+size_t iins_restorer_soft_ws_floats(const iins_config* cfg) {
+    Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0;
+    return mlp_ws(s, restorer_soft_spec(s)) + (((size_t)s.B * 2 + 3) & ~(size_t)3) + wpack_floats(s);
+}
+size_t iins_restorer_soft_scratch_floats(const iins_config* cfg) {
+    Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0;
+    return mlp_scratch(s, restorer_soft_spec(s)) + (((size_t)s.B * 2 + 3) & ~(size_t)3);
+}
+int iins_restorer_soft_forward(const iins_config* cfg, const float* const* params, const float* range_code, const float* noise,
+                               float* z, float* ws, iins_stream_t stream) {
+    IINS_SHAPES_OR_RETURN(cfg, s);
+    if (!params || !range_code || !noise || !z || !ws) return fail(IINS_ERR_NULL, "restorer_soft_forward: NULL argument");
+    const MlpSpec m = restorer_soft_spec(s);
+    const float* P[8] = {params[0], params[1], params[2], params[3], params[4], params[5], params[8], params[9]};   // ... linear_layer2
+    float* ml = ws + mlp_ws(s, m);
+    float* wpack = ml + (((size_t)s.B * 2 + 3) & ~(size_t)3);
+    int rc = mlp_forward(s, m, P, range_code, ml, ws, wpack, (cudaStream_t)stream);
+    if (rc != IINS_OK) return rc;
+    IINS_LAUNCH(iins_soft_reparam_kernel, grid_for((long)s.B * s.B), 256, 0, (cudaStream_t)stream, (const float*)ml, noise, z, s.B);
+    return check_cuda("restorer_soft_forward");
+}
+int iins_restorer_soft_backward(const iins_config* cfg, const float* const* params, const float* range_code, const float* noise,
+                                const float* ws, const float* d_z, float* const* grads, float* d_range_code, int accumulate,
+                                float* scratch, iins_stream_t stream) {
+    IINS_SHAPES_OR_RETURN(cfg, s);
+    if (!params || !range_code || !noise || !ws || !d_z || !grads || !scratch) return fail(IINS_ERR_NULL, "restorer_soft_backward: NULL argument");
+    const MlpSpec m = restorer_soft_spec(s);
+    const float* P[8] = {params[0], params[1], params[2], params[3], params[4], params[5], params[8], params[9]};
+    float* G[8] = {grads[0], grads[1], grads[2], grads[3], grads[4], grads[5], grads[8], grads[9]};       // linear_layer1 gets none
+    const float* ml = ws + mlp_ws(s, m);
+    float* d_ml = scratch + mlp_scratch(s, m);
+    int nb = (s.B + 7) / 8;
+    if (nb > 148 * 4) nb = 148 * 4;
+    IINS_LAUNCH(iins_soft_reparam_bwd_kernel, nb, 256, 0, (cudaStream_t)stream, ml, noise, d_z, d_ml, s.B);
+    return mlp_backward(s, m, P, range_code, nullptr, ws, d_ml, G, d_range_code, accumulate, scratch, (cudaStream_t)stream);
 }
 
 // ---- Conv1d heads

@@ -257,6 +257,35 @@ class _ConvHeadFn(torch.autograd.Function):
         return (d_in, None, None, None, None) + tuple(grads) + (None,) * (len(ctx.params) - n_used)
 
 
+class _SoftRestorerFn(torch.autograd.Function):
+    """RestorerLinear with soft=True (models.py:634-655): trunk -> linear_layer2 (mu, logvar) -> the reference's (B, B)-broadcast
+    reparameterisation z[i][j] = noise[i] * exp(logvar[j] / 2) + mu[j]."""
+
+    @staticmethod
+    def forward(ctx, rc, noise, cfg, *params):
+        lib = get_lib()
+        lib.check(lib.iins_validate_config(cfg), "restorer config")
+        B = rc.shape[0]
+        z = torch.empty(B, B, device=rc.device)
+        ws = _empty(lib.iins_restorer_soft_ws_floats(cfg), rc.device)
+        lib.check(lib.iins_restorer_soft_forward(cfg, ptr_array(params), ptr(rc), ptr(noise), ptr(z), ptr(ws), _stream()), "restorer (soft) forward")
+        ctx.cfg, ctx.params = cfg, params
+        ctx.save_for_backward(rc, noise, ws)
+        return z
+
+    @staticmethod
+    def backward(ctx, d_z):
+        lib = get_lib()
+        rc, noise, ws = ctx.saved_tensors
+        grads = [torch.zeros_like(p) for p in ctx.params]
+        d_rc = torch.empty_like(rc)
+        scratch = _empty(lib.iins_restorer_soft_scratch_floats(ctx.cfg), rc.device)
+        lib.check(lib.iins_restorer_soft_backward(ctx.cfg, ptr_array(ctx.params), ptr(rc), ptr(noise), ptr(ws), ptr(d_z.contiguous().float()),
+                                                  ptr_array(grads), ptr(d_rc), 0, ptr(scratch), _stream()), "restorer (soft) backward")
+        grads[6] = grads[7] = None                                   # linear_layer1 is not on the soft path
+        return (d_rc, None, None) + tuple(grads)
+
+
 def _conv_block(holder, first_index, cin, cout, ks, stride, pad, bn):
     """Parameter holders of one ``conv_block`` of the reference (Conv1d, LeakyReLU, Dropout[, BatchNorm1d(c, 0.8)]) under the
     reference's Sequential indices."""
@@ -394,8 +423,8 @@ class Restorer(_ConvHeadMixin, nn.Module):
         super().__init__()
         if net_type not in ("Linear", "Conv1d"):
             raise NotImplementedError("iins_vae_b200: net_type 'Linear' and 'Conv1d' are on the B200 path (Conv2d: SURVEY 8f row 3)")
-        if soft:
-            raise NotImplementedError("iins_vae_b200: soft=True (host np.random reparameterisation) is not on the path")
+        if soft and net_type != "Linear":
+            raise NotImplementedError("iins_vae_b200: soft=True is on the path for the Linear restorer only")
         self.soft, self.net_type = soft, net_type
         self.code_shape = tuple(int(v) for v in code_shape)
         n_in = int(np.prod(code_shape))
@@ -421,6 +450,10 @@ class Restorer(_ConvHeadMixin, nn.Module):
         if tuple(rc.shape[1:]) != self.code_shape or self.code_shape[-1] != 8:
             raise RuntimeError(f"Restorer expects range_code (B,{self.code_shape}) with code length 8")
         cfg = _cfg(rc.shape[0], range_dim=self.code_shape[0])
+        if self.net_type == "Linear" and self.soft:
+            # the reference draws np.random.normal(0, 1, (B, 1)) on the host (models.py:637): same call, same generator stream
+            noise = torch.from_numpy(np.random.normal(0, 1, (rc.shape[0], 1)).astype(np.float32)).to(rc.device).view(-1)
+            return _SoftRestorerFn.apply(rc, noise, cfg, *_params_of(self))
         if self.net_type == "Linear":
             return _HeadFn.apply(rc, "restorer", cfg, 1, *_params_of(self))
         hs = self._head_state(getattr(self.restorer.conv_blocks, "6"), masks, rc.device)

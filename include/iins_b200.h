@@ -114,6 +114,19 @@ int iins_classifier_backward(const iins_config* cfg, const float* const* params,
                              const float* ws, const float* d_logits, float* const* grads,
                              float* d_env_code, int accumulate, float* scratch, iins_stream_t stream);
 
+/* ---- soft Restorer (RestorerLinear, soft=True): models.py:634-655 --------------------------------------------------------
+ * The trunk ends in linear_layer2 (256 -> 2: mu, logvar); z = noise * exp(logvar / 2) + mu with noise of shape (B, 1) and
+ * mu / logvar of shape (B,), which torch BROADCASTS to (B, B): z[i][j] = noise[i] * std[j] + mu[j] -- the reference's
+ * behaviour, reproduced as is.  noise: (B,) standard normals (the reference draws np.random.normal on the host).
+ * params / grads: the Restorer's 10 tensors; linear_layer1 is not touched (grad None in the reference when soft=True). */
+size_t iins_restorer_soft_ws_floats(const iins_config* cfg);
+size_t iins_restorer_soft_scratch_floats(const iins_config* cfg);
+int iins_restorer_soft_forward(const iins_config* cfg, const float* const* params, const float* range_code, const float* noise,
+                               float* z, float* ws, iins_stream_t stream);
+int iins_restorer_soft_backward(const iins_config* cfg, const float* const* params, const float* range_code, const float* noise,
+                                const float* ws, const float* d_z, float* const* grads, float* d_range_code, int accumulate,
+                                float* scratch, iins_stream_t stream);
+
 /* ---- Conv1d heads (net_type='Conv1d'): RestorerConv1d models.py:661-716, ClassifierConv1d models.py:865-902 --------------
  * Conv1d + LeakyReLU(0.2) + Dropout(0.25) blocks, BatchNorm1d(eps = 0.8: the second positional argument of
  * nn.BatchNorm1d(c, 0.8) is eps) on the second block, Linear output (+ LeakyReLU(0.2) on the classifier's logits).

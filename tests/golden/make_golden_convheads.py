@@ -78,9 +78,32 @@ def run_case(store, prefix, kind, seed, batch, training, cfg):
         assert torch.allclose(rv, mod.state_dict()[key.replace("mean", "var")], rtol=1e-5, atol=1e-6)
 
 
+def run_soft_case(store, prefix, seed, batch, cfg):
+    """RestorerLinear with soft=True (models.py:634-655): the (B, 1) x (B,) broadcast makes the output (B, B)."""
+    gen = torch.Generator().manual_seed(seed)
+    p = orc.init_params(orc.restorer_param_shapes(cfg), gen)
+    x = torch.rand(batch, cfg.range_dim, cfg.code_len, generator=gen).requires_grad_(True)
+    mod = ref.Restorer(code_shape=(cfg.range_dim, cfg.code_len), soft=True, filters=cfg.dim, conv_type=1, expand=False, net_type="Linear")
+    mod.load_state_dict(p)
+    np.random.seed(seed)
+    out = mod(x)
+    assert out.shape == (batch, batch)
+    np.random.seed(seed)
+    noise = np.random.normal(0, 1, (batch, 1)).astype(np.float32)
+    d_out = torch.randn(out.shape, generator=gen) * 0.1
+    (out * d_out).sum().backward()
+    store[prefix + "meta"] = np.array([seed, batch], dtype=np.int64)
+    store[prefix + "x"] = x.detach().numpy(); store[prefix + "noise"] = noise; store[prefix + "out"] = out.detach().numpy()
+    store[prefix + "d_out"] = d_out.numpy(); store[prefix + "d_x"] = x.grad.numpy()
+    for k, v in mod.named_parameters():
+        store[prefix + "grad." + k] = np.zeros(0, dtype=np.float32) if v.grad is None else v.grad.numpy()
+
+
 def main():
     cfg = orc.PathConfig()
     store = {}
+    for seed, batch in ((0, 5), (1, 48)):
+        run_soft_case(store, f"soft.s{seed}.b{batch}.", seed, batch, cfg)
     for kind in ("res", "cls"):
         for seed, batch, training in ((0, 4, True), (1, 64, True), (2, 200, True), (3, 64, False)):
             run_case(store, f"{kind}.s{seed}.b{batch}.t{int(training)}.", kind, seed, batch, training, cfg)

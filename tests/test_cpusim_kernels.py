@@ -243,3 +243,41 @@ def test_conv1d_heads_match_reference_fixtures(sim, kind):
                 ref = [golden[f] for f in golden.files if f.startswith(pre + "buf.") and f.endswith(key)][0]
                 np.testing.assert_allclose(buf.numpy(), ref, rtol=1e-5, atol=1e-6)
             assert int(nbt) == 1
+
+
+def test_soft_restorer_matches_reference_fixture(sim):
+    """RestorerLinear with soft=True (models.py:634-655): linear_layer2 -> (mu, logvar) -> the reference's
+    (B, B)-broadcast reparameterisation, forward and backward, against fixtures recorded from the live reference (its host
+    np.random.normal noise replayed)."""
+    import os
+    from iins_vae_b200._capi import ptr, ptr_array
+    H, lib = sim
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "iins_golden_convheads.npz"))
+    cfg = orc.PathConfig()
+    for seed, batch in ((0, 5), (1, 48)):
+        pre = f"soft.s{seed}.b{batch}."
+        gen = torch.Generator().manual_seed(seed)
+        p = orc.init_params(orc.restorer_param_shapes(cfg), gen)
+        x = torch.rand(batch, cfg.range_dim, cfg.code_len, generator=gen)
+        assert np.array_equal(x.numpy(), golden[pre + "x"])
+        params = [v.contiguous() for v in p.values()]
+        noise = torch.from_numpy(golden[pre + "noise"]).reshape(-1).contiguous()
+        c = H.make_cfg(cfg, batch)
+        z = torch.zeros(batch, batch)
+        ws = torch.zeros(int(lib.iins_restorer_soft_ws_floats(c)) + 16)
+        lib.check(lib.iins_restorer_soft_forward(c, ptr_array(params), ptr(x), ptr(noise), ptr(z), ptr(ws), None), "soft fwd")
+        np.testing.assert_allclose(z.numpy(), golden[pre + "out"], rtol=2e-5, atol=2e-6)
+        G = [torch.zeros_like(v) for v in params]
+        d_x = torch.zeros_like(x)
+        scratch = torch.zeros(int(lib.iins_restorer_soft_scratch_floats(c)) + 16)
+        d_out = torch.from_numpy(golden[pre + "d_out"]).contiguous()
+        lib.check(lib.iins_restorer_soft_backward(c, ptr_array(params), ptr(x), ptr(noise), ptr(ws), ptr(d_out), ptr_array(G), ptr(d_x), 0,
+                                                  ptr(scratch), None), "soft bwd")
+        np.testing.assert_allclose(d_x.numpy(), golden[pre + "d_x"], rtol=2e-4, atol=1e-6)
+        for k, g in zip(p.keys(), G):
+            ref = golden[pre + "grad." + k]
+            if ref.size == 0:
+                assert float(g.abs().max()) == 0.0, k           # linear_layer1: not on the soft path
+                continue
+            err = np.linalg.norm(g.numpy().ravel() - ref.ravel())
+            assert err <= 2e-4 * np.linalg.norm(ref) + 1e-8, (pre, k, err, np.linalg.norm(ref))

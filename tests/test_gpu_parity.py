@@ -620,3 +620,33 @@ def test_engine_with_conv1d_heads_matches_oracle():
         eng2.step(cir, err, label, supervised=True)
         outs.append(_conv_head_masks(eng2, "restorer", batch)[0].clone())
     assert not torch.equal(outs[1], outs[2])
+
+
+def test_soft_restorer_module_matches_reference_fixture():
+    """Restorer(soft=True) (models.py:634-655) as a drop-in module on the B200: the host np.random.normal draw of the
+    reference (same call, same seed -> same noise), the (B, B)-broadcast output, gradients of linear_layer2 and the trunk,
+    linear_layer1 without gradient."""
+    from iins_vae_b200 import models as M
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "iins_golden_convheads.npz"))
+    cfg = orc.PathConfig()
+    for seed, batch in ((0, 5), (1, 48)):
+        pre = f"soft.s{seed}.b{batch}."
+        gen = torch.Generator().manual_seed(seed)
+        p = orc.init_params(orc.restorer_param_shapes(cfg), gen)
+        x = torch.rand(batch, cfg.range_dim, cfg.code_len, generator=gen).cuda().requires_grad_(True)
+        mod = M.Restorer((cfg.range_dim, cfg.code_len), soft=True)
+        mod.load_state_dict(p)
+        mod.cuda()
+        np.random.seed(seed)
+        out = mod(x)
+        assert out.shape == (batch, batch)
+        (out * torch.from_numpy(golden[pre + "d_out"]).cuda()).sum().backward()
+        np.testing.assert_allclose(out.detach().cpu().numpy(), golden[pre + "out"], rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(x.grad.cpu().numpy(), golden[pre + "d_x"], rtol=2e-4, atol=1e-6)
+        for k, v in mod.named_parameters():
+            ref = golden[pre + "grad." + k]
+            if ref.size == 0:
+                assert v.grad is None, k
+                continue
+            err = np.linalg.norm(v.grad.cpu().numpy().ravel() - ref.ravel())
+            assert err <= 2e-4 * np.linalg.norm(ref) + 1e-8, (pre, k, err)
