@@ -28,6 +28,8 @@ EXPORTS = [
     "iins_restorer_conv_ws_floats", "iins_restorer_conv_scratch_floats", "iins_restorer_conv_forward", "iins_restorer_conv_backward",
     "iins_classifier_conv_ws_floats", "iins_classifier_conv_scratch_floats", "iins_classifier_conv_forward",
     "iins_classifier_conv_backward",
+    "iins_ctx_create", "iins_ctx_destroy", "iins_ctx_make_current", "iins_ctx_get_current", "iins_ctx_set_compute_mode",
+    "iins_ctx_get_compute_mode", "iins_ctx_set_stream_concurrency",
     "iins_restorer_soft_ws_floats", "iins_restorer_soft_scratch_floats", "iins_restorer_soft_forward", "iins_restorer_soft_backward",
 ]
 
@@ -62,6 +64,14 @@ class IinsLib:
         self.dll = C.CDLL(path)
         d = self.dll
         d.iins_abi_version.restype = C.c_int
+        d.iins_ctx_create.restype = C.c_void_p
+        d.iins_ctx_get_current.restype = C.c_void_p
+        d.iins_ctx_destroy.argtypes = [C.c_void_p]
+        d.iins_ctx_destroy.restype = None
+        d.iins_ctx_make_current.argtypes = [C.c_void_p]
+        d.iins_ctx_set_compute_mode.argtypes = [C.c_void_p, C.c_int]
+        d.iins_ctx_get_compute_mode.argtypes = [C.c_void_p]
+        d.iins_ctx_set_stream_concurrency.argtypes = [C.c_void_p, C.c_int]
         d.iins_last_error.restype = C.c_char_p
         d.iins_validate_config.argtypes = [_CFG]
         for mod in ("encoder", "decoder", "restorer", "classifier"):

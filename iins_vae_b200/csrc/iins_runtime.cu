@@ -11,6 +11,7 @@
 
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 
 namespace {
 
@@ -21,11 +22,86 @@ int fail(int code, const char* msg) {
     return code;
 }
 
-// Compute mode of the GEMM-bearing layers (process-wide; set through iins_set_compute_mode):
-//   0  tcgen05 tensor cores, fp32-grade: operands split into 3 bf16 pieces, 6 MMAs / k-step ("bf16x3")
-//   1  tcgen05 tensor cores, plain bf16 operands, fp32 accumulate (looser tolerance, BASELINE configs[2])
-//   2  fp32 SIMT (FFMA) kernels -- the bring-up / cross-check path
-int g_mode = 0;
+}  // namespace
+
+// ---- context ---------------------------------------------------------------------------------------------------------
+// Everything the library keeps between calls lives in an explicit context object (no hidden global state):
+// the compute mode, the tuning / debugging switches (read from the environment ONCE, when the context is created -- no
+// getenv in launch code), and the helper streams + fork / join events of the callers' streams (created lazily on the
+// context's device, guarded by a mutex so that several host threads may share a context).  iins_ctx_create() /
+// iins_ctx_destroy() / iins_ctx_make_current() are the C ABI; a thread without a current context uses the process's
+// default context (created on first use), so the plain entry points keep working unchanged.
+struct IinsOptions {
+    // compute mode of the GEMM-bearing layers (iins_set_compute_mode / iins_ctx_set_compute_mode):
+    //   0  tcgen05 tensor cores, fp32-grade: operands split into 3 bf16 pieces, 6 MMAs / k-step ("bf16x3")
+    //   1  tcgen05 tensor cores, plain bf16 operands, fp32 accumulate (looser tolerance, BASELINE configs[2])
+    //   2  fp32 SIMT (FFMA) kernels -- the bring-up / cross-check path
+    int mode = 0;
+    int async_wgrad = 1;        // IINS_ASYNC_WGRAD: weight gradients on a helper stream
+    int branch_streams = 1;     // IINS_BRANCH_STREAMS: env encoder next to the range encoder
+    int nt_max = 64;            // IINS_NT_MAX: cap of the tensor-core tile width
+    int ep_regs = 1;            // IINS_EP_REGS: register-resident epilogues (0: SMEM-staged generic epilogue)
+    int fuse_nbwd = 1;          // IINS_FUSE_NBWD: norm backward in the data-gradient epilogue
+    int row2 = 1;               // IINS_ROW2: one-thread-per-row kernels for the small-channel layers
+    long row2_tn_minm = 16384;  // IINS_ROW2_TN_MINM
+    long tn_ctas = 148L * 2;    // IINS_TN_CTAS: CTAs a weight-gradient launch aims for
+    int fused_trunk = 1;        // IINS_FUSED_TRUNK / IINS_FUSED_TRUNK_BWD: the persistent residual-trunk kernels
+    int fused_trunk_bwd = 1;
+    int wgrad_batch = 1;        // IINS_WGRAD_BATCH: the trunk's weight gradients as one launch
+    int trunk_tmap = 1;         // IINS_TRUNK_TMAP: tensor-map TMA (0: plain bulk copies) for the trunk's weight ring
+};
+
+struct IinsHelperStreams { cudaStream_t main; cudaStream_t helper[2]; };
+
+struct iins_ctx {
+    IinsOptions opt;
+    int device = -1;
+    std::mutex mu;
+    IinsHelperStreams helpers[32];
+    int n_helpers = 0;
+    cudaEvent_t fork_events[256];
+    int fork_i = 0;
+    bool events_ready = false;
+};
+
+namespace {
+
+int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
+void options_from_env(IinsOptions& o) {
+    o.async_wgrad = env_int("IINS_ASYNC_WGRAD", 1);
+    o.branch_streams = env_int("IINS_BRANCH_STREAMS", 1);
+    o.nt_max = env_int("IINS_NT_MAX", 64);
+    if (o.nt_max != 16 && o.nt_max != 32) o.nt_max = 64;
+    o.ep_regs = env_int("IINS_EP_REGS", 1);
+    o.fuse_nbwd = env_int("IINS_FUSE_NBWD", 1);
+    o.row2 = env_int("IINS_ROW2", 1);
+    o.row2_tn_minm = env_int("IINS_ROW2_TN_MINM", 16384);
+    o.tn_ctas = env_int("IINS_TN_CTAS", 148 * 2);
+    if (o.tn_ctas < 1) o.tn_ctas = 148;
+    o.fused_trunk = env_int("IINS_FUSED_TRUNK", 1);
+    o.fused_trunk_bwd = env_int("IINS_FUSED_TRUNK_BWD", 1);
+    o.wgrad_batch = env_int("IINS_WGRAD_BATCH", 1);
+    o.trunk_tmap = env_int("IINS_TRUNK_TMAP", 1);
+}
+
+iins_ctx* new_ctx() {
+    iins_ctx* c = new iins_ctx();
+    options_from_env(c->opt);
+#ifndef IINS_CPUSIM
+    if (cudaGetDevice(&c->device) != cudaSuccess) { c->device = -1; (void)cudaGetLastError(); }
+#endif
+    return c;
+}
+
+thread_local iins_ctx* t_ctx = nullptr;         // the calling thread's current context (iins_ctx_make_current)
+
+iins_ctx& cur() {
+    if (t_ctx != nullptr) return *t_ctx;
+    static iins_ctx* dflt = new_ctx();          // C++11 guarantees a thread-safe one-time initialisation
+    return *dflt;
+}
+#define g_mode (cur().opt.mode)
 // arena for the packed weight tiles of every layer of one module pass: 8 MB up to a 64-channel trunk (dim <= 4), 32 MB for
 // the wider configurations (dim = 16: a 256-channel k3 trunk convolution alone packs to 1.2 MB in fp32-grade mode)
 #define IINS_WPACK_FLOATS_SMALL ((size_t)1 << 21)
@@ -122,8 +198,7 @@ void launch_nt_simt(const Ctx& c, const IinsNTParams& p) {
 
 #ifndef IINS_CPUSIM
 void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
-    static int nt_max = 0;                 // tuning knob: cap the tile width (more, smaller CTAs); env IINS_NT_MAX
-    if (nt_max == 0) { const char* e = getenv("IINS_NT_MAX"); nt_max = e ? atoi(e) : 64; if (nt_max != 16 && nt_max != 32) nt_max = 64; }
+    const int nt_max = cur().opt.nt_max;   // tuning knob: cap the tile width (more, smaller CTAs)
     int nt = p.N <= 16 ? 16 : (p.N <= 32 ? 32 : 64);
     if (nt > nt_max && (p.ep.norm == IINS_NORM_NONE || p.ep.norm == IINS_NORM_IN || p.ep.norm == IINS_NORM_ADAIN)) nt = nt_max;
     IinsPackParams pk;
@@ -155,8 +230,7 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     // epilogue kind: register-resident whenever its preconditions hold (iins_tc.cuh); IINS_EP_REGS=0 forces the SMEM path
     int epi = IINS_EPI_SMEM, ll = 1;
     {
-        static int ep_regs_on = -1;
-        if (ep_regs_on < 0) { const char* e = getenv("IINS_EP_REGS"); ep_regs_on = e ? atoi(e) : 1; }
+        const int ep_regs_on = cur().opt.ep_regs;
         const IinsEpilogue& ep = p.ep;
         auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
         bool ok = ep_regs_on && p.out_layout == IINS_NLC && p.N % nt == 0 && al16(ep.y) && al16(ep.add) && ep.act != IINS_ACT_TANH;
@@ -197,14 +271,12 @@ bool nbwd_fusable(const Ctx& c, const IinsNTParams& p, int L, int C, const float
 #ifdef IINS_CPUSIM
     return false;
 #else
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("IINS_FUSE_NBWD"); on = e ? atoi(e) : 1; }
+    const int on = cur().opt.fuse_nbwd;
     if (!on || g_mode == 2 || p.a_kind != 1 || p.ep.y != dy || p.N != C || p.Lrow != L) return false;
     {   // row kernel territory (same routing as launch_nt) or the SMEM epilogue forced by IINS_EP_REGS=0
         const int nacc = p.N <= 4 ? 4 : (p.N <= 8 ? 8 : 16);
         if (p.N <= 16 && ((p.K * nacc <= IINS_ROW2_WMAX && p.K <= 128) || p.K <= 64)) return false;
-        const char* e = getenv("IINS_EP_REGS");
-        if (e && atoi(e) == 0) return false;
+        if (cur().opt.ep_regs == 0) return false;
     }
     const int cs = ilog2_exact(p.g.Cout);
     if (cs < 3 || p.g.out_layout != IINS_NLC || p.out_layout != IINS_NLC) return false;
@@ -221,10 +293,8 @@ bool nbwd_fusable(const Ctx& c, const IinsNTParams& p, int L, int C, const float
 // Same question for a data gradient that runs on the one-thread-per-row kernel (small-channel layers): plain InstanceNorm
 // (no AdaIN) over L in {32, 64, 128} rows, all N == NACC channels in one thread, NLC, 16-byte aligned, no residual operand.
 bool row2_nbwd_fusable(const IinsNTParams& p, int L, int C, int norm, const float* dy, const float* xhat, const float* rstd, const float* dz) {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("IINS_FUSE_NBWD"); on = e ? atoi(e) : 1; }
-    const char* r2 = getenv("IINS_ROW2");
-    if (!on || (r2 && atoi(r2) == 0) || norm != IINS_NORM_IN || p.a_kind != 1 || p.ep.y != dy || p.N != C || p.Lrow != L) return false;
+    const int on = cur().opt.fuse_nbwd;
+    if (!on || cur().opt.row2 == 0 || norm != IINS_NORM_IN || p.a_kind != 1 || p.ep.y != dy || p.N != C || p.Lrow != L) return false;
     if (!(C == 4 || C == 8 || C == 16) || !(L == 32 || L == 64 || L == 128)) return false;
     if (p.K * C > IINS_ROW2_WMAX || p.K > 128 || p.ep.add != nullptr || p.out_layout != IINS_NLC) return false;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -247,8 +317,7 @@ void launch_nt(Ctx& c, IinsNTParams p) {
         const bool wide = p.N > 16 && p.N % 64 == 0 && p.K <= 16 && p.ep.norm == IINS_NORM_NONE;
         const int nacc = wide ? 64 : (p.N <= 4 ? 4 : (p.N <= 8 ? 8 : 16));
         const bool norm_ok = p.ep.norm == IINS_NORM_NONE || (p.a_kind == 0 && (p.Lrow == 32 || p.Lrow == 64 || p.Lrow == 128));
-        static int row2_on = -1;
-        if (row2_on < 0) { const char* e = getenv("IINS_ROW2"); row2_on = e ? atoi(e) : 1; }
+        const int row2_on = cur().opt.row2;
         if (row2_on && (p.N <= 16 || wide) && p.K * nacc <= IINS_ROW2_WMAX && p.K <= 128 && norm_ok) {
             if (c.phase == 1) return;
             IinsRowParams rp;
@@ -317,38 +386,31 @@ void conv_dgrad(Ctx& c, const IinsGeom& g, const IinsDz& dz, const float* w, flo
 // Every caller stream gets its own pair of helper streams (module passes may themselves run concurrently on different
 // streams: the engine overlaps the decoder with the two heads): [0] weight gradients, [1] an independent branch of
 // the module (the env encoder next to the range encoder).  IINS_ASYNC_WGRAD=0 / IINS_BRANCH_STREAMS=0 serialise.
-int g_async_wgrad = -1, g_branch_streams = -1;
-struct HelperStreams { cudaStream_t main; cudaStream_t helper[2]; };
-HelperStreams g_helpers[32];
-int g_n_helpers = 0;
-cudaEvent_t g_fork_events[256];
-int g_fork_i = 0;
-bool g_fork_events_ready = false;
-
+// Helper streams are owned by the context, created on ITS device on first use (a caller on another device runs serially).
 cudaStream_t helper_stream(cudaStream_t main_st, int which) {
-    if (!g_fork_events_ready) {
-        for (int i = 0; i < 256; ++i) cudaEventCreateWithFlags(&g_fork_events[i], cudaEventDisableTiming);
-        g_fork_events_ready = true;
+    iins_ctx& x = cur();
+    std::lock_guard<std::mutex> lock(x.mu);
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != x.device) return nullptr;
+    if (!x.events_ready) {
+        for (int i = 0; i < 256; ++i) cudaEventCreateWithFlags(&x.fork_events[i], cudaEventDisableTiming);
+        x.events_ready = true;
     }
-    for (int i = 0; i < g_n_helpers; ++i) if (g_helpers[i].main == main_st) return g_helpers[i].helper[which];
-    if (g_n_helpers >= 32) return nullptr;              // more caller streams than slots: that caller runs serially
-    HelperStreams& h = g_helpers[g_n_helpers];
+    for (int i = 0; i < x.n_helpers; ++i) if (x.helpers[i].main == main_st) return x.helpers[i].helper[which];
+    if (x.n_helpers >= 32) return nullptr;              // more caller streams than slots: that caller runs serially
+    IinsHelperStreams& h = x.helpers[x.n_helpers];
     h.main = main_st;
     for (int k = 0; k < 2; ++k)
         if (cudaStreamCreateWithFlags(&h.helper[k], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    ++g_n_helpers;
+    ++x.n_helpers;
     return h.helper[which];
 }
-cudaStream_t side_stream(cudaStream_t main_st) {
-    if (g_async_wgrad < 0) { const char* e = getenv("IINS_ASYNC_WGRAD"); g_async_wgrad = e ? atoi(e) : 1; }
-    return g_async_wgrad ? helper_stream(main_st, 0) : nullptr;
-}
-cudaStream_t branch_stream(cudaStream_t main_st) {
-    if (g_branch_streams < 0) { const char* e = getenv("IINS_BRANCH_STREAMS"); g_branch_streams = e ? atoi(e) : 1; }
-    return g_branch_streams ? helper_stream(main_st, 1) : nullptr;
-}
+cudaStream_t side_stream(cudaStream_t main_st) { return cur().opt.async_wgrad ? helper_stream(main_st, 0) : nullptr; }
+cudaStream_t branch_stream(cudaStream_t main_st) { return cur().opt.branch_streams ? helper_stream(main_st, 1) : nullptr; }
 void fork_to(cudaStream_t from, cudaStream_t to) {
-    cudaEvent_t e = g_fork_events[g_fork_i++ & 255];
+    iins_ctx& x = cur();
+    cudaEvent_t e;
+    { std::lock_guard<std::mutex> lock(x.mu); e = x.fork_events[x.fork_i++ & 255]; }
     cudaEventRecord(e, from);
     cudaStreamWaitEvent(to, e, 0);
 }
@@ -386,15 +448,13 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
     p.M = g.B * g.Lout;
     int K = g.ks * g.Cin;
     {   // small-channel conv layers with many rows: one thread per row, register outer products (iins_row2_tn_kernel)
-        static int row2_on = -1;
-        if (row2_on < 0) { const char* e = getenv("IINS_ROW2"); row2_on = e ? atoi(e) : 1; }
+        const int row2_on = cur().opt.row2;
         const int ls = ilog2_exact(g.Lout);
         const int nacc = g.Cout <= 4 ? 4 : (g.Cout <= 8 ? 8 : 16);
         int tps = 0;                                   // taps per k slice of the instantiated (NACC, CIN) pair
         if (nacc == 4 && g.Cin == 1) tps = 7; else if (nacc == 16 && g.Cin == 1) tps = 7; else if (nacc == 4 && g.Cin == 4) tps = 7;
         else if (nacc == 8 && g.Cin == 4) tps = 4; else if (nacc == 4 && g.Cin == 8) tps = 3; else if (nacc == 16 && g.Cin == 8) tps = 1;
-        static long min_m = -1;                        // below this many rows the end-of-kernel reduction dominates
-        if (min_m < 0) { const char* e = getenv("IINS_ROW2_TN_MINM"); min_m = e ? atol(e) : 16384; }
+        const long min_m = cur().opt.row2_tn_minm;       // below this many rows the end-of-kernel reduction dominates
         if (row2_on && tps > 0 && g.Cout <= 16 && ls >= 0 && p.M >= min_m && (g.Cin == 1 || g.in_layout == IINS_NLC)) {
             IinsRow2TNParams rp;
             memset(&rp, 0, sizeof(rp));
@@ -433,8 +493,7 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
     if (g_mode != 2 && tc_ok) {
         int nt = g.Cout <= 16 ? 16 : (g.Cout <= 32 ? 32 : 64);
         int ky = (K + 127) / 128, nz = (g.Cout + nt - 1) / nt;
-        static long tn_ctas = 0;               // total CTAs aimed for (tuning knob: env IINS_TN_CTAS)
-        if (tn_ctas == 0) { const char* e = getenv("IINS_TN_CTAS"); tn_ctas = e ? atol(e) : 148L * 2; if (tn_ctas < 1) tn_ctas = 148; }
+        const long tn_ctas = cur().opt.tn_ctas;        // total CTAs aimed for
         long want = (tn_ctas + (long)ky * nz - 1) / ((long)ky * nz);
         long max_parts = (p.M + 127) / 128;
         if (want > max_parts) want = max_parts;
@@ -498,8 +557,7 @@ void conv_wgrad_batch(Ctx& c, const IinsGeom& g, int n, const float* const* xs, 
     const int K = g.ks * g.Cin;
     auto chan_ok = [&](int cdim) { return ilog2_exact(cdim) >= 3 || (g.ks == 1 && cdim % 8 == 0); };
     const bool tc_ok = chan_ok(g.Cin) && g.Cout % 8 == 0 && g.Cout <= 64 && g.in_layout == IINS_NLC && g.out_layout == IINS_NLC;
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("IINS_WGRAD_BATCH"); on = e ? atoi(e) : 1; }
+    const int on = cur().opt.wgrad_batch;
     if (on && g_mode != 2 && tc_ok && n <= 8 && ilog2_exact(g.Lout) >= 0) {
         cudaStream_t wst = c.st;
         if (c.st2 != nullptr) { fork_to(c.st, c.st2); wst = c.st2; }
@@ -604,8 +662,7 @@ struct EncLayerRef { float* y; float* xhat; float* rstd; };
 // convolution (forward kind, 64-wide tiles), whose outputs are consecutive in the arena.  Returns false -> per-layer path.
 bool trunk_forward_fused(Ctx& c, int B, int D, int Lt, int nres, const float* x, const float* const* P, int pi,
                          const EncLayerRef* res1, const EncLayerRef* res2, const float* adain, int adain_ld) {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("IINS_FUSED_TRUNK"); on = e ? atoi(e) : 1; }
+    const int on = cur().opt.fused_trunk;
     if (!on || c.phase != 2 || g_mode == 2 || D != 64 || Lt != 8 || nres < 1 || 2 * nres > IINS_TRUNK_MAX_CONVS) return false;
     if (c.job_i + 2 * nres > c.njobs) return false;
     const int pieces = g_mode == 1 ? 1 : 3;
@@ -613,6 +670,7 @@ bool trunk_forward_fused(Ctx& c, int B, int D, int Lt, int nres, const float* x,
     IinsTrunkFwdParams tp;
     memset(&tp, 0, sizeof(tp));
     tp.B = B; tp.nconv = 2 * nres; tp.pieces = pieces; tp.x = x; tp.adain = adain; tp.adain_ld = adain_ld;
+    tp.use_tmap = cur().opt.trunk_tmap;
     tp.wpack = c.jobs.jobs[c.job_i].out;
     for (int k = 0; k < 2 * nres; ++k) {
         const IinsPackJob& j = c.jobs.jobs[c.job_i + k];
@@ -634,8 +692,7 @@ bool trunk_forward_fused(Ctx& c, int B, int D, int Lt, int nres, const float* x,
 bool trunk_backward_fused(Ctx& c, int B, int D, int Lt, int nres, const float* dh, float* dx, float* dh_scratch, float* const* dz,
                           const EncLayerRef* res1, const EncLayerRef* res2, const float* adain, float* dadain, int adain_ld,
                           const EncLayerRef* pre, float* pre_dz) {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("IINS_FUSED_TRUNK_BWD"); on = e ? atoi(e) : 1; }
+    const int on = cur().opt.fused_trunk_bwd;
     if (!on || c.phase != 2 || g_mode == 2 || D != 64 || Lt != 8 || nres < 1 || 2 * nres > IINS_TRUNK_MAX_CONVS) return false;
     flush_pending(c);              // `dh` may be the output of a held-back data gradient (which consumes ITS pack job first)
     if (c.job_i + 2 * nres > c.njobs) return false;
@@ -645,6 +702,7 @@ bool trunk_backward_fused(Ctx& c, int B, int D, int Lt, int nres, const float* d
     memset(&tp, 0, sizeof(tp));
     tp.B = B; tp.nconv = nconv; tp.pieces = pieces; tp.dh = dh; tp.dx = dx; tp.dh_scratch = dh_scratch;
     tp.adain = adain; tp.dadain = dadain; tp.adain_ld = adain_ld;
+    tp.use_tmap = cur().opt.trunk_tmap;
     tp.wpack = c.jobs.jobs[c.job_i].out;
     for (int k = 0; k < nconv; ++k) {
         const IinsPackJob& j = c.jobs.jobs[c.job_i + k];          // job k packs convolution nconv - 1 - k
@@ -1482,18 +1540,39 @@ extern "C" {
 int iins_abi_version(void) { return 2; }
 int iins_set_compute_mode(int mode) {
     if (mode < 0 || mode > 2) return fail(IINS_ERR_BAD_CONFIG, "compute mode must be 0 (bf16x3 tensor core), 1 (bf16 tensor core) or 2 (fp32 SIMT)");
-    g_mode = mode;
+    cur().opt.mode = mode;
+    return IINS_OK;
+}
+iins_ctx* iins_ctx_create(void) { return new_ctx(); }
+void iins_ctx_destroy(iins_ctx* ctx) {
+    if (ctx == nullptr) return;
+    if (t_ctx == ctx) t_ctx = nullptr;
+#ifndef IINS_CPUSIM
+    for (int i = 0; i < ctx->n_helpers; ++i) for (int k = 0; k < 2; ++k) cudaStreamDestroy(ctx->helpers[i].helper[k]);
+    if (ctx->events_ready) for (int i = 0; i < 256; ++i) cudaEventDestroy(ctx->fork_events[i]);
+#endif
+    delete ctx;
+}
+int iins_ctx_make_current(iins_ctx* ctx) { t_ctx = ctx; return IINS_OK; }
+iins_ctx* iins_ctx_get_current(void) { return t_ctx; }
+int iins_ctx_set_compute_mode(iins_ctx* ctx, int mode) {
+    if (ctx == nullptr) return fail(IINS_ERR_NULL, "ctx is NULL");
+    if (mode < 0 || mode > 2) return fail(IINS_ERR_BAD_CONFIG, "compute mode must be 0, 1 or 2");
+    ctx->opt.mode = mode;
+    return IINS_OK;
+}
+int iins_ctx_get_compute_mode(const iins_ctx* ctx) { return ctx ? ctx->opt.mode : IINS_ERR_NULL; }
+int iins_ctx_set_stream_concurrency(iins_ctx* ctx, int enable) {
+    if (ctx == nullptr) return fail(IINS_ERR_NULL, "ctx is NULL");
+    ctx->opt.async_wgrad = enable ? 1 : 0;
+    ctx->opt.branch_streams = enable ? 1 : 0;
     return IINS_OK;
 }
 int iins_get_compute_mode(void) { return g_mode; }
 const char* iins_last_error(void) { return g_err; }
 int iins_set_stream_concurrency(int enable) {
-#ifndef IINS_CPUSIM
-    g_async_wgrad = enable ? 1 : 0;
-    g_branch_streams = enable ? 1 : 0;
-#else
-    (void)enable;
-#endif
+    cur().opt.async_wgrad = enable ? 1 : 0;
+    cur().opt.branch_streams = enable ? 1 : 0;
     return IINS_OK;
 }
 int iins_validate_config(const iins_config* cfg) { Shapes s; return make_shapes(cfg, s); }

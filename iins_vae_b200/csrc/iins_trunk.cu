@@ -516,12 +516,6 @@ void launch_bwd_variant(cudaStream_t st, const IinsTrunkBwdParams& p, const CUte
     IINS_LAUNCH(iins_trunk_bwd_kernel_, grid, 320, smem, st, p, map);
 }
 
-int trunk_use_tmap() {
-    static int use_tmap = -1;
-    if (use_tmap < 0) { const char* e = getenv("IINS_TRUNK_TMAP"); use_tmap = e ? atoi(e) : 1; }
-    return use_tmap;
-}
-
 }  // namespace
 
 bool iins_trunk_backward_launch(cudaStream_t st, const IinsTrunkBwdParams& p) {
@@ -538,7 +532,7 @@ bool iins_trunk_backward_launch(cudaStream_t st, const IinsTrunkBwdParams& p) {
     if (p.pre.xhat != nullptr && (!p.pre.rstd || !p.pre.dz || !al16(p.pre.xhat) || !al16(p.pre.rstd) || !al16(p.pre.dz) || p.adain != nullptr)) return false;
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
-    bool tmap = trunk_use_tmap() != 0 && make_weight_map(&map, p.wpack, p.pieces, p.nconv);
+    bool tmap = p.use_tmap != 0 && make_weight_map(&map, p.wpack, p.pieces, p.nconv);
     const int ntiles = (p.B + TR_SAMPLES - 1) / TR_SAMPLES;
     const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;
     IINS_SET_FLOPS(2.0 * (double)p.B * 8.0 * 64.0 * 192.0 * p.nconv); IINS_SET_SHAPE(p.B * 8, 64, 192 * p.nconv);
@@ -562,7 +556,7 @@ bool iins_trunk_forward_launch(cudaStream_t st, const IinsTrunkFwdParams& p) {
     }
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
-    bool tmap = trunk_use_tmap() != 0 && make_weight_map(&map, p.wpack, p.pieces, p.nconv);
+    bool tmap = p.use_tmap != 0 && make_weight_map(&map, p.wpack, p.pieces, p.nconv);
     const int ntiles = (p.B + TR_SAMPLES - 1) / TR_SAMPLES;
     const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;                  // persistent: 2 CTAs per SM
     IINS_SET_FLOPS(2.0 * (double)p.B * 8.0 * 64.0 * 192.0 * p.nconv); IINS_SET_SHAPE(p.B * 8, 64, 192 * p.nconv);

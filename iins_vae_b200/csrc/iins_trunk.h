@@ -22,6 +22,7 @@ struct IinsTrunkFwdParams {
     int B;                     // samples
     int nconv;                 // 2 * n_residual
     int pieces;                // 3 (fp32-grade) or 1 (bf16)
+    int use_tmap;              // weight ring by tensor-map TMA (cp.async.bulk.tensor); 0: plain bulk copies
     const float* x;            // (B, 8, 64) trunk input
     const float* adain;        // (B, adain_ld) AdaIN parameters, or nullptr: plain InstanceNorm
     int adain_ld;
@@ -44,6 +45,7 @@ struct IinsTrunkBwdLayer {
 
 struct IinsTrunkBwdParams {
     int B, nconv, pieces;
+    int use_tmap;
     const float* dh;           // (B, 8, 64) gradient w.r.t. the trunk output
     float* dx;                 // OUT (B, 8, 64) gradient w.r.t. the trunk input (may be nullptr when `pre` is given)
     float* dh_scratch;         // (B, 8, 64) scratch: gradient w.r.t. the output of the residual block being left

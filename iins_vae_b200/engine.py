@@ -520,6 +520,11 @@ class InferenceEngine:
                                                  ptr(self.logits), ptr(self.label), None, self.label_offset, 1.0, 1.0, 1.0,
                                                  ptr(self.out), None, None, None, ptr(self.pred), st), "metrics")
 
+    def close(self):
+        """Drop the captured graph (call before destroy_process_group under torchrun)."""
+        torch.cuda.synchronize(self.device)
+        self._graph = None
+
     def run(self, cir=None, err=None, label=None):
         """Returns (err_est (B,1), pred (B,) int32, out[8]) as device tensors (static buffers, overwritten next call)."""
         if cir is not None:

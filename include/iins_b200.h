@@ -50,7 +50,23 @@ typedef struct iins_config {
 } iins_config;
 
 int iins_abi_version(void);
-/* Arithmetic of the conv / linear GEMMs (process-wide):
+
+/* ---- Context: everything the library keeps between calls (compute mode, tuning switches read from the environment once at
+ * creation, the helper streams / events it forks a caller's stream into) lives in an explicit handle.  A context is bound to
+ * the device that was current when it was created and may be shared by host threads.  iins_ctx_make_current() selects the
+ * calling THREAD's context for all entry points below; a thread without one uses the process's default context, so callers
+ * that never touch this section behave as before.  (The launch counter / in-process profile at the end of this header are
+ * process-wide diagnostics.) */
+typedef struct iins_ctx iins_ctx;
+iins_ctx* iins_ctx_create(void);
+void iins_ctx_destroy(iins_ctx* ctx);
+int iins_ctx_make_current(iins_ctx* ctx);            /* NULL: back to the default context */
+iins_ctx* iins_ctx_get_current(void);
+int iins_ctx_set_compute_mode(iins_ctx* ctx, int mode);
+int iins_ctx_get_compute_mode(const iins_ctx* ctx);
+int iins_ctx_set_stream_concurrency(iins_ctx* ctx, int enable);
+
+/* Arithmetic of the conv / linear GEMMs (of the calling thread's current context):
  *   0 (default) tcgen05 tensor cores, fp32-grade: every fp32 operand is split into three bf16 pieces and the
  *               six significant piece products are accumulated in fp32 in TMEM ("bf16x3", error ~2^-23);
  *   1           tcgen05 tensor cores, plain bf16 operands, fp32 accumulation (BASELINE configs[2]);

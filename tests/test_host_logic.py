@@ -46,6 +46,31 @@ def test_config_validation_and_sizes_without_gpu():
     assert lib.iins_set_compute_mode(7) != 0 and lib.iins_set_compute_mode(0) == 0
 
 
+def test_contexts_hold_the_state():
+    """SURVEY 8(b) "no global state": compute mode and concurrency live in iins_ctx handles; a thread's current context is
+    what the plain entry points use, other contexts (and other threads) are unaffected."""
+    import threading
+    from iins_vae_b200._capi import IinsLib
+    from iins_vae_b200 import build
+    lib = IinsLib(build.build())
+    d = lib.dll
+    assert d.iins_set_compute_mode(0) == 0
+    a, b = d.iins_ctx_create(), d.iins_ctx_create()
+    assert a and b and a != b
+    assert d.iins_ctx_set_compute_mode(a, 1) == 0 and d.iins_ctx_set_compute_mode(b, 2) == 0
+    assert d.iins_ctx_set_compute_mode(a, 9) != 0
+    assert d.iins_get_compute_mode() == 0                      # the default context is untouched
+    assert d.iins_ctx_make_current(a) == 0 and d.iins_get_compute_mode() == 1 and d.iins_ctx_get_current() == a
+    seen = []
+    t = threading.Thread(target=lambda: seen.append((d.iins_ctx_get_current(), d.iins_get_compute_mode())))
+    t.start(); t.join()
+    assert seen == [(None, 0)]                                 # another thread: no current context -> default context
+    assert d.iins_ctx_make_current(b) == 0 and d.iins_get_compute_mode() == 2
+    assert d.iins_set_compute_mode(0) == 0 and d.iins_ctx_get_compute_mode(b) == 0 and d.iins_ctx_get_compute_mode(a) == 1
+    assert d.iins_ctx_make_current(None) == 0 and d.iins_get_compute_mode() == 0
+    d.iins_ctx_destroy(a); d.iins_ctx_destroy(b)
+
+
 def test_modules_fail_loudly_on_cpu_tensors():
     from iins_vae_b200 import models as M
     with pytest.raises(RuntimeError, match="CUDA"):
