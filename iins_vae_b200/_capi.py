@@ -30,6 +30,7 @@ EXPORTS = [
     "iins_classifier_conv_backward",
     "iins_ctx_create", "iins_ctx_destroy", "iins_ctx_make_current", "iins_ctx_get_current", "iins_ctx_set_compute_mode",
     "iins_ctx_get_compute_mode", "iins_ctx_set_stream_concurrency",
+    "iins_set_deferred_join", "iins_join_helpers",
     "iins_restorer_soft_ws_floats", "iins_restorer_soft_scratch_floats", "iins_restorer_soft_forward", "iins_restorer_soft_backward",
 ]
 
@@ -64,6 +65,7 @@ class IinsLib:
         self.dll = C.CDLL(path)
         d = self.dll
         d.iins_abi_version.restype = C.c_int
+        d.iins_join_helpers.argtypes = [C.c_void_p, C.c_void_p]
         d.iins_ctx_create.restype = C.c_void_p
         d.iins_ctx_get_current.restype = C.c_void_p
         d.iins_ctx_destroy.argtypes = [C.c_void_p]

@@ -49,6 +49,7 @@ struct IinsOptions {
     int fused_trunk_bwd = 1;
     int wgrad_batch = 1;        // IINS_WGRAD_BATCH: the trunk's weight gradients as one launch
     int trunk_tmap = 1;         // IINS_TRUNK_TMAP: tensor-map TMA (0: plain bulk copies) for the trunk's weight ring
+    int defer_join = 0;         // iins_set_deferred_join: a backward pass does NOT wait for its weight-gradient stream at its end
 };
 
 struct IinsHelperStreams { cudaStream_t main; cudaStream_t helper[2]; };
@@ -420,7 +421,17 @@ cudaStream_t branch_stream(cudaStream_t) { return nullptr; }
 void fork_to(cudaStream_t, cudaStream_t) {}
 #endif
 void begin_async_wgrad(Ctx& c) { if (c.phase != 1) c.st2 = side_stream(c.st); }
-void end_async_wgrad(Ctx& c) { flush_pending(c); if (c.phase != 1 && c.st2 != nullptr) { fork_to(c.st2, c.st); c.st2 = nullptr; } }
+// At the end of a backward pass the caller's stream normally waits for the weight-gradient stream (the gradients are then
+// complete in stream order, as the autograd path needs).  With deferred joins (iins_set_deferred_join, used by the fused
+// engine) it does not: the next module's data-gradient chain starts while this module's weight gradients still run, and the
+// caller joins once -- iins_join_helpers() -- before it consumes the gradients (all-reduce / Adam).
+void end_async_wgrad(Ctx& c) {
+    flush_pending(c);
+    if (c.phase != 1 && c.st2 != nullptr) {
+        if (!cur().opt.defer_join) fork_to(c.st2, c.st);
+        c.st2 = nullptr;
+    }
+}
 // Run an independent part of a module pass on the branch stream: begin_branch() redirects the launches of `c`,
 // end_branch() restores the main stream; join_branch() makes the main stream wait for the branch.
 struct Branch { cudaStream_t main = nullptr, br = nullptr; };
@@ -1552,6 +1563,24 @@ void iins_ctx_destroy(iins_ctx* ctx) {
     if (ctx->events_ready) for (int i = 0; i < 256; ++i) cudaEventDestroy(ctx->fork_events[i]);
 #endif
     delete ctx;
+}
+int iins_set_deferred_join(int enable) { cur().opt.defer_join = enable ? 1 : 0; return IINS_OK; }
+int iins_join_helpers(iins_stream_t producer, iins_stream_t waiter) {
+#ifndef IINS_CPUSIM
+    iins_ctx& x = cur();
+    cudaStream_t helpers[2] = {nullptr, nullptr};
+    {
+        std::lock_guard<std::mutex> lock(x.mu);
+        for (int i = 0; i < x.n_helpers; ++i)
+            if (x.helpers[i].main == (cudaStream_t)producer) { helpers[0] = x.helpers[i].helper[0]; helpers[1] = x.helpers[i].helper[1]; }
+    }
+    for (int k = 0; k < 2; ++k)
+        if (helpers[k] != nullptr) fork_to(helpers[k], (cudaStream_t)(waiter != nullptr ? waiter : producer));
+    return check_cuda("join_helpers");
+#else
+    (void)producer; (void)waiter;
+    return IINS_OK;
+#endif
 }
 int iins_ctx_make_current(iins_ctx* ctx) { t_ctx = ctx; return IINS_OK; }
 iins_ctx* iins_ctx_get_current(void) { return t_ctx; }

@@ -294,6 +294,7 @@ class SemiTrainEngine:
             return
         main = torch.cuda.current_stream()
         self.comm_stream.wait_stream(main)
+        self._join_weight_gradients(self.comm_stream)          # the Dec / Res / Cls weight gradients may still be in flight
         with torch.cuda.stream(self.comm_stream):
             dist.all_reduce(self.flat.grad[enc_end:end], op=dist.ReduceOp.SUM, group=self.pg)
 
@@ -318,10 +319,24 @@ class SemiTrainEngine:
                                                self._ge, act, 3, ptr(self.steps), ptr(self.lr), self.betas[0], self.betas[1],
                                                self.eps, 1.0 / self.world, 1, _stream()), "adam")
 
+    def _join_weight_gradients(self, waiter=None):
+        """Make ``waiter`` (default: the current stream) wait for the library's weight-gradient streams of the streams this
+        engine launched backward passes on (deferred joins, include/iins_b200.h)."""
+        main = torch.cuda.current_stream()
+        w = C.c_void_p((waiter or main).cuda_stream)
+        for st in (main, self.head_stream):
+            self.lib.check(self.lib.iins_join_helpers(C.c_void_p(st.cuda_stream), w), "join_helpers")
+
     def _step_body(self, supervised: bool, update: bool = True):
         self._forward(supervised)
         self._loss(supervised)
-        self._backward(supervised)
+        # the decoder's / heads' weight gradients keep running next to the encoder backward: one join before they are consumed
+        self.lib.check(self.lib.iins_set_deferred_join(int(self.concurrent)), "set_deferred_join")
+        try:
+            self._backward(supervised)
+        finally:
+            self.lib.check(self.lib.iins_set_deferred_join(0), "set_deferred_join")
+        self._join_weight_gradients()
         self._allreduce(supervised)
         if update:
             self._adam(supervised)

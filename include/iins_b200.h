@@ -223,6 +223,15 @@ int iins_accumulate2(float* dst1, const float* src1, size_t n1, float* dst2, con
  * used when individual kernels are timed with events (bench.py roofline, tools/step_profile.py). Default 1. */
 int iins_set_stream_concurrency(int enable);
 
+/* Deferred joins.  By default a backward entry point returns with the caller's stream ordered after ALL its work, weight
+ * gradients included (what an autograd caller needs).  With iins_set_deferred_join(1) (current context) the stream is only
+ * ordered after the data-gradient outputs; the weight gradients of that pass keep running on the context's helper stream of
+ * that caller stream, next to whatever the caller enqueues next (the following module's backward).  The caller must then
+ * call iins_join_helpers(producer, waiter) before the gradients are consumed: `waiter` (NULL = `producer` itself) waits for
+ * the helper streams of `producer`. */
+int iins_set_deferred_join(int enable);
+int iins_join_helpers(iins_stream_t producer, iins_stream_t waiter);
+
 /* ---- launch accounting / in-process kernel timing (used by bench.py; not a profiler replacement) ------ */
 unsigned long long iins_launch_count(void);           /* kernels launched by this library so far */
 int iins_profile_begin(void);                          /* record a CUDA-event pair around every launch */
