@@ -65,7 +65,7 @@ class IinsLib:
         self.dll = C.CDLL(path)
         d = self.dll
         d.iins_abi_version.restype = C.c_int
-        d.iins_join_helpers.argtypes = [C.c_void_p, C.c_void_p]
+        d.iins_join_helpers.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         d.iins_ctx_create.restype = C.c_void_p
         d.iins_ctx_get_current.restype = C.c_void_p
         d.iins_ctx_destroy.argtypes = [C.c_void_p]

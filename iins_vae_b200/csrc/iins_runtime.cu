@@ -52,7 +52,7 @@ struct IinsOptions {
     int defer_join = 0;         // iins_set_deferred_join: a backward pass does NOT wait for its weight-gradient stream at its end
 };
 
-struct IinsHelperStreams { cudaStream_t main; cudaStream_t helper[2]; };
+struct IinsHelperStreams { cudaStream_t main; cudaStream_t helper[2]; bool unjoined; /* deferred join outstanding on helper[0] */ };
 
 struct iins_ctx {
     IinsOptions opt;
@@ -400,7 +400,7 @@ cudaStream_t helper_stream(cudaStream_t main_st, int which) {
     for (int i = 0; i < x.n_helpers; ++i) if (x.helpers[i].main == main_st) return x.helpers[i].helper[which];
     if (x.n_helpers >= 32) return nullptr;              // more caller streams than slots: that caller runs serially
     IinsHelperStreams& h = x.helpers[x.n_helpers];
-    h.main = main_st;
+    h.main = main_st; h.unjoined = false;
     for (int k = 0; k < 2; ++k)
         if (cudaStreamCreateWithFlags(&h.helper[k], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     ++x.n_helpers;
@@ -429,6 +429,13 @@ void end_async_wgrad(Ctx& c) {
     flush_pending(c);
     if (c.phase != 1 && c.st2 != nullptr) {
         if (!cur().opt.defer_join) fork_to(c.st2, c.st);
+        else {
+#ifndef IINS_CPUSIM
+            iins_ctx& x = cur();
+            std::lock_guard<std::mutex> lock(x.mu);
+            for (int i = 0; i < x.n_helpers; ++i) if (x.helpers[i].main == c.st) x.helpers[i].unjoined = true;
+#endif
+        }
         c.st2 = nullptr;
     }
 }
@@ -1565,20 +1572,24 @@ void iins_ctx_destroy(iins_ctx* ctx) {
     delete ctx;
 }
 int iins_set_deferred_join(int enable) { cur().opt.defer_join = enable ? 1 : 0; return IINS_OK; }
-int iins_join_helpers(iins_stream_t producer, iins_stream_t waiter) {
+int iins_join_helpers(iins_stream_t producer, iins_stream_t waiter, int keep_pending) {
 #ifndef IINS_CPUSIM
     iins_ctx& x = cur();
-    cudaStream_t helpers[2] = {nullptr, nullptr};
+    // only a helper stream with an outstanding deferred join is touched (an idle one may not even belong to a running capture)
+    cudaStream_t helper = nullptr;
     {
         std::lock_guard<std::mutex> lock(x.mu);
         for (int i = 0; i < x.n_helpers; ++i)
-            if (x.helpers[i].main == (cudaStream_t)producer) { helpers[0] = x.helpers[i].helper[0]; helpers[1] = x.helpers[i].helper[1]; }
+            if (x.helpers[i].main == (cudaStream_t)producer && x.helpers[i].unjoined) {
+                helper = x.helpers[i].helper[0];
+                // keep_pending: an additional waiter (the communication stream); the final join comes later
+                if (!keep_pending) x.helpers[i].unjoined = false;
+            }
     }
-    for (int k = 0; k < 2; ++k)
-        if (helpers[k] != nullptr) fork_to(helpers[k], (cudaStream_t)(waiter != nullptr ? waiter : producer));
+    if (helper != nullptr) fork_to(helper, (cudaStream_t)(waiter != nullptr ? waiter : producer));
     return check_cuda("join_helpers");
 #else
-    (void)producer; (void)waiter;
+    (void)producer; (void)waiter; (void)keep_pending;
     return IINS_OK;
 #endif
 }

@@ -325,7 +325,7 @@ class SemiTrainEngine:
         main = torch.cuda.current_stream()
         w = C.c_void_p((waiter or main).cuda_stream)
         for st in (main, self.head_stream):
-            self.lib.check(self.lib.iins_join_helpers(C.c_void_p(st.cuda_stream), w), "join_helpers")
+            self.lib.check(self.lib.iins_join_helpers(C.c_void_p(st.cuda_stream), w, int(waiter is not None)), "join_helpers")
 
     def _step_body(self, supervised: bool, update: bool = True):
         self._forward(supervised)

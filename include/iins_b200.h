@@ -227,10 +227,11 @@ int iins_set_stream_concurrency(int enable);
  * gradients included (what an autograd caller needs).  With iins_set_deferred_join(1) (current context) the stream is only
  * ordered after the data-gradient outputs; the weight gradients of that pass keep running on the context's helper stream of
  * that caller stream, next to whatever the caller enqueues next (the following module's backward).  The caller must then
- * call iins_join_helpers(producer, waiter) before the gradients are consumed: `waiter` (NULL = `producer` itself) waits for
- * the helper streams of `producer`. */
+ * call iins_join_helpers(producer, waiter, 0) before the gradients are consumed: `waiter` (NULL = `producer` itself) waits for
+ * the outstanding weight-gradient work of `producer`.  keep_pending = 1 adds a waiter without settling the join (a
+ * communication stream that reduces one bucket early; the final join still has to follow). */
 int iins_set_deferred_join(int enable);
-int iins_join_helpers(iins_stream_t producer, iins_stream_t waiter);
+int iins_join_helpers(iins_stream_t producer, iins_stream_t waiter, int keep_pending);
 
 /* ---- launch accounting / in-process kernel timing (used by bench.py; not a profiler replacement) ------ */
 unsigned long long iins_launch_count(void);           /* kernels launched by this library so far */
