@@ -518,12 +518,13 @@ def main():
         achieved = top[1][1] / (top[1][0] * 1e-3) / 1e12 if top[1][0] > 0 else 0.0
         # DRAM traffic per launch of that kernel from the committed ncu --set full capture (profiles/), if present
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01b_ncu_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                rows = [r for r in json.load(f) if top[0].rstrip("_") in r["kernel"]]
-            if rows:
-                traffic = sum(r["dram_bytes"] for r in rows) / len(rows)
+        for tname in ("r02a_ncu_traffic.json", "r01b_ncu_traffic.json"):     # newest capture that holds this kernel family
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if traffic is None and os.path.exists(tpath):
+                with open(tpath) as f:
+                    rows = [r for r in json.load(f) if top[0].rstrip("_") in r["kernel"]]
+                if rows:
+                    traffic = sum(r["dram_bytes"] for r in rows) / len(rows)
         roofline = {"bound": "tensor", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic,
                     "share_of_step": top[1][0] / total_ms, "avg_launch_ms": top[1][0] / top[1][2],

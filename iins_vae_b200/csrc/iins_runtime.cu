@@ -49,6 +49,7 @@ struct IinsOptions {
     int fused_trunk_bwd = 1;
     int wgrad_batch = 1;        // IINS_WGRAD_BATCH: the trunk's weight gradients as one launch
     int trunk_tmap = 1;         // IINS_TRUNK_TMAP: tensor-map TMA (0: plain bulk copies) for the trunk's weight ring
+    int dgrad_parity = 1;       // IINS_DGRAD_PARITY: stride-2 data gradients split by the parity of the input position
     int defer_join = 0;         // iins_set_deferred_join: a backward pass does NOT wait for its weight-gradient stream at its end
 };
 
@@ -84,6 +85,7 @@ void options_from_env(IinsOptions& o) {
     o.fused_trunk_bwd = env_int("IINS_FUSED_TRUNK_BWD", 1);
     o.wgrad_batch = env_int("IINS_WGRAD_BATCH", 1);
     o.trunk_tmap = env_int("IINS_TRUNK_TMAP", 1);
+    o.dgrad_parity = env_int("IINS_DGRAD_PARITY", 1);
 }
 
 iins_ctx* new_ctx() {
@@ -209,18 +211,36 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     pk.pieces = g_mode == 1 ? 1 : 3;
     size_t bytes = (size_t)pk.nblk * pk.nkb * pk.pieces * 4 * nt * 16;
     long chunks = (long)pk.nblk * pk.nkb * 4 * nt;
+    // Data gradient of a k4 / stride-2 / zero-pad-1 convolution: split by the parity of the input position (iins_tc.cuh, AKIND 2):
+    // two GEMMs over half the rows with K' = 2 Cout each -- half the gather / convert / MMA work.  Whether the launch takes
+    // that form is only known at execute time (a norm backward may get fused into this data gradient, which needs whole
+    // samples per tile), so the collect phase records the plain pack job AND the two parity pack jobs for such a geometry.
+    const IinsGeom& g0 = p.g;
+    const bool par_geom = cur().opt.dgrad_parity && p.a_kind == 1 && g0.stride == 2 && g0.ks == 4 && g0.pad == 1 && g0.mode == IINS_PAD_ZERO &&
+                          (g0.Lin & 1) == 0 && ilog2_exact(g0.Lin / 2) >= 0 && g0.Lout * 2 == g0.Lin && p.cshift >= 3 && p.cshift < 31;
+    const int K2 = 2 * g0.Cout, nkb2 = (K2 + 31) / 32;
+    const size_t bytes2 = (size_t)pk.nblk * nkb2 * pk.pieces * 4 * nt * 16;
+    const long chunks2 = (long)pk.nblk * nkb2 * 4 * nt;
     if (c.phase == 1) {                                // collect
-        if (c.wpack == nullptr || c.arena + bytes > c.wpack_cap || c.njobs >= IINS_PACK_MAX_JOBS) { c.err = 1; return; }
-        IinsPackJob& j = c.jobs.jobs[c.njobs++];
-        j.w = p.w; j.out = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(c.wpack) + c.arena);
-        j.Cin = p.g.Cin; j.Cout = p.g.Cout; j.ks = p.g.ks; j.kind = p.a_kind; j.N = p.N; j.K = p.K; j.NT = nt;
-        j.nkb = pk.nkb; j.nblk = pk.nblk; j.chunk_begin = c.jobs.total;
-        c.jobs.total += chunks;
-        c.arena += (bytes + 255) & ~(size_t)255;
+        const int need = par_geom ? 3 : 1;
+        if (c.wpack == nullptr || c.arena + bytes + (par_geom ? 2 * ((bytes2 + 255) & ~(size_t)255) + 256 : 0) > c.wpack_cap ||
+            c.njobs + need > IINS_PACK_MAX_JOBS) { c.err = 1; return; }
+        for (int v = 0; v < need; ++v) {
+            IinsPackJob& j = c.jobs.jobs[c.njobs++];
+            j.w = p.w; j.out = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(c.wpack) + c.arena);
+            j.Cin = p.g.Cin; j.Cout = p.g.Cout; j.ks = p.g.ks; j.kind = v == 0 ? p.a_kind : 1 + v; j.N = p.N; j.K = v == 0 ? p.K : K2; j.NT = nt;
+            j.nkb = v == 0 ? pk.nkb : nkb2; j.nblk = pk.nblk; j.chunk_begin = c.jobs.total;
+            c.jobs.total += v == 0 ? chunks : chunks2;
+            c.arena += ((v == 0 ? bytes : bytes2) + 255) & ~(size_t)255;
+        }
         return;
     }
-    if (c.phase == 2) pk.out = c.jobs.jobs[c.job_i++].out;
-    else {
+    const uint16_t* pack_even = nullptr;
+    const uint16_t* pack_odd = nullptr;
+    if (c.phase == 2) {
+        pk.out = c.jobs.jobs[c.job_i++].out;
+        if (par_geom) { pack_even = c.jobs.jobs[c.job_i++].out; pack_odd = c.jobs.jobs[c.job_i++].out; }
+    } else {
         if (c.wpack == nullptr || bytes > c.wpack_cap) { c.err = 1; return; }
         IINS_LAUNCH(iins_pack_kernel, grid_for(chunks), 256, 0, c.st, pk);
     }
@@ -252,8 +272,16 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     }
     dim3 grid((p.M + 127) / 128, pk.nblk, 1);
     IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K); IINS_SET_SHAPE(p.M, p.N, p.K);
-    const bool launched = tp.pieces == 3 ? iins_launch_tc_nt_p3(c.st, tp, grid, nt, p.a_kind, epi, ll)
-                                         : iins_launch_tc_nt_p1(c.st, tp, grid, nt, p.a_kind, epi, ll);
+    int akind = p.a_kind;
+    if (par_geom && pack_even != nullptr && epi == IINS_EPI_PLAIN && p.out_layout == IINS_NLC) {
+        // parity classes as two GEMMs in one grid (blockIdx.z): rows (b, j) <-> input position 2 j + parity
+        akind = 2;
+        tp.wpack = pack_even; tp.wpack_odd = pack_odd;
+        tp.nt.M = p.M / 2; tp.nt.K = K2; tp.nt.Lrow = p.Lrow / 2; tp.nt.lshift = p.lshift - 1; tp.nkb = nkb2;
+        grid = dim3((tp.nt.M + 127) / 128, pk.nblk, 2);
+    }
+    const bool launched = tp.pieces == 3 ? iins_launch_tc_nt_p3(c.st, tp, grid, nt, akind, epi, ll)
+                                         : iins_launch_tc_nt_p1(c.st, tp, grid, nt, akind, epi, ll);
     if (!launched) c.err = 4;
 }
 #endif

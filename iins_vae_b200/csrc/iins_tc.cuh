@@ -100,6 +100,18 @@ __device__ __forceinline__ void iins_gather8_dgrad_fast(const IinsGeom& g, const
     }
 }
 
+// Data gradient of a k4 / stride-2 / zero-pad-1 convolution split by the PARITY of the input position (AKIND 2).
+// Input position pos = 2 j + par receives only the taps t with t = pos + 1 (mod 2): par 0 -> {1, 3}, par 1 -> {0, 2}; the
+// plain gather would build K = 4 Cout entries per row of which every other 8-wide chunk is structurally zero.  Rows of one
+// parity class form a GEMM with K' = 2 Cout:  k = u * Cout + co,  t = 2 u + (1 - par),  output row l = j - u + par.
+__device__ __forceinline__ void iins_gather8_dgrad_parity(const IinsGeom& g, const IinsDz& d, int K2, int cs, int b, int j, int par,
+                                                          int k0, float* v) {
+    const int u = k0 >> cs, c0 = k0 & (int)((1u << cs) - 1u);
+    const int l = j - u + par;
+    const bool ok = k0 < K2 && l >= 0 && l < g.Lout;
+    iins_dz8_fast(g, d, b, l, c0, ok, v);
+}
+
 // ---- quad gathers for the forward / data-gradient kernel -----------------------------------------------------
 // A thread fetches 4 consecutive k (one 16-byte load) of one row; the 8 lanes that share a row cover one whole
 // 32-wide K block of it (128 contiguous bytes when the block lies in one tap), so a warp-level load touches 4 rows x
@@ -265,7 +277,9 @@ static __global__ void __launch_bounds__(256) iins_pack_all_kernel(const IinsPac
         for (int i = 0; i < 8; ++i) {
             float x = 0.f;
             if (n < q.N && k0 + i < q.K) {
-                long wi = q.kind == 0 ? ((long)n * q.Cin + c) * q.ks + t : ((long)c * q.Cin + n) * q.ks + t;
+                // kinds 2 / 3: parity-split data gradient (even / odd input positions): k = u * Cout + co, tap = 2 u + 1 - parity
+                const int tt = q.kind >= 2 ? 2 * t + (3 - q.kind) : t;
+                long wi = q.kind == 0 ? ((long)n * q.Cin + c) * q.ks + tt : ((long)c * q.Cin + n) * q.ks + tt;
                 x = __ldg(q.w + wi);
             }
             v[i] = x;
@@ -374,7 +388,7 @@ enum { IINS_EPI_PLAIN = 0,     // bias, ReLU / LeakyReLU, residual / accumulate 
 
 template <int NT, int PIECES, int EPI, int LL>
 __device__ __forceinline__ void iins_tc_epilogue_regs(const IinsNTParams& p, uint32_t tmem, int tile_m, int n0, int warp, int lane,
-                                                      float* xch) {
+                                                      float* xch, int row_scale = 1, int row_off = 0) {
     constexpr int CW = NT >= 32 ? NT / 2 : NT;          // columns per thread
     const IinsEpilogue& ep = p.ep;
     const int q = warp & 3, hf = warp >> 2;
@@ -386,7 +400,8 @@ __device__ __forceinline__ void iins_tc_epilogue_regs(const IinsNTParams& p, uin
     constexpr int L = LL;                               // rows per sample (== p.Lrow when a norm is fused)
     const int b = gr >> p.lshift, l = gr & (p.Lrow - 1);
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
-    const long orow = (long)gr * p.N + n0 + cbeg;
+    // (row_scale, row_off) = (2, parity) for the parity-split data gradient: GEMM row (b, j) is input position 2 j + parity
+    const long orow = ((long)gr * row_scale + row_off) * p.N + n0 + cbeg;
 
     float ln_mean = 0.f, ln_rs = 0.f;
     if (EPI == IINS_EPI_LN) {
@@ -553,6 +568,7 @@ __device__ __forceinline__ void iins_tc_epilogue_regs(const IinsNTParams& p, uin
 struct IinsTCParams {
     IinsNTParams nt;
     const uint16_t* wpack;
+    const uint16_t* wpack_odd;   // AKIND 2: packed weights of the odd-position class (blockIdx.z = 1)
     int pieces;          // 3 (fp32-grade) or 1 (bf16)
     int nkb;             // K blocks of 32
 };
@@ -597,7 +613,7 @@ static __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCP
     // per-row candidate arithmetic (reflected / strided taps) would be done four times per thread otherwise, and that
     // kernel is bound by instruction issue, not by L1 wavefronts (measured both ways).
     const int a_quad = lane & 7;
-    const int a_row0 = AKIND == 0 ? (warp & 7) * 16 + (lane >> 3) : (tid & 127);
+    const int a_row0 = AKIND == 0 ? (warp & 7) * 16 + (lane >> 3) : (tid & 127);      // AKIND 1 / 2: one row per lane
     const int a_half = (tid >> 7) & 1;
     int a_b[4], a_l[4];
     bool a_ok[4];
@@ -618,6 +634,16 @@ static __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCP
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
                 dst[jj] = a_ok[jj] ? iins_gather4_fwd(g, p.x, p.K, cs, a_b[jj], a_l[jj], k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (AKIND == 2) {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int k0 = kb * 32 + (a_half * 2 + jj) * 8;
+                float v[8];
+                if (!a_ok[0]) iins_zero8(v);
+                else iins_gather8_dgrad_parity(g, p.dz, p.K, cs, a_b[0], a_l[0], (int)blockIdx.z, k0, v);
+                dst[2 * jj] = make_float4(v[0], v[1], v[2], v[3]);
+                dst[2 * jj + 1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
         } else {
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
@@ -660,7 +686,8 @@ static __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCP
             if (kb >= 2) umma::mbar_wait(umma::smem_u32(&mbar_done[s]), (uint32_t)(((kb >> 1) - 1) & 1));
             const bool leader = umma::elect_one();
             if (leader) {
-                const unsigned char* src = reinterpret_cast<const unsigned char*>(tp.wpack) + ((long)blockIdx.y * nkb + kb) * B_TILE;
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(AKIND == 2 && blockIdx.z == 1 ? tp.wpack_odd : tp.wpack) +
+                                           ((long)blockIdx.y * nkb + kb) * B_TILE;
                 umma::mbar_arrive_expect_tx(umma::smem_u32(&mbar_b[s]), B_TILE);
                 umma::tma_bulk_g2s(umma::smem_u32(sB), src, B_TILE, umma::smem_u32(&mbar_b[s]));
             }
@@ -709,7 +736,8 @@ static __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCP
     umma::tc_fence_after();
 
     if (EPI != IINS_EPI_SMEM) {
-        if (warp < 8) iins_tc_epilogue_regs<NT, PIECES, EPI, LL>(p, tmem, tile_m, n0, warp, lane, st_mean);
+        if (warp < 8) iins_tc_epilogue_regs<NT, PIECES, EPI, LL>(p, tmem, tile_m, n0, warp, lane, st_mean, AKIND == 2 ? 2 : 1,
+                                                                 AKIND == 2 ? (int)blockIdx.z : 0);
     } else if (warp < 8) {
         // ---- generic path: TMEM -> SMEM (+ bias).  Warp w owns TMEM lanes 32*(w&3) .. +31; with NT >= 32 the two
         // warps sharing a lane quarter split the columns.

@@ -18,6 +18,7 @@ static bool launch_tc_nt_variant(cudaStream_t st, const IinsTCParams& tp, dim3 g
     if (nt == NT_ && akind == AK_ && epi == EPI_ && ll == LL_) { launch_tc_nt_v<NT_, PIECES, AK_, EPI_, LL_>(st, tp, grid); return true; }
     IINS_V(16, 0, IINS_EPI_PLAIN, 1) IINS_V(32, 0, IINS_EPI_PLAIN, 1) IINS_V(64, 0, IINS_EPI_PLAIN, 1)
     IINS_V(16, 1, IINS_EPI_PLAIN, 1) IINS_V(32, 1, IINS_EPI_PLAIN, 1) IINS_V(64, 1, IINS_EPI_PLAIN, 1)
+    IINS_V(16, 2, IINS_EPI_PLAIN, 1) IINS_V(32, 2, IINS_EPI_PLAIN, 1) IINS_V(64, 2, IINS_EPI_PLAIN, 1)
     IINS_V(64, 0, IINS_EPI_IN, 8) IINS_V(64, 0, IINS_EPI_IN, 16) IINS_V(32, 0, IINS_EPI_IN, 8) IINS_V(32, 0, IINS_EPI_IN, 16)
     IINS_V(32, 0, IINS_EPI_LN, 16) IINS_V(16, 0, IINS_EPI_LN, 32)
     IINS_V(64, 1, IINS_EPI_NBWD, 8) IINS_V(32, 1, IINS_EPI_NBWD, 16) IINS_V(16, 1, IINS_EPI_NBWD, 32)
