@@ -5,6 +5,7 @@
 #include "iins_tc.cuh"
 #include "iins_launchers.h"
 #include "iins_trunk.h"
+#include "iins_win.h"
 #include "iins_misc.cuh"
 #include "iins_heads.cuh"
 #include "../../include/iins_b200.h"
@@ -50,6 +51,7 @@ struct IinsOptions {
     int wgrad_batch = 1;        // IINS_WGRAD_BATCH: the trunk's weight gradients as one launch
     int trunk_tmap = 1;         // IINS_TRUNK_TMAP: tensor-map TMA (0: plain bulk copies) for the trunk's weight ring
     int dgrad_parity = 1;       // IINS_DGRAD_PARITY: stride-2 data gradients split by the parity of the input position
+    int win = 3;                // IINS_WIN: persistent window kernels for the stride-2 convolutions (iins_win.cu): bit 0 forward / data gradient, bit 1 weight gradient
     int defer_join = 0;         // iins_set_deferred_join: a backward pass does NOT wait for its weight-gradient stream at its end
 };
 
@@ -86,6 +88,7 @@ void options_from_env(IinsOptions& o) {
     o.wgrad_batch = env_int("IINS_WGRAD_BATCH", 1);
     o.trunk_tmap = env_int("IINS_TRUNK_TMAP", 1);
     o.dgrad_parity = env_int("IINS_DGRAD_PARITY", 1);
+    o.win = env_int("IINS_WIN", 3);
 }
 
 iins_ctx* new_ctx() {
@@ -273,12 +276,30 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     dim3 grid((p.M + 127) / 128, pk.nblk, 1);
     IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K); IINS_SET_SHAPE(p.M, p.N, p.K);
     int akind = p.a_kind;
+    // k4 / stride-2 / zero-pad-1 convolution over whole groups of 8 output rows: the persistent window kernels (iins_win.cu)
+    const bool s2_geom = g0.stride == 2 && g0.ks == 4 && g0.pad == 1 && g0.mode == IINS_PAD_ZERO && g0.Lin == 2 * g0.Lout &&
+                         ilog2_exact(g0.Lout) >= 3 && g0.Lout <= 128 && g0.in_layout == IINS_NLC && g0.out_layout == IINS_NLC &&
+                         p.out_layout == IINS_NLC && p.N == nt && pk.nblk == 1 && (cur().opt.win & 1) != 0;
+    if (s2_geom && p.a_kind == 0 && (epi == IINS_EPI_PLAIN || epi == IINS_EPI_IN) &&
+        iins_win_nt_supported(nt, tp.pieces, IINS_WIN_S2F, epi, ll, g0.Cin)) {
+        IinsWinParams wp;
+        memset(&wp, 0, sizeof(wp));
+        wp.nt = tp.nt; wp.wpack = tp.wpack; wp.pieces = tp.pieces; wp.nkb = pk.nkb; wp.ca = g0.Cin; wp.lsh_in = ilog2_exact(g0.Lin);
+        if (iins_win_nt_launch(c.st, wp, nt, IINS_WIN_S2F, epi, ll)) return;
+    }
     if (par_geom && pack_even != nullptr && epi == IINS_EPI_PLAIN && p.out_layout == IINS_NLC) {
         // parity classes as two GEMMs in one grid (blockIdx.z): rows (b, j) <-> input position 2 j + parity
         akind = 2;
         tp.wpack = pack_even; tp.wpack_odd = pack_odd;
         tp.nt.M = p.M / 2; tp.nt.K = K2; tp.nt.Lrow = p.Lrow / 2; tp.nt.lshift = p.lshift - 1; tp.nkb = nkb2;
         grid = dim3((tp.nt.M + 127) / 128, pk.nblk, 2);
+        if (s2_geom && iins_win_nt_supported(nt, tp.pieces, IINS_WIN_S2D, epi, ll, g0.Cout)) {
+            IinsWinParams wp;
+            memset(&wp, 0, sizeof(wp));
+            wp.nt = tp.nt; wp.wpack = pack_even; wp.wpack_odd = pack_odd; wp.pieces = tp.pieces; wp.nkb = nkb2; wp.ca = g0.Cout;
+            wp.lsh_in = ilog2_exact(g0.Lout);
+            if (iins_win_nt_launch(c.st, wp, nt, IINS_WIN_S2D, epi, ll)) return;
+        }
     }
     const bool launched = tp.pieces == 3 ? iins_launch_tc_nt_p3(c.st, tp, grid, nt, akind, epi, ll)
                                          : iins_launch_tc_nt_p1(c.st, tp, grid, nt, akind, epi, ll);
@@ -534,6 +555,10 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
         return;
     }
 #ifndef IINS_CPUSIM
+    if (g_mode != 2 && (cur().opt.win & 2) != 0) {       // k4 / stride-2 convolutions: persistent window kernel (iins_win.cu)
+        IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K); IINS_SET_SHAPE(p.M, g.Cout, K);
+        if (iins_win_tn_launch(wst, p, g_mode == 1 ? 1 : 3)) return;
+    }
     auto chan_ok = [&](int cdim) { return ilog2_exact(cdim) >= 3 || (g.ks == 1 && cdim % 8 == 0); };
     const bool tc_ok = chan_ok(g.Cin) && g.Cout % 8 == 0 && g.in_layout == IINS_NLC && g.out_layout == IINS_NLC;
     if (g_mode != 2 && tc_ok) {

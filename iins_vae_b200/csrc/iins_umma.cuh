@@ -79,6 +79,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar_saddr, uint32_t parity) 
         : "memory");
 }
 
+// same, for waits that are expected to be long (another warp role is working): each try suspends the thread for up to
+// ~`ns` nanoseconds (it resumes as soon as the phase completes), so the spinning warps leave the issue slots to the others
+__device__ __forceinline__ void mbar_wait_suspend(uint32_t mbar_saddr, uint32_t parity, uint32_t ns = 4000u) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(mbar_saddr), "r"(parity), "r"(ns)
+        : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar_saddr) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar_saddr) : "memory");
 }
