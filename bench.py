@@ -315,10 +315,10 @@ def run_reference(args):
     _emit(line)
 
 
-def workload_config(batch, gpus):
+def workload_config(batch, gpus, dim=4):
     return {"workload": "IIns-VAE semi-supervised train step (Enc+Dec+Res+Cls, recon+KL+L1+CE, Adam), "
-                        f"BASELINE configs[1]: batch {batch} per GPU, fp32",
-            "batch_per_gpu": batch, "global_batch": batch * gpus, "cir_len": 157, "dim": 4, "env_dim": 16,
+                        f"BASELINE configs[1]: batch {batch} per GPU, fp32" + ("" if dim == 4 else f", dim = {dim} (--filters {dim})"),
+            "batch_per_gpu": batch, "global_batch": batch * gpus, "cir_len": 157, "dim": dim, "env_dim": 16,
             "range_dim": 2, "num_classes": 5, "supervision_rate": 0.1, "parallelism": f"dp{gpus}",
             "l2_policy": f"{N_BATCHES} distinct input batches cycled; per-step working set (saved activations "
                          "~0.5 MB/sample) is far larger than the 126 MB L2"}
@@ -359,6 +359,8 @@ def main():
                     help="strong scaling (BASELINE configs[3]): fixed GLOBAL batch, per-GPU batch = global / world")
     ap.add_argument("--compute-mode", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-overlap", action="store_true", help="one all-reduce after the backward instead of overlapped buckets")
+    ap.add_argument("--dim", type=int, default=4,
+                    help="base channel count (models.py:33 `dim`; 4 = the benchmarked configuration, 16 = utils.py:38 --filters 16)")
     args = ap.parse_args()
     _capture_stdout()
     args.warmup = max(args.warmup, 3)
@@ -384,6 +386,7 @@ def main():
         pg = dist.group.WORLD
     lib = get_lib()
     cfg = PathShape()
+    cfg.dim = args.dim
     scaling = "weak"
     if args.global_batch:
         if args.global_batch % world:
@@ -502,40 +505,72 @@ def main():
     eng.set_concurrency(False)              # serial launches: an event pair then brackets exactly one kernel
     prof = []
     for sup in (True, False):
-        prof += lib.profile(lambda: eng.step(*dev[0], supervised=sup))
+        rows = lib.profile(lambda: eng.step(*dev[0], supervised=sup))
+        prof += [(n_, ms_, fl_, float(lib.last_bytes[i])) for i, (n_, ms_, fl_) in enumerate(rows)]
     eng.set_concurrency(True)
     eng.use_graph = eng_eager
     barrier()
     if rank == 0:
-        agg = {}
-        for name, kms, fl in prof:
-            a = agg.setdefault(name, [0.0, 0.0, 0])
-            a[0] += kms; a[1] += fl; a[2] += 1
-        total_ms = sum(a[0] for a in agg.values())
-        top = max(agg.items(), key=lambda kv: kv[1][0])
+        # Roofline of a kernel family: each launch is bounded by the SLOWER of its two rooflines,
+        #   t_roof = max(algorithmic flops / measured bf16 tensor peak, algorithmic HBM bytes / measured HBM bandwidth)
+        # (flops = 2*M*N*K of the layer; bytes = every operand tensor read once + every result tensor written once, fp32:
+        # iins_runtime.cu nt_bytes / dz_bytes).  frac = sum(t_roof) / sum(measured time); `bound` says
+        # which roofline supplies most of sum(t_roof); `achieved` / `peak` are quoted in that roofline's unit.
         peaks, peak_src = measured_peaks()
-        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-        achieved = top[1][1] / (top[1][0] * 1e-3) / 1e12 if top[1][0] > 0 else 0.0
+        peak_t = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        peak_h = float(peaks.get("hbm_gbs", 6548.8))
+        agg = {}
+        for name, kms, fl, by in prof:
+            a = agg.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0, "roof_ms": 0.0, "roof_hbm_ms": 0.0, "roof_tensor_ms": 0.0})
+            t_t, t_h = fl / (peak_t * 1e12) * 1e3, by / (peak_h * 1e9) * 1e3
+            a["ms"] += kms; a["flops"] += fl; a["bytes"] += by; a["n"] += 1
+            a["roof_ms"] += max(t_t, t_h)
+            if t_h >= t_t:
+                a["roof_hbm_ms"] += t_h
+            else:
+                a["roof_tensor_ms"] += t_t
+        total_ms = sum(a["ms"] for a in agg.values())
+        top_name, top = max(agg.items(), key=lambda kv: kv[1]["ms"])
         # DRAM traffic per launch of that kernel from the committed ncu --set full capture (profiles/), if present
         traffic = None
-        for tname in ("r02a_ncu_traffic.json", "r01b_ncu_traffic.json"):     # newest capture that holds this kernel family
+        for tname in ("r02c_ncu_traffic.json", "r02a_ncu_traffic.json", "r01b_ncu_traffic.json"):   # newest capture that holds this family
             tpath = os.path.join(ROOT, "profiles", tname)
             if traffic is None and os.path.exists(tpath):
                 with open(tpath) as f:
-                    rows = [r for r in json.load(f) if top[0].rstrip("_") in r["kernel"]]
+                    rows = [r for r in json.load(f) if top_name.rstrip("_") in r["kernel"]]
                 if rows:
                     traffic = sum(r["dram_bytes"] for r in rows) / len(rows)
-        roofline = {"bound": "tensor", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": traffic,
-                    "share_of_step": top[1][0] / total_ms, "avg_launch_ms": top[1][0] / top[1][2],
-                    "peak_source": peak_src + ", bf16 dense sustained (kernel timed inside a long step)",
-                    "note": "achieved = algorithmic 2*M*N*K of the kernel's launches / their CUDA-event time inside an "
-                            "instrumented step; the fp32-grade mode issues 3 bf16 tcgen05.mma per k-step (bf16x3 split), so "
-                            "the tensor pipe does ~3x this work; traffic = mean DRAM bytes per launch from the committed "
-                            "ncu capture (bytes, outputs mostly stay in L2); whole-step algorithmic TFLOP/s = "
-                            f"{flops / (ms * 1e-3) / 1e12:.2f}"}
-        kernel_table = {k: {"ms": round(v[0], 4), "launches": v[2], "tflops": round(v[1] / max(v[0], 1e-9) / 1e9, 3)}
-                        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+
+        def family_roofline(a):
+            hbm = a["roof_hbm_ms"] >= a["roof_tensor_ms"]
+            t = max(a["ms"], 1e-9) * 1e-3
+            return {"bound": "hbm" if hbm else "tensor",
+                    "achieved": a["bytes"] / t / 1e9 if hbm else a["flops"] / t / 1e12,
+                    "peak": peak_h if hbm else peak_t, "unit": "GB/s" if hbm else "TFLOP/s",
+                    "frac": a["roof_ms"] / max(a["ms"], 1e-9),
+                    "tensor_tflops": a["flops"] / t / 1e12, "tensor_frac": a["flops"] / t / 1e12 / peak_t,
+                    "hbm_gbs": a["bytes"] / t / 1e9, "hbm_frac": a["bytes"] / t / 1e9 / peak_h}
+
+        roofline = family_roofline(top)
+        roofline.update({"kernel": top_name, "traffic": traffic, "share_of_step": top["ms"] / total_ms,
+                         "avg_launch_ms": top["ms"] / top["n"],
+                         "algorithmic_bytes_per_launch": top["bytes"] / top["n"], "algorithmic_flops_per_launch": top["flops"] / top["n"],
+                         "peak_source": peak_src + ": HBM copy bandwidth / bf16 dense sustained (kernels timed inside a long step)",
+                         "step": {"frac": sum(a["roof_ms"] for a in agg.values()) / total_ms,
+                                  "roof_ms": sum(a["roof_ms"] for a in agg.values()), "kernel_ms": total_ms,
+                                  "note": "sum over ALL launches of one supervised + one unsupervised step; launches without a byte / "
+                                          "flop model (pooling, reparameterisation, small reductions) count as time with no roofline"},
+                         "note": "every launch is bounded by the slower of its two rooflines, max(2*M*N*K / tensor peak, algorithmic "
+                                 "bytes / HBM peak); frac = sum of those bounds / CUDA-event time of the family's launches inside an "
+                                 "instrumented step (launches serialised); tensor_* / hbm_* give both rooflines separately; the "
+                                 "fp32-grade mode issues 8 bf16 piece products per fp32 product (bf16x3 split), so the tensor pipe "
+                                 "does ~2.7x the algorithmic flops; traffic = mean DRAM bytes per launch from the committed ncu "
+                                 f"capture; whole-step algorithmic TFLOP/s = {flops / (ms * 1e-3) / 1e12:.2f}"})
+        kernel_table = {}
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            r = family_roofline(a)
+            kernel_table[k] = {"ms": round(a["ms"], 4), "launches": a["n"], "tflops": round(r["tensor_tflops"], 3),
+                               "gbs": round(r["hbm_gbs"], 1), "bound": r["bound"], "frac": round(r["frac"], 4)}
 
     hbm_rooflines = None
     if rank == 0 and world == 1:
@@ -566,7 +601,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "fp32" if args.compute_mode == "fp32" else "bf16",
-            "data": "synthetic", "config": workload_config(B, world),
+            "data": "synthetic", "config": workload_config(B, world, cfg.dim),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                     "ms_per_step": ms_e2e / K,
                     "pipeline": "H2D of batch i+1 on a copy stream during step i; loss of step i read back after step i+1 is queued"},

@@ -24,7 +24,7 @@ EXPORTS = [
     "iins_loss_forward_backward", "iins_adam_step",
     "iins_adaptive_pool_forward", "iins_adaptive_pool_backward", "iins_accumulate2", "iins_set_stream_concurrency",
     "iins_launch_count", "iins_profile_begin", "iins_profile_collect",
-    "iins_set_compute_mode", "iins_get_compute_mode", "iins_profile_shapes",
+    "iins_set_compute_mode", "iins_get_compute_mode", "iins_profile_shapes", "iins_profile_bytes",
     "iins_restorer_conv_ws_floats", "iins_restorer_conv_scratch_floats", "iins_restorer_conv_forward", "iins_restorer_conv_backward",
     "iins_classifier_conv_ws_floats", "iins_classifier_conv_scratch_floats", "iins_classifier_conv_forward",
     "iins_classifier_conv_backward",
@@ -113,6 +113,7 @@ class IinsLib:
         d.iins_accumulate2.argtypes = [_P, _P, C.c_size_t, _P, _P, C.c_size_t, _P]
         d.iins_launch_count.restype = C.c_ulonglong
         d.iins_profile_collect.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int]
+        d.iins_profile_bytes.argtypes = [C.POINTER(C.c_double), C.c_int]
 
     def profile(self, fn):
         """Run fn() with a CUDA-event pair around every kernel launch; returns [(kernel name, ms, flops), ...]."""
@@ -125,6 +126,8 @@ class IinsLib:
         n = self.dll.iins_profile_collect(names, ms, fl, cap)
         self.last_shapes = (C.c_int * (3 * cap))()
         self.dll.iins_profile_shapes(self.last_shapes, cap)
+        self.last_bytes = (C.c_double * cap)()
+        self.dll.iins_profile_bytes(self.last_bytes, cap)
         return [(names[i].decode(), float(ms[i]), float(fl[i])) for i in range(n)]
 
     def check(self, rc: int, what: str):

@@ -19,6 +19,8 @@ struct IinsProfState {
     const char* names[4096];
     double flops[4096];
     double cur_flops;                    // set by the GEMM launchers just before IINS_LAUNCH
+    double bytes[4096];                  // algorithmic HBM bytes of the launch (operands read once + results written once)
+    double cur_bytes;
     int shape[4096][3];
     int cur_shape[3];
     cudaEvent_t ev0[4096], ev1[4096];
@@ -37,6 +39,7 @@ static inline void iins_prof_pre(const char* name, cudaStream_t st) {
     if (g_iins_prof.enabled && g_iins_prof.n < 4096) {
         g_iins_prof.names[g_iins_prof.n] = name;
         g_iins_prof.flops[g_iins_prof.n] = g_iins_prof.cur_flops;
+        g_iins_prof.bytes[g_iins_prof.n] = g_iins_prof.cur_bytes;
         for (int i = 0; i < 3; ++i) g_iins_prof.shape[g_iins_prof.n][i] = g_iins_prof.cur_shape[i];
         cudaEventRecord(g_iins_prof.ev0[g_iins_prof.n], st);
     }
@@ -47,6 +50,7 @@ static inline void iins_prof_post(cudaStream_t st) {
         g_iins_prof.n++;
     }
     g_iins_prof.cur_flops = 0.0;
+    g_iins_prof.cur_bytes = 0.0;
     g_iins_prof.cur_shape[0] = g_iins_prof.cur_shape[1] = g_iins_prof.cur_shape[2] = 0;
 }
 // Every kernel of the library is launched with programmatic dependent launch allowed: it becomes resident while its
@@ -74,6 +78,7 @@ static inline int iins_pdl_enabled() {
     } while (0)
 #define IINS_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
 #define IINS_SET_FLOPS(f) (g_iins_prof.cur_flops = (f))
+#define IINS_SET_BYTES(b) (g_iins_prof.cur_bytes = (b))
 #define IINS_SET_SHAPE(m, n, k) (g_iins_prof.cur_shape[0] = (m), g_iins_prof.cur_shape[1] = (n), g_iins_prof.cur_shape[2] = (k))
 #endif
 

@@ -192,6 +192,24 @@ int ilog2_exact(int v) {
     return (1 << s) == v ? s : -1;
 }
 
+
+// Algorithmic HBM bytes of a layer launch (the roofline denominator bench.py uses): every operand tensor read once, every
+// result tensor written once, fp32; weights and per-sample vectors are negligible and left out.
+double dz_bytes(const IinsGeom& g, const IinsDz& d) {
+    const double full = 4.0 * g.B * (double)g.Lout * g.Cout;
+    return (d.dy_bcast ? 4.0 * g.B * g.Cout : full) + ((d.y != nullptr && d.act != IINS_ACT_NONE) ? full : 0.0);
+}
+double nt_bytes(const IinsNTParams& p) {
+    const IinsGeom& g = p.g;
+    const double out = 4.0 * (double)p.M * p.N;
+    double b = p.a_kind == 0 ? 4.0 * g.B * (double)g.Lin * g.Cin : dz_bytes(g, p.dz);
+    if (p.ep.y != nullptr) b += out;
+    if (p.ep.xhat != nullptr) b += out;
+    if (p.ep.add != nullptr) b += out;
+    if (p.ep.nb_dz != nullptr) b += 2.0 * out;             // fused norm backward: reads x-hat, writes dz
+    return b;
+}
+
 void launch_nt_simt(const Ctx& c, const IinsNTParams& p) {
     int bn = p.N <= 8 ? 8 : (p.N <= 16 ? 16 : (p.N <= 32 ? 32 : 64));
     dim3 grid((p.M + 127) / 128, (p.N + bn - 1) / bn, 1);
@@ -354,6 +372,7 @@ bool row2_nbwd_fusable(const IinsNTParams& p, int L, int C, int norm, const floa
 void launch_nt(Ctx& c, IinsNTParams p) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) return;          // empty layer (e.g. n_residual = 0: no AdaIN parameters)
     p.lshift = ilog2_exact(p.Lrow);
+    IINS_SET_BYTES(nt_bytes(p));
     {   // k -> (tap, channel) split of the tensor-core gathers: a shift for power-of-two channel counts; a Linear layer has
         // one tap, so any channel count that is a multiple of 8 works with the "infinite" shift 31 (t = 0, c = k)
         const int cdim = p.a_kind == 0 ? p.g.Cin : p.g.Cout;
@@ -514,6 +533,7 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
     if (c.st2 != nullptr) { fork_to(c.st, c.st2); wst = c.st2; }
     p.M = g.B * g.Lout;
     int K = g.ks * g.Cin;
+    IINS_SET_BYTES(4.0 * g.B * (double)g.Lin * g.Cin + dz_bytes(g, dz));
     {   // small-channel conv layers with many rows: one thread per row, register outer products (iins_row2_tn_kernel)
         const int row2_on = cur().opt.row2;
         const int ls = ilog2_exact(g.Lout);
@@ -654,6 +674,7 @@ void conv_wgrad_batch(Ctx& c, const IinsGeom& g, int n, const float* const* xs, 
         for (int i = 0; i < n; ++i) { tp.bx[i] = xs[i]; tp.bdy[i] = dzs[i]; tp.bdw[i] = dws[i]; tp.bdb[i] = dbs[i]; }
         dim3 grid((unsigned)((p.M + rpp - 1) / rpp), ky, n);
         IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K * n); IINS_SET_SHAPE(p.M, g.Cout, K * n);
+        IINS_SET_BYTES(n * (4.0 * g.B * (double)g.Lin * g.Cin + 4.0 * g.B * (double)g.Lout * g.Cout));
         iins_launch_tc_tn(wst, tp, grid, nt);
         return;
     }
@@ -697,6 +718,7 @@ void norm_backward(Ctx& c, int B, int L, int C, int norm, int act, const float* 
         p.ldc = C; p.rstd_ld = C;
         int nb = (B + 7) / 8;
         if (nb > 148 * 4) nb = 148 * 4;                 // persistent: the kernel strides over the samples
+        IINS_SET_BYTES(12.0 * B * (double)L * Cb);
         IINS_LAUNCH(iins_norm_bwd_kernel, nb, 256, 0, c.st, p);
     }
 }
@@ -711,6 +733,7 @@ void run_phases(Ctx& c, F&& body) {
         if (c.njobs > 0) {
             c.jobs.njobs = c.njobs;
             c.jobs.pieces = g_mode == 1 ? 1 : 3;
+            IINS_SET_FLOPS(0.0); IINS_SET_BYTES(0.0); IINS_SET_SHAPE(0, 0, 0);      // (the collect pass set them without launching)
             IINS_LAUNCH(iins_pack_all_kernel, grid_for(c.jobs.total), 256, 0, c.st, c.jobs);
         }
         c.phase = 2; c.job_i = 0;
@@ -1874,6 +1897,7 @@ int iins_loss_forward_backward(int batch, int cir_len, int num_classes, const fl
     cudaMemsetAsync(out, 0, 8 * sizeof(float), st);
     long n = x ? (long)batch * cir_len / 4 : batch;       // 128-bit accesses over the reconstruction stream
     int lg = grid_for(n / 8);                             // >= 8 iterations per thread: every CTA ends with 5 atomics on the same 32 bytes of `out`
+    IINS_SET_BYTES((double)batch * (x ? 3.0 * cir_len * 4 : 0.0) + (err ? (double)batch * (16.0 + 8.0 * num_classes) : 0.0));
     IINS_LAUNCH(iins_loss_kernel, lg, 256, 0, st, p);
     return check_cuda("loss");
 }
@@ -1897,6 +1921,7 @@ int iins_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_s
         if (group_active[i]) { mask |= 1u << i; total += (long)(group_end[i] - group_begin[i]); }
     }
     if (mask == 0) return IINS_OK;
+    IINS_SET_BYTES(28.0 * (double)total);
     IINS_LAUNCH(iins_adam_kernel, grid_for(total / 4), 256, 0, st, a);
     return check_cuda("adam");
 }
@@ -1919,6 +1944,12 @@ int iins_profile_begin(void) {
 
 // Stops recording, synchronises the device and writes, for up to `cap` recorded launches in launch order,
 // the kernel name (pointer to a static string) and its duration in milliseconds.  Returns the count.
+int iins_profile_bytes(double* bytes, int cap) {
+    int n = g_iins_prof.n < cap ? g_iins_prof.n : cap;
+    for (int i = 0; i < n; ++i) bytes[i] = g_iins_prof.bytes[i];
+    return n;
+}
+
 int iins_profile_shapes(int* shapes, int cap) {
     int n = g_iins_prof.n < cap ? g_iins_prof.n : cap;
     for (int i = 0; i < n; ++i) for (int j = 0; j < 3; ++j) shapes[3 * i + j] = g_iins_prof.shape[i][j];
@@ -1942,6 +1973,7 @@ unsigned long long iins_launch_count(void) { return 0; }
 int iins_profile_begin(void) { return IINS_OK; }
 int iins_profile_collect(const char**, float*, double*, int) { return 0; }
 int iins_profile_shapes(int*, int) { return 0; }
+int iins_profile_bytes(double*, int) { return 0; }
 #endif
 
 int iins_accumulate2(float* dst1, const float* src1, size_t n1, float* dst2, const float* src2, size_t n2, iins_stream_t stream) {

@@ -536,6 +536,8 @@ bool iins_trunk_backward_launch(cudaStream_t st, const IinsTrunkBwdParams& p) {
     const int ntiles = (p.B + TR_SAMPLES - 1) / TR_SAMPLES;
     const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;
     IINS_SET_FLOPS(2.0 * (double)p.B * 8.0 * 64.0 * 192.0 * p.nconv); IINS_SET_SHAPE(p.B * 8, 64, 192 * p.nconv);
+    // reads dh and every layer's x-hat, writes every layer's dz and the input gradient (+ the block-skip gradients once each way)
+    IINS_SET_BYTES(2048.0 * p.B * (2.0 * p.nconv + 2.0 + p.nconv));
     const bool adain = p.adain != nullptr;
 #define IINS_TRB(P_, A_, T_) if (p.pieces == P_ && adain == A_ && tmap == T_) { launch_bwd_variant<P_, A_, T_>(st, p, map, grid); return true; }
     IINS_TRB(3, false, true) IINS_TRB(3, true, true) IINS_TRB(1, false, true) IINS_TRB(1, true, true)
@@ -560,6 +562,8 @@ bool iins_trunk_forward_launch(cudaStream_t st, const IinsTrunkFwdParams& p) {
     const int ntiles = (p.B + TR_SAMPLES - 1) / TR_SAMPLES;
     const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;                  // persistent: 2 CTAs per SM
     IINS_SET_FLOPS(2.0 * (double)p.B * 8.0 * 64.0 * 192.0 * p.nconv); IINS_SET_SHAPE(p.B * 8, 64, 192 * p.nconv);
+    // reads the input, writes y and x-hat of every layer, re-reads the block input for the skip
+    IINS_SET_BYTES(2048.0 * p.B * (1.0 + 2.0 * p.nconv + 0.5 * p.nconv));
     const bool adain = p.adain != nullptr;
 #define IINS_TRV(P_, A_, T_) if (p.pieces == P_ && adain == A_ && tmap == T_) { launch_variant<P_, A_, T_>(st, p, map, grid); return true; }
     IINS_TRV(3, false, true) IINS_TRV(3, true, true) IINS_TRV(1, false, true) IINS_TRV(1, true, true)

@@ -237,6 +237,7 @@ int iins_join_helpers(iins_stream_t producer, iins_stream_t waiter, int keep_pen
 unsigned long long iins_launch_count(void);           /* kernels launched by this library so far */
 int iins_profile_begin(void);                          /* record a CUDA-event pair around every launch */
 int iins_profile_collect(const char** names, float* ms, double* flops, int cap);
+int iins_profile_bytes(double* bytes, int cap);       /* after collect: algorithmic HBM bytes of each launch (0 = not modelled) */
 int iins_profile_shapes(int* shapes_mnk, int cap);   /* after collect: (M,N,K) of each GEMM launch, zeros otherwise */
         /* sync; per launch: kernel name, milliseconds, algorithmic FLOPs (2*M*N*K for the GEMM kernels, else 0) */
 

@@ -650,3 +650,52 @@ def test_soft_restorer_module_matches_reference_fixture():
                 continue
             err = np.linalg.norm(v.grad.cpu().numpy().ravel() - ref.ravel())
             assert err <= 2e-4 * np.linalg.norm(ref) + 1e-8, (pre, k, err)
+
+
+@pytest.mark.parametrize("batch,mode", [(37, "fp32"), (4096, "fp32"), (4096, "bf16")])
+def test_window_kernels_match_per_layer_kernels(batch, mode):
+    """The persistent window kernels of the stride-2 convolutions (csrc/iins_win.cu: forward, parity-split data gradient,
+    weight gradient) against the per-layer tensor-core kernels of the same library: two contexts in one process, one
+    created with IINS_WIN=0 (the switches are read when a context is created).  Both use the same bf16 pieces, the same
+    packed weights and the same k order, so the forward tensors are BIT-IDENTICAL and every gradient tensor agrees to
+    summation-order noise (stated bound 5e-6 rel-L2; measured 1e-7 .. 1e-6); ragged batch = partial last tile."""
+    import iins_vae_b200
+    from iins_vae_b200._capi import get_lib
+    from iins_vae_b200.engine import SemiTrainEngine
+    d = get_lib().dll
+    cfg = orc.PathConfig()
+    cir, err, label = orc.synthetic_batch(cfg, batch, 977)
+    res = {}
+    old = os.environ.get("IINS_WIN")
+    try:
+        for win in ("0", "3"):
+            os.environ["IINS_WIN"] = win
+            ctx = d.iins_ctx_create()
+            assert ctx
+            d.iins_ctx_make_current(ctx)
+            iins_vae_b200.set_compute_mode(mode)
+            mods, _ = _mods(cfg, 41)
+            eng = SemiTrainEngine(*mods, batch_size=batch, cir_len=cfg.cir_len, use_graph=False)
+            launches = get_lib().profile(lambda: eng.step(cir, err, label, supervised=True, update=False))
+            torch.cuda.synchronize()
+            res[win] = ({k: v.clone() for k, v in eng.named_grads().items()}, eng.xrec.clone(), eng.rc.clone(), eng.cat.clone(),
+                        sum(1 for n, _, _ in launches if "iins_win" in n))
+            d.iins_ctx_make_current(None)
+            d.iins_ctx_destroy(ctx)
+    finally:
+        if old is None:
+            os.environ.pop("IINS_WIN", None)
+        else:
+            os.environ["IINS_WIN"] = old
+    (g0, x0, r0, c0, n0), (g1, x1, r1, c1, n1) = res["0"], res["3"]
+    assert n0 == 0 and n1 >= 8, f"window kernels launched: {n0} (IINS_WIN=0) / {n1} (default)"
+    assert torch.equal(x0, x1) and torch.equal(r0, r1) and torch.equal(c0, c1), "forward tensors differ"
+    worst = 0.0
+    for k, e in g0.items():
+        if orc.grad_is_structurally_zero(k):
+            continue                    # conv bias in front of an InstanceNorm: the true gradient is 0, both values are rounding noise
+        n = float(e.norm())
+        if n > 0:
+            worst = max(worst, float((g1[k] - e).norm()) / n)
+    print(f"window vs per-layer kernels, B={batch} {mode}: {n1} window launches, worst gradient rel-L2 diff {worst:.2e}")
+    assert worst <= 5e-6
