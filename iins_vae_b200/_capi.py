@@ -7,7 +7,7 @@ or PyTorch fallback anywhere in this package.
 import ctypes as C
 import os
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libiins_b200.so")
 
@@ -25,6 +25,8 @@ EXPORTS = [
     "iins_adaptive_pool_forward", "iins_adaptive_pool_backward", "iins_accumulate2", "iins_set_stream_concurrency",
     "iins_launch_count", "iins_profile_begin", "iins_profile_collect",
     "iins_set_compute_mode", "iins_get_compute_mode", "iins_profile_shapes", "iins_profile_bytes",
+    "iins_encoder2d_ws_floats", "iins_encoder2d_scratch_floats", "iins_encoder2d_forward", "iins_encoder2d_backward",
+    "iins_decoder2d_ws_floats", "iins_decoder2d_scratch_floats", "iins_decoder2d_forward", "iins_decoder2d_backward",
     "iins_restorer_conv_ws_floats", "iins_restorer_conv_scratch_floats", "iins_restorer_conv_forward", "iins_restorer_conv_backward",
     "iins_classifier_conv_ws_floats", "iins_classifier_conv_scratch_floats", "iins_classifier_conv_forward",
     "iins_classifier_conv_backward",
@@ -37,7 +39,7 @@ EXPORTS = [
 
 class IinsConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("batch", "cir_len", "dim", "n_residual", "n_downsample", "env_dim",
-                                       "range_dim", "num_classes", "cls_filters")]
+                                       "range_dim", "num_classes", "cls_filters", "conv_type")]
 
 
 class IinsHeadState(C.Structure):
@@ -86,6 +88,15 @@ class IinsLib:
         d.iins_encoder_backward.argtypes = [_CFG, _PP, _P, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, _PP, _P, _P]
         d.iins_decoder_forward.argtypes = [_CFG, _PP, _P, _P, _P, _P, _P]
         d.iins_decoder_backward.argtypes = [_CFG, _PP, _P, _P, _P, _P, _PP, _P, _P, C.c_int, _P, _P]
+        for mod in ("encoder2d", "decoder2d"):
+            for suffix in ("ws_floats", "scratch_floats"):
+                f = getattr(d, f"iins_{mod}_{suffix}")
+                f.argtypes = [_CFG]
+                f.restype = C.c_size_t
+        d.iins_encoder2d_forward.argtypes = d.iins_encoder_forward.argtypes
+        d.iins_encoder2d_backward.argtypes = d.iins_encoder_backward.argtypes
+        d.iins_decoder2d_forward.argtypes = d.iins_decoder_forward.argtypes
+        d.iins_decoder2d_backward.argtypes = d.iins_decoder_backward.argtypes
         d.iins_restorer_forward.argtypes = [_CFG, _PP, _P, _P, _P, _P]
         d.iins_restorer_backward.argtypes = [_CFG, _PP, _P, _P, _P, _PP, _P, C.c_int, _P, _P]
         d.iins_classifier_forward.argtypes = [_CFG, _PP, _P, _P, _P, _P]

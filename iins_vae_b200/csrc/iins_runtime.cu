@@ -8,6 +8,7 @@
 #include "iins_win.h"
 #include "iins_misc.cuh"
 #include "iins_heads.cuh"
+#include "iins_conv2d.cuh"
 #include "../../include/iins_b200.h"
 
 #include <stdio.h>
@@ -822,6 +823,8 @@ struct Shapes {
     int Lt;       // trunk length    128 / 2^n_downsample
     int env_extra;
     int n_adain;
+    int conv_type;  // 1 = the 1-D path, 2 = the 2-D variant (expand = True)
+    int code_elems; // elements of a sample's range code per channel: Lt (1-D) or Lt * Lt (2-D)
 };
 
 int make_shapes(const iins_config* cfg, Shapes& s) {
@@ -845,6 +848,10 @@ int make_shapes(const iins_config* cfg, Shapes& s) {
     s.Lt = s.P >> s.ndown;
     s.env_extra = s.ndown - 4 > 0 ? s.ndown - 4 : 0;
     s.n_adain = 4 * s.nres * s.D;
+    s.conv_type = cfg->conv_type == 0 ? 1 : cfg->conv_type;
+    if (s.conv_type != 1 && s.conv_type != 2) return fail(IINS_ERR_BAD_CONFIG, "conv_type must be 1 (Conv1d) or 2 (Conv2d, expand = True)");
+    if (s.conv_type == 2 && (s.d < 4 || s.D > 256)) return fail(IINS_ERR_BAD_CONFIG, "conv_type 2 needs 4 <= dim <= 16 (norm kernels: >= 4 channels)");
+    s.code_elems = s.conv_type == 2 ? s.Lt * s.Lt : s.Lt;
     return IINS_OK;
 }
 
@@ -1363,7 +1370,7 @@ struct MlpSpec { int n; int dims[6]; float slopes[5]; };
 
 MlpSpec restorer_spec(const Shapes& s) {
     MlpSpec m; m.n = 4;
-    m.dims[0] = s.R * s.Lt; m.dims[1] = 512; m.dims[2] = 256; m.dims[3] = 256; m.dims[4] = 1;
+    m.dims[0] = s.R * s.code_elems; m.dims[1] = 512; m.dims[2] = 256; m.dims[3] = 256; m.dims[4] = 1;
     m.slopes[0] = m.slopes[1] = m.slopes[2] = 0.2f; m.slopes[3] = -1.f;         // models.py:621-631
     return m;
 }
@@ -1624,6 +1631,8 @@ int conv_head_backward(const Shapes& s, const ConvHead& h, const float* const* P
     return check_cuda("conv_head_backward");
 }
 
+#include "iins_plan2d.inc"
+
 #define IINS_SHAPES_OR_RETURN(cfg, s) Shapes s; { int rc_ = make_shapes(cfg, s); if (rc_ != IINS_OK) return rc_; }
 
 }  // namespace
@@ -1631,7 +1640,7 @@ int conv_head_backward(const Shapes& s, const ConvHead& h, const float* const* P
 // ============================================================================================ C ABI
 extern "C" {
 
-int iins_abi_version(void) { return 2; }
+int iins_abi_version(void) { return 3; }
 int iins_set_compute_mode(int mode) {
     if (mode < 0 || mode > 2) return fail(IINS_ERR_BAD_CONFIG, "compute mode must be 0 (bf16x3 tensor core), 1 (bf16 tensor core) or 2 (fp32 SIMT)");
     cur().opt.mode = mode;
@@ -1741,6 +1750,52 @@ int iins_decoder_backward(const iins_config* cfg, const float* const* params, co
     return decoder_backward(s, params, range_code, env_code, ws, d_x_recon, grads, d_range_code, d_env_code, accumulate,
                             scratch, (cudaStream_t)stream);
 }
+
+
+#ifndef IINS_CPUSIM
+// ---- 2-D variant (conv_type = 2, expand = True): same signatures as the 1-D entry points; range_code is (B, R, 8, 8)
+#define IINS_SHAPES2D_OR_RETURN(cfg, s) IINS_SHAPES_OR_RETURN(cfg, s); if (s.conv_type != 2) return fail(IINS_ERR_BAD_CONFIG, "2-D entry point called with conv_type != 2")
+size_t iins_encoder2d_ws_floats(const iins_config* cfg) {
+    Shapes s; if (make_shapes(cfg, s) != IINS_OK || s.conv_type != 2) return 0;
+    Enc2dPlan pl; return plan_encoder2d(s, nullptr, pl) + IINS_WPACK_FLOATS_LARGE;
+}
+size_t iins_encoder2d_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK || s.conv_type != 2) return 0; return encoder2d_scratch(s); }
+int iins_encoder2d_forward(const iins_config* cfg, const float* const* params, const float* x, const float* noise,
+                           uint64_t seed, uint64_t offset, float* range_code, float* env_code, float* env_code_rv,
+                           float* kl, float* ws, iins_stream_t stream) {
+    IINS_SHAPES2D_OR_RETURN(cfg, s);
+    if (!params || !x || !range_code || !env_code || !kl || !ws) return fail(IINS_ERR_NULL, "encoder2d_forward: NULL argument");
+    return encoder2d_forward(s, params, x, noise, seed, offset, range_code, env_code, env_code_rv, kl, ws, (cudaStream_t)stream);
+}
+int iins_encoder2d_backward(const iins_config* cfg, const float* const* params, const float* noise, uint64_t seed,
+                            uint64_t offset, const float* range_code, const float* env_code, const float* ws,
+                            const float* d_range_code, const float* d_env_code, const float* d_env_code_rv, const float* d_kl,
+                            float* const* grads, float* scratch, iins_stream_t stream) {
+    IINS_SHAPES2D_OR_RETURN(cfg, s);
+    if (!params || !ws || !grads || !scratch || !range_code || !env_code) return fail(IINS_ERR_NULL, "encoder2d_backward: NULL argument");
+    return encoder2d_backward(s, params, noise, seed, offset, range_code, env_code, ws, d_range_code, d_env_code, d_env_code_rv, d_kl,
+                              grads, scratch, (cudaStream_t)stream);
+}
+size_t iins_decoder2d_ws_floats(const iins_config* cfg) {
+    Shapes s; if (make_shapes(cfg, s) != IINS_OK || s.conv_type != 2) return 0;
+    Dec2dPlan pl; return plan_decoder2d(s, nullptr, pl) + IINS_WPACK_FLOATS_LARGE;
+}
+size_t iins_decoder2d_scratch_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK || s.conv_type != 2) return 0; return decoder2d_scratch(s); }
+int iins_decoder2d_forward(const iins_config* cfg, const float* const* params, const float* range_code, const float* env_code,
+                           float* x_recon, float* ws, iins_stream_t stream) {
+    IINS_SHAPES2D_OR_RETURN(cfg, s);
+    if (!params || !range_code || !env_code || !x_recon || !ws) return fail(IINS_ERR_NULL, "decoder2d_forward: NULL argument");
+    return decoder2d_forward(s, params, range_code, env_code, x_recon, ws, (cudaStream_t)stream);
+}
+int iins_decoder2d_backward(const iins_config* cfg, const float* const* params, const float* range_code, const float* env_code,
+                            const float* ws, const float* d_x_recon, float* const* grads, float* d_range_code, float* d_env_code,
+                            int accumulate, float* scratch, iins_stream_t stream) {
+    IINS_SHAPES2D_OR_RETURN(cfg, s);
+    if (!params || !range_code || !env_code || !ws || !d_x_recon || !grads || !scratch) return fail(IINS_ERR_NULL, "decoder2d_backward: NULL argument");
+    return decoder2d_backward(s, params, range_code, env_code, ws, d_x_recon, grads, d_range_code, d_env_code, accumulate, scratch,
+                              (cudaStream_t)stream);
+}
+#endif
 
 int iins_restorer_num_params(const iins_config* cfg) { IINS_SHAPES_OR_RETURN(cfg, s); return 10; }
 size_t iins_restorer_ws_floats(const iins_config* cfg) { Shapes s; if (make_shapes(cfg, s) != IINS_OK) return 0; return mlp_ws(s, restorer_spec(s)) + wpack_floats(s); }

@@ -77,13 +77,14 @@ class _Slots(nn.Module):
         return module
 
 
-def _res_block(features, adain):
+def _res_block(features, adain, conv=nn.Conv1d):
+    """ResidualBlock1d (models.py:988-1005) / ResidualBlock2d (:1008-1025): the same Sequential indices in both."""
     blk = _Slots()
     inner = blk.put("block", _Slots())
-    inner.put(1, nn.Conv1d(features, features, 3))
+    inner.put(1, conv(features, features, 3))
     if adain:
-        inner.put(2, AdaptiveInstanceNorm1d(features))
-    inner.put(5, nn.Conv1d(features, features, 3))
+        inner.put(2, AdaptiveInstanceNorm1d(features))      # AdaptiveInstanceNorm2d (:1082-1113) holds the same two buffers
+    inner.put(5, conv(features, features, 3))
     if adain:
         inner.put(6, AdaptiveInstanceNorm1d(features))
     return blk
@@ -109,9 +110,9 @@ def _params_of(module):
     return ps
 
 
-def _cfg(batch, cir_len=157, dim=4, n_residual=3, n_downsample=4, env_dim=16, range_dim=2, num_classes=2, filters=16):
+def _cfg(batch, cir_len=157, dim=4, n_residual=3, n_downsample=4, env_dim=16, range_dim=2, num_classes=2, filters=16, conv_type=1):
     return IinsConfig(int(batch), int(cir_len), int(dim), int(n_residual), int(n_downsample), int(env_dim),
-                      int(range_dim), int(num_classes), int(filters))
+                      int(range_dim), int(num_classes), int(filters), int(conv_type))
 
 
 def _empty(n, dev):
@@ -124,16 +125,22 @@ class _EncoderFn(torch.autograd.Function):
     def forward(ctx, x, noise, opts, *params):
         lib = get_lib()
         B = x.shape[0]
-        cfg = _cfg(B, x.shape[1], opts["dim"], opts["n_residual"], opts["n_downsample"], opts["env_dim"], opts["range_dim"])
+        two_d = opts.get("conv_type", 1) == 2
+        mod = "encoder2d" if two_d else "encoder"
+        cfg = _cfg(B, x.shape[1], opts["dim"], opts["n_residual"], opts["n_downsample"], opts["env_dim"], opts["range_dim"],
+                   conv_type=2 if two_d else 1)
         lib.check(lib.iins_validate_config(cfg), "Encoder config")
         dev = x.device
         E, R = opts["env_dim"], opts["range_dim"]
-        rc = torch.empty(B, R, 128 >> opts["n_downsample"], device=dev)
-        cat = torch.empty(B, E, 1, device=dev)
-        lat = torch.empty(B, E // 2, 1, device=dev)
+        code = 128 >> opts["n_downsample"]
+        tail = (1, 1) if two_d else (1,)                            # models.py:60: (B, 8, 1, 1) / (B, 8, 1)
+        rc = torch.empty((B, R, code, code) if two_d else (B, R, code), device=dev)
+        cat = torch.empty((B, E) + tail, device=dev)
+        lat = torch.empty((B, E // 2) + tail, device=dev)
         kl = torch.empty((), device=dev)
-        ws = _empty(lib.iins_encoder_ws_floats(cfg), dev)
-        lib.check(lib.iins_encoder_forward(cfg, ptr_array(params), ptr(x), ptr(noise), opts["seed"], opts["offset"],
+        ws = _empty(getattr(lib, f"iins_{mod}_ws_floats")(cfg), dev)
+        ctx.mod = mod
+        lib.check(getattr(lib, f"iins_{mod}_forward")(cfg, ptr_array(params), ptr(x), ptr(noise), opts["seed"], opts["offset"],
                                            ptr(rc), ptr(cat), ptr(lat), ptr(kl), ptr(ws), _stream()), "Encoder forward")
         ctx.cfg, ctx.opts, ctx.params = cfg, opts, params
         ctx.save_for_backward(rc, cat, ws, noise if noise is not None else torch.empty(0, device=dev))
@@ -147,10 +154,10 @@ class _EncoderFn(torch.autograd.Function):
         rc, cat, ws, noise = ctx.saved_tensors
         dev = rc.device
         grads = [torch.zeros_like(p) for p in ctx.params]
-        scratch = _empty(lib.iins_encoder_scratch_floats(ctx.cfg), dev)
+        scratch = _empty(getattr(lib, f"iins_{ctx.mod}_scratch_floats")(ctx.cfg), dev)
         fix = lambda g: None if g is None else g.contiguous().float()
         d_rc, d_cat, d_lat, d_kl = fix(d_rc), fix(d_cat), fix(d_lat), fix(d_kl)
-        lib.check(lib.iins_encoder_backward(ctx.cfg, ptr_array(ctx.params), ptr(noise) if ctx.has_noise else None,
+        lib.check(getattr(lib, f"iins_{ctx.mod}_backward")(ctx.cfg, ptr_array(ctx.params), ptr(noise) if ctx.has_noise else None,
                                             ctx.opts["seed"], ctx.opts["offset"], ptr(rc), ptr(cat), ptr(ws),
                                             ptr(d_rc), ptr(d_cat), ptr(d_lat), ptr(d_kl), ptr_array(grads),
                                             ptr(scratch), _stream()), "Encoder backward")
@@ -162,12 +169,16 @@ class _DecoderFn(torch.autograd.Function):
     def forward(ctx, rc, cat, opts, *params):
         lib = get_lib()
         B = rc.shape[0]
-        cfg = _cfg(B, opts["in_dim"], opts["dim"], opts["n_residual"], opts["n_downsample"], opts["env_dim"], opts["range_dim"])
+        two_d = opts.get("conv_type", 1) == 2
+        mod = "decoder2d" if two_d else "decoder"
+        cfg = _cfg(B, opts["in_dim"], opts["dim"], opts["n_residual"], opts["n_downsample"], opts["env_dim"], opts["range_dim"],
+                   conv_type=2 if two_d else 1)
         lib.check(lib.iins_validate_config(cfg), "Decoder config")
         dev = rc.device
         xrec = torch.empty(B, opts["in_dim"], device=dev)
-        ws = _empty(lib.iins_decoder_ws_floats(cfg), dev)
-        lib.check(lib.iins_decoder_forward(cfg, ptr_array(params), ptr(rc), ptr(cat), ptr(xrec), ptr(ws), _stream()),
+        ws = _empty(getattr(lib, f"iins_{mod}_ws_floats")(cfg), dev)
+        ctx.mod = mod
+        lib.check(getattr(lib, f"iins_{mod}_forward")(cfg, ptr_array(params), ptr(rc), ptr(cat), ptr(xrec), ptr(ws), _stream()),
                   "Decoder forward")
         ctx.cfg, ctx.params = cfg, params
         ctx.save_for_backward(rc, cat, ws)
@@ -179,8 +190,8 @@ class _DecoderFn(torch.autograd.Function):
         rc, cat, ws = ctx.saved_tensors
         grads = [torch.zeros_like(p) for p in ctx.params]
         d_rc, d_cat = torch.empty_like(rc), torch.empty_like(cat)
-        scratch = _empty(lib.iins_decoder_scratch_floats(ctx.cfg), rc.device)
-        lib.check(lib.iins_decoder_backward(ctx.cfg, ptr_array(ctx.params), ptr(rc), ptr(cat), ptr(ws),
+        scratch = _empty(getattr(lib, f"iins_{ctx.mod}_scratch_floats")(ctx.cfg), rc.device)
+        lib.check(getattr(lib, f"iins_{ctx.mod}_backward")(ctx.cfg, ptr_array(ctx.params), ptr(rc), ptr(cat), ptr(ws),
                                             ptr(d_xrec.contiguous().float()), ptr_array(grads), ptr(d_rc), ptr(d_cat), 0,
                                             ptr(scratch), _stream()), "Decoder backward")
         return (d_rc, d_cat, None) + tuple(grads)
@@ -309,6 +320,17 @@ class _ConvHeadMixin:
 
 
 # ------------------------------------------------------------------------------------ modules
+def _check_conv_type(conv_type, expand):
+    """conv_type 1: the Conv1d path; conv_type 2 with expand=True: the Conv2d variant (models.py:179-346, 474-539).  The reference's
+    conv_type 2 with expand=False squeezes the decoder output to (B, L, L) and cannot be trained against a (B, L) CIR; conv_type 3
+    ("NoExpand") is marked "not available yet" in the reference itself (models.py:45-47)."""
+    if conv_type == 1:
+        return
+    if conv_type == 2 and expand:
+        return
+    raise NotImplementedError("iins_vae_b200: conv_type=1, or conv_type=2 with expand=True (the reference's other combinations are not runnable)")
+
+
 class Encoder(nn.Module):
     """models.py:32-64.  ``forward(x:(B,L)) -> (range_code (B,out_dim,8), env_code (B,style_dim,1),
     env_code_rv (B,style_dim/2,1), kl_div ())``.
@@ -320,42 +342,43 @@ class Encoder(nn.Module):
     def __init__(self, conv_type=1, dim=4, n_residual=3, n_downsample=4, style_dim=8, out_dim=2, expand=False,
                  noise="torch", seed=0):
         super().__init__()
-        if conv_type != 1:
-            raise NotImplementedError("iins_vae_b200 implements the 1-D path (conv_type=1) only")
+        _check_conv_type(conv_type, expand)
+        conv = nn.Conv2d if conv_type == 2 else nn.Conv1d
         self.conv_type, self.expand, self.latent_dim = conv_type, expand, style_dim
-        self.opts = dict(dim=dim, n_residual=n_residual, n_downsample=n_downsample, env_dim=style_dim, range_dim=out_dim)
+        self.opts = dict(dim=dim, n_residual=n_residual, n_downsample=n_downsample, env_dim=style_dim, range_dim=out_dim,
+                         conv_type=conv_type)
         self.noise_mode, self.seed, self._calls = noise, seed, 0
-        # ---- RangeEncoder1d (models.py:140-173): indices into the reference's nn.Sequential
+        # ---- RangeEncoder1d (models.py:140-173) / RangeEncoder2d (:179-215): indices into the reference's nn.Sequential
         self.range_encoder = _Slots()
         m = self.range_encoder.put("model", _Slots())
         idx = 2
-        m.put(idx, nn.Conv1d(1, dim, 7))
+        m.put(idx, conv(1, dim, 7))
         idx += 3
         c = dim
         for _ in range(n_downsample):
-            m.put(idx, nn.Conv1d(c, 2 * c, 4, stride=2, padding=1))
+            m.put(idx, conv(c, 2 * c, 4, stride=2, padding=1))
             c *= 2
             idx += 3
         for _ in range(n_residual):
-            m.put(idx, _res_block(c, adain=False))
+            m.put(idx, _res_block(c, adain=False, conv=conv))
             idx += 1
-        m.put(idx, nn.Conv1d(c, out_dim, 1, 1, 0))
-        # ---- EnvEncoder1d(dim*4, n_downsample-2, style_dim) (models.py:258-281)
+        m.put(idx, conv(c, out_dim, 1, 1, 0))
+        # ---- EnvEncoder1d(dim*4, n_downsample-2, style_dim) (models.py:258-281) / EnvEncoder2d (:304-329)
         self.env_encoder = _Slots()
         m = self.env_encoder.put("model", _Slots())
         e = 4 * dim
         idx = 2
-        m.put(idx, nn.Conv1d(1, e, 7))
+        m.put(idx, conv(1, e, 7))
         idx += 2
         for _ in range(2):
-            m.put(idx, nn.Conv1d(e, 2 * e, 4, stride=2, padding=1))
+            m.put(idx, conv(e, 2 * e, 4, stride=2, padding=1))
             e *= 2
             idx += 2
         for _ in range(n_downsample - 2 - 2):
-            m.put(idx, nn.Conv1d(e, e, 4, stride=2, padding=1))
+            m.put(idx, conv(e, e, 4, stride=2, padding=1))
             idx += 2
         idx += 1
-        m.put(idx, nn.Conv1d(e, style_dim, 1, 1, 0))
+        m.put(idx, conv(e, style_dim, 1, 1, 0))
 
     def forward(self, x, noise=None):
         """``noise`` (extension, optional): explicit (B, style_dim/2[, 1]) standard normals to use instead of
@@ -364,10 +387,11 @@ class Encoder(nn.Module):
         x = x.view(x.size(0), -1)
         opts = dict(self.opts, seed=int(self.seed), offset=int(self._calls) * 64)
         self._calls += 1
+        nshape = (x.size(0), self.latent_dim // 2, 1, 1) if self.conv_type == 2 else (x.size(0), self.latent_dim // 2, 1)
         if noise is not None:
-            noise = _check_input(noise, "noise").view(x.size(0), self.latent_dim // 2, 1)
+            noise = _check_input(noise, "noise").view(nshape)
         elif self.noise_mode == "torch":
-            noise = torch.randn(x.size(0), self.latent_dim // 2, 1, device=x.device)
+            noise = torch.randn(nshape, device=x.device)
         return _EncoderFn.apply(x, noise, opts, *_params_of(self))
 
     def sample(self, n):
@@ -379,26 +403,26 @@ class Decoder(nn.Module):
 
     def __init__(self, conv_type=1, dim=4, n_residual=3, n_upsample=4, style_dim=8, in_dim=152, out_dim=2, expand=False):
         super().__init__()
-        if conv_type != 1:
-            raise NotImplementedError("iins_vae_b200 implements the 1-D path (conv_type=1) only")
+        _check_conv_type(conv_type, expand)
+        conv = nn.Conv2d if conv_type == 2 else nn.Conv1d           # Decoder1d (models.py:405-471) / Decoder2d (:474-539)
         self.conv_type, self.expand = conv_type, expand
         self.opts = dict(dim=dim, n_residual=n_residual, n_downsample=n_upsample, env_dim=style_dim, range_dim=out_dim,
-                         in_dim=in_dim)
+                         in_dim=in_dim, conv_type=conv_type)
         D = dim * 2 ** n_upsample
         self.decoder = _Slots()
         m = self.decoder.put("model", _Slots())
-        m.put(0, nn.Conv1d(out_dim, D, 1, 1, 0))
+        m.put(0, conv(out_dim, D, 1, 1, 0))
         idx = 2
         for _ in range(n_residual):
-            m.put(idx, _res_block(D, adain=True))
+            m.put(idx, _res_block(D, adain=True, conv=conv))
             idx += 1
         c = D
         for _ in range(n_upsample):
-            m.put(idx + 1, nn.Conv1d(c, c // 2, 5, stride=1, padding=2))
+            m.put(idx + 1, conv(c, c // 2, 5, stride=1, padding=2))
             m.put(idx + 2, LayerNorm(c // 2))
             c //= 2
             idx += 4
-        m.put(idx + 1, nn.Conv1d(c, 1, 7))
+        m.put(idx + 1, conv(c, 1, 7))
         mlp = self.decoder.put("mlp", _Slots())
         mm = mlp.put("model", _Slots())
         n_adain = 2 * n_residual * 2 * D
@@ -447,9 +471,12 @@ class Restorer(_ConvHeadMixin, nn.Module):
 
     def forward(self, range_code, masks=None):
         rc = _check_input(range_code, "range_code")
-        if tuple(rc.shape[1:]) != self.code_shape or self.code_shape[-1] != 8:
+        if tuple(rc.shape[1:]) != self.code_shape or any(v != 8 for v in self.code_shape[1:]):
             raise RuntimeError(f"Restorer expects range_code (B,{self.code_shape}) with code length 8")
-        cfg = _cfg(rc.shape[0], range_dim=self.code_shape[0])
+        two_d = len(self.code_shape) == 3                       # (R, 8, 8): the 2-D variant's code, flattened like the reference's view(B, -1)
+        if two_d and (self.net_type != "Linear" or self.soft):
+            raise NotImplementedError("iins_vae_b200: the 2-D range code goes through the Linear restorer (soft=False)")
+        cfg = _cfg(rc.shape[0], range_dim=self.code_shape[0], conv_type=2 if two_d else 1)
         if self.net_type == "Linear" and self.soft:
             # the reference draws np.random.normal(0, 1, (B, 1)) on the host (models.py:637): same call, same generator stream
             noise = torch.from_numpy(np.random.normal(0, 1, (rc.shape[0], 1)).astype(np.float32)).to(rc.device).view(-1)

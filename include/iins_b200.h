@@ -47,6 +47,7 @@ typedef struct iins_config {
     int range_dim;      /* out_dim, 2                                     */
     int num_classes;    /* Classifier num_classes                         */
     int cls_filters;    /* Classifier filters, 16                         */
+    int conv_type;      /* 1 (or 0): Conv1d path; 2: the Conv2d variant with expand = True (models.py:33-61, 179-346, 474-539) */
 } iins_config;
 
 int iins_abi_version(void);
@@ -107,6 +108,30 @@ int iins_decoder_backward(const iins_config* cfg, const float* const* params, co
                           const float* env_code, const float* ws, const float* d_x_recon,
                           float* const* grads, float* d_range_code, float* d_env_code, int accumulate,
                           float* scratch, iins_stream_t stream);
+
+/* ---- 2-D variant, SURVEY.md 8(f) row 3 (conv_type = 2, expand = True; models.py:179-215 RangeEncoder2d, :304-346 EnvEncoder2d,
+ * :474-539 Decoder2d, :1008-1025 ResidualBlock2d, :1082-1113 AdaptiveInstanceNorm2d).  Same argument meaning as the 1-D entry
+ * points; range_code is (B, range_dim, 8, 8) NCHW; cfg->conv_type must be 2.  The Restorer / Classifier entry points take the
+ * same cfg (the Restorer's first Linear then has range_dim * 64 inputs). */
+size_t iins_encoder2d_ws_floats(const iins_config* cfg);
+size_t iins_encoder2d_scratch_floats(const iins_config* cfg);
+int iins_encoder2d_forward(const iins_config* cfg, const float* const* params, const float* x,
+                           const float* noise, uint64_t seed, uint64_t offset,
+                           float* range_code, float* env_code, float* env_code_rv, float* kl,
+                           float* ws, iins_stream_t stream);
+int iins_encoder2d_backward(const iins_config* cfg, const float* const* params, const float* noise,
+                            uint64_t seed, uint64_t offset, const float* range_code, const float* env_code,
+                            const float* ws, const float* d_range_code, const float* d_env_code,
+                            const float* d_env_code_rv, const float* d_kl, float* const* grads,
+                            float* scratch, iins_stream_t stream);
+size_t iins_decoder2d_ws_floats(const iins_config* cfg);
+size_t iins_decoder2d_scratch_floats(const iins_config* cfg);
+int iins_decoder2d_forward(const iins_config* cfg, const float* const* params, const float* range_code,
+                           const float* env_code, float* x_recon, float* ws, iins_stream_t stream);
+int iins_decoder2d_backward(const iins_config* cfg, const float* const* params, const float* range_code,
+                            const float* env_code, const float* ws, const float* d_x_recon,
+                            float* const* grads, float* d_range_code, float* d_env_code, int accumulate,
+                            float* scratch, iins_stream_t stream);
 
 /* ---- Restorer (RestorerLinear, soft=False): models.py:642-658.  range_code -> err_est (B,1).
  * params: 10 tensors (layers.{0,2,4}, linear_layer1, linear_layer2); linear_layer2 is never touched

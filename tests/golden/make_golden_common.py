@@ -10,6 +10,15 @@ def sample_positions(n: int) -> np.ndarray:
     return np.sort(rs.choice(n, N_SAMPLES, replace=False))
 
 
+N_SAMPLES_2D = 1024
+
+
+def sample_positions_2d(n: int) -> np.ndarray:
+    """Sampled entries of a large gradient tensor of the 2-D fixture (tests/golden/make_golden2d.py)."""
+    rs = np.random.RandomState((n * 31 + 7) % 65521)
+    return np.sort(rs.choice(n, N_SAMPLES_2D, replace=False))
+
+
 def conv_head_case_inputs(kind, seed, batch, cfg):
     """Inputs and parameters of one Conv1d-head fixture case (tests/golden/make_golden_convheads.py records the reference's
     outputs for exactly these): x, the parameter / buffer dict in state_dict order."""

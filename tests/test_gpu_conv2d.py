@@ -1,0 +1,124 @@
+"""GPU parity of the 2-D variant (conv_type = 2, expand = True) through the drop-in modules and the C ABI
+(iins_encoder2d_* / iins_decoder2d_*), against (a) the fixture recorded from the live reference's own 2-D modules
+(tests/golden/make_golden2d.py) and (b) the CPU oracle (oracle/iins_oracle2d.py, fp64) on a fresh seeded batch.
+
+Tolerances: forward tensors rtol 1e-4 / atol 2e-5 (tests/parity.py); gradients per tensor rel-L2 <= max(1e-4, 5 x the fp32 CPU
+oracle's own error against fp64) -- the rule of the 1-D tensor-core path (tests/parity.py REF_FACTOR_TC) -- with the same capped
+kink-flip band (a ReLU input within rounding of zero decided differently moves upstream tensors by O(1 / (B * H * W)))."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import iins_oracle as orc
+from oracle import iins_oracle2d as orc2
+from tests import parity
+from tests.test_oracle_golden import _digest_rel_error_2d, _golden2d
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods2d(cfg, seed):
+    from iins_vae_b200 import models as M
+    pe, pd, pr = orc2.init_all(cfg, seed)
+    Enc = M.Encoder(2, cfg.dim, cfg.n_residual, cfg.n_downsample, cfg.env_dim, cfg.range_dim, expand=True)
+    Dec = M.Decoder(2, cfg.dim, cfg.n_residual, cfg.n_downsample, cfg.env_dim, cfg.cir_len, cfg.range_dim, expand=True)
+    Res = M.Restorer((cfg.range_dim, cfg.code_len, cfg.code_len))
+    for m, p in ((Enc, pe), (Dec, pd), (Res, pr)):
+        m.load_state_dict(p)
+        m.cuda()
+    return (Enc, Dec, Res), (pe, pd, pr)
+
+
+def _step(mods, cir, err, noise):
+    Enc, Dec, Res = mods
+    rc, cat, lat, kl = Enc(cir, noise=noise)
+    xrec = Dec(rc, cat)
+    err_est = Res(rc)
+    loss = torch.nn.L1Loss()(xrec, cir) + kl + 10.0 * torch.nn.L1Loss()(err_est, err)
+    loss.backward()
+    return loss, dict(rc=rc, cat=cat, latent=lat, kl=kl, xrec=xrec, err_est=err_est)
+
+
+def test_modules_reject_unrunnable_combinations():
+    from iins_vae_b200 import models as M
+    with pytest.raises(NotImplementedError):
+        M.Encoder(2, expand=False)          # the reference's (B, L, L) output cannot be trained against a (B, L) CIR
+    with pytest.raises(NotImplementedError):
+        M.Decoder(3, expand=True)           # "not available yet" in the reference itself (models.py:45-47)
+
+
+def test_conv2d_modules_match_reference_fixture():
+    g2 = _golden2d()
+    cfg = orc.PathConfig()
+    cases = sorted(k[:-len("meta")] for k in g2.files if k.endswith(".meta"))
+    for pre in cases:
+        seed, batch = (int(v) for v in g2[pre + "meta"])
+        mods, _ = _mods2d(cfg, seed)
+        cir, err, noise = (torch.from_numpy(g2[pre + k]).cuda() for k in ("cir", "err", "noise"))
+        loss, outs = _step(mods, cir, err, noise)
+        assert outs["rc"].shape == (batch, cfg.range_dim, 8, 8) and outs["cat"].shape == (batch, cfg.env_dim, 1, 1)
+        assert outs["latent"].shape == (batch, cfg.env_dim // 2, 1, 1) and outs["xrec"].shape == (batch, cfg.cir_len)
+        np.testing.assert_allclose(float(loss), float(g2[pre + "out.loss"]), rtol=1e-4)
+        for k, v in outs.items():
+            parity.assert_out_close(f"{pre}{k}", v, g2[pre + "out." + k])
+        worst, n_band = 0.0, 0
+        for grp, m in zip(("enc", "dec", "res"), mods):
+            for k, p in m.named_parameters():
+                key = f"{pre}g.{grp}.{k}"
+                if key + "|full" not in g2.files and key + "|norm" not in g2.files:
+                    assert p.grad is None, f"{key}: the reference gives this parameter no gradient"
+                    continue
+                assert p.grad is not None, key
+                if orc.grad_is_structurally_zero(k):
+                    continue
+                rel, norm = _digest_rel_error_2d(g2, key, p.grad)
+                worst = max(worst, rel)
+                if rel > 5e-4:                       # fixture = the reference's own fp32 numbers (3.5e-5 from the oracle)
+                    n_band += 1
+                    assert rel <= parity.FLIP_C / (batch * 64), f"{key}: rel error {rel:.2e}"
+        print(f"2-D fixture {pre} worst gradient rel error {worst:.2e}, {n_band} tensors in the kink band")
+        assert n_band <= parity.MAX_FLIP_TENSORS
+
+
+@pytest.mark.parametrize("batch", [4])
+def test_conv2d_step_matches_fp64_oracle(batch):
+    cfg = orc.PathConfig()
+    seed = 11
+    mods, pdicts = _mods2d(cfg, seed)
+    cir, err, _ = orc.synthetic_batch(cfg, batch, seed + 300)
+    gen = torch.Generator().manual_seed(seed + 5)
+    noise = torch.randn(batch, cfg.env_dim // 2, 1, 1, generator=gen)
+    loss, outs = _step(mods, cir.cuda(), err.cuda(), noise.cuda())
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        tp = [{k: v.clone().to(dt).requires_grad_(not orc.is_buffer(k)) for k, v in p.items()} for p in pdicts]
+        l, o = orc2.step_loss(tp[0], tp[1], tp[2], cir.to(dt), err.to(dt), cfg, noise.to(dt))
+        l.backward()
+        res[dt] = (l, o, tp)
+    l64, o64, t64 = res[torch.float64]
+    _, _, t32 = res[torch.float32]
+    np.testing.assert_allclose(float(loss), float(l64), rtol=1e-4)
+    for k, v in outs.items():
+        parity.assert_out_close(k, v, o64[k].detach().float().numpy())
+    worst, n_band = 0.0, 0
+    for grp, m, p64, p32 in zip(("enc", "dec", "res"), mods, t64, t32):
+        for k, p in m.named_parameters():
+            if p64[k].grad is None:
+                assert p.grad is None, k
+                continue
+            if orc.grad_is_structurally_zero(k):
+                continue
+            truth = p64[k].grad
+            n = float(truth.norm())
+            if n == 0.0:
+                continue
+            rel = float((p.grad.double().cpu() - truth).norm()) / n
+            referr = float((p32[k].grad.double() - truth).norm()) / n
+            worst = max(worst, rel)
+            if rel > max(parity.RTOL_FP32, parity.REF_FACTOR_TC * referr):
+                n_band += 1
+                assert rel <= parity.FLIP_C / (batch * 64), f"{grp}.{k}: rel error {rel:.2e} (fp32 oracle's own: {referr:.2e})"
+    print(f"2-D step vs fp64 oracle, B={batch}: worst gradient rel error {worst:.2e}, {n_band} tensors in the kink band")
+    assert n_band <= parity.MAX_FLIP_TENSORS

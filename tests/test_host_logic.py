@@ -27,7 +27,7 @@ def test_cabi_library_loads_and_exports_every_declared_symbol():
     from iins_vae_b200._capi import EXPORTS
     assert set(EXPORTS) <= declared
     dll.iins_abi_version.restype = ctypes.c_int
-    assert dll.iins_abi_version() == 2
+    assert dll.iins_abi_version() == 3
 
 
 def test_config_validation_and_sizes_without_gpu():

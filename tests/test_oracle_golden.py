@@ -1,5 +1,6 @@
 """CPU: pin the oracle restatement against the fixtures recorded from the live reference
 (tests/golden/make_golden.py).  No GPU, no /root/reference needed."""
+import os
 import re
 
 import numpy as np
@@ -151,3 +152,54 @@ def test_adam_trajectory_matches_reference(golden, case):
                     pos = parity.sample_positions(got.size)
                     args = (name, got[pos], golden[key + "|samples"], step + 1)
                     check(*args) if step == 0 else check(*args, start[pos])
+
+
+# ------------------------------------------------------------------------------------------------ 2-D variant
+def _golden2d():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "iins_golden2d.npz"))
+
+
+def _digest_rel_error_2d(g2, key, got):
+    from tests.golden.make_golden_common import sample_positions_2d
+    got = got.detach().double().cpu().numpy().ravel()
+    if key + "|full" in g2.files:
+        ref = g2[key + "|full"].astype(np.float64)
+        return float(np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-300)), float(np.linalg.norm(ref))
+    ref = g2[key + "|samples"].astype(np.float64)
+    norm = float(g2[key + "|norm"])
+    rel_s = float(np.linalg.norm(got[sample_positions_2d(got.size)] - ref) / (np.linalg.norm(ref) + 1e-300))
+    rel_n = abs(float(np.linalg.norm(got)) - norm) / (norm + 1e-300)
+    return max(rel_s, rel_n), norm
+
+
+def test_oracle2d_matches_reference_fixture():
+    """oracle/iins_oracle2d.py (conv_type = 2, expand = True) against the fixture recorded from the live reference modules
+    (tests/golden/make_golden2d.py): parameters regenerated from the seed (checksum pinned), outputs rtol 1e-4, every
+    parameter gradient 2e-4 rel-L2 (two fp32 evaluations in different operation order)."""
+    from oracle import iins_oracle2d as orc2
+    g2 = _golden2d()
+    cfg = orc.PathConfig()
+    cases = sorted(k[:-len("meta")] for k in g2.files if k.endswith(".meta"))
+    assert len(cases) >= 2
+    for pre in cases:
+        seed, batch = (int(v) for v in g2[pre + "meta"])
+        ps = orc2.init_all(cfg, seed)
+        chk = np.array([float(sum(v.double().abs().sum() for v in p.values())) for p in ps])
+        np.testing.assert_allclose(chk, g2[pre + "param_checksum"], rtol=1e-12)
+        tp = [{k: v.clone().requires_grad_(not orc.is_buffer(k)) for k, v in p.items()} for p in ps]
+        cir, err, noise = (torch.from_numpy(g2[pre + k]) for k in ("cir", "err", "noise"))
+        loss, outs = orc2.step_loss(tp[0], tp[1], tp[2], cir, err, cfg, noise)
+        loss.backward()
+        np.testing.assert_allclose(float(loss), float(g2[pre + "out.loss"]), rtol=1e-5)
+        for k in ("rc", "cat", "latent", "xrec", "err_est"):
+            np.testing.assert_allclose(outs[k].detach().numpy(), g2[pre + "out." + k], rtol=1e-4, atol=1e-5, err_msg=k)
+        for grp, p in zip(("enc", "dec", "res"), tp):
+            for k, v in p.items():
+                key = f"{pre}g.{grp}.{k}"
+                if key + "|full" not in g2.files and key + "|norm" not in g2.files:
+                    assert v.grad is None or float(v.grad.abs().max()) == 0.0, key      # restorer.linear_layer2: never used
+                    continue
+                if orc.grad_is_structurally_zero(k):
+                    continue
+                rel, norm = _digest_rel_error_2d(g2, key, v.grad)
+                assert rel <= 2e-4 or norm == 0.0, f"{key}: rel error {rel:.2e}"
