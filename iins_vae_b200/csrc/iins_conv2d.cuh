@@ -33,8 +33,28 @@ IINS_HD int iins_v2c_src_row(int ho, int kh, int Hi, int stride, int pad, int mo
 
 static __global__ void __launch_bounds__(256) iins_v2c_fwd_kernel(const IinsV2cParams p) {
     iins_pdl_enter();
-    const long n = (long)p.B * p.Ho * p.Wi * p.Cp;
     const int KC = p.k * p.C;
+    if ((p.C & 3) == 0 && !p.in_w_bcast) {
+        // 16 bytes per thread: four consecutive channels of one tap (C % 4 == 0, so a float4 never straddles two taps)
+        const int Cq = p.Cp >> 2;
+        const long n = (long)p.B * p.Ho * p.Wi * Cq;
+        for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+            const int q = (int)(e % Cq) * 4;
+            long r = e / Cq;
+            const int w = (int)(r % p.Wi);
+            r /= p.Wi;
+            const int ho = (int)(r % p.Ho), b = (int)(r / p.Ho);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < KC) {
+                const int kh = q / p.C, c = q - kh * p.C;
+                const int h = iins_v2c_src_row(ho, kh, p.Hi, p.stride, p.pad, p.mode);
+                if (h >= 0) v = __ldg(reinterpret_cast<const float4*>(p.x + (((long)b * p.Hi + h) * p.Wi + w) * p.C + c));
+            }
+            reinterpret_cast<float4*>(p.xs)[e] = v;
+        }
+        return;
+    }
+    const long n = (long)p.B * p.Ho * p.Wi * p.Cp;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
         const int q = (int)(e % p.Cp);
         long r = e / p.Cp;
@@ -59,12 +79,13 @@ struct IinsV2cBwdParams {
     int B, Hi, Wi, C, Ho, k, stride, pad, mode, Cp;
 };
 
-static __global__ void __launch_bounds__(256) iins_v2c_bwd_kernel(const IinsV2cBwdParams p) {
-    iins_pdl_enter();
-    const long n = (long)p.B * p.Hi * p.Wi * p.C;
+template <int V>          // V = 4: float4 over channels (C % 4 == 0), V = 1: scalar
+__device__ __forceinline__ void iins_v2c_bwd_body(const IinsV2cBwdParams& p) {
+    const int Cv = p.C / V;
+    const long n = (long)p.B * p.Hi * p.Wi * Cv;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(e % p.C);
-        long r = e / p.C;
+        const int c = (int)(e % Cv) * V;
+        long r = e / Cv;
         const int w = (int)(r % p.Wi);
         r /= p.Wi;
         const int h = (int)(r % p.Hi), b = (int)(r / p.Hi);
@@ -81,18 +102,28 @@ static __global__ void __launch_bounds__(256) iins_v2c_bwd_kernel(const IinsV2cB
         } else {
             cand[nc++] = h;
         }
-        float acc = p.add != nullptr ? __ldg(p.add + e) : 0.f;
+        float acc[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = p.add != nullptr ? __ldg(p.add + e * V + j) : 0.f;
         for (int i = 0; i < nc; ++i) {
             for (int kh = 0; kh < p.k; ++kh) {
                 const int t = cand[i] + p.pad - kh;            // = ho * stride
                 if (t < 0) continue;
                 const int ho = t / p.stride;
                 if (ho * p.stride != t || ho >= p.Ho) continue;
-                acc += __ldg(p.dxs + (((long)b * p.Ho + ho) * p.Wi + w) * p.Cp + kh * p.C + c);
+                const float* src = p.dxs + (((long)b * p.Ho + ho) * p.Wi + w) * p.Cp + kh * p.C + c;
+                if (V == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(src)); acc[0] += v.x; acc[1 % V] += v.y; acc[2 % V] += v.z; acc[3 % V] += v.w; }
+                else acc[0] += __ldg(src);
             }
         }
-        p.dx[e] = acc;
+        if (V == 4) reinterpret_cast<float4*>(p.dx)[e] = make_float4(acc[0], acc[1 % V], acc[2 % V], acc[3 % V]);
+        else p.dx[e] = acc[0];
     }
+}
+static __global__ void __launch_bounds__(256) iins_v2c_bwd_kernel(const IinsV2cBwdParams p) {
+    iins_pdl_enter();
+    if ((p.C & 3) == 0) iins_v2c_bwd_body<4>(p);
+    else iins_v2c_bwd_body<1>(p);
 }
 
 // W[co][ci][kh][kw] -> W'[co][kh * C + ci (zero-padded to Cp)][kw]  and the inverse accumulation for the gradient
@@ -313,4 +344,20 @@ static __global__ void __launch_bounds__(256) iins_col0_put_kernel(const float* 
 static __global__ void __launch_bounds__(256) iins_tanh_bwd_kernel(float* __restrict__ dy, const float* __restrict__ y, long n) {
     iins_pdl_enter();
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) { const float t = __ldg(y + e); dy[e] *= (1.f - t * t); }
+}
+
+// (n, C) -> (n, Cp) with zero channels appended: the weight-gradient GEMMs gather 8 channels of dz at a time, so a convolution
+// with fewer than 8 output channels (the last up-sampling stage, the output convolution) runs them on a padded copy
+static __global__ void __launch_bounds__(256) iins_pad_channels_kernel(const float* __restrict__ src, float* __restrict__ dst, long n, int C, int Cp) {
+    iins_pdl_enter();
+    const long tot = n * Cp;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % Cp);
+        dst[e] = c < C ? __ldg(src + (e / Cp) * C + c) : 0.f;
+    }
+}
+static __global__ void __launch_bounds__(64) iins_add_n_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
+    iins_pdl_enter();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += __ldg(src + i);
 }
