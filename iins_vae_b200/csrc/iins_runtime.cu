@@ -52,7 +52,7 @@ struct IinsOptions {
     int wgrad_batch = 1;        // IINS_WGRAD_BATCH: the trunk's weight gradients as one launch
     int trunk_tmap = 1;         // IINS_TRUNK_TMAP: tensor-map TMA (0: plain bulk copies) for the trunk's weight ring
     int dgrad_parity = 1;       // IINS_DGRAD_PARITY: stride-2 data gradients split by the parity of the input position
-    int win = 3;                // IINS_WIN: persistent window kernels for the stride-2 convolutions (iins_win.cu): bit 0 forward / data gradient, bit 1 weight gradient
+    int win = 7;                // IINS_WIN: persistent window kernels (iins_win.cu): bit 0 stride-2 forward / data gradient, bit 1 stride-2 weight gradient, bit 2 trunk weight gradients
     int defer_join = 0;         // iins_set_deferred_join: a backward pass does NOT wait for its weight-gradient stream at its end
 };
 
@@ -89,7 +89,7 @@ void options_from_env(IinsOptions& o) {
     o.wgrad_batch = env_int("IINS_WGRAD_BATCH", 1);
     o.trunk_tmap = env_int("IINS_TRUNK_TMAP", 1);
     o.dgrad_parity = env_int("IINS_DGRAD_PARITY", 1);
-    o.win = env_int("IINS_WIN", 3);
+    o.win = env_int("IINS_WIN", 7);
 }
 
 iins_ctx* new_ctx() {
@@ -653,6 +653,12 @@ void conv_wgrad_batch(Ctx& c, const IinsGeom& g, int n, const float* const* xs, 
     if (on && g_mode != 2 && tc_ok && n <= 8 && ilog2_exact(g.Lout) >= 0) {
         cudaStream_t wst = c.st;
         if (c.st2 != nullptr) { fork_to(c.st, c.st2); wst = c.st2; }
+        if ((cur().opt.win & 4) != 0 && g.Cin == 64 && g.Cout == 64 && g.ks == 3 && g.stride == 1 && g.pad == 1 && g.mode == IINS_PAD_REFLECT &&
+            g.Lin == 8 && g.Lout == 8) {
+            IINS_SET_FLOPS(2.0 * (double)g.B * 8.0 * 64.0 * 192.0 * n); IINS_SET_SHAPE(g.B * 8, 64, 192 * n);
+            IINS_SET_BYTES(n * 2.0 * 2048.0 * g.B);
+            if (iins_win_k3_tn_launch(wst, g.B, n, xs, dzs, dws, dbs, g_mode == 1 ? 1 : 3)) return;
+        }
         IinsTCTNParams tp;
         memset(&tp, 0, sizeof(tp));
         IinsTNParams& p = tp.tn;

@@ -556,6 +556,204 @@ void launch_win_tn_v(cudaStream_t st, const IinsWinTNParams& p) {
     IINS_LAUNCH(iins_win_tn_kernel_, dim3(gx, T::NROLE, 1), WIN_THREADS, T::SMEM, st, p);
 }
 
+// ======================================================================================== trunk weight gradients (k3, 64 -> 64, L = 8)
+// The weight gradients of the residual trunk's k3 reflect-pad convolutions (up to 8 convolutions of identical geometry in one
+// launch: blockIdx.y), in the same resident / MN-major form.  A tile is 16 samples = 128 rows; x is stored as in the fused
+// trunk kernels -- 10 rows per sample, the reflected edge rows materialised, tap t = row shift t -- and dz as 8-row groups.
+// 64 output channels x 64 input channels x 3 taps with every piece product in its own accumulator would need 960 TMEM columns;
+// instead the products are grouped by magnitude class (fp32-grade mode, pieces d0 > d1 > d2 of dz and x0 > x1 > x2 of x):
+//     A = [d0; d1] (M-stacked)  x  x0  -> block 0:  lanes 0-63  d0 x0,            lanes 64-127  d1 x0
+//     A = [d0; d1]              x  x1  -> block 1:  lanes 0-63  d0 x1,            lanes 64-127  d1 x1
+//     A = [d0; d1]              x  x2  -> block 1:  lanes 0-63  + d0 x2,          lanes 64-127  + d1 x2
+//     A = [d2; 0 ]              x  x0  -> block 1:  lanes 0-63  + d2 x0           (the zero block follows d2 in shared memory)
+// i.e. 128 columns per tap, 384 in all; seven of the nine products (d2 x1 and d2 x2, <= 2^-24 of the result, are dropped).
+struct IinsWinK3Params {
+    int B, nconv, db_on;
+    const float* x[8]; const float* dz[8]; float* dw[8]; float* db[8];
+};
+
+template <int PIECES>
+struct WinK3 {
+    static constexpr int NBLK = PIECES == 3 ? 4 : 1;                       // dz blocks of 8 chunks: [d0][d1][d2][zero] / [d]
+    static constexpr uint32_t CSZ = 16 * 128 + 16;                         // dz: bytes between 8-channel chunks
+    static constexpr uint32_t PSZ = 8 * CSZ;
+    static constexpr uint32_t XL = 16 * 160 + 16;                          // x: bytes between 8-channel chunks (16 samples x 10 rows)
+    static constexpr uint32_t PSX = 8 * XL;
+    static constexpr uint32_t DZ_BYTES = (NBLK > 2 ? NBLK : 2) * PSZ;      // M = 128 lanes always read 16 chunks from the A start
+    static constexpr uint32_t X_BYTES = PIECES * PSX;
+    static constexpr uint32_t SMEM = align128(DZ_BYTES + X_BYTES);
+    static constexpr int CPT = PIECES == 3 ? 128 : 64;                     // accumulator columns per tap
+    static constexpr int TCOLS = win_tmem_cols(3 * CPT);
+};
+
+template <int PIECES>
+__global__ void __launch_bounds__(WIN_THREADS, 1) iins_win_k3_tn_kernel(const IinsWinK3Params wp) {
+    using T = WinK3<PIECES>;
+    extern __shared__ __align__(1024) unsigned char dsm[];
+    __shared__ __align__(8) unsigned long long a_full, a_empty, done;
+    __shared__ uint32_t tmem_slot;
+    __shared__ double sbias[64];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int conv = blockIdx.y;
+    const float* __restrict__ px = wp.x[conv];
+    const float* __restrict__ pz = wp.dz[conv];
+    const int ntiles = (wp.B + 15) >> 4;
+    const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    unsigned char* zb = dsm;
+    unsigned char* xb = dsm + T::DZ_BYTES;
+
+    iins_pdl_launch_dependents();
+    if (tid == 0) {
+        umma::mbar_init(umma::smem_u32(&a_full), 256);
+        umma::mbar_init(umma::smem_u32(&a_empty), 1);
+        umma::mbar_init(umma::smem_u32(&done), 1);
+        umma::fence_mbar_init();
+    }
+    if (tid < 64) sbias[tid] = 0.0;
+    if (warp == 16) umma::tmem_alloc(umma::smem_u32(&tmem_slot), T::TCOLS);
+    for (uint32_t i = (uint32_t)tid * 16u; i < T::SMEM; i += WIN_THREADS * 16u) *reinterpret_cast<uint4*>(dsm + i) = make_uint4(0u, 0u, 0u, 0u);
+    umma::fence_async_smem();
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    iins_pdl_wait();
+
+    double bsum[4] = {0.0, 0.0, 0.0, 0.0};
+    if (warp == 16) {
+        // ------------------------------------------------------------------ MMA issue (one stage: the tile is refilled after its MMAs)
+        const uint32_t z0 = umma::smem_u32(zb), x0 = umma::smem_u32(xb);
+        for (int it = 0; it < my_tiles; ++it) {
+            umma::mbar_wait(umma::smem_u32(&a_full), (uint32_t)it & 1u);
+            umma::tc_fence_after();
+            const bool leader = umma::elect_one();
+            for (int ks = 0; ks < 8; ++ks) {                       // 16 rows = 2 samples per instruction
+                const uint32_t acc_on = (it | ks) ? 1u : 0u;
+                // MN-major: LBO = bytes between 8-row (K) groups, SBO = bytes between 8-channel chunks
+                const uint64_t ad = umma::make_desc(z0 + (uint32_t)ks * 256u, 128, T::CSZ);
+                for (int t = 0; t < 3; ++t) {
+                    const uint32_t col = tmem + (uint32_t)(t * T::CPT);
+                    const uint32_t xa = x0 + (uint32_t)t * 16u + (uint32_t)ks * 320u;
+                    const uint64_t b0 = umma::make_desc(xa, 160, T::XL);
+                    if (leader) umma::mma_bf16_ss(col, ad, b0, umma::make_idesc_bf16(128, 64, 1, 1), acc_on);
+                    if (PIECES == 3) {
+                        const uint64_t b1 = umma::make_desc(xa + T::PSX, 160, T::XL), b2 = umma::make_desc(xa + 2 * T::PSX, 160, T::XL);
+                        if (leader) {
+                            umma::mma_bf16_ss(col + 64, ad, b1, umma::make_idesc_bf16(128, 64, 1, 1), acc_on);
+                            umma::mma_bf16_ss(col + 64, ad, b2, umma::make_idesc_bf16(128, 64, 1, 1), 1u);
+                            umma::mma_bf16_ss(col + 64, ad + ((2 * T::PSZ) >> 4), b0, umma::make_idesc_bf16(128, 64, 1, 1), 1u);
+                        }
+                    }
+                }
+            }
+            if (leader) {
+                umma::commit(umma::smem_u32(&a_empty));
+                if (it == my_tiles - 1) umma::commit(umma::smem_u32(&done));
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 8) {
+        // ------------------------------------------------------------------ producers: 8 x units + 8 dz units per thread and tile
+        const int pt = tid - 256, c4 = pt & 15, r0 = pt >> 4;
+        const uint32_t coffx = (uint32_t)(c4 >> 1) * T::XL + (uint32_t)(c4 & 1) * 8u;
+        const uint32_t coffz = (uint32_t)(c4 >> 1) * T::CSZ + (uint32_t)(c4 & 1) * 8u;
+        const long lim = (long)wp.B * 8;                           // rows that exist
+        const bool do_bias = wp.db_on != 0;
+        float4 v[8];
+        auto issue = [&](int slot, int u, int it) {                // units 0-7: x, 8-15: dz; row = r0 + 16 * (u & 7)
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (it < my_tiles) {
+                const long grow = (long)((int)blockIdx.x + it * (int)gridDim.x) * 128 + r0 + 16 * (u & 7);
+                if (grow < lim) a = __ldg(reinterpret_cast<const float4*>((u < 8 ? px : pz) + grow * 64 + c4 * 4));
+            }
+            v[slot] = a;
+        };
+#pragma unroll
+        for (int u = 0; u < 8; ++u) issue(u, u, 0);
+        for (int it = 0; it < my_tiles; ++it) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                if (u == 0 && it >= 1) umma::mbar_wait_suspend(umma::smem_u32(&a_empty), ((uint32_t)it & 1u) ^ 1u);
+                const int row = r0 + 16 * (u & 7);
+                uint2 w[3];
+                win_split4<PIECES>(v[u & 7], w);
+                if (u < 8) {
+                    // sample s occupies rows 10 s .. 10 s + 9: [x(1) | x(0) .. x(7) | x(6)] (ReflectionPad1d(1), models.py:993)
+                    const int s = row >> 3, pos = row & 7;
+                    unsigned char* d = xb + coffx + (uint32_t)(s * 160 + (pos + 1) * 16);
+                    win_store<PIECES>(w, d, T::PSX);
+                    if (pos == 1) win_store<PIECES>(w, d - 32, T::PSX);
+                    if (pos == 6) win_store<PIECES>(w, d + 32, T::PSX);
+                } else {
+                    win_store<PIECES>(w, zb + coffz + (uint32_t)row * 16u, T::PSZ);
+                    if (do_bias) { const float4 q = v[u & 7]; bsum[0] += (double)q.x; bsum[1] += (double)q.y; bsum[2] += (double)q.z; bsum[3] += (double)q.w; }
+                }
+                issue(u & 7, (u + 8) & 15, it + (u >= 8 ? 1 : 0));
+                if (u == 15) {
+                    umma::fence_async_smem();
+                    umma::mbar_arrive(umma::smem_u32(&a_full));
+                }
+            }
+        }
+    }
+    // ---- flush
+    umma::mbar_wait_suspend(umma::smem_u32(&done), 0);
+    umma::tc_fence_after();
+    float* red = reinterpret_cast<float*>(dsm);                    // [tap][ci][co]
+    constexpr int NRED = 3 * 64 * 64;
+    for (int e = tid; e < NRED; e += WIN_THREADS) red[e] = 0.f;
+    __syncthreads();
+    if (warp < 8) {
+        // TMEM lane = piece block * 64 + co; the two warps that share a lane quarter split the 64 input channels of every tap
+        const int q = warp & 3, hf = warp >> 2;
+        const int r = q * 32 + lane, co = r & 63;
+        const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+        if (PIECES == 3 || r < 64) {                               // warp-uniform
+            for (int t = 0; t < 3; ++t) {
+#pragma unroll
+                for (int c0 = 0; c0 < 32; c0 += 16) {
+                    float a[16];
+                    umma::tmem_ld16(tl + (uint32_t)(t * T::CPT + hf * 32 + c0), a);
+                    if (PIECES == 3) {
+                        float b[16];
+                        umma::tmem_ld16(tl + (uint32_t)(t * T::CPT + 64 + hf * 32 + c0), b);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) a[i] += b[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) atomicAdd(red + (t * 64 + hf * 32 + c0 + i) * 64 + co, a[i]);
+                }
+            }
+        }
+    } else if (warp < 16 && wp.db_on) {
+        const int c4 = (tid - 256) & 15;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(&sbias[c4 * 4 + k], bsum[k]);
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    float* pdw = wp.dw[conv];
+    for (int e = tid; e < NRED; e += WIN_THREADS) {
+        const int co = e & 63, ci = (e >> 6) & 63, t = e >> 12;
+        atomicAdd(pdw + ((long)co * 64 + ci) * 3 + t, red[e]);
+    }
+    if (wp.db_on && wp.db[conv] != nullptr && tid < 64) atomicAdd(wp.db[conv] + tid, (float)sbias[tid]);
+    if (warp == 16) umma::tmem_dealloc(tmem, T::TCOLS);
+}
+
+template <int PIECES>
+void launch_win_k3_v(cudaStream_t st, const IinsWinK3Params& p) {
+    using T = WinK3<PIECES>;
+    static bool attr = false;
+    auto iins_win_k3_tn_kernel_ = iins_win_k3_tn_kernel<PIECES>;
+    if (!attr) { cudaFuncSetAttribute(iins_win_k3_tn_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM); attr = true; }
+    const int ntiles = (p.B + 15) / 16;
+    int gx = sm_count() / p.nconv;
+    if (gx < 1) gx = 1;
+    if (gx > ntiles) gx = ntiles;
+    IINS_LAUNCH(iins_win_k3_tn_kernel_, dim3(gx, p.nconv, 1), WIN_THREADS, T::SMEM, st, p);
+}
+
 template <int NT, int PIECES, int WK, int EPI, int LL>
 void launch_win_v(cudaStream_t st, const IinsWinParams& p) {
     const int smem = (int)win_smem_bytes(NT, PIECES, WK, p.ca);
@@ -617,4 +815,19 @@ bool iins_win_tn_launch(cudaStream_t st, const IinsTNParams& tn, int pieces) {
     IINS_WTN(16, 32) IINS_WTN(32, 64)
 #undef IINS_WTN
     return false;
+}
+
+bool iins_win_k3_tn_launch(cudaStream_t st, int B, int nconv, const float* const* xs, const float* const* dzs, float* const* dws,
+                           float* const* dbs, int pieces) {
+    if (B < 1 || nconv < 1 || nconv > 8 || (pieces != 1 && pieces != 3)) return false;
+    IinsWinK3Params p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.nconv = nconv;
+    for (int i = 0; i < nconv; ++i) {
+        if ((reinterpret_cast<uintptr_t>(xs[i]) & 15) != 0 || (reinterpret_cast<uintptr_t>(dzs[i]) & 15) != 0 || dws[i] == nullptr) return false;
+        p.x[i] = xs[i]; p.dz[i] = dzs[i]; p.dw[i] = dws[i]; p.db[i] = dbs[i];
+        if (dbs[i] != nullptr) p.db_on = 1;
+    }
+    if (pieces == 3) launch_win_k3_v<3>(st, p); else launch_win_k3_v<1>(st, p);
+    return true;
 }

@@ -29,4 +29,7 @@ bool iins_win_nt_supported(int nt, int pieces, int wk, int epi, int ll, int ca);
 bool iins_win_nt_launch(cudaStream_t st, const IinsWinParams& p, int nt, int wk, int epi, int ll);
 // weight gradient of a k4 / s2 / p1 convolution (tn.M = B * Lout set by the caller); false: no instance for (Cin, Cout)
 bool iins_win_tn_launch(cudaStream_t st, const IinsTNParams& tn, int pieces);
+// weight (+ bias) gradients of up to 8 k3 / reflect-pad / 64 -> 64 channel convolutions over (B, 8, 64) tensors (the residual trunk)
+bool iins_win_k3_tn_launch(cudaStream_t st, int B, int nconv, const float* const* xs, const float* const* dzs, float* const* dws,
+                           float* const* dbs, int pieces);
 #endif

@@ -1,7 +1,7 @@
 """On-device A/B check of one library switch: the same engine step with SWITCH=0 and SWITCH=1 (two child processes, the
 switches are read when the context is created), every forward tensor and every gradient compared.
 
-    python tools/path_check.py IINS_WIN            # persistent window kernels vs the per-layer tensor-core kernels
+    python tools/path_check.py IINS_WIN [0 7]      # persistent window kernels (bit mask) vs the per-layer tensor-core kernels
     python tools/path_check.py IINS_FUSED_TRUNK
 
 Both settings use the same bf16 pieces and the same k order, so fp32-grade results agree to summation-order noise."""
@@ -50,8 +50,9 @@ if __name__ == "__main__":
         sys.exit(0)
     import torch
     switch = sys.argv[1] if len(sys.argv) > 1 else "IINS_WIN"
-    run(switch, "0", "/tmp/path_a.pt")
-    run(switch, "1", "/tmp/path_b.pt")
+    va, vb = (sys.argv[2], sys.argv[3]) if len(sys.argv) > 3 else ("0", "7" if switch == "IINS_WIN" else "1")
+    run(switch, va, "/tmp/path_a.pt")
+    run(switch, vb, "/tmp/path_b.pt")
     a, b = torch.load("/tmp/path_a.pt"), torch.load("/tmp/path_b.pt")
     bad = 0
     from oracle import iins_oracle as orc
