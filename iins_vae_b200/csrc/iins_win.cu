@@ -574,14 +574,17 @@ struct IinsWinK3Params {
 
 template <int PIECES>
 struct WinK3 {
+    static constexpr int TS = 8;                                           // samples per tile (64 rows): two stages fit shared memory
     static constexpr int NBLK = PIECES == 3 ? 4 : 1;                       // dz blocks of 8 chunks: [d0][d1][d2][zero] / [d]
-    static constexpr uint32_t CSZ = 16 * 128 + 16;                         // dz: bytes between 8-channel chunks
+    static constexpr uint32_t CSZ = TS * 128 + 16;                         // dz: bytes between 8-channel chunks
     static constexpr uint32_t PSZ = 8 * CSZ;
-    static constexpr uint32_t XL = 16 * 160 + 16;                          // x: bytes between 8-channel chunks (16 samples x 10 rows)
+    static constexpr uint32_t XL = TS * 160 + 16;                          // x: bytes between 8-channel chunks (TS samples x 10 rows)
     static constexpr uint32_t PSX = 8 * XL;
     static constexpr uint32_t DZ_BYTES = (NBLK > 2 ? NBLK : 2) * PSZ;      // M = 128 lanes always read 16 chunks from the A start
     static constexpr uint32_t X_BYTES = PIECES * PSX;
-    static constexpr uint32_t SMEM = align128(DZ_BYTES + X_BYTES);
+    static constexpr uint32_t STAGE = align128(DZ_BYTES + X_BYTES);
+    static constexpr uint32_t RED_BYTES = 3 * 64 * 64 * 4;                 // flush buffer (aliases the stages)
+    static constexpr uint32_t SMEM = 2 * STAGE > RED_BYTES ? 2 * STAGE : RED_BYTES;
     static constexpr int CPT = PIECES == 3 ? 128 : 64;                     // accumulator columns per tap
     static constexpr int TCOLS = win_tmem_cols(3 * CPT);
 };
@@ -589,23 +592,24 @@ struct WinK3 {
 template <int PIECES>
 __global__ void __launch_bounds__(WIN_THREADS, 1) iins_win_k3_tn_kernel(const IinsWinK3Params wp) {
     using T = WinK3<PIECES>;
+    constexpr int TS = T::TS, TROWS = TS * 8;
     extern __shared__ __align__(1024) unsigned char dsm[];
-    __shared__ __align__(8) unsigned long long a_full, a_empty, done;
+    __shared__ __align__(8) unsigned long long a_full[2], a_empty[2], done;
     __shared__ uint32_t tmem_slot;
     __shared__ double sbias[64];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int conv = blockIdx.y;
     const float* __restrict__ px = wp.x[conv];
     const float* __restrict__ pz = wp.dz[conv];
-    const int ntiles = (wp.B + 15) >> 4;
+    const int ntiles = (wp.B + TS - 1) / TS;
     const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    unsigned char* zb = dsm;
-    unsigned char* xb = dsm + T::DZ_BYTES;
 
     iins_pdl_launch_dependents();
     if (tid == 0) {
-        umma::mbar_init(umma::smem_u32(&a_full), 256);
-        umma::mbar_init(umma::smem_u32(&a_empty), 1);
+        for (int i = 0; i < 2; ++i) {
+            umma::mbar_init(umma::smem_u32(&a_full[i]), 256);
+            umma::mbar_init(umma::smem_u32(&a_empty[i]), 1);
+        }
         umma::mbar_init(umma::smem_u32(&done), 1);
         umma::fence_mbar_init();
     }
@@ -621,13 +625,14 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) iins_win_k3_tn_kernel(const Ii
 
     double bsum[4] = {0.0, 0.0, 0.0, 0.0};
     if (warp == 16) {
-        // ------------------------------------------------------------------ MMA issue (one stage: the tile is refilled after its MMAs)
-        const uint32_t z0 = umma::smem_u32(zb), x0 = umma::smem_u32(xb);
+        // ------------------------------------------------------------------ MMA issue (warp-uniform code)
         for (int it = 0; it < my_tiles; ++it) {
-            umma::mbar_wait(umma::smem_u32(&a_full), (uint32_t)it & 1u);
+            const int s = it & 1;
+            umma::mbar_wait(umma::smem_u32(&a_full[s]), (uint32_t)(it >> 1) & 1u);
             umma::tc_fence_after();
             const bool leader = umma::elect_one();
-            for (int ks = 0; ks < 8; ++ks) {                       // 16 rows = 2 samples per instruction
+            const uint32_t z0 = umma::smem_u32(dsm + s * T::STAGE), x0 = z0 + T::DZ_BYTES;
+            for (int ks = 0; ks < TS / 2; ++ks) {                  // 16 rows = 2 samples per instruction
                 const uint32_t acc_on = (it | ks) ? 1u : 0u;
                 // MN-major: LBO = bytes between 8-row (K) groups, SBO = bytes between 8-channel chunks
                 const uint64_t ad = umma::make_desc(z0 + (uint32_t)ks * 256u, 128, T::CSZ);
@@ -647,53 +652,55 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) iins_win_k3_tn_kernel(const Ii
                 }
             }
             if (leader) {
-                umma::commit(umma::smem_u32(&a_empty));
+                umma::commit(umma::smem_u32(&a_empty[s]));
                 if (it == my_tiles - 1) umma::commit(umma::smem_u32(&done));
             }
             __syncwarp();
         }
     } else if (warp >= 8) {
-        // ------------------------------------------------------------------ producers: 8 x units + 8 dz units per thread and tile
+        // ------------------------------------------------------------------ producers: 4 x units + 4 dz units per thread and tile;
+        // the raw data of the NEXT tile rides in the register ring while this one is split and stored
         const int pt = tid - 256, c4 = pt & 15, r0 = pt >> 4;
         const uint32_t coffx = (uint32_t)(c4 >> 1) * T::XL + (uint32_t)(c4 & 1) * 8u;
         const uint32_t coffz = (uint32_t)(c4 >> 1) * T::CSZ + (uint32_t)(c4 & 1) * 8u;
         const long lim = (long)wp.B * 8;                           // rows that exist
         const bool do_bias = wp.db_on != 0;
         float4 v[8];
-        auto issue = [&](int slot, int u, int it) {                // units 0-7: x, 8-15: dz; row = r0 + 16 * (u & 7)
+        auto issue = [&](int u, int it) {                          // units 0-3: x, 4-7: dz; row = r0 + 16 * (u & 3)
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
             if (it < my_tiles) {
-                const long grow = (long)((int)blockIdx.x + it * (int)gridDim.x) * 128 + r0 + 16 * (u & 7);
-                if (grow < lim) a = __ldg(reinterpret_cast<const float4*>((u < 8 ? px : pz) + grow * 64 + c4 * 4));
+                const long grow = (long)((int)blockIdx.x + it * (int)gridDim.x) * TROWS + r0 + 16 * (u & 3);
+                if (grow < lim) a = __ldg(reinterpret_cast<const float4*>((u < 4 ? px : pz) + grow * 64 + c4 * 4));
             }
-            v[slot] = a;
+            v[u] = a;
         };
 #pragma unroll
-        for (int u = 0; u < 8; ++u) issue(u, u, 0);
+        for (int u = 0; u < 8; ++u) issue(u, 0);
         for (int it = 0; it < my_tiles; ++it) {
+            const int s = it & 1;
+            unsigned char* zb = dsm + s * T::STAGE;
+            unsigned char* xb = zb + T::DZ_BYTES;
+            if (it >= 2) umma::mbar_wait_suspend(umma::smem_u32(&a_empty[s]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                if (u == 0 && it >= 1) umma::mbar_wait_suspend(umma::smem_u32(&a_empty), ((uint32_t)it & 1u) ^ 1u);
-                const int row = r0 + 16 * (u & 7);
+            for (int u = 0; u < 8; ++u) {
+                const int row = r0 + 16 * (u & 3);
                 uint2 w[3];
-                win_split4<PIECES>(v[u & 7], w);
-                if (u < 8) {
+                win_split4<PIECES>(v[u], w);
+                if (u < 4) {
                     // sample s occupies rows 10 s .. 10 s + 9: [x(1) | x(0) .. x(7) | x(6)] (ReflectionPad1d(1), models.py:993)
-                    const int s = row >> 3, pos = row & 7;
-                    unsigned char* d = xb + coffx + (uint32_t)(s * 160 + (pos + 1) * 16);
+                    const int sm = row >> 3, pos = row & 7;
+                    unsigned char* d = xb + coffx + (uint32_t)(sm * 160 + (pos + 1) * 16);
                     win_store<PIECES>(w, d, T::PSX);
                     if (pos == 1) win_store<PIECES>(w, d - 32, T::PSX);
                     if (pos == 6) win_store<PIECES>(w, d + 32, T::PSX);
                 } else {
                     win_store<PIECES>(w, zb + coffz + (uint32_t)row * 16u, T::PSZ);
-                    if (do_bias) { const float4 q = v[u & 7]; bsum[0] += (double)q.x; bsum[1] += (double)q.y; bsum[2] += (double)q.z; bsum[3] += (double)q.w; }
+                    if (do_bias) { const float4 q = v[u]; bsum[0] += (double)q.x; bsum[1] += (double)q.y; bsum[2] += (double)q.z; bsum[3] += (double)q.w; }
                 }
-                issue(u & 7, (u + 8) & 15, it + (u >= 8 ? 1 : 0));
-                if (u == 15) {
-                    umma::fence_async_smem();
-                    umma::mbar_arrive(umma::smem_u32(&a_full));
-                }
+                issue(u, it + 1);
             }
+            umma::fence_async_smem();
+            umma::mbar_arrive(umma::smem_u32(&a_full[s]));
         }
     }
     // ---- flush
@@ -747,7 +754,7 @@ void launch_win_k3_v(cudaStream_t st, const IinsWinK3Params& p) {
     static bool attr = false;
     auto iins_win_k3_tn_kernel_ = iins_win_k3_tn_kernel<PIECES>;
     if (!attr) { cudaFuncSetAttribute(iins_win_k3_tn_kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM); attr = true; }
-    const int ntiles = (p.B + 15) / 16;
+    const int ntiles = (p.B + T::TS - 1) / T::TS;
     int gx = sm_count() / p.nconv;
     if (gx < 1) gx = 1;
     if (gx > ntiles) gx = ntiles;
