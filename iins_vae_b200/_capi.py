@@ -88,15 +88,16 @@ class IinsLib:
         d.iins_encoder_backward.argtypes = [_CFG, _PP, _P, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, _PP, _P, _P]
         d.iins_decoder_forward.argtypes = [_CFG, _PP, _P, _P, _P, _P, _P]
         d.iins_decoder_backward.argtypes = [_CFG, _PP, _P, _P, _P, _P, _PP, _P, _P, C.c_int, _P, _P]
-        for mod in ("encoder2d", "decoder2d"):
-            for suffix in ("ws_floats", "scratch_floats"):
-                f = getattr(d, f"iins_{mod}_{suffix}")
-                f.argtypes = [_CFG]
-                f.restype = C.c_size_t
-        d.iins_encoder2d_forward.argtypes = d.iins_encoder_forward.argtypes
-        d.iins_encoder2d_backward.argtypes = d.iins_encoder_backward.argtypes
-        d.iins_decoder2d_forward.argtypes = d.iins_decoder_forward.argtypes
-        d.iins_decoder2d_backward.argtypes = d.iins_decoder_backward.argtypes
+        if hasattr(d, "iins_encoder2d_forward"):         # (the logic-simulator build of the tests has no 2-D plans)
+            for mod in ("encoder2d", "decoder2d"):
+                for suffix in ("ws_floats", "scratch_floats"):
+                    f = getattr(d, f"iins_{mod}_{suffix}")
+                    f.argtypes = [_CFG]
+                    f.restype = C.c_size_t
+            d.iins_encoder2d_forward.argtypes = d.iins_encoder_forward.argtypes
+            d.iins_encoder2d_backward.argtypes = d.iins_encoder_backward.argtypes
+            d.iins_decoder2d_forward.argtypes = d.iins_decoder_forward.argtypes
+            d.iins_decoder2d_backward.argtypes = d.iins_decoder_backward.argtypes
         d.iins_restorer_forward.argtypes = [_CFG, _PP, _P, _P, _P, _P]
         d.iins_restorer_backward.argtypes = [_CFG, _PP, _P, _P, _P, _PP, _P, C.c_int, _P, _P]
         d.iins_classifier_forward.argtypes = [_CFG, _PP, _P, _P, _P, _P]

@@ -609,12 +609,22 @@ static __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowP
     for (int j = 0; j < NACC; ++j) acc[j] = s_bias[j];
     if (ok) {
         if (AKIND == 0) {
+            // (index arithmetic hoisted out of the tap loop: these kernels are bound by instruction issue, ncu: IPC 2.7-3.0)
+            const bool ncl = g.in_layout == IINS_NCL;
+            const float* xb = p.x + (long)b * g.Lin * g.Cin;
+            const int pstride = ncl ? 1 : g.Cin;
+            const int u0 = l * g.stride - g.pad;
             for (int t = 0; t < g.ks; ++t) {
-                const int pos = iins_src_pos(g, l, t);
+                int pos = u0 + t;
+                if (g.mode == IINS_PAD_REFLECT) pos = pos < 0 ? -pos : (pos >= g.Lin ? 2 * (g.Lin - 1) - pos : pos);
+                else if (g.mode == IINS_PAD_UP2) pos = (pos < 0 || pos >= 2 * g.Lin) ? -1 : (pos >> 1);
+                else if (pos >= g.Lin) pos = -1;
                 if (pos < 0) continue;
-                const float* xr = p.x + iins_in_index(g, b, pos, 0);
+                const float* xr = xb + pos * pstride;
                 const float* wr = Ws + t * Cdim * NACC;
-                if (g.in_layout == IINS_NLC && (Cdim & 3) == 0) {
+                if (Cdim == 1) {
+                    iins_row2_fma<NACC>(acc, __ldg(xr), wr);
+                } else if (g.in_layout == IINS_NLC && (Cdim & 3) == 0) {
                     for (int c = 0; c < Cdim; c += 4) {
                         const float4 a4 = __ldg(reinterpret_cast<const float4*>(xr + c));
                         iins_row2_fma<NACC>(acc, a4.x, wr + c * NACC);
@@ -638,6 +648,7 @@ static __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowP
                 q[1] = q[0] + 1;
             }
             const bool vec = g.out_layout == IINS_NLC && (Cdim & 3) == 0 && !p.dz.dy_bcast;
+            const long zb0 = (long)b * g.Lout * g.Cout;
             const bool masked = p.dz.y != nullptr && p.dz.act != IINS_ACT_NONE;
             const float sc = p.dz.dy_scale;
             for (int t = 0; t < g.ks; ++t) {
@@ -650,7 +661,7 @@ static __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowP
                     const int lo = r / g.stride;
                     if (lo * g.stride != r || lo >= g.Lout) continue;
                     if (vec) {
-                        const long base = ((long)b * g.Lout + lo) * g.Cout;
+                        const long base = zb0 + (long)lo * g.Cout;
                         for (int c = 0; c < Cdim; c += 4) {
                             float4 a4 = __ldg(reinterpret_cast<const float4*>(p.dz.dy + base + c));
                             if (masked) {
@@ -695,8 +706,8 @@ static __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowP
                 const int w0 = warp & ~(nw - 1);
 #pragma unroll
                 for (int j = 0; j < NACC; ++j) {
-                    float t = 0.f;
-                    for (int i = 0; i < nw; ++i) t += xchv[w0 + i][j];
+                    float t = xchv[w0][j] + xchv[w0 + 1][j];           // nw is 2 or 4
+                    if (nw == 4) t += xchv[w0 + 2][j] + xchv[w0 + 3][j];
                     v[j] = t;
                 }
                 __syncthreads();

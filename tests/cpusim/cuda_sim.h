@@ -242,4 +242,5 @@ static inline const char* cudaGetErrorString(cudaError_t) { return "cudasim"; }
     cudasim::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kernel(__VA_ARGS__); })
 #define IINS_DYN_SMEM(name) unsigned char* name = cudasim::W().dyn_smem
 #define IINS_SET_FLOPS(f) ((void)(f))
+#define IINS_SET_BYTES(b) ((void)(b))
 #define IINS_SET_SHAPE(m, n, k) ((void)0)
