@@ -260,7 +260,7 @@ def cpu_reference_run(batch, steps, warmup, threads):
     return batch * steps / dt, dt / steps * 1e3, "port", "oracle port of models.py + train_semi.py:183-228, torch CPU"
 
 
-def gpu_eager_reference(batch, steps=10, warmup=3):
+def gpu_eager_reference(batch, steps=10, warmup=3, dim=4):
     """SURVEY.md 2.2 / BASELINE.md section 4: "the kernel to beat on the same box" = the UNMODIFIED reference modules in eager
     PyTorch-CUDA (cuDNN / cuBLAS / ATen) on this B200, same step, same batch.  Timed with CUDA events outside the headline
     timed region.  `value`: inputs resident in HBM, no host read-back; `e2e`: the reference's own loop shape -- pageable
@@ -269,7 +269,7 @@ def gpu_eager_reference(batch, steps=10, warmup=3):
     import ref_step
     if not ref_step.available():
         return {"unavailable": "baseline/_ref/models.py not installed (run baseline/install_ref.py where /root/reference exists)"}
-    tr = ref_step.ReferenceTrainer("cuda")
+    tr = ref_step.ReferenceTrainer("cuda", dim=dim)
     host = ref_step.synthetic_batches(4, batch)
     dev = [tuple(t.cuda() for t in b) for b in host]
     masks = ref_step.mask_stream()
@@ -533,7 +533,7 @@ def main():
         top_name, top = max(agg.items(), key=lambda kv: kv[1]["ms"])
         # DRAM traffic per launch of that kernel from the committed ncu --set full capture (profiles/), if present
         traffic = None
-        for tname in ("r02c_ncu_traffic.json", "r02a_ncu_traffic.json", "r01b_ncu_traffic.json"):   # newest capture that holds this family
+        for tname in ("r02e_ncu_traffic.json", "r02a_ncu_traffic.json", "r01b_ncu_traffic.json"):   # newest capture that holds this family
             tpath = os.path.join(ROOT, "profiles", tname)
             if traffic is None and os.path.exists(tpath):
                 with open(tpath) as f:
@@ -589,7 +589,7 @@ def main():
     gpu_ref = None
     if rank == 0 and world == 1 and not args.no_gpu_reference:
         try:
-            gpu_ref = gpu_eager_reference(B)
+            gpu_ref = gpu_eager_reference(B, dim=cfg.dim)
         except Exception as e:
             gpu_ref = {"error": repr(e)}
 
