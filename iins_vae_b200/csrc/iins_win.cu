@@ -791,7 +791,9 @@ bool launch_win_p(cudaStream_t st, const IinsWinParams& p, int nt, int wk, int e
 
 bool iins_win_nt_supported(int nt, int pieces, int wk, int epi, int ll, int ca) {
     if (pieces != 1 && pieces != 3) return false;
-    if (ca < 16 || (ca & 15) != 0) return false;
+    if (ca < 16 || (ca & (ca - 1)) != 0) return false;             // a power of two >= 16
+    // the producers hold one unrolled round of 8 units per thread: a tile is ca / 4 (forward) or ca / 8 (data gradient) units
+    if (ca > (wk == IINS_WIN_S2F ? 32 : 64)) return false;
     bool inst = false;
 #define IINS_WS(NT_, WK_, EPI_, LL_) if (nt == NT_ && wk == WK_ && epi == EPI_ && ll == LL_) inst = true;
     IINS_WIN_INSTANCES(IINS_WS)

@@ -699,3 +699,23 @@ def test_window_kernels_match_per_layer_kernels(batch, mode):
             worst = max(worst, float((g1[k] - e).norm()) / n)
     print(f"window vs per-layer kernels, B={batch} {mode}: {n1} window launches, worst gradient rel-L2 diff {worst:.2e}")
     assert worst <= 5e-6
+
+
+def test_dim16_bf16_mode_loss_is_close():
+    """dim = 16 in bf16 mode: the one-piece operands of the 64-channel stride-2 layers fit the persistent window kernels' shared
+    memory, whose producers hold at most 8 units per thread and tile -- that geometry (ca = 64) is refused by
+    iins_win_nt_supported and runs on the per-layer kernels.  Stated tolerance: loss terms within 1e-2 relative of the fp32 oracle."""
+    import iins_vae_b200
+    from iins_vae_b200.engine import SemiTrainEngine
+    cfg = orc.PathConfig(dim=16)
+    batch = 64
+    mods, pdicts = _mods(cfg, 3)
+    cir, err, label = orc.synthetic_batch(cfg, batch, 5)
+    iins_vae_b200.set_compute_mode("bf16")
+    eng = SemiTrainEngine(*mods, batch_size=batch, cir_len=cfg.cir_len, use_graph=False)
+    eng.step(cir, err, label, supervised=True, update=False)
+    torch.cuda.synchronize()
+    ref, _ = orc.semi_step_with_grads(*pdicts, cir, err, label, cfg, True, torch.zeros(batch, cfg.env_dim // 2, 1))
+    got = eng.loss_terms()
+    for k in ("loss", "loss_ae", "loss_res", "loss_env"):
+        assert abs(got[k] - float(ref[k])) <= 1e-2 * abs(float(ref[k])) + 1e-6, (k, got[k], float(ref[k]))

@@ -165,3 +165,28 @@ def test_data_parallel_helpers_gloo_world2(tmp_path):
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_conv2d_variant_config_sizes_and_state_dict_surface():
+    """2-D variant (conv_type = 2, expand = True): the config is accepted only with conv_type 2 by the 2-D entry points' sizing
+    functions, the modules hold the reference's 2-D keys / shapes (oracle2d.*_param_shapes, pinned to the live reference by
+    tests/golden/make_golden2d.py), unrunnable combinations raise."""
+    from iins_vae_b200._capi import IinsConfig, IinsLib
+    from iins_vae_b200 import build, models as M
+    from oracle import iins_oracle as orc, iins_oracle2d as orc2
+    lib = IinsLib(build.build())
+    c1, c2 = IinsConfig(8, 157, 4, 3, 4, 16, 2, 5, 16, 1), IinsConfig(8, 157, 4, 3, 4, 16, 2, 5, 16, 2)
+    assert lib.iins_validate_config(c2) == 0 and lib.iins_validate_config(IinsConfig(8, 157, 4, 3, 4, 16, 2, 5, 16, 3)) != 0
+    assert lib.iins_validate_config(IinsConfig(8, 157, 2, 3, 4, 16, 2, 5, 16, 2)) != 0          # dim < 4: norm kernels need >= 4 channels
+    assert lib.iins_encoder2d_ws_floats(c1) == 0 and lib.iins_decoder2d_scratch_floats(c1) == 0  # wrong conv_type: refused
+    assert lib.iins_encoder2d_ws_floats(c2) > 8 * 128 * 128 * 4 * 2 and lib.iins_decoder2d_ws_floats(c2) > 8 * 128 * 128 * 4 * 2
+    assert lib.iins_restorer_ws_floats(c2) == lib.iins_restorer_ws_floats(c1)                   # hidden layers only; input is 128 wide
+    cfg = orc.PathConfig()
+    Enc = M.Encoder(2, cfg.dim, cfg.n_residual, cfg.n_downsample, cfg.env_dim, cfg.range_dim, expand=True)
+    Dec = M.Decoder(2, cfg.dim, cfg.n_residual, cfg.n_downsample, cfg.env_dim, cfg.cir_len, cfg.range_dim, expand=True)
+    Res = M.Restorer((cfg.range_dim, cfg.code_len, cfg.code_len))
+    for m, shapes in ((Enc, orc2.encoder_param_shapes(cfg)), (Dec, orc2.decoder_param_shapes(cfg)), (Res, orc2.restorer_param_shapes(cfg))):
+        assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(v)) for k, v in shapes.items()]
+    for bad in (lambda: M.Encoder(2, expand=False), lambda: M.Decoder(3, expand=True), lambda: M.Restorer((2, 8, 8), net_type="Conv1d")(torch.zeros(1))):
+        with pytest.raises((NotImplementedError, RuntimeError)):
+            bad()
