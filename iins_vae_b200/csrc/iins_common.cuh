@@ -53,13 +53,16 @@ static inline void iins_prof_post(cudaStream_t st) {
     g_iins_prof.cur_bytes = 0.0;
     g_iins_prof.cur_shape[0] = g_iins_prof.cur_shape[1] = g_iins_prof.cur_shape[2] = 0;
 }
-// Every kernel of the library is launched with programmatic dependent launch allowed: it becomes resident while its
-// predecessor in the stream is still draining, runs its prologue (index math, barrier / TMEM set-up, weight staging
-// address arithmetic) and then blocks in iins_pdl_wait() (griddepcontrol.wait = the predecessor grid has completed
-// and its memory is visible) before it touches global memory.  The step is a chain of ~100 dependent 10-30 us
-// kernels: this hides the launch gap and the prologue of each.  IINS_PDL=0 turns the attribute off.
+// Every kernel of the library CAN be launched with programmatic dependent launch allowed (IINS_PDL=1): it then becomes
+// resident while its predecessor in the stream is still draining, runs its prologue (index math, barrier / TMEM set-up,
+// weight staging address arithmetic) and blocks in iins_pdl_wait() (griddepcontrol.wait = the predecessor grid has
+// completed and its memory is visible) before it touches global memory.  In round 1 (a chain of ~124 dependent 10-30 us
+// kernels on few streams) that hid the launch gap and the prologue of each (+3 %).  Since the persistent one-CTA-per-SM
+// kernels and the wider stream concurrency of round 2 the early-resident grids cost more than they hide: measured
+// (profiles/r02e_pdl_switches.log) the step is 1.3 % faster at B = 4096 and within +/- 1 % elsewhere with the attribute
+// OFF, which is now the default.
 static inline int iins_pdl_enabled() {
-    if (g_iins_pdl < 0) { const char* e = getenv("IINS_PDL"); g_iins_pdl = e ? atoi(e) : 1; }
+    if (g_iins_pdl < 0) { const char* e = getenv("IINS_PDL"); g_iins_pdl = e ? atoi(e) : 0; }
     return g_iins_pdl;
 }
 #define IINS_LAUNCH(kernel, grid_, block_, smem_, stream_, ...)                                    \
@@ -99,6 +102,15 @@ IINS_D void iins_pdl_wait() {
 #endif
 }
 IINS_D void iins_pdl_enter() { iins_pdl_launch_dependents(); iins_pdl_wait(); }
+// Persistent kernels (one CTA per SM for the kernel's whole life: the window and fused trunk kernels) do NOT trigger their
+// dependents early: a dependent grid that becomes resident while they run only holds registers / shared memory / TMEM columns of
+// the SMs it lands on (taken from the kernels of the OTHER streams) and spins in griddepcontrol.wait.  Measured on the B200
+// (profiles/r02e_pdl_switches.log): the step is 3-5 % faster without the early trigger.  -DIINS_PERSISTENT_PDL=1 restores it.
+#if defined(IINS_PERSISTENT_PDL) && IINS_PERSISTENT_PDL
+#define IINS_PERSISTENT_PDL_TRIGGER() iins_pdl_launch_dependents()
+#else
+#define IINS_PERSISTENT_PDL_TRIGGER() ((void)0)
+#endif
 
 enum { IINS_PAD_ZERO = 0, IINS_PAD_REFLECT = 1, IINS_PAD_UP2 = 2 };
 enum { IINS_ACT_NONE = 0, IINS_ACT_RELU = 1, IINS_ACT_LRELU = 2, IINS_ACT_TANH = 3 };

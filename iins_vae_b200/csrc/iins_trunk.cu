@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(320, 2) iins_trunk_fwd_kernel(const IinsTrunkF
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = (p.B + TR_SAMPLES - 1) / TR_SAMPLES;
 
-    iins_pdl_launch_dependents();
+    IINS_PERSISTENT_PDL_TRIGGER();
     if (tid == 0) {
         for (int i = 0; i < TR_NSLOT; ++i) {
             umma::mbar_init(umma::smem_u32(&w_full[i]), 1);
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(320, 2) iins_trunk_bwd_kernel(const IinsTrunkB
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = (p.B + TR_SAMPLES - 1) / TR_SAMPLES;
 
-    iins_pdl_launch_dependents();
+    IINS_PERSISTENT_PDL_TRIGGER();
     if (tid == 0) {
         for (int i = 0; i < TR_NSLOT; ++i) {
             umma::mbar_init(umma::smem_u32(&w_full[i]), 1);

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) iins_win_nt_kernel(const IinsW
     unsigned char* sA = dsm + align128(wbytes);
     const int ntiles = (p.M + 127) >> 7;
 
-    iins_pdl_launch_dependents();
+    IINS_PERSISTENT_PDL_TRIGGER();
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             umma::mbar_init(umma::smem_u32(&a_full[i]), 256);
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) iins_win_tn_kernel(const IinsW
     const int role = NROLE == 2 ? (int)blockIdx.y : 0;             // NROLE 2: role 0 = plane O' (taps 0, 2), role 1 = plane E (taps 1, 3)
     const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    iins_pdl_launch_dependents();
+    IINS_PERSISTENT_PDL_TRIGGER();
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             umma::mbar_init(umma::smem_u32(&a_full[i]), 256);
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) iins_win_k3_tn_kernel(const Ii
     const int ntiles = (wp.B + TS - 1) / TS;
     const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    iins_pdl_launch_dependents();
+    IINS_PERSISTENT_PDL_TRIGGER();
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             umma::mbar_init(umma::smem_u32(&a_full[i]), 256);
