@@ -31,6 +31,19 @@ def _shared_stream(device, role):
     return _SHARED_STREAMS[key]
 
 
+def _capture_stream(device):
+    """The stream a step is captured on = the stream of the step's critical path (forward chain, loss, data-gradient chain, Adam).
+    IINS_MAIN_PRIORITY=-1 creates it with a higher stream priority than the library's helper streams (weight gradients, the
+    env-encoder branch, the heads); measured on the B200: no effect on the step time (1.6986 vs 1.6993 ms: every kernel fills
+    the machine, there is rarely a choice between pending thread blocks), so the default stays 0."""
+    import os
+    prio = int(os.environ.get("IINS_MAIN_PRIORITY", "0"))
+    key = (torch.device(device).index, "capture", prio)
+    if key not in _SHARED_STREAMS:
+        _SHARED_STREAMS[key] = torch.cuda.Stream(device=device, priority=prio)
+    return _SHARED_STREAMS[key]
+
+
 def _warmup_stream(device):
     """The side stream on which a step is run once eagerly before it is captured."""
     return _shared_stream(device, "warmup")
@@ -400,7 +413,7 @@ class SemiTrainEngine:
                     self._step_body(*key)
                 torch.cuda.current_stream().wait_stream(s)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, stream=_capture_stream(self.device)):
                     self._step_body(*key)
                 # the warm-up and the capture pass must not count as optimisation steps
                 self.flat.flat.copy_(state[0]); self.flat.exp_avg.copy_(state[1]); self.flat.exp_avg_sq.copy_(state[2])
