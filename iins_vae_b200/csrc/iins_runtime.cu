@@ -53,6 +53,7 @@ struct IinsOptions {
     int trunk_tmap = 1;         // IINS_TRUNK_TMAP: tensor-map TMA (0: plain bulk copies) for the trunk's weight ring
     int dgrad_parity = 1;       // IINS_DGRAD_PARITY: stride-2 data gradients split by the parity of the input position
     int win = 7;                // IINS_WIN: persistent window kernels (iins_win.cu): bit 0 stride-2 forward / data gradient, bit 1 stride-2 weight gradient, bit 2 trunk weight gradients
+    int nbwd_over_win = 0;      // IINS_NBWD_OVER_WIN=1: keep the fused norm backward even where the window data-gradient kernel applies
     int defer_join = 0;         // iins_set_deferred_join: a backward pass does NOT wait for its weight-gradient stream at its end
 };
 
@@ -90,6 +91,7 @@ void options_from_env(IinsOptions& o) {
     o.trunk_tmap = env_int("IINS_TRUNK_TMAP", 1);
     o.dgrad_parity = env_int("IINS_DGRAD_PARITY", 1);
     o.win = env_int("IINS_WIN", 7);
+    o.nbwd_over_win = env_int("IINS_NBWD_OVER_WIN", 0);
 }
 
 iins_ctx* new_ctx() {
@@ -350,6 +352,14 @@ bool nbwd_fusable(const Ctx& c, const IinsNTParams& p, int L, int C, const float
     const int cs = ilog2_exact(p.g.Cout);
     if (cs < 3 || p.g.out_layout != IINS_NLC || p.out_layout != IINS_NLC) return false;
     const int nt = p.N <= 16 ? 16 : (p.N <= 32 ? 32 : 64);
+    {   // a k4 / stride-2 data gradient that the persistent parity-split window kernel can take runs faster there with the norm
+        // backward as its own (HBM-bound) kernel than fused into the per-layer kernel (measured: profiles/r02e_pdl_switches.log)
+        const IinsGeom& g0 = p.g;
+        const bool s2 = cur().opt.dgrad_parity && (cur().opt.win & 1) && g0.stride == 2 && g0.ks == 4 && g0.pad == 1 && g0.mode == IINS_PAD_ZERO &&
+                        g0.Lin == 2 * g0.Lout && ilog2_exact(g0.Lout) >= 3 && g0.Lout <= 128 && g0.in_layout == IINS_NLC && p.N == nt &&
+                        cur().opt.nbwd_over_win == 0;
+        if (s2 && p.ep.add == nullptr && iins_win_nt_supported(nt, g_mode == 1 ? 1 : 3, IINS_WIN_S2D, IINS_EPI_PLAIN, 1, g0.Cout)) return false;
+    }
     if (p.N % nt != 0 || !((nt == 64 && L == 8) || (nt == 32 && L == 16) || (nt == 16 && L == 32))) return false;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (!al16(p.ep.y) || !al16(p.ep.add) || !al16(xhat) || !al16(rstd) || !al16(dz) || !al16(adain) || !al16(dadain)) return false;
