@@ -22,7 +22,7 @@ def _sources():
 
 
 def _headers():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))] + [
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h", ".inc"))] + [
         os.path.join(os.path.dirname(HERE), "include", "iins_b200.h")]
 
 
