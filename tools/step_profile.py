@@ -11,8 +11,9 @@ from iins_vae_b200._capi import get_lib
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "fp32"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+DIM = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 iins_vae_b200.set_compute_mode(mode)
-cfg = orc.PathConfig()
+cfg = orc.PathConfig(dim=DIM)
 pe, pd, pr, pc = orc.init_all(cfg, 0)
 Enc = M.Encoder(1, cfg.dim, cfg.n_residual, cfg.n_downsample, cfg.env_dim, cfg.range_dim)
 Dec = M.Decoder(1, cfg.dim, cfg.n_residual, cfg.n_downsample, cfg.env_dim, cfg.cir_len, cfg.range_dim)
