@@ -12,6 +12,7 @@ from iins_vae_b200._capi import get_lib
 mode = sys.argv[1] if len(sys.argv) > 1 else "fp32"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 DIM = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+SUP = (sys.argv[4] != "unsup") if len(sys.argv) > 4 else True
 iins_vae_b200.set_compute_mode(mode)
 cfg = orc.PathConfig(dim=DIM)
 pe, pd, pr, pc = orc.init_all(cfg, 0)
@@ -24,10 +25,10 @@ cir, err, label = orc.synthetic_batch(cfg, B, 1)
 eng = SemiTrainEngine(Enc, Dec, Res, Cls, batch_size=B, use_graph=False)
 eng.set_concurrency(False)          # serial launches: one event pair = one kernel
 for _ in range(3):
-    eng.step(cir, err, label, supervised=True)
+    eng.step(cir, err, label, supervised=SUP)
 torch.cuda.synchronize()
 lib = get_lib()
-prof = lib.profile(lambda: eng.step(cir, err, label, supervised=True))
+prof = lib.profile(lambda: eng.step(cir, err, label, supervised=SUP))
 sh = lib.last_shapes
 tot = sum(p[1] for p in prof)
 print(f"mode {mode} B {B}: {len(prof)} launches, sum of kernel times {tot:.3f} ms")
