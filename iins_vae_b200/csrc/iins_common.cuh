@@ -64,11 +64,12 @@ static inline void iins_prof_post(cudaStream_t st) {
 // (profiles/r02e_pdl_switches.log) the step is 1.3 % faster at B = 4096 and within +/- 1 % elsewhere with the attribute
 // OFF, which is now the default.
 static inline int iins_pdl_enabled() {
-    // a single-stream launch plan (the 2-D variant: ~330 small dependent launches, no helper streams) turns it on for its
-    // duration unless IINS_PDL is set explicitly: there the overlapped prologues are a net gain (8.4 vs 9.1 ms per step)
-    if (t_iins_pdl_force >= 0 && getenv("IINS_PDL") == nullptr) return t_iins_pdl_force;
-    if (g_iins_pdl < 0) { const char* e = getenv("IINS_PDL"); g_iins_pdl = e ? atoi(e) : 0; }
-    return g_iins_pdl;
+    // the environment is read ONCE (first launch of the process); a single-stream launch plan (the 2-D variant: ~330 small
+    // dependent launches, no helper streams) turns the attribute on for its duration unless IINS_PDL was set explicitly: there
+    // the overlapped prologues are a net gain (8.4 vs 9.1 ms per step)
+    if (g_iins_pdl < 0) { const char* e = getenv("IINS_PDL"); g_iins_pdl = e ? (atoi(e) != 0 ? 3 : 2) : 0; }   // bit 1: explicit
+    if (t_iins_pdl_force >= 0 && (g_iins_pdl & 2) == 0) return t_iins_pdl_force;
+    return g_iins_pdl & 1;
 }
 #define IINS_LAUNCH(kernel, grid_, block_, smem_, stream_, ...)                                    \
     do {                                                                                            \
