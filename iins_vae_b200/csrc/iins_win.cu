@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) iins_win_tn_kernel(const IinsW
     IINS_PERSISTENT_PDL_TRIGGER();
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            umma::mbar_init(umma::smem_u32(&a_full[i]), 256);
+            umma::mbar_init(umma::smem_u32(&a_full[i]), 512);
             umma::mbar_init(umma::smem_u32(&a_empty[i]), 1);
         }
         umma::mbar_init(umma::smem_u32(&done), 1);
@@ -397,11 +397,12 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) iins_win_tn_kernel(const IinsW
             }
             __syncwarp();
         }
-    } else if (warp >= 8) {
-        // ------------------------------------------------------------------ producers
-        const int pt = tid - 256;
-        constexpr int C4X = CIN / 4, RSX = 256 / C4X, NX = (NROLE == 1 ? 256 : 128) / RSX;
-        constexpr int C4Z = COUT / 4, RSZ = 256 / C4Z, NZ = 128 / RSZ;
+    } else {
+        // ------------------------------------------------------------------ producers: ALL 16 other warps (this kernel has no per-tile
+        // epilogue; the producers run at IPC ~1 on global-load and conversion latency, so twice the warps is close to twice the rate)
+        const int pt = tid;
+        constexpr int C4X = CIN / 4, RSX = 512 / C4X, NX = (NROLE == 1 ? 256 : 128) / RSX;
+        constexpr int C4Z = COUT / 4, RSZ = 512 / C4Z, NZ = 128 / RSZ;
         constexpr int UPT = NX + NZ;
         const int c4x = pt % C4X, r0x = pt / C4X, c4z = pt % C4Z, r0z = pt / C4Z;
         const uint32_t coffx = (uint32_t)(c4x >> 1) * T::LBOX + (uint32_t)(c4x & 1) * 8u;
@@ -414,7 +415,8 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) iins_win_tn_kernel(const IinsW
         // RAW operand data rides in a register ring (see the forward kernel); a tile is UPT units per thread: NX of x, then NZ of dz
         auto run = [&](auto tag) {
             constexpr bool HAS_Y = decltype(tag)::value;
-            constexpr int D = HAS_Y ? 4 : (UPT % 8 == 0 ? 8 : 6);  // ring depth: divides UPT, so a unit's slot is the same in every tile
+            constexpr int D = HAS_Y ? (UPT % 4 == 0 ? 4 : 3) : UPT;   // ring depth: divides UPT (<= 8), so a unit's slot is the same in every tile
+            static_assert(UPT <= 8, "units per tile");
             static_assert(UPT % D == 0, "ring depth must divide the units per tile");
             float4 vd[D], vy[HAS_Y ? D : 1];
             auto issue = [&](int slot, int u, int it) {            // unit u (compile-time after unrolling) of this CTA's tile number `it`
@@ -528,8 +530,9 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) iins_win_tn_kernel(const IinsW
                 }
             }
         }
-    } else if (warp < 16 && p.db != nullptr && role == 0) {
-        const int c4z = (tid - 256) % (COUT / 4);
+    }
+    if (warp < 16 && p.db != nullptr && role == 0) {
+        const int c4z = tid % (COUT / 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) atomicAdd(&sbias[c4z * 4 + k], bsum[k]);
     }
@@ -607,7 +610,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) iins_win_k3_tn_kernel(const Ii
     IINS_PERSISTENT_PDL_TRIGGER();
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            umma::mbar_init(umma::smem_u32(&a_full[i]), 256);
+            umma::mbar_init(umma::smem_u32(&a_full[i]), 512);
             umma::mbar_init(umma::smem_u32(&a_empty[i]), 1);
         }
         umma::mbar_init(umma::smem_u32(&done), 1);
@@ -657,36 +660,36 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) iins_win_k3_tn_kernel(const Ii
             }
             __syncwarp();
         }
-    } else if (warp >= 8) {
-        // ------------------------------------------------------------------ producers: 4 x units + 4 dz units per thread and tile;
-        // the raw data of the NEXT tile rides in the register ring while this one is split and stored
-        const int pt = tid - 256, c4 = pt & 15, r0 = pt >> 4;
+    } else {
+        // ------------------------------------------------------------------ producers: ALL 16 other warps, 2 x units + 2 dz units per
+        // thread and tile; the raw data of the NEXT tile rides in the register ring while this one is split and stored
+        const int pt = tid, c4 = pt & 15, r0 = pt >> 4;            // r0 = 0 .. 31
         const uint32_t coffx = (uint32_t)(c4 >> 1) * T::XL + (uint32_t)(c4 & 1) * 8u;
         const uint32_t coffz = (uint32_t)(c4 >> 1) * T::CSZ + (uint32_t)(c4 & 1) * 8u;
         const long lim = (long)wp.B * 8;                           // rows that exist
         const bool do_bias = wp.db_on != 0;
-        float4 v[8];
-        auto issue = [&](int u, int it) {                          // units 0-3: x, 4-7: dz; row = r0 + 16 * (u & 3)
+        float4 v[4];
+        auto issue = [&](int u, int it) {                          // units 0-1: x, 2-3: dz; row = r0 + 32 * (u & 1)
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
             if (it < my_tiles) {
-                const long grow = (long)((int)blockIdx.x + it * (int)gridDim.x) * TROWS + r0 + 16 * (u & 3);
-                if (grow < lim) a = __ldg(reinterpret_cast<const float4*>((u < 4 ? px : pz) + grow * 64 + c4 * 4));
+                const long grow = (long)((int)blockIdx.x + it * (int)gridDim.x) * TROWS + r0 + 32 * (u & 1);
+                if (grow < lim) a = __ldg(reinterpret_cast<const float4*>((u < 2 ? px : pz) + grow * 64 + c4 * 4));
             }
             v[u] = a;
         };
 #pragma unroll
-        for (int u = 0; u < 8; ++u) issue(u, 0);
+        for (int u = 0; u < 4; ++u) issue(u, 0);
         for (int it = 0; it < my_tiles; ++it) {
             const int s = it & 1;
             unsigned char* zb = dsm + s * T::STAGE;
             unsigned char* xb = zb + T::DZ_BYTES;
             if (it >= 2) umma::mbar_wait_suspend(umma::smem_u32(&a_empty[s]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int row = r0 + 16 * (u & 3);
+            for (int u = 0; u < 4; ++u) {
+                const int row = r0 + 32 * (u & 1);
                 uint2 w[3];
                 win_split4<PIECES>(v[u], w);
-                if (u < 4) {
+                if (u < 2) {
                     // sample s occupies rows 10 s .. 10 s + 9: [x(1) | x(0) .. x(7) | x(6)] (ReflectionPad1d(1), models.py:993)
                     const int sm = row >> 3, pos = row & 7;
                     unsigned char* d = xb + coffx + (uint32_t)(sm * 160 + (pos + 1) * 16);
@@ -732,8 +735,9 @@ __global__ void __launch_bounds__(WIN_THREADS, 1) iins_win_k3_tn_kernel(const Ii
                 }
             }
         }
-    } else if (warp < 16 && wp.db_on) {
-        const int c4 = (tid - 256) & 15;
+    }
+    if (warp < 16 && wp.db_on) {
+        const int c4 = tid & 15;
 #pragma unroll
         for (int k = 0; k < 4; ++k) atomicAdd(&sbias[c4 * 4 + k], bsum[k]);
     }
