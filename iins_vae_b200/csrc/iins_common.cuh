@@ -149,6 +149,35 @@ IINS_D float iins_warp_sum(float v) {
     return v;
 }
 
+// Warp sums of N per-lane values (N = 4, 8, 16) with N - 1 + (5 - log2 N) shuffles instead of 5 N: at each of the first log2 N
+// butterfly steps a lane keeps the half of the values its lane bit selects and sends the other half, so the number of values
+// halves while the distance halves; the remaining steps are plain butterflies.  Every value is added in exactly the order
+// iins_warp_sum uses (own + partner at distance 16, 8, 4, 2, 1), so the totals are bit-identical to N calls of it.
+// Returns the total of value index iins_warp_sums_slot<N>(lane).
+template <int N> IINS_D int iins_warp_sums_slot(int lane) {
+    return N == 16 ? (lane >> 1) & 15 : N == 8 ? (lane >> 2) & 7 : (lane >> 3) & 3;
+}
+template <int N> IINS_D float iins_warp_sums(const float* v, int lane) {
+    static_assert(N == 4 || N == 8 || N == 16, "N");
+    float r[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) r[j] = v[j];
+    int d = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1, d >>= 1) {
+        const bool hi = (lane & d) != 0;
+#pragma unroll
+        for (int j = 0; j < n / 2; ++j) {
+            const float keep = hi ? r[j + n / 2] : r[j];
+            const float send = hi ? r[j] : r[j + n / 2];
+            r[j] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+        }
+    }
+#pragma unroll
+    for (; d >= 1; d >>= 1) r[0] += __shfl_xor_sync(0xffffffffu, r[0], d);
+    return r[0];
+}
+
 // sum over aligned groups of G consecutive lanes (G power of two <= 32)
 IINS_D float iins_group_sum(float v, int G) {
     for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

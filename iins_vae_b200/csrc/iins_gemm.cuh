@@ -550,17 +550,33 @@ static __global__ void __launch_bounds__(256) iins_row_nt_kernel(const IinsRowPa
 // Preconditions (host): N <= NACC, K <= IINS_ROW2_KMAX(NACC); with a fused norm: L in {32, 64, 128}.
 #define IINS_ROW2_WMAX 1024            // floats of weights in shared memory: K * NACC <= 1024
 
-template <int NACC>
-IINS_D void iins_row2_fma(float* acc, float a, const float* w) {
+// acc[r][0..NACC) += a[r] * w[0..NACC) for the R rows of a thread.  ONE 16-byte shared-memory read per four weights serves all R
+// rows: a warp-uniform LDS.128 still occupies the shared-memory pipe for four passes, and with one row per thread that pipe
+// (ncu: l1tex throughput 60-76 %, short-scoreboard stalls) -- not instruction issue, not HBM -- bounds these kernels.  The FMAs
+// are packed (FFMA2: two IEEE fp32 FMAs per issue slot; bit-identical to scalar fmaf).
+template <int NACC, int R>
+IINS_D void iins_row2_fma(float (*acc)[NACC], const float* a, const float* w) {
 #pragma unroll
     for (int j = 0; j < NACC; j += 4) {
         const float4 w4 = *reinterpret_cast<const float4*>(w + j);
-        acc[j] = fmaf(a, w4.x, acc[j]); acc[j + 1] = fmaf(a, w4.y, acc[j + 1]);
-        acc[j + 2] = fmaf(a, w4.z, acc[j + 2]); acc[j + 3] = fmaf(a, w4.w, acc[j + 3]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#if defined(__CUDA_ARCH__) && !defined(IINS_CPUSIM)
+            unsigned long long a2;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(a2) : "f"(a[r]));
+            asm("{\n\t.reg .b64 rw, rc;\n\tmov.b64 rw, {%2, %3};\n\tmov.b64 rc, {%0, %1};\n\tfma.rn.f32x2 rc, %4, rw, rc;\n\t"
+                "mov.b64 {%0, %1}, rc;\n\t}" : "+f"(acc[r][j]), "+f"(acc[r][j + 1]) : "f"(w4.x), "f"(w4.y), "l"(a2));
+            asm("{\n\t.reg .b64 rw, rc;\n\tmov.b64 rw, {%2, %3};\n\tmov.b64 rc, {%0, %1};\n\tfma.rn.f32x2 rc, %4, rw, rc;\n\t"
+                "mov.b64 {%0, %1}, rc;\n\t}" : "+f"(acc[r][j + 2]), "+f"(acc[r][j + 3]) : "f"(w4.z), "f"(w4.w), "l"(a2));
+#else
+            acc[r][j] = fmaf(a[r], w4.x, acc[r][j]); acc[r][j + 1] = fmaf(a[r], w4.y, acc[r][j + 1]);
+            acc[r][j + 2] = fmaf(a[r], w4.z, acc[r][j + 2]); acc[r][j + 3] = fmaf(a[r], w4.w, acc[r][j + 3]);
+#endif
+        }
     }
 }
 
-// sum of v over the L rows of this thread's sample (L in {32,64,128}: whole warps); xch: [4] floats per call site
+// sum of v over the rows of this thread's sample that live in nw whole warps (nw = 1, 2, 4); xch: [4] floats per call site
 IINS_D float iins_row2_sample_sum(float v, int nw, int warp, int lane, float* xch) {
     v = iins_warp_sum(v);
     if (nw > 1) {                                   // CTA-uniform
@@ -575,7 +591,11 @@ IINS_D float iins_row2_sample_sum(float v, int nw, int warp, int lane, float* xc
     return v;
 }
 
-template <int NACC, int AKIND, int EPI>      // EPI: 0 plain, 1 InstanceNorm / AdaIN, 2 LayerNorm, 3 data gradient + fused IN backward
+// EPI: 0 plain, 1 InstanceNorm / AdaIN, 2 LayerNorm, 3 data gradient + fused IN backward.
+// R rows per thread (1 or 2).  The R rows of a thread are H rows apart: H = 128 for the plain epilogue (a CTA owns 128 R
+// consecutive rows), H = L / R with a fused norm, so that the L rows of a sample are the R rows of H consecutive lanes and the
+// statistics stay warp-shuffle sums (R = 2 needs L in {64, 128}; M is a whole number of samples there).
+template <int NACC, int AKIND, int EPI, int R>
 static __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowParams rp) {
     iins_pdl_enter();
     constexpr int BM = 128;
@@ -586,7 +606,7 @@ static __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowP
     const IinsGeom& g = p.g;
     const IinsEpilogue& ep = p.ep;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile_m = blockIdx.x * BM;
+    const int tile_m = blockIdx.x * BM * R;
     const int n0 = blockIdx.y * NACC;                    // column block (only the wide plain layers use more than one)
     const int Cdim = AKIND == 0 ? g.Cin : g.Cout;
     for (int e = tid; e < p.K * NACC; e += BM) {
@@ -601,81 +621,153 @@ static __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowP
     if (tid < NACC) s_bias[tid] = (ep.bias != nullptr && n0 + tid < p.N) ? __ldg(ep.bias + n0 + tid) : 0.f;
     __syncthreads();
 
-    const int grow = tile_m + tid;
-    const bool ok = grow < p.M;
-    const int b = ok ? grow >> p.lshift : 0, l = ok ? grow & (p.Lrow - 1) : 0;
-    float acc[NACC];
+    const int L = p.Lrow;
+    const int hs = (R == 1 || EPI == 0) ? 7 : p.lshift - (R == 2 ? 1 : 0);      // log2 H
+    int grow[R], b[R], l[R];
+    bool ok[R], any_ok = false;
 #pragma unroll
-    for (int j = 0; j < NACC; ++j) acc[j] = s_bias[j];
-    if (ok) {
+    for (int r = 0; r < R; ++r) {
+        grow[r] = tile_m + (((tid >> hs) * R + r) << hs) + (tid & ((1 << hs) - 1));
+        ok[r] = grow[r] < p.M;
+        any_ok |= ok[r];
+        b[r] = ok[r] ? grow[r] >> p.lshift : 0;
+        l[r] = ok[r] ? grow[r] & (L - 1) : 0;
+    }
+    float acc[R][NACC];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) acc[r][j] = s_bias[j];
+    if (any_ok) {
         if (AKIND == 0) {
-            // (index arithmetic hoisted out of the tap loop: these kernels are bound by instruction issue, ncu: IPC 2.7-3.0)
+            // (index arithmetic hoisted out of the tap loop)
             const bool ncl = g.in_layout == IINS_NCL;
-            const float* xb = p.x + (long)b * g.Lin * g.Cin;
             const int pstride = ncl ? 1 : g.Cin;
-            const int u0 = l * g.stride - g.pad;
+            const int hi2 = 2 * (g.Lin - 1);
+            const float* xb[R];
+            int u0[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) { xb[r] = p.x + (long)b[r] * g.Lin * g.Cin; u0[r] = l[r] * g.stride - g.pad; }
             for (int t = 0; t < g.ks; ++t) {
-                int pos = u0 + t;
-                if (g.mode == IINS_PAD_REFLECT) pos = pos < 0 ? -pos : (pos >= g.Lin ? 2 * (g.Lin - 1) - pos : pos);
-                else if (g.mode == IINS_PAD_UP2) pos = (pos < 0 || pos >= 2 * g.Lin) ? -1 : (pos >> 1);
-                else if (pos >= g.Lin) pos = -1;
-                if (pos < 0) continue;
-                const float* xr = xb + pos * pstride;
+                const float* xr[R];
+                bool any = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    int pos = u0[r] + t;
+                    if (g.mode == IINS_PAD_REFLECT) { pos = pos < 0 ? -pos : pos; const int rf = hi2 - pos; pos = rf < pos ? rf : pos; }   // pad < Lin
+                    else if (g.mode == IINS_PAD_UP2) pos = (pos < 0 || pos >= 2 * g.Lin) ? -1 : (pos >> 1);
+                    else if (pos >= g.Lin) pos = -1;
+                    xr[r] = (pos >= 0 && ok[r]) ? xb[r] + pos * pstride : nullptr;
+                    any |= xr[r] != nullptr;
+                }
+                if (!any) continue;
                 const float* wr = Ws + t * Cdim * NACC;
+                float a[R];
                 if (Cdim == 1) {
-                    iins_row2_fma<NACC>(acc, __ldg(xr), wr);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) a[r] = xr[r] != nullptr ? __ldg(xr[r]) : 0.f;
+                    iins_row2_fma<NACC, R>(acc, a, wr);
                 } else if (g.in_layout == IINS_NLC && (Cdim & 3) == 0) {
                     for (int c = 0; c < Cdim; c += 4) {
-                        const float4 a4 = __ldg(reinterpret_cast<const float4*>(xr + c));
-                        iins_row2_fma<NACC>(acc, a4.x, wr + c * NACC);
-                        iins_row2_fma<NACC>(acc, a4.y, wr + (c + 1) * NACC);
-                        iins_row2_fma<NACC>(acc, a4.z, wr + (c + 2) * NACC);
-                        iins_row2_fma<NACC>(acc, a4.w, wr + (c + 3) * NACC);
+                        float4 a4[R];
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+                            a4[r] = xr[r] != nullptr ? __ldg(reinterpret_cast<const float4*>(xr[r] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) a[r] = a4[r].x;
+                        iins_row2_fma<NACC, R>(acc, a, wr + c * NACC);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) a[r] = a4[r].y;
+                        iins_row2_fma<NACC, R>(acc, a, wr + (c + 1) * NACC);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) a[r] = a4[r].z;
+                        iins_row2_fma<NACC, R>(acc, a, wr + (c + 2) * NACC);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) a[r] = a4[r].w;
+                        iins_row2_fma<NACC, R>(acc, a, wr + (c + 3) * NACC);
                     }
                 } else {
                     const long cstride = g.in_layout == IINS_NCL ? g.Lin : 1;
-                    for (int c = 0; c < Cdim; ++c) iins_row2_fma<NACC>(acc, __ldg(xr + c * cstride), wr + c * NACC);
+                    for (int c = 0; c < Cdim; ++c) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) a[r] = xr[r] != nullptr ? __ldg(xr[r] + c * cstride) : 0.f;
+                        iins_row2_fma<NACC, R>(acc, a, wr + c * NACC);
+                    }
                 }
             }
         } else {
             // data gradient: output rows whose tap t reads this input position (<= 3 candidates)
-            int q[3] = {l + g.pad, -1, -1};
-            if (g.mode == IINS_PAD_REFLECT) {
-                if (l >= 1 && l <= g.pad) q[1] = g.pad - l;
-                if (l <= g.Lin - 2 && l >= g.Lin - 1 - g.pad) q[2] = g.pad + 2 * (g.Lin - 1) - l;
-            } else if (g.mode == IINS_PAD_UP2) {
-                q[0] = 2 * l + g.pad;
-                q[1] = q[0] + 1;
+            int q[R][3];
+            long zb0[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                q[r][0] = l[r] + g.pad; q[r][1] = -1; q[r][2] = -1;
+                if (g.mode == IINS_PAD_REFLECT) {
+                    if (l[r] >= 1 && l[r] <= g.pad) q[r][1] = g.pad - l[r];
+                    if (l[r] <= g.Lin - 2 && l[r] >= g.Lin - 1 - g.pad) q[r][2] = g.pad + 2 * (g.Lin - 1) - l[r];
+                } else if (g.mode == IINS_PAD_UP2) {
+                    q[r][0] = 2 * l[r] + g.pad;
+                    q[r][1] = q[r][0] + 1;
+                }
+                if (!ok[r]) { q[r][0] = -1; q[r][1] = -1; q[r][2] = -1; }
+                zb0[r] = (long)b[r] * g.Lout * g.Cout;
             }
             const bool vec = g.out_layout == IINS_NLC && (Cdim & 3) == 0 && !p.dz.dy_bcast;
-            const long zb0 = (long)b * g.Lout * g.Cout;
             const bool masked = p.dz.y != nullptr && p.dz.act != IINS_ACT_NONE;
             const float sc = p.dz.dy_scale;
             for (int t = 0; t < g.ks; ++t) {
                 const float* wr = Ws + t * Cdim * NACC;
 #pragma unroll
                 for (int jq = 0; jq < 3; ++jq) {
-                    if (q[jq] < 0) continue;
-                    const int r = q[jq] - t;
-                    if (r < 0) continue;
-                    const int lo = r / g.stride;
-                    if (lo * g.stride != r || lo >= g.Lout) continue;
+                    int lo[R];
+                    bool any = false;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        lo[r] = -1;
+                        const int rr = q[r][jq] - t;
+                        if (q[r][jq] >= 0 && rr >= 0) {
+                            const int o = g.stride == 1 ? rr : (g.stride == 2 ? rr >> 1 : rr / g.stride);     // (uniform branches: no integer division)
+                            if (o * g.stride == rr && o < g.Lout) lo[r] = o;
+                        }
+                        any |= lo[r] >= 0;
+                    }
+                    if (!any) continue;
+                    float a[R];
                     if (vec) {
-                        const long base = zb0 + (long)lo * g.Cout;
                         for (int c = 0; c < Cdim; c += 4) {
-                            float4 a4 = __ldg(reinterpret_cast<const float4*>(p.dz.dy + base + c));
-                            if (masked) {
-                                const float4 y4 = __ldg(reinterpret_cast<const float4*>(p.dz.y + base + c));
-                                a4.x *= iins_dact_from_y(y4.x, p.dz.act, p.dz.slope); a4.y *= iins_dact_from_y(y4.y, p.dz.act, p.dz.slope);
-                                a4.z *= iins_dact_from_y(y4.z, p.dz.act, p.dz.slope); a4.w *= iins_dact_from_y(y4.w, p.dz.act, p.dz.slope);
+                            float4 a4[R];
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                a4[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (lo[r] >= 0) {
+                                    const long base = zb0[r] + (long)lo[r] * g.Cout + c;
+                                    a4[r] = __ldg(reinterpret_cast<const float4*>(p.dz.dy + base));
+                                    if (masked) {
+                                        const float4 y4 = __ldg(reinterpret_cast<const float4*>(p.dz.y + base));
+                                        a4[r].x *= iins_dact_from_y(y4.x, p.dz.act, p.dz.slope); a4[r].y *= iins_dact_from_y(y4.y, p.dz.act, p.dz.slope);
+                                        a4[r].z *= iins_dact_from_y(y4.z, p.dz.act, p.dz.slope); a4[r].w *= iins_dact_from_y(y4.w, p.dz.act, p.dz.slope);
+                                    }
+                                }
                             }
-                            iins_row2_fma<NACC>(acc, a4.x * sc, wr + c * NACC);
-                            iins_row2_fma<NACC>(acc, a4.y * sc, wr + (c + 1) * NACC);
-                            iins_row2_fma<NACC>(acc, a4.z * sc, wr + (c + 2) * NACC);
-                            iins_row2_fma<NACC>(acc, a4.w * sc, wr + (c + 3) * NACC);
+#pragma unroll
+                            for (int r = 0; r < R; ++r) a[r] = a4[r].x * sc;
+                            iins_row2_fma<NACC, R>(acc, a, wr + c * NACC);
+#pragma unroll
+                            for (int r = 0; r < R; ++r) a[r] = a4[r].y * sc;
+                            iins_row2_fma<NACC, R>(acc, a, wr + (c + 1) * NACC);
+#pragma unroll
+                            for (int r = 0; r < R; ++r) a[r] = a4[r].z * sc;
+                            iins_row2_fma<NACC, R>(acc, a, wr + (c + 2) * NACC);
+#pragma unroll
+                            for (int r = 0; r < R; ++r) a[r] = a4[r].w * sc;
+                            iins_row2_fma<NACC, R>(acc, a, wr + (c + 3) * NACC);
                         }
                     } else {
-                        for (int c = 0; c < Cdim; ++c) iins_row2_fma<NACC>(acc, iins_dz_at(g, p.dz, b, lo, c), wr + c * NACC);
+                        for (int c = 0; c < Cdim; ++c) {
+#pragma unroll
+                            for (int r = 0; r < R; ++r) a[r] = lo[r] >= 0 ? iins_dz_at(g, p.dz, b[r], lo[r], c) : 0.f;
+                            iins_row2_fma<NACC, R>(acc, a, wr + c * NACC);
+                        }
                     }
                 }
             }
@@ -683,161 +775,194 @@ static __global__ void __launch_bounds__(128) iins_row2_nt_kernel(const IinsRowP
     }
 
     // ---- epilogue in registers
-    const int L = p.Lrow;
-    const int nw = L >> 5;                               // warps per sample (1, 2 or 4) when a norm is fused
-    float xh[NACC];                                      // normalised pre-affine values (dead when EPI == 0)
+    const int nw = EPI == 0 ? 1 : (L / R) >> 5;          // warps that hold one sample (1, 2 or 4) when a norm is fused
+    float xh[R][NACC];                                   // normalised pre-affine values (dead when EPI == 0)
 #pragma unroll
-    for (int j = 0; j < NACC; ++j) xh[j] = 0.f;
-    if (EPI == 1) {
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) xh[r][j] = 0.f;
+    if constexpr (EPI == 1) {
         const float invL = 1.0f / (float)L;
-        // all NACC columns share ONE shared-memory exchange per statistic (mean, then centred sum of squares) when a
-        // sample spans several warps: 4 CTA barriers instead of 4 per column
-        __shared__ float xchv[4][NACC];
+        // all NACC columns share ONE shared-memory exchange per statistic (mean, then centred sum of squares)
+        __shared__ __align__(16) float xchv[4][NACC];
         float tot[NACC];
-        auto sample_sums = [&](float* v) {               // v[j] -> sum of v[j] over the L rows of this thread's sample
+        auto sample_sums = [&](float* v) {               // v[j] -> sum of v[j] over the rows of this thread's sample held by other lanes
+            const float mine = iins_warp_sums<NACC>(v, lane);        // total of column iins_warp_sums_slot(lane) over this warp
+            if ((lane & (32 / NACC - 1)) == 0) xchv[warp][iins_warp_sums_slot<NACC>(lane)] = mine;
+            if (nw > 1) __syncthreads(); else __syncwarp();          // nw is CTA-uniform
+            const int w0 = warp & ~(nw - 1);
 #pragma unroll
-            for (int j = 0; j < NACC; ++j) v[j] = iins_warp_sum(v[j]);
-            if (nw > 1) {                                // CTA-uniform
-                if (lane == 0) {
-#pragma unroll
-                    for (int j = 0; j < NACC; ++j) xchv[warp][j] = v[j];
+            for (int j = 0; j < NACC; j += 4) {
+                float4 t = *reinterpret_cast<const float4*>(&xchv[w0][j]);
+                if (nw > 1) {
+                    const float4 u = *reinterpret_cast<const float4*>(&xchv[w0 + 1][j]);
+                    t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
                 }
-                __syncthreads();
-                const int w0 = warp & ~(nw - 1);
-#pragma unroll
-                for (int j = 0; j < NACC; ++j) {
-                    float t = xchv[w0][j] + xchv[w0 + 1][j];           // nw is 2 or 4
-                    if (nw == 4) t += xchv[w0 + 2][j] + xchv[w0 + 3][j];
-                    v[j] = t;
+                if (nw == 4) {
+                    const float4 u = *reinterpret_cast<const float4*>(&xchv[w0 + 2][j]);
+                    const float4 c = *reinterpret_cast<const float4*>(&xchv[w0 + 3][j]);
+                    t.x += u.x + c.x; t.y += u.y + c.y; t.z += u.z + c.z; t.w += u.w + c.w;
                 }
-                __syncthreads();
+                v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
             }
+            if (nw > 1) __syncthreads(); else __syncwarp();          // xchv is reused by the next statistic
         };
 #pragma unroll
-        for (int j = 0; j < NACC; ++j) tot[j] = acc[j];
-        sample_sums(tot);
-        float dev[NACC];
+        for (int j = 0; j < NACC; ++j) {
+            tot[j] = acc[0][j];
 #pragma unroll
-        for (int j = 0; j < NACC; ++j) { dev[j] = acc[j] - tot[j] * invL; tot[j] = dev[j] * dev[j]; }
+            for (int r = 1; r < R; ++r) tot[j] += acc[r][j];
+        }
         sample_sums(tot);
 #pragma unroll
         for (int j = 0; j < NACC; ++j) {
-            const float d = dev[j];
+            const float mean = tot[j] * invL;
+            tot[j] = 0.f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) { xh[r][j] = acc[r][j] - mean; tot[j] = r == 0 ? xh[r][j] * xh[r][j] : fmaf(xh[r][j], xh[r][j], tot[j]); }
+        }
+        sample_sums(tot);
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
             const float vpe = fmaf(tot[j], invL, IINS_EPS);
-            float r = rsqrtf(vpe);
-            r = r * fmaf(-0.5f * vpe, r * r, 1.5f);
-            xh[j] = d * r;
-            if (ok && l == 0 && j < p.N && ep.rstd != nullptr) ep.rstd[(long)b * p.N + j] = r;
-            acc[j] = xh[j];
-            if (ep.norm == IINS_NORM_ADAIN && j < p.N) {
-                const float* ab = ep.adain + (long)b * ep.adain_ld;
-                acc[j] = fmaf(xh[j], __ldg(ab + ep.adain_off_w + j), __ldg(ab + ep.adain_off_b + j));
+            float rs = rsqrtf(vpe);
+            rs = rs * fmaf(-0.5f * vpe, rs * rs, 1.5f);
+            if (ok[0] && l[0] == 0 && j < p.N && ep.rstd != nullptr) ep.rstd[(long)b[0] * p.N + j] = rs;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                xh[r][j] *= rs;
+                acc[r][j] = xh[r][j];
+                if (ep.norm == IINS_NORM_ADAIN && j < p.N) {
+                    const float* ab = ep.adain + (long)b[r] * ep.adain_ld;
+                    acc[r][j] = fmaf(xh[r][j], __ldg(ab + ep.adain_off_w + j), __ldg(ab + ep.adain_off_b + j));
+                }
             }
         }
-    } else if (EPI == 2) {
+    } else if constexpr (EPI == 2) {
         // per-sample mean and UNBIASED std over (C*L), eps added to std (models.py:976-981)
         const float nel = (float)(L * p.N);
         float part = 0.f;
 #pragma unroll
-        for (int j = 0; j < NACC; ++j) part += j < p.N ? acc[j] : 0.f;
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int j = 0; j < NACC; ++j) part += j < p.N ? acc[r][j] : 0.f;
         const float mean = iins_row2_sample_sum(part, nw, warp, lane, xch) / nel;
         float sq = 0.f;
 #pragma unroll
-        for (int j = 0; j < NACC; ++j) { const float d = acc[j] - mean; sq += j < p.N ? d * d : 0.f; }
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int j = 0; j < NACC; ++j) { const float d = acc[r][j] - mean; sq += j < p.N ? d * d : 0.f; }
         sq = iins_row2_sample_sum(sq, nw, warp, lane, xch);
         const float rs = 1.0f / (sqrtf(sq / (nel - 1.f)) + IINS_EPS);
-        if (ok && l == 0 && ep.rstd != nullptr) ep.rstd[b] = rs;
+        if (ok[0] && l[0] == 0 && ep.rstd != nullptr) ep.rstd[b[0]] = rs;
 #pragma unroll
-        for (int j = 0; j < NACC; ++j) {
-            xh[j] = (acc[j] - mean) * rs;
-            acc[j] = j < p.N ? fmaf(xh[j], __ldg(ep.gamma + j), __ldg(ep.beta + j)) : 0.f;
-        }
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int j = 0; j < NACC; ++j) {
+                xh[r][j] = (acc[r][j] - mean) * rs;
+                acc[r][j] = j < p.N ? fmaf(xh[r][j], __ldg(ep.gamma + j), __ldg(ep.beta + j)) : 0.f;
+            }
     }
-    if (EPI == 3) {
+    if constexpr (EPI == 3) {
         // acc = gradient w.r.t. the previous layer's output (this kernel is that layer's consumer's data gradient); the
         // InstanceNorm backward of the previous layer follows in registers (same fusion as IINS_EPI_NBWD of the tensor-core
         // kernel):  dz = rstd * (raw - mean_l(raw) - xhat * mean_l(raw * xhat)),  raw = relu'(xhat) * dy.  Needs N == NACC.
         __shared__ float xchn[4][2 * NACC];
         const float invL = 1.0f / (float)L;
-        const long oi = (long)grow * NACC;
-        float xv[NACC], s1[NACC], s2[NACC];
-#pragma unroll
-        for (int j = 0; j < NACC; j += 4) {
-            const float4 x4 = ok ? __ldg(reinterpret_cast<const float4*>(ep.nb_xhat + oi + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            xv[j] = x4.x; xv[j + 1] = x4.y; xv[j + 2] = x4.z; xv[j + 3] = x4.w;
-        }
-        if (ep.y != nullptr && ok) {
-#pragma unroll
-            for (int j = 0; j < NACC; j += 4)
-                *reinterpret_cast<float4*>(ep.y + oi + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-        }
+        float s1[NACC], s2[NACC];
         const bool relu = ep.nb_act == IINS_ACT_RELU;
 #pragma unroll
-        for (int j = 0; j < NACC; ++j) {
-            if (relu && !(xv[j] > 0.f)) acc[j] = 0.f;                // raw
-            s1[j] = iins_warp_sum(acc[j]);
-            s2[j] = iins_warp_sum(acc[j] * xv[j]);
-        }
-        if (nw > 1) {                                                // CTA-uniform: the sample spans nw warps
-            if (lane == 0) {
+        for (int r = 0; r < R; ++r) {                                // xh holds xhat of the previous layer here
+            const long oi = (long)grow[r] * NACC;
 #pragma unroll
-                for (int j = 0; j < NACC; ++j) { xchn[warp][j] = s1[j]; xchn[warp][NACC + j] = s2[j]; }
+            for (int j = 0; j < NACC; j += 4) {
+                const float4 x4 = ok[r] ? __ldg(reinterpret_cast<const float4*>(ep.nb_xhat + oi + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                xh[r][j] = x4.x; xh[r][j + 1] = x4.y; xh[r][j + 2] = x4.z; xh[r][j + 3] = x4.w;
             }
-            __syncthreads();
+            if (ep.y != nullptr && ok[r]) {
+#pragma unroll
+                for (int j = 0; j < NACC; j += 4)
+                    *reinterpret_cast<float4*>(ep.y + oi + j) = make_float4(acc[r][j], acc[r][j + 1], acc[r][j + 2], acc[r][j + 3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (relu && !(xh[r][j] > 0.f)) acc[r][j] = 0.f;      // raw
+                s1[j] = r == 0 ? acc[r][j] : s1[j] + acc[r][j];
+                s2[j] = r == 0 ? acc[r][j] * xh[r][j] : fmaf(acc[r][j], xh[r][j], s2[j]);
+            }
+        }
+        {
+            const float m1 = iins_warp_sums<NACC>(s1, lane), m2 = iins_warp_sums<NACC>(s2, lane);
+            if ((lane & (32 / NACC - 1)) == 0) {
+                const int slot = iins_warp_sums_slot<NACC>(lane);
+                xchn[warp][slot] = m1; xchn[warp][NACC + slot] = m2;
+            }
+            if (nw > 1) __syncthreads(); else __syncwarp();          // nw is CTA-uniform
             const int w0 = warp & ~(nw - 1);
 #pragma unroll
             for (int j = 0; j < NACC; ++j) {
                 float a = 0.f, c2 = 0.f;
-                for (int i = 0; i < nw; ++i) { a += xchn[w0 + i][j]; c2 += xchn[w0 + i][NACC + j]; }
+                if (nw == 1) { a = xchn[warp][j]; c2 = xchn[warp][NACC + j]; }
+                else for (int i = 0; i < nw; ++i) { a += xchn[w0 + i][j]; c2 += xchn[w0 + i][NACC + j]; }
                 s1[j] = a; s2[j] = c2;
             }
         }
-        if (!ok) return;
 #pragma unroll
-        for (int j = 0; j < NACC; j += 4) {
-            const float4 r4 = __ldg(reinterpret_cast<const float4*>(ep.nb_rstd + (long)b * NACC + j));
-            const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
-            float o[4];
+        for (int r = 0; r < R; ++r) {
+            if (!ok[r]) continue;
+            const long oi = (long)grow[r] * NACC;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = rv[i] * (acc[j + i] - s1[j + i] * invL - xv[j + i] * s2[j + i] * invL);
-            *reinterpret_cast<float4*>(ep.nb_dz + oi + j) = make_float4(o[0], o[1], o[2], o[3]);
+            for (int j = 0; j < NACC; j += 4) {
+                const float4 r4 = __ldg(reinterpret_cast<const float4*>(ep.nb_rstd + (long)b[r] * NACC + j));
+                const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = rv[i] * (acc[r][j + i] - s1[j + i] * invL - xh[r][j + i] * s2[j + i] * invL);
+                *reinterpret_cast<float4*>(ep.nb_dz + oi + j) = make_float4(o[0], o[1], o[2], o[3]);
+            }
         }
         return;
     }
-    if (ep.act == IINS_ACT_RELU) {
 #pragma unroll
-        for (int j = 0; j < NACC; ++j) acc[j] = fmaxf(acc[j], 0.f);
-    } else if (ep.act != IINS_ACT_NONE) {
+    for (int r = 0; r < R; ++r) {
+        if (ep.act == IINS_ACT_RELU) {
 #pragma unroll
-        for (int j = 0; j < NACC; ++j) acc[j] = iins_act(acc[j], ep.act, ep.slope);
-    }
-    if (!ok) return;
-    if (p.out_layout == IINS_NLC && (p.N % NACC) == 0) {
-        const long oi = (long)grow * p.N + n0;
-        if ((EPI == 1 || EPI == 2) && ep.xhat != nullptr) {
+            for (int j = 0; j < NACC; ++j) acc[r][j] = fmaxf(acc[r][j], 0.f);
+        } else if (ep.act != IINS_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < NACC; ++j) acc[r][j] = iins_act(acc[r][j], ep.act, ep.slope);
+        }
+        if (!ok[r]) continue;
+        if (p.out_layout == IINS_NLC && (p.N % NACC) == 0) {
+            const long oi = (long)grow[r] * p.N + n0;
+            if ((EPI == 1 || EPI == 2) && ep.xhat != nullptr) {
+#pragma unroll
+                for (int j = 0; j < NACC; j += 4)
+                    *reinterpret_cast<float4*>(ep.xhat + oi + j) = make_float4(xh[r][j], xh[r][j + 1], xh[r][j + 2], xh[r][j + 3]);
+            }
+            if (ep.add != nullptr) {
+#pragma unroll
+                for (int j = 0; j < NACC; j += 4) {
+                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(ep.add + oi + j));
+                    acc[r][j] += a4.x; acc[r][j + 1] += a4.y; acc[r][j + 2] += a4.z; acc[r][j + 3] += a4.w;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < NACC; j += 4)
-                *reinterpret_cast<float4*>(ep.xhat + oi + j) = make_float4(xh[j], xh[j + 1], xh[j + 2], xh[j + 3]);
-        }
-        if (ep.add != nullptr) {
+                *reinterpret_cast<float4*>(ep.y + oi + j) = make_float4(acc[r][j], acc[r][j + 1], acc[r][j + 2], acc[r][j + 3]);
+        } else {
 #pragma unroll
-            for (int j = 0; j < NACC; j += 4) {
-                const float4 a4 = __ldg(reinterpret_cast<const float4*>(ep.add + oi + j));
-                acc[j] += a4.x; acc[j + 1] += a4.y; acc[j + 2] += a4.z; acc[j + 3] += a4.w;
+            for (int j = 0; j < NACC; ++j) {
+                if (n0 + j >= p.N) continue;
+                const long oi = p.out_layout == IINS_NCL ? (((long)b[r] * p.N + n0 + j) << p.lshift) + l[r] : (long)grow[r] * p.N + n0 + j;
+                if ((EPI == 1 || EPI == 2) && ep.xhat != nullptr) ep.xhat[oi] = xh[r][j];
+                float o = acc[r][j];
+                if (ep.add != nullptr) o += ep.add[oi];
+                ep.y[oi] = o;
             }
-        }
-#pragma unroll
-        for (int j = 0; j < NACC; j += 4)
-            *reinterpret_cast<float4*>(ep.y + oi + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < NACC; ++j) {
-            if (n0 + j >= p.N) continue;
-            const long oi = p.out_layout == IINS_NCL ? (((long)b * p.N + n0 + j) << p.lshift) + l : (long)grow * p.N + n0 + j;
-            if ((EPI == 1 || EPI == 2) && ep.xhat != nullptr) ep.xhat[oi] = xh[j];
-            float o = acc[j];
-            if (ep.add != nullptr) o += ep.add[oi];
-            ep.y[oi] = o;
         }
     }
 }

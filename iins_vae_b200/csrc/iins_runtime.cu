@@ -45,6 +45,8 @@ struct IinsOptions {
     int ep_regs = 1;            // IINS_EP_REGS: register-resident epilogues (0: SMEM-staged generic epilogue)
     int fuse_nbwd = 1;          // IINS_FUSE_NBWD: norm backward in the data-gradient epilogue
     int row2 = 1;               // IINS_ROW2: one-thread-per-row kernels for the small-channel layers
+    int row_pair_mask = 31;     // IINS_ROW_PAIR_MASK (diagnostics): 1 forward plain, 2 forward + IN, 4 forward + LN, 8 data gradient, 16 data gradient + IN backward
+    long row_pair = 65536;      // IINS_ROW_PAIR: two rows per thread in those kernels for layers with at least this many rows (0: never)
     long row2_tn_minm = 16384;  // IINS_ROW2_TN_MINM
     long tn_ctas = 148L * 2;    // IINS_TN_CTAS: CTAs a weight-gradient launch aims for
     int fused_trunk = 1;        // IINS_FUSED_TRUNK / IINS_FUSED_TRUNK_BWD: the persistent residual-trunk kernels
@@ -82,6 +84,8 @@ void options_from_env(IinsOptions& o) {
     o.ep_regs = env_int("IINS_EP_REGS", 1);
     o.fuse_nbwd = env_int("IINS_FUSE_NBWD", 1);
     o.row2 = env_int("IINS_ROW2", 1);
+    o.row_pair = env_int("IINS_ROW_PAIR", 65536);
+    o.row_pair_mask = env_int("IINS_ROW_PAIR_MASK", 31);
     o.row2_tn_minm = env_int("IINS_ROW2_TN_MINM", 16384);
     o.tn_ctas = env_int("IINS_TN_CTAS", 148 * 2);
     if (o.tn_ctas < 1) o.tn_ctas = 148;
@@ -403,13 +407,26 @@ void launch_nt(Ctx& c, IinsNTParams p) {
             IinsRowParams rp;
             rp.nt = p;
             const int epi = p.ep.nb_dz != nullptr ? 3 : (p.ep.norm == IINS_NORM_NONE ? 0 : (p.ep.norm == IINS_NORM_LN ? 2 : 1));
-            const dim3 grid((p.M + 127) / 128, (p.N + nacc - 1) / nacc, 1);
+            // two rows per thread halve the shared-memory weight reads per row (the pipe that bounds these kernels); with a fused
+            // norm the two rows are L/2 apart, so L >= 64 keeps a sample in whole warps
+            // (measured per layer at B = 4096, profiles/r02f_row_pair.txt: it pays for <= 8 accumulators per row and, for data
+            // gradients, K >= 32; 16 accumulators x 2 rows cost too much occupancy)
+            const bool pair = cur().opt.row_pair > 0 && nacc <= 8 && p.M >= cur().opt.row_pair && (epi == 0 || p.Lrow >= 64) &&
+                              (p.a_kind == 0 || p.K >= 32) && ((cur().opt.row_pair_mask >> (epi == 3 ? 4 : (p.a_kind == 1 ? 3 : epi))) & 1);
+            const int rows = pair ? 256 : 128;
+            const dim3 grid((p.M + rows - 1) / rows, (p.N + nacc - 1) / nacc, 1);
             IINS_SET_FLOPS(2.0 * (double)p.M * (double)p.N * (double)p.K); IINS_SET_SHAPE(p.M, p.N, p.K);
+#define IINS_R2_(NA_, AK_, EP_, R_) \
+            { auto iins_row2_nt_kernel_ = iins_row2_nt_kernel<NA_, AK_, EP_, R_>; IINS_LAUNCH(iins_row2_nt_kernel_, grid, 128, 0, c.st, rp); return; }
 #define IINS_R2(NA_, AK_, EP_) \
-            if (nacc == NA_ && p.a_kind == AK_ && epi == EP_) { auto iins_row2_nt_kernel_ = iins_row2_nt_kernel<NA_, AK_, EP_>; IINS_LAUNCH(iins_row2_nt_kernel_, grid, 128, 0, c.st, rp); return; }
-            IINS_R2(4, 0, 0) IINS_R2(8, 0, 0) IINS_R2(16, 0, 0) IINS_R2(4, 1, 0) IINS_R2(8, 1, 0) IINS_R2(16, 1, 0)
-            IINS_R2(4, 0, 1) IINS_R2(8, 0, 1) IINS_R2(16, 0, 1) IINS_R2(4, 0, 2) IINS_R2(8, 0, 2) IINS_R2(16, 0, 2)
-            IINS_R2(64, 0, 0) IINS_R2(64, 1, 0) IINS_R2(4, 1, 3) IINS_R2(8, 1, 3) IINS_R2(16, 1, 3)
+            if (nacc == NA_ && p.a_kind == AK_ && epi == EP_) { if (pair) IINS_R2_(NA_, AK_, EP_, 2) else IINS_R2_(NA_, AK_, EP_, 1) }
+#define IINS_R2W(NA_, AK_, EP_) \
+            if (nacc == NA_ && p.a_kind == AK_ && epi == EP_) IINS_R2_(NA_, AK_, EP_, 1)
+            IINS_R2(4, 0, 0) IINS_R2(8, 0, 0) IINS_R2W(16, 0, 0) IINS_R2(4, 1, 0) IINS_R2(8, 1, 0) IINS_R2W(16, 1, 0)
+            IINS_R2(4, 0, 1) IINS_R2(8, 0, 1) IINS_R2W(16, 0, 1) IINS_R2(4, 0, 2) IINS_R2(8, 0, 2) IINS_R2W(16, 0, 2)
+            IINS_R2W(64, 0, 0) IINS_R2W(64, 1, 0) IINS_R2(4, 1, 3) IINS_R2(8, 1, 3) IINS_R2W(16, 1, 3)
+#undef IINS_R2W
+#undef IINS_R2_
 #undef IINS_R2
         }
     }

@@ -54,6 +54,31 @@ def test_dim16_decoder_gradients_match_autograd(sim):
     assert float((d_cat.double() - catd.grad.view(B, -1)).norm()) <= 2e-4 * float(catd.grad.norm())
 
 
+@pytest.fixture
+def paired_rows_ctx(sim):
+    """A library context created with IINS_ROW_PAIR=1: every eligible small-channel layer runs the two-rows-per-thread
+    instance of the row kernel (the default pairs only layers with >= 65536 rows, too large for the simulator)."""
+    import os
+    _, lib = sim
+    old = os.environ.get("IINS_ROW_PAIR")
+    os.environ["IINS_ROW_PAIR"] = "1"
+    ctx = lib.dll.iins_ctx_create()
+    if old is None:
+        os.environ.pop("IINS_ROW_PAIR", None)
+    else:
+        os.environ["IINS_ROW_PAIR"] = old
+    assert ctx
+    lib.dll.iins_ctx_make_current(ctx)
+    yield ctx
+    lib.dll.iins_ctx_make_current(None)
+    lib.dll.iins_ctx_destroy(ctx)
+
+
+def test_semi_step_matches_oracle_with_paired_rows(sim, paired_rows_ctx):
+    test_semi_step_matches_oracle(sim, 5, True, 3)
+    test_semi_step_matches_oracle(sim, 6, False, 6)
+
+
 @pytest.mark.parametrize("batch,supervised,seed", [(2, True, 0), (5, False, 1), (19, True, 2)])
 def test_semi_step_matches_oracle(sim, batch, supervised, seed):
     H, lib = sim

@@ -574,6 +574,12 @@ def _conv_head_masks(eng, m, B):
     return m1, m2
 
 
+# (weights, batch) seeds of the test below: a pair with no ReLU input within rounding of zero, so that no gradient tensor needs the
+# kink-flip band whatever the summation order of the kernels (picked with tools/heads_seed_scan.py; a flip is a property of the
+# data, not of the kernels: at the previous pair (61, 161) ANY 1e-7 perturbation of the input moved four tensors into the band)
+CONV_HEADS_SEEDS = (64, 164)
+
+
 def test_engine_with_conv1d_heads_matches_oracle():
     """regressor_type / identifier_type = 2 (utils.py:43-44) through the fused engine: the semi-supervised step with
     RestorerConv1d + ClassifierConv1d (Philox dropout, BatchNorm over the batch) against the oracle replaying the masks the
@@ -581,8 +587,8 @@ def test_engine_with_conv1d_heads_matches_oracle():
     from iins_vae_b200.engine import SemiTrainEngine
     cfg = orc.PathConfig()
     batch = 512
-    mods, pdicts = _conv_mods(cfg, 61)
-    cir, err, label = orc.synthetic_batch(cfg, batch, 161)
+    mods, pdicts = _conv_mods(cfg, CONV_HEADS_SEEDS[0])
+    cir, err, label = orc.synthetic_batch(cfg, batch, CONV_HEADS_SEEDS[1])
     eng = SemiTrainEngine(*mods, batch_size=batch, use_graph=False)
     eng.step(cir, err, label, supervised=True, update=False)
     torch.cuda.synchronize()
@@ -723,3 +729,56 @@ def test_dim16_bf16_mode_loss_is_close():
     got = eng.loss_terms()
     for k in ("loss", "loss_ae", "loss_res", "loss_env"):
         assert abs(got[k] - float(ref[k])) <= 1e-2 * abs(float(ref[k])) + 1e-6, (k, got[k], float(ref[k]))
+
+
+@pytest.mark.parametrize("batch", [37, 256])
+def test_paired_row_kernels_match_single_row_kernels(batch):
+    """The one-thread-per-row kernels of the small-channel layers with TWO rows per thread (iins_row2_nt_kernel<.., R = 2>: one
+    shared-memory weight read serves both rows; the default for layers with >= 65536 rows) against the same kernels with one row
+    per thread: two contexts in one process, IINS_ROW_PAIR = 1 (pair every eligible layer, also at this small batch) and 0.
+    The convolution sums are the same FMAs in the same order; the InstanceNorm / LayerNorm statistics add a thread's two rows
+    before the warp sum, so tensors agree to fp32 summation-order noise: stated bound 1e-5 rel-L2 forward (measured 3e-6 on the
+    range code, 2e-7 on the reconstruction), 2e-4 per gradient tensor (measured 3e-5; fp32-grade mode).  Larger batches are
+    left to the oracle tests: a batch that holds ONE ReLU input within rounding of zero moves the range encoder's gradients by
+    1e-2 under ANY 1e-7 perturbation, paired or not (tools/diag_row_pair.py shows both)."""
+    import iins_vae_b200
+    from iins_vae_b200._capi import get_lib
+    from iins_vae_b200.engine import SemiTrainEngine
+    d = get_lib().dll
+    cfg = orc.PathConfig()
+    cir, err, label = orc.synthetic_batch(cfg, batch, 977)
+    res = {}
+    old = os.environ.get("IINS_ROW_PAIR")
+    try:
+        for sw in ("0", "1"):
+            os.environ["IINS_ROW_PAIR"] = sw
+            ctx = d.iins_ctx_create()
+            assert ctx
+            d.iins_ctx_make_current(ctx)
+            iins_vae_b200.set_compute_mode("fp32")
+            mods, _ = _mods(cfg, 41)
+            eng = SemiTrainEngine(*mods, batch_size=batch, cir_len=cfg.cir_len, use_graph=False)
+            launches = get_lib().profile(lambda: eng.step(cir, err, label, supervised=True, update=False))
+            torch.cuda.synchronize()
+            res[sw] = ({k: v.clone() for k, v in eng.named_grads().items()}, eng.xrec.clone(), eng.rc.clone(),
+                       [s for n, _, s in launches if "iins_row2_nt" in n])
+            d.iins_ctx_make_current(None)
+            d.iins_ctx_destroy(ctx)
+    finally:
+        if old is None:
+            os.environ.pop("IINS_ROW_PAIR", None)
+        else:
+            os.environ["IINS_ROW_PAIR"] = old
+    (g0, x0, r0, l0), (g1, x1, r1, l1) = res["0"], res["1"]
+    assert len(l0) == len(l1) and len(l0) >= 20
+    for a, b, name in ((x0, x1, "xrec"), (r0, r1, "rc")):
+        assert float((a - b).norm()) <= 1e-5 * float(a.norm()), name
+    worst = 0.0
+    for k, e in g0.items():
+        if orc.grad_is_structurally_zero(k):
+            continue
+        n = float(e.norm())
+        if n > 0:
+            worst = max(worst, float((g1[k] - e).norm()) / n)
+    print(f"paired vs single row kernels, B={batch}: worst gradient rel-L2 diff {worst:.2e}")
+    assert worst <= 2e-4

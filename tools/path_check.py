@@ -4,7 +4,10 @@ switches are read when the context is created), every forward tensor and every g
     python tools/path_check.py IINS_WIN [0 7]      # persistent window kernels (bit mask) vs the per-layer tensor-core kernels
     python tools/path_check.py IINS_FUSED_TRUNK
 
-Both settings use the same bf16 pieces and the same k order, so fp32-grade results agree to summation-order noise."""
+Both settings use the same bf16 pieces and the same k order, so fp32-grade results agree to summation-order noise.
+A switch that changes the rounding of a FORWARD tensor (IINS_ROW_PAIR) can flip a ReLU input that sits within rounding of zero:
+at the seeds used here that moves the range encoder's weight gradients by 3e-3 at B = 4096 -- and so does a 1e-7 perturbation of
+the input without touching any switch (tools/diag_row_pair.py), so read a MISMATCH there with that tool before blaming a kernel."""
 import os
 import subprocess
 import sys
