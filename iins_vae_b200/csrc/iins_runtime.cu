@@ -567,14 +567,18 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
         const int ls = ilog2_exact(g.Lout);
         const int nacc = g.Cout <= 4 ? 4 : (g.Cout <= 8 ? 8 : 16);
         int tps = 0;                                   // taps per k slice of the instantiated (NACC, CIN) pair
-        if (nacc == 4 && g.Cin == 1) tps = 7; else if (nacc == 16 && g.Cin == 1) tps = 7; else if (nacc == 4 && g.Cin == 4) tps = 7;
-        else if (nacc == 8 && g.Cin == 4) tps = 4; else if (nacc == 4 && g.Cin == 8) tps = 3; else if (nacc == 16 && g.Cin == 8) tps = 1;
+        // (few taps per slice = few accumulators per thread = more resident warps: the kernel walks its rows one after the other, each
+        // a dependent load -> FMA step, so what hides the load latency is the number of warps per SM, not the work per thread)
+        if (nacc == 4 && g.Cin == 1) tps = 7; else if (nacc == 16 && g.Cin == 1) tps = 4; else if (nacc == 4 && g.Cin == 4) tps = 2;
+        else if (nacc == 8 && g.Cin == 4) tps = 1; else if (nacc == 4 && g.Cin == 8) tps = 1; else if (nacc == 16 && g.Cin == 8) tps = 1;
         const long min_m = cur().opt.row2_tn_minm;       // below this many rows the end-of-kernel reduction dominates
         if (row2_on && tps > 0 && g.Cout <= 16 && ls >= 0 && p.M >= min_m && (g.Cin == 1 || g.in_layout == IINS_NLC)) {
             IinsRow2TNParams rp;
             memset(&rp, 0, sizeof(rp));
             const int nsl = (g.ks + tps - 1) / tps;
-            long want = (148L * 2 + nsl - 1) / nsl, max_parts = (p.M + 511) / 512;
+            const int na = nacc * g.Cin * tps;             // accumulators per thread -> CTAs per SM the registers allow
+            const int occ = na <= 36 ? 6 : (na <= 64 ? 4 : 2);
+            long want = (148L * occ + nsl - 1) / nsl, max_parts = (p.M + 511) / 512;
             if (want > max_parts) want = max_parts;
             if (want < 1) want = 1;
             long rpp = ((p.M + want - 1) / want + 127) / 128 * 128;
@@ -584,7 +588,7 @@ void conv_wgrad(Ctx& c, const IinsGeom& g, const float* x, const IinsDz& dz, flo
             IINS_SET_FLOPS(2.0 * (double)p.M * (double)g.Cout * (double)K); IINS_SET_SHAPE(p.M, g.Cout, K);
 #define IINS_R2T(NA_, CI_, TP_) \
             if (nacc == NA_ && g.Cin == CI_) { auto iins_row2_tn_kernel_ = iins_row2_tn_kernel<NA_, CI_, TP_>; IINS_LAUNCH(iins_row2_tn_kernel_, grid, 128, 0, wst, rp); return; }
-            IINS_R2T(4, 1, 7) IINS_R2T(16, 1, 7) IINS_R2T(4, 4, 7) IINS_R2T(8, 4, 4) IINS_R2T(4, 8, 3) IINS_R2T(16, 8, 1)
+            IINS_R2T(4, 1, 7) IINS_R2T(16, 1, 4) IINS_R2T(4, 4, 2) IINS_R2T(8, 4, 1) IINS_R2T(4, 8, 1) IINS_R2T(16, 8, 1)
 #undef IINS_R2T
         }
     }
