@@ -46,6 +46,7 @@ struct IinsOptions {
     int fuse_nbwd = 1;          // IINS_FUSE_NBWD: norm backward in the data-gradient epilogue
     int row2 = 1;               // IINS_ROW2: one-thread-per-row kernels for the small-channel layers
     int row_pair_mask = 31;     // IINS_ROW_PAIR_MASK (diagnostics): 1 forward plain, 2 forward + IN, 4 forward + LN, 8 data gradient, 16 data gradient + IN backward
+    int lin_dgrad_fwd = 1;      // IINS_LIN_DGRAD_FWD: data gradients of Linear layers through the forward-mapped tensor-core instance
     long row_pair = 65536;      // IINS_ROW_PAIR: two rows per thread in those kernels for layers with at least this many rows (0: never)
     long row2_tn_minm = 16384;  // IINS_ROW2_TN_MINM
     long tn_ctas = 148L * 2;    // IINS_TN_CTAS: CTAs a weight-gradient launch aims for
@@ -86,6 +87,7 @@ void options_from_env(IinsOptions& o) {
     o.row2 = env_int("IINS_ROW2", 1);
     o.row_pair = env_int("IINS_ROW_PAIR", 65536);
     o.row_pair_mask = env_int("IINS_ROW_PAIR_MASK", 31);
+    o.lin_dgrad_fwd = env_int("IINS_LIN_DGRAD_FWD", 1);
     o.row2_tn_minm = env_int("IINS_ROW2_TN_MINM", 16384);
     o.tn_ctas = env_int("IINS_TN_CTAS", 148 * 2);
     if (o.tn_ctas < 1) o.tn_ctas = 148;
@@ -325,6 +327,16 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
             wp.lsh_in = ilog2_exact(g0.Lout);
             if (iins_win_nt_launch(c.st, wp, nt, IINS_WIN_S2D, epi, ll)) return;
         }
+    }
+    if (akind == 1 && cur().opt.lin_dgrad_fwd && g0.ks == 1 && g0.Lin == 1 && g0.Lout == 1 && g0.stride == 1 && g0.pad == 0 &&
+        g0.out_layout == IINS_NLC && !p.dz.dy_bcast && (g0.Cout & 3) == 0 && (epi == IINS_EPI_PLAIN || epi == IINS_EPI_SMEM)) {
+        // data gradient of a Linear layer: dz is a plain row-major matrix, so the forward instance's coalesced quad loads apply
+        // (the dgrad instance keeps one row per lane for the conv candidates' arithmetic); same packed weights, same k order
+        akind = 0;
+        tp.lin_dz = 1;
+        tp.nt.x = p.dz.dy;
+        tp.nt.g.Cin = g0.Cout;                        // row stride of the A operand
+        tp.nt.g.in_layout = IINS_NLC;
     }
     const bool launched = tp.pieces == 3 ? iins_launch_tc_nt_p3(c.st, tp, grid, nt, akind, epi, ll)
                                          : iins_launch_tc_nt_p1(c.st, tp, grid, nt, akind, epi, ll);

@@ -571,6 +571,7 @@ struct IinsTCParams {
     const uint16_t* wpack_odd;   // AKIND 2: packed weights of the odd-position class (blockIdx.z = 1)
     int pieces;          // 3 (fp32-grade) or 1 (bf16)
     int nkb;             // K blocks of 32
+    int lin_dz;          // 1: the A operand of this AKIND 0 launch is dz of a Linear layer (nt.x = dy, row stride nt.g.Cin): apply nt.dz's mask / scale
 };
 
 // 288 threads: warps 0-7 are PRODUCERS (gather / split / store the A tile, later the epilogue), warp 8 is the
@@ -627,13 +628,40 @@ static __global__ void __launch_bounds__(288, 2) iins_tc_nt_kernel(const IinsTCP
     // raw operand data of TWO K blocks ahead lives in registers (the loads of block kb+2 are issued right after
     // block kb is handed to the MMA warp), so a K block costs its convert/store work, not a global-load latency
     float4 raw[2][4];
+    // a Linear layer (one tap, one position per sample) reads a plain row-major matrix: row pointers are set up once and a K block
+    // costs an add per load (the generic gather spends ~45 % of this kernel's instructions on tap / padding arithmetic there: ncu)
+    const bool a_lin = AKIND == 0 && g.ks == 1 && g.Lin == 1 && g.Lout == 1 && g.stride == 1 && g.pad == 0 && g.in_layout == IINS_NLC;
+    const float* a_ptr[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) a_ptr[jj] = p.x + (long)(a_ok[jj] ? tile_m + a_row0 + 4 * jj : 0) * g.Cin;
     auto load_raw = [&](int kb, float4* dst) {
         // the host routes layers without 16-byte gathers (< 8 channels, NCL operand) to the SIMT kernels
         if (AKIND == 0) {
             const int k0 = kb * 32 + a_quad * 4;
+            if (a_lin) {
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-                dst[jj] = a_ok[jj] ? iins_gather4_fwd(g, p.x, p.K, cs, a_b[jj], a_l[jj], k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int jj = 0; jj < 4; ++jj) dst[jj] = iins_ld4(a_ptr[jj] + k0, a_ok[jj] && k0 < p.K);
+                if (tp.lin_dz) {
+                    // data gradient of a Linear layer through the forward mapping (4 rows x 128 B per warp-level load instead of
+                    // 32 rows x 16 B):  dz = dy * act'(y) * scale
+                    if (p.dz.y != nullptr && p.dz.act != IINS_ACT_NONE) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const float4 y = iins_ld4(p.dz.y + (a_ptr[jj] - p.x) + k0, a_ok[jj] && k0 < p.K);
+                            dst[jj].x *= iins_dact_from_y(y.x, p.dz.act, p.dz.slope); dst[jj].y *= iins_dact_from_y(y.y, p.dz.act, p.dz.slope);
+                            dst[jj].z *= iins_dact_from_y(y.z, p.dz.act, p.dz.slope); dst[jj].w *= iins_dact_from_y(y.w, p.dz.act, p.dz.slope);
+                        }
+                    }
+                    if (p.dz.dy_scale != 1.f) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) { dst[jj].x *= p.dz.dy_scale; dst[jj].y *= p.dz.dy_scale; dst[jj].z *= p.dz.dy_scale; dst[jj].w *= p.dz.dy_scale; }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    dst[jj] = a_ok[jj] ? iins_gather4_fwd(g, p.x, p.K, cs, a_b[jj], a_l[jj], k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         } else if (AKIND == 2) {
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
