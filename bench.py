@@ -533,7 +533,7 @@ def main():
         top_name, top = max(agg.items(), key=lambda kv: kv[1]["ms"])
         # DRAM traffic per launch of that kernel from the committed ncu --set full capture (profiles/), if present
         traffic = None
-        for tname in ("r02e_ncu_traffic.json", "r02a_ncu_traffic.json", "r01b_ncu_traffic.json"):   # newest capture that holds this family
+        for tname in ("r02f_ncu_traffic.json", "r02e_ncu_traffic.json", "r02a_ncu_traffic.json", "r01b_ncu_traffic.json"):   # newest capture that holds this family
             tpath = os.path.join(ROOT, "profiles", tname)
             if traffic is None and os.path.exists(tpath):
                 with open(tpath) as f:
