@@ -47,6 +47,7 @@ struct IinsOptions {
     int row2 = 1;               // IINS_ROW2: one-thread-per-row kernels for the small-channel layers
     int row_pair_mask = 31;     // IINS_ROW_PAIR_MASK (diagnostics): 1 forward plain, 2 forward + IN, 4 forward + LN, 8 data gradient, 16 data gradient + IN backward
     int lin_dgrad_fwd = 1;      // IINS_LIN_DGRAD_FWD: data gradients of Linear layers through the forward-mapped tensor-core instance
+    int pack_async = 1;         // IINS_PACK_ASYNC: a pass packs its weights on a helper stream; the first tensor-core launch of each stream waits for it
     long row_pair = 65536;      // IINS_ROW_PAIR: two rows per thread in those kernels for layers with at least this many rows (0: never)
     long row2_tn_minm = 16384;  // IINS_ROW2_TN_MINM
     long tn_ctas = 148L * 2;    // IINS_TN_CTAS: CTAs a weight-gradient launch aims for
@@ -60,7 +61,7 @@ struct IinsOptions {
     int defer_join = 0;         // iins_set_deferred_join: a backward pass does NOT wait for its weight-gradient stream at its end
 };
 
-struct IinsHelperStreams { cudaStream_t main; cudaStream_t helper[2]; bool unjoined; /* deferred join outstanding on helper[0] */ };
+struct IinsHelperStreams { cudaStream_t main; cudaStream_t helper[3]; bool unjoined; /* deferred join outstanding on helper[0] */ };   // [2]: weight packing
 
 struct iins_ctx {
     IinsOptions opt;
@@ -87,6 +88,7 @@ void options_from_env(IinsOptions& o) {
     o.row2 = env_int("IINS_ROW2", 1);
     o.row_pair = env_int("IINS_ROW_PAIR", 65536);
     o.row_pair_mask = env_int("IINS_ROW_PAIR_MASK", 31);
+    o.pack_async = env_int("IINS_PACK_ASYNC", 1);
     o.lin_dgrad_fwd = env_int("IINS_LIN_DGRAD_FWD", 1);
     o.row2_tn_minm = env_int("IINS_ROW2_TN_MINM", 16384);
     o.tn_ctas = env_int("IINS_TN_CTAS", 148 * 2);
@@ -133,6 +135,9 @@ struct Ctx {
     int njobs = 0, job_i = 0;
     size_t arena = 0;           // bytes of the arena handed out so far
     cudaStream_t st2 = nullptr; // side stream: weight gradients run here, concurrently with the dgrad chain
+    cudaEvent_t pack_ev = nullptr;       // the pass's weight packs run on a helper stream: recorded behind them ...
+    cudaStream_t pack_waited[4] = {nullptr, nullptr, nullptr, nullptr};   // ... and awaited once by every stream that launches a consumer
+    int n_pack_waited = 0;
     // A data-gradient GEMM is held back until the next call: if that call is the InstanceNorm / AdaIN backward of the
     // tensor it produces, both run as ONE kernel (fused epilogue); any other call launches it unchanged first.
     bool has_pending = false;
@@ -230,6 +235,7 @@ void launch_nt_simt(const Ctx& c, const IinsNTParams& p) {
 }
 
 #ifndef IINS_CPUSIM
+void wait_pack(Ctx& c);
 void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     const int nt_max = cur().opt.nt_max;   // tuning knob: cap the tile width (more, smaller CTAs)
     int nt = p.N <= 16 ? 16 : (p.N <= 32 ? 32 : 64);
@@ -267,6 +273,7 @@ void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     }
     const uint16_t* pack_even = nullptr;
     const uint16_t* pack_odd = nullptr;
+    wait_pack(c);
     if (c.phase == 2) {
         pk.out = c.jobs.jobs[c.job_i++].out;
         if (par_geom) { pack_even = c.jobs.jobs[c.job_i++].out; pack_odd = c.jobs.jobs[c.job_i++].out; }
@@ -509,7 +516,7 @@ cudaStream_t helper_stream(cudaStream_t main_st, int which) {
     if (x.n_helpers >= 32) return nullptr;              // more caller streams than slots: that caller runs serially
     IinsHelperStreams& h = x.helpers[x.n_helpers];
     h.main = main_st; h.unjoined = false;
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 3; ++k)
         if (cudaStreamCreateWithFlags(&h.helper[k], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     ++x.n_helpers;
     return h.helper[which];
@@ -528,6 +535,18 @@ cudaStream_t side_stream(cudaStream_t) { return nullptr; }
 cudaStream_t branch_stream(cudaStream_t) { return nullptr; }
 void fork_to(cudaStream_t, cudaStream_t) {}
 #endif
+// The packed weights of a pass are written by one kernel on a helper stream (run_phases); a stream that is about to launch a
+// kernel reading them waits for that kernel once.
+void wait_pack(Ctx& c) {
+#ifndef IINS_CPUSIM
+    if (c.pack_ev == nullptr) return;
+    for (int i = 0; i < c.n_pack_waited; ++i) if (c.pack_waited[i] == c.st) return;
+    cudaStreamWaitEvent(c.st, c.pack_ev, 0);
+    if (c.n_pack_waited < 4) c.pack_waited[c.n_pack_waited++] = c.st;
+#else
+    (void)c;
+#endif
+}
 void begin_async_wgrad(Ctx& c) { if (c.phase != 1) c.st2 = side_stream(c.st); }
 // At the end of a backward pass the caller's stream normally waits for the weight-gradient stream (the gradients are then
 // complete in stream order, as the autograd path needs).  With deferred joins (iins_set_deferred_join, used by the fused
@@ -786,11 +805,24 @@ void run_phases(Ctx& c, F&& body) {
             c.jobs.njobs = c.njobs;
             c.jobs.pieces = g_mode == 1 ? 1 : 3;
             IINS_SET_FLOPS(0.0); IINS_SET_BYTES(0.0); IINS_SET_SHAPE(0, 0, 0);      // (the collect pass set them without launching)
-            IINS_LAUNCH(iins_pack_all_kernel, grid_for(c.jobs.total), 256, 0, c.st, c.jobs);
+            cudaStream_t ps = cur().opt.pack_async ? helper_stream(c.st, 2) : nullptr;
+            if (ps != nullptr) {
+                // the layers in front of the first tensor-core layer of a pass (stems, row kernels, pooling) run next to the pack
+                iins_ctx& x = cur();
+                fork_to(c.st, ps);
+                IINS_LAUNCH(iins_pack_all_kernel, grid_for(c.jobs.total), 256, 0, ps, c.jobs);
+                { std::lock_guard<std::mutex> lock(x.mu); c.pack_ev = x.fork_events[x.fork_i++ & 255]; }
+                cudaEventRecord(c.pack_ev, ps);
+                c.n_pack_waited = 0;
+            } else {
+                IINS_LAUNCH(iins_pack_all_kernel, grid_for(c.jobs.total), 256, 0, c.st, c.jobs);
+            }
         }
+        cudaStream_t main_st = c.st;
         c.phase = 2; c.job_i = 0;
         body();
         flush_pending(c);
+        if (c.pack_ev != nullptr) { c.st = main_st; wait_pack(c); c.pack_ev = nullptr; }      // (joins the helper stream: graph capture)
         c.phase = 0;
         return;
     }
@@ -817,6 +849,7 @@ bool trunk_forward_fused(Ctx& c, int B, int D, int Lt, int nres, const float* x,
     memset(&tp, 0, sizeof(tp));
     tp.B = B; tp.nconv = 2 * nres; tp.pieces = pieces; tp.x = x; tp.adain = adain; tp.adain_ld = adain_ld;
     tp.use_tmap = cur().opt.trunk_tmap;
+    wait_pack(c);
     tp.wpack = c.jobs.jobs[c.job_i].out;
     for (int k = 0; k < 2 * nres; ++k) {
         const IinsPackJob& j = c.jobs.jobs[c.job_i + k];
@@ -849,6 +882,7 @@ bool trunk_backward_fused(Ctx& c, int B, int D, int Lt, int nres, const float* d
     tp.B = B; tp.nconv = nconv; tp.pieces = pieces; tp.dh = dh; tp.dx = dx; tp.dh_scratch = dh_scratch;
     tp.adain = adain; tp.dadain = dadain; tp.adain_ld = adain_ld;
     tp.use_tmap = cur().opt.trunk_tmap;
+    wait_pack(c);
     tp.wpack = c.jobs.jobs[c.job_i].out;
     for (int k = 0; k < nconv; ++k) {
         const IinsPackJob& j = c.jobs.jobs[c.job_i + k];          // job k packs convolution nconv - 1 - k
@@ -1702,7 +1736,7 @@ void iins_ctx_destroy(iins_ctx* ctx) {
     if (ctx == nullptr) return;
     if (t_ctx == ctx) t_ctx = nullptr;
 #ifndef IINS_CPUSIM
-    for (int i = 0; i < ctx->n_helpers; ++i) for (int k = 0; k < 2; ++k) cudaStreamDestroy(ctx->helpers[i].helper[k]);
+    for (int i = 0; i < ctx->n_helpers; ++i) for (int k = 0; k < 3; ++k) cudaStreamDestroy(ctx->helpers[i].helper[k]);
     if (ctx->events_ready) for (int i = 0; i < 256; ++i) cudaEventDestroy(ctx->fork_events[i]);
 #endif
     delete ctx;
