@@ -79,6 +79,31 @@ def test_semi_step_matches_oracle_with_paired_rows(sim, paired_rows_ctx):
     test_semi_step_matches_oracle(sim, 6, False, 6)
 
 
+@pytest.fixture
+def row_wgrad_ctx(sim):
+    """A context created with IINS_ROW2_TN_MINM=1: the small-channel weight gradients run on the one-thread-per-row kernel
+    (iins_row2_tn_kernel: k slices of <= 32 accumulators per thread, CTA reduction, one atomic per weight) at ANY row count --
+    by default only from 16384 rows up, which the simulator never reaches."""
+    import os
+    _, lib = sim
+    old = os.environ.get("IINS_ROW2_TN_MINM")
+    os.environ["IINS_ROW2_TN_MINM"] = "1"
+    ctx = lib.dll.iins_ctx_create()
+    if old is None:
+        os.environ.pop("IINS_ROW2_TN_MINM", None)
+    else:
+        os.environ["IINS_ROW2_TN_MINM"] = old
+    assert ctx
+    lib.dll.iins_ctx_make_current(ctx)
+    yield ctx
+    lib.dll.iins_ctx_make_current(None)
+    lib.dll.iins_ctx_destroy(ctx)
+
+
+def test_semi_step_matches_oracle_with_row_weight_gradient_kernel(sim, row_wgrad_ctx):
+    test_semi_step_matches_oracle(sim, 5, True, 3)
+
+
 @pytest.mark.parametrize("batch,supervised,seed", [(2, True, 0), (5, False, 1), (19, True, 2)])
 def test_semi_step_matches_oracle(sim, batch, supervised, seed):
     H, lib = sim
