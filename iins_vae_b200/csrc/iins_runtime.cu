@@ -239,7 +239,8 @@ void wait_pack(Ctx& c);
 void launch_nt_tc(Ctx& c, const IinsNTParams& p) {
     const int nt_max = cur().opt.nt_max;   // tuning knob: cap the tile width (more, smaller CTAs)
     int nt = p.N <= 16 ? 16 : (p.N <= 32 ? 32 : 64);
-    if (nt > nt_max && (p.ep.norm == IINS_NORM_NONE || p.ep.norm == IINS_NORM_IN || p.ep.norm == IINS_NORM_ADAIN)) nt = nt_max;
+    // (not under a fused norm backward: nbwd_fusable() has already matched that epilogue to the uncapped tile width)
+    if (nt > nt_max && p.ep.nb_dz == nullptr && (p.ep.norm == IINS_NORM_NONE || p.ep.norm == IINS_NORM_IN || p.ep.norm == IINS_NORM_ADAIN)) nt = nt_max;
     IinsPackParams pk;
     memset(&pk, 0, sizeof(pk));
     pk.g = p.g; pk.kind = p.a_kind; pk.w = p.w; pk.out = reinterpret_cast<uint16_t*>(c.wpack);
