@@ -541,12 +541,12 @@ static __global__ void __launch_bounds__(256) iins_row_nt_kernel(const IinsRowPa
 }
 
 // ---- one thread per output row ("row2") --------------------------------------------------------------------
-// The small-channel layers are HBM streams (L = 32..128 positions, <= 16 channels): what limits them is the number
-// of instructions per output row, not arithmetic.  One thread owns one GEMM row and all NACC (4 / 8 / 16) output
-// channels in registers: a tap/channel step is NACC/4 16-byte weight loads from shared memory + NACC FFMAs, the
-// InstanceNorm / AdaIN / LayerNorm statistics are warp-shuffle sums (+ one shared-memory exchange between the
-// L/32 warps of a sample), and the row leaves the registers as 16-byte stores -- no staging of the tile in shared
-// memory, no second thread per row.  128 threads = 128 rows = whole samples (L <= 128).
+// The small-channel layers are HBM streams (L = 32..128 positions, <= 16 channels) with next to no arithmetic.  One thread
+// owns one GEMM row (or R rows) and all NACC (4 / 8 / 16) output channels in registers: a tap/channel step is NACC/4
+// 16-byte weight loads from shared memory + NACC FMAs per row, the InstanceNorm / AdaIN / LayerNorm statistics are
+// warp-shuffle sums (+ one shared-memory exchange between the warps of a sample), and the row leaves the registers as
+// 16-byte stores -- no staging of the tile in shared memory.  128 threads = 128 R rows = whole samples (L <= 128).
+// What limits them (measured, profiles/r02f_row_pair.txt) is the shared-memory pipe of those weight reads: see iins_row2_fma.
 // Preconditions (host): N <= NACC, K <= IINS_ROW2_KMAX(NACC); with a fused norm: L in {32, 64, 128}.
 #define IINS_ROW2_WMAX 1024            // floats of weights in shared memory: K * NACC <= 1024
 
