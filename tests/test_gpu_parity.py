@@ -462,6 +462,8 @@ def test_bf16_mode_full_gradient_parity(batch):
         worst = max(rows, key=lambda r: r[1])
         print(f"[bf16] B={batch} sup={supervised}: gradient rel-L2 vs fp64: worst {worst[1]:.2e} ({worst[0]}; bf16-operand reference "
               f"{worst[2]:.2e}); CUDA/reference error ratio median {ratio[len(ratio) // 2]:.2f} max {ratio[-1]:.2f}")
+        top = max(rows, key=lambda r: r[1] / max(r[2], 1e-12))
+        print(f"       largest ratio: {top[0]} CUDA {top[1]:.2e} vs bf16-operand reference {top[2]:.2e} (floor {BF16_FLOOR:.0e})")
         for name, e_got, e_emu in rows:
             assert e_got <= max(BF16_FLOOR, BF16_FACTOR * e_emu), (f"{name}: rel-L2 {e_got:.2e} vs fp64, beyond {BF16_FACTOR}x the "
                                                                   f"bf16-operand reference's own {e_emu:.2e}")
